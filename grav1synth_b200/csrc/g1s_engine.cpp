@@ -1,0 +1,487 @@
+// The engine behind include/g1s.h: owns the device buffers, the CUDA stream and the
+// host noise model, and turns pushed frame pairs into grain-table segments.
+//
+// Data flow per batch ("slot") of B frame pairs:
+//   caller planes --memcpy--> pinned staging --cudaMemcpyAsync--> HBM frame store
+//   HBM frames --flat_features / flat_select / gram kernels--> HBM per-frame records
+//   records --cudaMemcpyAsync--> pinned host --DiffSequencer (f64 solves, in frame order)
+// Three slots rotate, so the caller fills slot k+1 while the device works on slot k and
+// the records of slot k-1 are folded into the model.  There is no CPU fallback: every
+// device failure is reported as G1S_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/g1s.h"
+#include "g1s_kernels.h"
+#include "g1s_model.h"
+
+using namespace g1s;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kSlots = 3;
+
+struct PlaneGeom {
+  int w, h;          // storage size in samples
+  size_t pitch[2];   // [0] source, [1] denoised: bytes per row in the HBM frame store
+  size_t off[2];     // byte offset inside one frame-pair slot entry
+};
+
+struct Slot {
+  uint8_t *d_frames = nullptr;   // B * pair_bytes
+  uint8_t *h_frames = nullptr;   // pinned mirror
+  FrameDesc *d_descs = nullptr;
+  FrameDesc *h_descs = nullptr;  // pinned
+  uint8_t *d_records = nullptr;
+  uint8_t *h_records = nullptr;  // pinned
+  cudaEvent_t done = nullptr, k0_beg = nullptr, k0_end = nullptr, k1_beg = nullptr, k1_end = nullptr;
+  int count = 0;                 // frames staged
+  int host_frames = 0;           // of which need the H2D copy (contiguous prefix is not required)
+  bool in_flight = false;
+};
+
+}  // namespace
+
+struct g1s_diff {
+  g1s_diff_config cfg{};
+  Geometry geom{};
+  StreamGeometry sgeom{};
+  RecordLayout rl{};
+  FlatConsts fc{};
+  PlaneGeom pg[3]{};
+  size_t pair_bytes = 0;
+  int batch = 1;
+  cudaStream_t stream = nullptr;
+  Slot slots[kSlots];
+  int cur = 0;            // slot being filled
+  int oldest = 0;         // oldest slot possibly in flight
+  std::unique_ptr<DiffSequencer> seq;
+  std::string err;
+  bool finished = false;
+  int64_t pushed = 0;
+  int64_t retired = 0;
+  g1s_record_fn tap = nullptr;
+  void *tap_user = nullptr;
+  // counters
+  double kernels_launched = 0, k1_ms = 0, k1_launches = 0, k0_ms = 0, k0_launches = 0, frames_done = 0;
+};
+
+namespace {
+
+#define CU_TRY(d, expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      (d)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                            \
+      return G1S_E_CUDA;                                                                        \
+    }                                                                                           \
+  } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+FrameRecordView view_of(const g1s_diff *d, const uint8_t *rec) {
+  FrameRecordView v;
+  v.gram = reinterpret_cast<const int64_t *>(rec + d->rl.off_gram);
+  v.nobs = reinterpret_cast<const int64_t *>(rec + d->rl.off_nobs);
+  v.num_flat = *reinterpret_cast<const int64_t *>(rec + d->rl.off_num_flat);
+  v.luma_sum = reinterpret_cast<const uint32_t *>(rec + d->rl.off_luma_sum);
+  v.rsum = reinterpret_cast<const int32_t *>(rec + d->rl.off_rsum);
+  v.rsq = reinterpret_cast<const uint32_t *>(rec + d->rl.off_rsq);
+  v.flat = rec + d->rl.off_flat;
+  return v;
+}
+
+int submit(g1s_diff *d, Slot &s) {
+  if (s.count == 0) return G1S_OK;
+  cudaStream_t st = d->stream;
+  if (s.host_frames > 0)
+    CU_TRY(d, cudaMemcpyAsync(s.d_frames, s.h_frames, (size_t)s.count * d->pair_bytes, cudaMemcpyHostToDevice, st));
+  CU_TRY(d, cudaMemcpyAsync(s.d_descs, s.h_descs, sizeof(FrameDesc) * s.count, cudaMemcpyHostToDevice, st));
+  CU_TRY(d, cudaMemsetAsync(s.d_records, 0, d->rl.bytes * s.count, st));
+  CU_TRY(d, cudaEventRecord(s.k0_beg, st));
+  launch_flat_features(s.d_descs, s.count, d->geom, d->fc, s.d_records, d->rl, st);
+  CU_TRY(d, cudaEventRecord(s.k0_end, st));
+  launch_flat_select(s.count, d->geom, s.d_records, d->rl, st);
+  CU_TRY(d, cudaEventRecord(s.k1_beg, st));
+  launch_gram_generic(s.d_descs, s.count, d->geom, s.d_records, d->rl, st);
+  CU_TRY(d, cudaEventRecord(s.k1_end, st));
+  CU_TRY(d, cudaGetLastError());
+  CU_TRY(d, cudaMemcpyAsync(s.h_records, s.d_records, d->rl.bytes * s.count, cudaMemcpyDeviceToHost, st));
+  CU_TRY(d, cudaEventRecord(s.done, st));
+  s.in_flight = true;
+  d->kernels_launched += 3;
+  d->k0_launches += 1;
+  d->k1_launches += 1;
+  return G1S_OK;
+}
+
+// Waits for a slot's device work and folds its records into the model (frame order).
+int retire(g1s_diff *d, Slot &s) {
+  if (!s.in_flight) return G1S_OK;
+  CU_TRY(d, cudaEventSynchronize(s.done));
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, s.k0_beg, s.k0_end) == cudaSuccess) d->k0_ms += ms;
+  if (cudaEventElapsedTime(&ms, s.k1_beg, s.k1_end) == cudaSuccess) d->k1_ms += ms;
+  for (int i = 0; i < s.count; ++i) {
+    const uint8_t *rec = s.h_records + (size_t)i * d->rl.bytes;
+    if (d->tap) d->tap(d->tap_user, d->retired, rec, d->rl.bytes);
+    if (d->cfg.mode != G1S_MODE_PRODUCER) d->seq->consume(view_of(d, rec));
+    d->retired++;
+  }
+  d->frames_done += s.count;
+  s.in_flight = false;
+  s.count = 0;
+  s.host_frames = 0;
+  return G1S_OK;
+}
+
+int rotate(g1s_diff *d) {
+  int rc = submit(d, d->slots[d->cur]);
+  if (rc != G1S_OK) return rc;
+  d->cur = (d->cur + 1) % kSlots;
+  // the slot we are about to fill must be free; retire in submission order
+  while (d->slots[d->cur].in_flight) {
+    rc = retire(d, d->slots[d->oldest]);
+    if (rc != G1S_OK) return rc;
+    d->oldest = (d->oldest + 1) % kSlots;
+  }
+  return G1S_OK;
+}
+
+int drain(g1s_diff *d) {
+  int rc = submit(d, d->slots[d->cur]);
+  if (rc != G1S_OK) return rc;
+  if (d->slots[d->cur].in_flight) d->cur = (d->cur + 1) % kSlots;
+  for (int k = 0; k < kSlots; ++k) {
+    rc = retire(d, d->slots[d->oldest]);
+    if (rc != G1S_OK) return rc;
+    d->oldest = (d->oldest + 1) % kSlots;
+  }
+  d->oldest = d->cur;
+  return G1S_OK;
+}
+
+int check_frames(g1s_diff *d, const g1s_frame *s, const g1s_frame *n) {
+  if (!s || !n) {
+    d->err = "null frame";
+    return G1S_E_ARG;
+  }
+  if (s->width != n->width || s->height != n->height) {
+    char b[160];
+    std::snprintf(b, sizeof b, "Luma dimensions do not match: source %dx%d, denoised %dx%d", s->width, s->height,
+                  n->width, n->height);
+    d->err = b;
+    return G1S_E_DIMS;
+  }
+  if (s->width != d->cfg.width || s->height != d->cfg.height) {
+    d->err = "frame size differs from the size the handle was created for";
+    return G1S_E_ARG;
+  }
+  for (int c = 0; c < d->geom.planes; ++c)
+    if (!s->plane[c] || !n->plane[c]) {
+      d->err = "missing plane";
+      return G1S_E_ARG;
+    }
+  return G1S_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int g1s_abi_version(void) { return G1S_ABI_VERSION; }
+
+int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
+  if (!cfg || !out) {
+    g_create_error = "null argument";
+    return G1S_E_ARG;
+  }
+  *out = nullptr;
+  if (cfg->width <= 0 || cfg->height <= 0 || cfg->fps_num <= 0 || cfg->fps_den <= 0 || cfg->src_bit_depth < 8 ||
+      cfg->src_bit_depth > 16 || cfg->den_bit_depth < 8 || cfg->den_bit_depth > 16 || cfg->ss_x < 0 ||
+      cfg->ss_x > 1 || cfg->ss_y < 0 || cfg->ss_y > 1) {
+    g_create_error = "unsupported configuration (bit depths 8..16, subsampling log2 0..1, positive size and fps)";
+    return G1S_E_ARG;
+  }
+  if (cfg->mode < G1S_MODE_FULL || cfg->mode > G1S_MODE_CONSUMER) {
+    g_create_error = "unknown mode";
+    return G1S_E_ARG;
+  }
+  const bool consumer = cfg->mode == G1S_MODE_CONSUMER;
+  int ndev = 0;
+  cudaError_t ce = consumer ? cudaSuccess : cudaGetDeviceCount(&ndev);
+  if (!consumer && (ce != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev)) {
+    g_create_error = std::string("no usable CUDA device (this engine has no CPU fallback): ") +
+                     (ce != cudaSuccess ? cudaGetErrorString(ce) : "device ordinal out of range");
+    return G1S_E_CUDA;
+  }
+  std::unique_ptr<g1s_diff> d(new g1s_diff);
+  d->cfg = *cfg;
+  auto fail = [&](int code) {
+    g_create_error = d->err;
+    g1s_diff_destroy(d.release());
+    return code;
+  };
+#define CU_NEW(expr)                                                     \
+  do {                                                                   \
+    cudaError_t e_ = (expr);                                             \
+    if (e_ != cudaSuccess) {                                             \
+      d->err = std::string(#expr) + ": " + cudaGetErrorString(e_);       \
+      return fail(e_ == cudaErrorMemoryAllocation ? G1S_E_NOMEM : G1S_E_CUDA); \
+    }                                                                    \
+  } while (0)
+  if (!consumer) CU_NEW(cudaSetDevice(cfg->device));
+
+  Geometry &g = d->geom;
+  g.width = cfg->width;
+  g.height = cfg->height;
+  g.ss_x = cfg->ss_x;
+  g.ss_y = cfg->ss_y;
+  g.planes = cfg->monochrome ? 1 : 3;
+  g.src_shift = cfg->src_bit_depth - 8;
+  g.den_shift = cfg->den_bit_depth - 8;
+  g.src_bytes = cfg->src_bit_depth > 8 ? 2 : 1;
+  g.den_bytes = cfg->den_bit_depth > 8 ? 2 : 1;
+  g.nbw = (g.width + kBlock - 1) / kBlock;
+  g.nbh = (g.height + kBlock - 1) / kBlock;
+  g.nb = g.nbw * g.nbh;
+  d->sgeom.width = g.width;
+  d->sgeom.height = g.height;
+  d->sgeom.ss_x = g.ss_x;
+  d->sgeom.ss_y = g.ss_y;
+  d->sgeom.planes = g.planes;
+  d->sgeom.nbw = g.nbw;
+  d->sgeom.nbh = g.nbh;
+  d->sgeom.nb = g.nb;
+  d->rl = RecordLayout::make(g.nb);
+  flat_block_ata_inv(d->fc.ata_inv);
+  d->seq.reset(new DiffSequencer(cfg->fps_num, cfg->fps_den, d->sgeom));
+
+  size_t off = 0;
+  for (int c = 0; c < g.planes; ++c) {
+    PlaneGeom &p = d->pg[c];
+    p.w = c ? (g.width + g.ss_x) >> g.ss_x : g.width;
+    p.h = c ? (g.height + g.ss_y) >> g.ss_y : g.height;
+    const int bytes[2] = {g.src_bytes, g.den_bytes};
+    for (int k = 0; k < 2; ++k) {
+      p.pitch[k] = align_up((size_t)p.w * bytes[k], 16);
+      p.off[k] = off;
+      off += align_up(p.pitch[k] * p.h, 256);
+    }
+  }
+  d->pair_bytes = off;
+  // default batch: about 384 MiB of frame pairs per slot, at most 64 frames
+  int batch = cfg->batch_frames;
+  if (batch <= 0) batch = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)384 << 20) / d->pair_bytes));
+  d->batch = batch;
+
+  if (consumer) {
+    *out = d.release();
+    return G1S_OK;
+  }
+  CU_NEW(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  for (Slot &s : d->slots) {
+    CU_NEW(cudaMalloc(&s.d_frames, (size_t)batch * d->pair_bytes));
+    CU_NEW(cudaMallocHost(&s.h_frames, (size_t)batch * d->pair_bytes));
+    CU_NEW(cudaMalloc(&s.d_descs, sizeof(FrameDesc) * batch));
+    CU_NEW(cudaMallocHost(&s.h_descs, sizeof(FrameDesc) * batch));
+    CU_NEW(cudaMalloc(&s.d_records, d->rl.bytes * batch));
+    CU_NEW(cudaMallocHost(&s.h_records, d->rl.bytes * batch));
+    CU_NEW(cudaEventCreate(&s.done));
+    CU_NEW(cudaEventCreate(&s.k0_beg));
+    CU_NEW(cudaEventCreate(&s.k0_end));
+    CU_NEW(cudaEventCreate(&s.k1_beg));
+    CU_NEW(cudaEventCreate(&s.k1_end));
+  }
+#undef CU_NEW
+  *out = d.release();
+  return G1S_OK;
+}
+
+int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *denoised) {
+  if (!d) return G1S_E_ARG;
+  if (d->finished || d->cfg.mode == G1S_MODE_CONSUMER) {
+    d->err = d->finished ? "push after finish" : "consumer handles take records, not frames";
+    return G1S_E_STATE;
+  }
+  int rc = check_frames(d, source, denoised);
+  if (rc != G1S_OK) return rc;
+  Slot &s = d->slots[d->cur];
+  const size_t base = (size_t)s.count * d->pair_bytes;
+  FrameDesc &fd = s.h_descs[s.count];
+  std::memset(&fd, 0, sizeof fd);
+  const g1s_frame *fr[2] = {source, denoised};
+  const int bytes[2] = {d->geom.src_bytes, d->geom.den_bytes};
+  for (int c = 0; c < d->geom.planes; ++c) {
+    const PlaneGeom &p = d->pg[c];
+    for (int k = 0; k < 2; ++k) {
+      const size_t row_bytes = (size_t)p.w * bytes[k];
+      if (fr[k]->stride_bytes[c] < row_bytes) {
+        d->err = "stride smaller than a row";
+        return G1S_E_ARG;
+      }
+      uint8_t *dst = s.h_frames + base + p.off[k];
+      const uint8_t *src = static_cast<const uint8_t *>(fr[k]->plane[c]);
+      if (fr[k]->stride_bytes[c] == p.pitch[k]) {
+        std::memcpy(dst, src, p.pitch[k] * (size_t)(p.h - 1) + row_bytes);
+      } else {
+        for (int y = 0; y < p.h; ++y) std::memcpy(dst + (size_t)y * p.pitch[k], src + (size_t)y * fr[k]->stride_bytes[c], row_bytes);
+      }
+      const void *dev = s.d_frames + base + p.off[k];
+      if (k == 0) {
+        fd.src[c] = dev;
+        fd.src_stride[c] = (uint32_t)p.pitch[k];
+      } else {
+        fd.den[c] = dev;
+        fd.den_stride[c] = (uint32_t)p.pitch[k];
+      }
+    }
+  }
+  s.count++;
+  s.host_frames++;
+  d->pushed++;
+  if (s.count == d->batch) return rotate(d);
+  return G1S_OK;
+}
+
+int g1s_diff_push_frame_device(g1s_diff *d, const g1s_frame *source, const g1s_frame *denoised) {
+  if (!d) return G1S_E_ARG;
+  if (d->finished || d->cfg.mode == G1S_MODE_CONSUMER) {
+    d->err = d->finished ? "push after finish" : "consumer handles take records, not frames";
+    return G1S_E_STATE;
+  }
+  int rc = check_frames(d, source, denoised);
+  if (rc != G1S_OK) return rc;
+  Slot &s = d->slots[d->cur];
+  FrameDesc &fd = s.h_descs[s.count];
+  std::memset(&fd, 0, sizeof fd);
+  for (int c = 0; c < d->geom.planes; ++c) {
+    fd.src[c] = source->plane[c];
+    fd.den[c] = denoised->plane[c];
+    fd.src_stride[c] = (uint32_t)source->stride_bytes[c];
+    fd.den_stride[c] = (uint32_t)denoised->stride_bytes[c];
+  }
+  s.count++;
+  d->pushed++;
+  if (s.count == d->batch) return rotate(d);
+  return G1S_OK;
+}
+
+int g1s_diff_flush(g1s_diff *d) {
+  if (!d) return G1S_E_ARG;
+  if (d->cfg.mode == G1S_MODE_CONSUMER) return G1S_OK;
+  return drain(d);
+}
+
+size_t g1s_record_layout(int32_t num_blocks, size_t off[8]) {
+  const RecordLayout rl = RecordLayout::make(num_blocks);
+  if (off) {
+    const size_t v[8] = {rl.off_gram, rl.off_nobs, rl.off_num_flat, rl.off_luma_sum,
+                         rl.off_rsum, rl.off_rsq,  rl.off_score,    rl.off_flat};
+    std::memcpy(off, v, sizeof v);
+  }
+  return rl.bytes;
+}
+
+size_t g1s_diff_record_bytes(const g1s_diff *d) { return d ? d->rl.bytes : 0; }
+
+int g1s_diff_set_record_tap(g1s_diff *d, g1s_record_fn fn, void *user) {
+  if (!d) return G1S_E_ARG;
+  d->tap = fn;
+  d->tap_user = user;
+  return G1S_OK;
+}
+
+int g1s_diff_consume_record(g1s_diff *d, const void *record, size_t bytes) {
+  if (!d || !record) return G1S_E_ARG;
+  if (d->cfg.mode != G1S_MODE_CONSUMER || d->finished) {
+    d->err = "consume_record needs an unfinished CONSUMER handle";
+    return G1S_E_STATE;
+  }
+  if (bytes != d->rl.bytes) {
+    d->err = "record size does not match this stream's geometry";
+    return G1S_E_ARG;
+  }
+  d->seq->consume(view_of(d, static_cast<const uint8_t *>(record)));
+  d->pushed++;
+  d->frames_done += 1;
+  return G1S_OK;
+}
+
+int g1s_diff_finish(g1s_diff *d, g1s_segment *out, size_t cap, size_t *n) {
+  if (!d || !n) return G1S_E_ARG;
+  if (d->cfg.mode == G1S_MODE_PRODUCER) {
+    d->err = "producer handles have no model; finish the CONSUMER handle";
+    return G1S_E_STATE;
+  }
+  int rc = d->cfg.mode == G1S_MODE_CONSUMER ? G1S_OK : drain(d);
+  if (rc != G1S_OK) return rc;
+  std::vector<g1s_segment> segs = d->seq->finish();
+  *n = segs.size();
+  if (cap < segs.size() || !out) {
+    d->err = "segment capacity too small";
+    return G1S_E_STATE;
+  }
+  std::memcpy(out, segs.data(), segs.size() * sizeof(g1s_segment));
+  d->finished = true;
+  return G1S_OK;
+}
+
+void g1s_diff_destroy(g1s_diff *d) {
+  if (!d) return;
+  if (d->stream) cudaStreamSynchronize(d->stream);
+  for (Slot &s : d->slots) {
+    if (s.d_frames) cudaFree(s.d_frames);
+    if (s.h_frames) cudaFreeHost(s.h_frames);
+    if (s.d_descs) cudaFree(s.d_descs);
+    if (s.h_descs) cudaFreeHost(s.h_descs);
+    if (s.d_records) cudaFree(s.d_records);
+    if (s.h_records) cudaFreeHost(s.h_records);
+    for (cudaEvent_t e : {s.done, s.k0_beg, s.k0_end, s.k1_beg, s.k1_end})
+      if (e) cudaEventDestroy(e);
+  }
+  if (d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+}
+
+const char *g1s_diff_last_error(const g1s_diff *d) { return d ? d->err.c_str() : g_create_error.c_str(); }
+
+int64_t g1s_diff_frames_pushed(const g1s_diff *d) { return d ? d->pushed : 0; }
+
+int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n) {
+  if (!d || !out) return G1S_E_ARG;
+  const double v[6] = {d->kernels_launched, d->k1_ms, d->k1_launches, d->k0_ms, d->k0_launches, d->frames_done};
+  for (size_t i = 0; i < n && i < 6; ++i) out[i] = v[i];
+  return G1S_OK;
+}
+
+int64_t g1s_format_grain_table(const g1s_segment *segs, size_t n, char *buf, size_t cap) {
+  if (!segs && n) return G1S_E_ARG;
+  const std::string s = format_grain_table(segs, n);
+  if (buf && cap) {
+    const size_t k = std::min(cap - 1, s.size());
+    std::memcpy(buf, s.data(), k);
+    buf[k] = 0;
+  }
+  return (int64_t)s.size();
+}
+
+int g1s_write_grain_table(const g1s_segment *segs, size_t n, const char *path) {
+  if ((!segs && n) || !path) return G1S_E_ARG;
+  const std::string s = format_grain_table(segs, n);
+  FILE *f = std::fopen(path, "wb");
+  if (!f) return G1S_E_IO;
+  const bool ok = std::fwrite(s.data(), 1, s.size(), f) == s.size();
+  return (std::fclose(f) == 0 && ok) ? G1S_OK : G1S_E_IO;
+}
+
+}  // extern "C"

@@ -1,0 +1,475 @@
+// sm_100a kernels of the grain-estimation hot path (grav1synth `diff`).
+//
+//   flat_features_kernel   FlatBlockFinder::run per 32x32 source-luma block, f64 in the
+//                          reference's operation order (av1-grain diff/solver.rs; call
+//                          site /root/reference/src/main.rs:442)
+//   flat_select_kernel     90th-percentile score threshold + final flat flags per frame
+//   gram_generic_kernel    fused residual (source - denoised) + AR normal-equation
+//                          (Gram) accumulation + per-block noise statistics, exact
+//                          integers, any residual magnitude (NoiseModel::
+//                          add_block_observations / get_block_mean / get_noise_var)
+//
+// Everything that the reference computes from integers is kept in integers here
+// (bit-exact, order independent); the flat-block features are genuinely f64 and are
+// evaluated with explicit round-to-nearest intrinsics in the reference's summation
+// order so no FMA contraction or reassociation can change a bit.
+#include "g1s_kernels.h"
+
+#include <stdio.h>
+
+namespace g1s {
+
+RecordLayout RecordLayout::make(int nb) {
+  RecordLayout r;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o += (bytes + 7) & ~size_t(7);
+    return at;
+  };
+  r.off_gram = take(sizeof(int64_t) * 3 * kPairs);
+  r.off_nobs = take(sizeof(int64_t) * 3);
+  r.off_num_flat = take(sizeof(int64_t));
+  r.off_luma_sum = take(sizeof(uint32_t) * nb);
+  r.off_rsum = take(sizeof(int32_t) * 3 * nb);
+  r.off_rsq = take(sizeof(uint32_t) * 3 * nb);
+  r.off_score = take(sizeof(float) * nb);
+  r.off_flat = take(nb);
+  r.bytes = (o + 15) & ~size_t(15);
+  return r;
+}
+
+// ----------------------------------------------------------------------------- helpers
+
+__device__ __forceinline__ int load_sample8(const void *base, uint32_t stride, int y, int x, int bytes, int shift) {
+  const uint8_t *row = reinterpret_cast<const uint8_t *>(base) + (size_t)y * stride;
+  if (bytes == 1) return row[x];
+  const int v = reinterpret_cast<const uint16_t *>(row)[x];
+  return (v >> shift) & 0xFF;  // util.rs::frame_into_u8: truncating shift, then `as u8`
+}
+
+// pix / 255.0 correctly rounded without a divide: q = p*(1/255); r = fma(-q,255,p); q += r*(1/255).
+// Verified exhaustively for p = 0..255 (tests/test_host_logic.py::test_div255_sequence).
+__device__ __forceinline__ double div255(int p) {
+  const double inv = 1.0 / 255.0;
+  const double pd = (double)p;
+  const double q = __dmul_rn(pd, inv);
+  const double r = __fma_rn(-q, 255.0, pd);
+  return __fma_rn(r, inv, q);
+}
+
+// Same fixed sequence as oracle/g1s_oracle.c::g1s_exp_fixed.
+__device__ __forceinline__ double exp_fixed(double x) {
+  const double inv_ln2 = 1.4426950408889634074;
+  const double ln2_hi = 6.93147180369123816490e-01;
+  const double ln2_lo = 1.90821492927058770002e-10;
+  const double shift = 6755399441055744.0;
+  const double kd = __dsub_rn(__dadd_rn(__dmul_rn(x, inv_ln2), shift), shift);
+  const int k = __double2int_rz(kd);
+  double r = __fma_rn(-kd, ln2_hi, x);
+  r = __fma_rn(-kd, ln2_lo, r);
+  double p = 1.0 / 6227020800.0;
+  p = __fma_rn(p, r, 1.0 / 479001600.0);
+  p = __fma_rn(p, r, 1.0 / 39916800.0);
+  p = __fma_rn(p, r, 1.0 / 3628800.0);
+  p = __fma_rn(p, r, 1.0 / 362880.0);
+  p = __fma_rn(p, r, 1.0 / 40320.0);
+  p = __fma_rn(p, r, 1.0 / 5040.0);
+  p = __fma_rn(p, r, 1.0 / 720.0);
+  p = __fma_rn(p, r, 1.0 / 120.0);
+  p = __fma_rn(p, r, 1.0 / 24.0);
+  p = __fma_rn(p, r, 1.0 / 6.0);
+  p = __fma_rn(p, r, 0.5);
+  p = __fma_rn(p, r, 1.0);
+  p = __fma_rn(p, r, 1.0);
+  const double sc = __longlong_as_double((long long)(1023 + k) << 52);
+  return __dmul_rn(p, sc);
+}
+
+// ------------------------------------------------------------------- flat_features_kernel
+//
+// One thread per (frame, block).  The reference's sums are sequential f64 chains in
+// row-major pixel order, so the block is walked by one thread; parallelism comes from
+// the 8160 blocks per 4K frame times the frames of a batch.  The plane-fit residual
+// rows needed by the central differences live in a 3-row shared-memory ring laid out
+// [row][x][thread] (conflict-free: consecutive lanes touch consecutive doubles).
+
+constexpr int kFlatThreads = 128;
+
+__global__ void __launch_bounds__(kFlatThreads)
+flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, FlatConsts fc,
+                     uint8_t *__restrict__ records, RecordLayout rl) {
+  extern __shared__ double ring[];  // [3][32][kFlatThreads]
+  const int gid = blockIdx.x * kFlatThreads + threadIdx.x;
+  const int total = nframes * g.nb;
+  const bool active = gid < total;
+  const int f = active ? gid / g.nb : 0;
+  const int b = active ? gid - f * g.nb : 0;
+  const int by = b / g.nbw, bx = b - by * g.nbw;
+  const void *src = frames[f].src[0];
+  const uint32_t stride = frames[f].src_stride[0];
+  const int w = g.width, h = g.height;
+  const int x0 = bx * kBlock, y0 = by * kBlock;
+  const int tid = threadIdx.x;
+
+  auto pix = [&](int yi, int xi) -> int {
+    const int y = min(y0 + yi, h - 1);
+    const int x = min(x0 + xi, w - 1);
+    return load_sample8(src, stride, y, x, g.src_bytes, g.src_shift);
+  };
+
+  // --- A^T * block (multiply_mat(block, A, ., 1, 1024, 3)): three sequential chains
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  if (active) {
+    for (int yi = 0; yi < kBlock; ++yi) {
+      const double yd = (double)(yi - 16) * 0.0625;
+#pragma unroll 4
+      for (int xi = 0; xi < kBlock; ++xi) {
+        const double xd = (double)(xi - 16) * 0.0625;
+        const double v = div255(pix(yi, xi));
+        s0 = __dadd_rn(s0, __dmul_rn(v, yd));
+        s1 = __dadd_rn(s1, __dmul_rn(v, xd));
+        s2 = __dadd_rn(s2, v);  // v * 1.0 is exact
+      }
+    }
+  }
+  // --- (A^T A)^-1 * (A^T block)
+  double pc[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double s = __dadd_rn(0.0, __dmul_rn(fc.ata_inv[r * 3 + 0], s0));
+    s = __dadd_rn(s, __dmul_rn(fc.ata_inv[r * 3 + 1], s1));
+    s = __dadd_rn(s, __dmul_rn(fc.ata_inv[r * 3 + 2], s2));
+    pc[r] = s;
+  }
+  // block[i] -= (A * plane_coords)[i], row by row into the ring
+  auto fill_row = [&](int yi) {
+    const double yd = (double)(yi - 16) * 0.0625;
+    const double ty = __dadd_rn(0.0, __dmul_rn(yd, pc[0]));
+    double *dst = ring + ((size_t)(yi % 3) * kBlock) * kFlatThreads + tid;
+#pragma unroll 4
+    for (int xi = 0; xi < kBlock; ++xi) {
+      const double xd = (double)(xi - 16) * 0.0625;
+      double fit = __dadd_rn(ty, __dmul_rn(xd, pc[1]));
+      fit = __dadd_rn(fit, pc[2]);  // 1.0 * pc[2] is exact
+      dst[(size_t)xi * kFlatThreads] = __dsub_rn(div255(pix(yi, xi)), fit);
+    }
+  };
+  double Gxx = 0, Gxy = 0, Gyy = 0, var = 0, mean = 0;
+  if (active) {
+    fill_row(0);
+    fill_row(1);
+    for (int yi = 1; yi < kBlock - 1; ++yi) {
+      fill_row(yi + 1);
+      const double *up = ring + ((size_t)((yi - 1) % 3) * kBlock) * kFlatThreads + tid;
+      const double *cur = ring + ((size_t)(yi % 3) * kBlock) * kFlatThreads + tid;
+      const double *dn = ring + ((size_t)((yi + 1) % 3) * kBlock) * kFlatThreads + tid;
+      double left = cur[0], mid = cur[kFlatThreads];
+#pragma unroll 2
+      for (int xi = 1; xi < kBlock - 1; ++xi) {
+        const double right = cur[(size_t)(xi + 1) * kFlatThreads];
+        const double gx = __dmul_rn(__dsub_rn(right, left), 0.5);
+        const double gy = __dmul_rn(__dsub_rn(dn[(size_t)xi * kFlatThreads], up[(size_t)xi * kFlatThreads]), 0.5);
+        Gxx = __dadd_rn(Gxx, __dmul_rn(gx, gx));
+        Gxy = __dadd_rn(Gxy, __dmul_rn(gx, gy));
+        Gyy = __dadd_rn(Gyy, __dmul_rn(gy, gy));
+        mean = __dadd_rn(mean, mid);
+        var = __dadd_rn(var, __dmul_rn(mid, mid));
+        left = mid;
+        mid = right;
+      }
+    }
+  }
+  if (!active) return;
+
+  const double nf = 900.0;  // (BLOCK_SIZE - 2)^2
+  mean = __ddiv_rn(mean, nf);
+  Gxx = __ddiv_rn(Gxx, nf);
+  Gxy = __ddiv_rn(Gxy, nf);
+  Gyy = __ddiv_rn(Gyy, nf);
+  var = __dsub_rn(__ddiv_rn(var, nf), __dmul_rn(mean, mean));
+
+  const double trace = __dadd_rn(Gxx, Gyy);
+  const double det = __dsub_rn(__dmul_rn(Gxx, Gyy), __dmul_rn(Gxy, Gxy));
+  double disc = __dsub_rn(__dmul_rn(trace, trace), __dmul_rn(4.0, det));
+  disc = disc > 0.0 ? disc : 0.0;  // f64::max(x, 0.)
+  const double e_sub = __dsqrt_rn(disc);
+  const double e1 = __dmul_rn(__dadd_rn(trace, e_sub), 0.5);
+  const double e2 = __dmul_rn(__dsub_rn(trace, e_sub), 0.5);
+  const double norm = e1;
+  const double ratio = __ddiv_rn(e1, e2 > 1e-6 ? e2 : 1e-6);
+
+  const double kTrace = 0.15 / 1024.0, kRatio = 1.25, kNorm = 0.08 / 1024.0, kVar = 0.005 / 1024.0;
+  const bool is_flat = (trace < kTrace) && (ratio < kRatio) && (norm < kNorm) && (var > kVar);
+  double sw = __fma_rn(-6682.0, var,
+                       __fma_rn(-0.2056, ratio, __fma_rn(13087.0, trace, __fma_rn(-12434.0, norm, 2.5694))));
+  sw = sw < -25.0 ? -25.0 : (sw > 100.0 ? 100.0 : sw);
+  const double e = exp_fixed(-sw);
+  const float score = __double2float_rn(__ddiv_rn(1.0, __dadd_rn(1.0, e)));
+
+  uint8_t *rec = records + (size_t)f * rl.bytes;
+  reinterpret_cast<float *>(rec + rl.off_score)[b] = var > kVar ? score : 0.0f;
+  (rec + rl.off_flat)[b] = is_flat ? 255 : 0;
+}
+
+void launch_flat_features(const FrameDesc *frames, int nframes, const Geometry &g, const FlatConsts &fc,
+                          uint8_t *records, const RecordLayout &rl, cudaStream_t st) {
+  const int total = nframes * g.nb;
+  const int grid = (total + kFlatThreads - 1) / kFlatThreads;
+  const size_t smem = sizeof(double) * 3 * kBlock * kFlatThreads;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(flat_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  flat_features_kernel<<<grid, kFlatThreads, smem, st>>>(frames, nframes, g, fc, records, rl);
+}
+
+// --------------------------------------------------------------------- flat_select_kernel
+//
+// scores.sort(); thr = scores[nb * 90 / 100]; every block with score >= thr gets flat |= 1.
+// Scores are non-negative floats, so their bit patterns order like unsigned integers and
+// the k-th smallest is found by a 4-pass MSB-first radix select; one CTA per frame.
+
+__global__ void __launch_bounds__(256)
+flat_select_kernel(int nframes, Geometry g, uint8_t *__restrict__ records, RecordLayout rl) {
+  __shared__ unsigned hist[256];
+  __shared__ unsigned s_prefix, s_k;
+  __shared__ unsigned s_count;
+  const int f = blockIdx.x;
+  uint8_t *rec = records + (size_t)f * rl.bytes;
+  const unsigned *scores = reinterpret_cast<const unsigned *>(rec + rl.off_score);
+  uint8_t *flat = rec + rl.off_flat;
+  const int nb = g.nb;
+  if (threadIdx.x == 0) {
+    s_prefix = 0;
+    s_k = (unsigned)(nb * 90 / 100);
+    s_count = 0;
+  }
+  for (int pass = 3; pass >= 0; --pass) {
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix;
+    const unsigned himask = pass == 3 ? 0u : (0xFFFFFFFFu << (8 * (pass + 1)));
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+      const unsigned v = scores[i];
+      if ((v & himask) == prefix) atomicAdd(&hist[(v >> (8 * pass)) & 0xFF], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned k = s_k, acc = 0;
+      int d = 0;
+      for (; d < 256; ++d) {
+        if (acc + hist[d] > k) break;
+        acc += hist[d];
+      }
+      s_k = k - acc;
+      s_prefix = prefix | ((unsigned)d << (8 * pass));
+    }
+    __syncthreads();
+  }
+  const unsigned thr = s_prefix;
+  unsigned local = 0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+    uint8_t v = flat[i];
+    if (scores[i] >= thr) v |= 1;
+    flat[i] = v;
+    local += v != 0;
+  }
+  atomicAdd(&s_count, local);
+  __syncthreads();
+  if (threadIdx.x == 0) *reinterpret_cast<int64_t *>(rec + rl.off_num_flat) = (int64_t)s_count;
+}
+
+void launch_flat_select(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, cudaStream_t st) {
+  flat_select_kernel<<<nframes, 256, 0, st>>>(nframes, g, records, rl);
+}
+
+// --------------------------------------------------------------------- gram_generic_kernel
+//
+// One CTA per (frame, plane, block row); it walks the blocks of the row, and for every
+// flat block stages the residual tile (with the 3-sample halo the lag-3 taps reach) in
+// shared memory as int16, then each thread owns up to two of the 351 tap pairs and sums
+// tap_i * tap_j over the block's observation rectangle.  int32 per block is exact
+// (<= 1024 * 1020^2 would overflow only for the luma-tap square, which is bounded by
+// 256 chroma samples * 1020^2 = 2.7e8), int64 across blocks; one atomicAdd per pair per CTA.
+
+constexpr int kGramThreads = 256;
+constexpr int kTilePitch = 40;             // >= 32 + 2*3, even
+constexpr int kTileRows = kBlock + kLag;   // 35
+constexpr int kTileElems = kTilePitch * kTileRows;
+
+__global__ void __launch_bounds__(kGramThreads)
+gram_generic_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, uint8_t *__restrict__ records,
+                    RecordLayout rl) {
+  __shared__ int16_t tile[2 * kTileElems];  // [0]: residual with halo, [1]: luma tap (same geometry)
+  __shared__ int red_i[kGramThreads / 32];
+  __shared__ unsigned red_u[kGramThreads / 32];
+  __shared__ unsigned red_l[kGramThreads / 32];
+
+  const int by = blockIdx.x;
+  const int c = blockIdx.y;
+  const int f = blockIdx.z;
+  const int tid = threadIdx.x;
+  const FrameDesc fd = frames[f];
+  uint8_t *rec = records + (size_t)f * rl.bytes;
+  const uint8_t *flat = rec + rl.off_flat;
+
+  const int sx = c ? g.ss_x : 0, sy = c ? g.ss_y : 0;
+  const int bw = kBlock >> sx, bh = kBlock >> sy;
+  const int pw = g.width >> sx, ph = g.height >> sy;  // loop extents use the floor (reference: w >> sub_log2)
+  const int sw = (g.width + sx) >> sx, sh = (g.height + sy) >> sy;  // plane storage size
+  const void *sp = fd.src[c], *dp = fd.den[c];
+  const uint32_t ss = fd.src_stride[c], ds = fd.den_stride[c];
+
+  // pair -> (i, j), i <= j, row-major over the upper triangle
+  int pi[2], pj[2], off_i[2], off_j[2];
+  long long acc64[2] = {0, 0};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    int p = tid + q * kGramThreads;
+    int i = 0, j = 0;
+    if (p < kPairs) {
+      int rem = p;
+      i = 0;
+      while (rem >= kTaps - i) {
+        rem -= kTaps - i;
+        ++i;
+      }
+      j = i + rem;
+    } else {
+      i = j = -1;
+    }
+    pi[q] = i;
+    pj[q] = j;
+    auto tap_off = [&](int t) -> int {
+      if (t < 0) return 0;
+      if (t < 24) {
+        const int cy = t / 7 - 3, cx = t % 7 - 3;
+        return cy * kTilePitch + cx;
+      }
+      if (t == 24) return kTileElems;  // luma tap plane
+      return 0;                         // centre sample
+    };
+    off_i[q] = tap_off(i);
+    off_j[q] = tap_off(j);
+  }
+  const bool use24 = c > 0;
+  long long nobs = 0;
+
+  for (int bx = 0; bx < g.nbw; ++bx) {
+    const int bidx = by * g.nbw + bx;
+    if (!flat[bidx]) continue;
+    const int x_o = bx * bw, y_o = by * bh;
+    // ---- stage residual tile: tile(ty, tx) <-> plane (y_o - 3 + ty, x_o - 3 + tx)
+    for (int e = tid; e < kTileRows * (bw + 2 * kLag); e += kGramThreads) {
+      const int ty = e / (bw + 2 * kLag), tx = e - ty * (bw + 2 * kLag);
+      const int y = y_o - kLag + ty, x = x_o - kLag + tx;
+      int r = 0;
+      if (ty < bh + kLag && y >= 0 && y < sh && x >= 0 && x < sw)
+        r = load_sample8(sp, ss, y, x, g.src_bytes, g.src_shift) - load_sample8(dp, ds, y, x, g.den_bytes, g.den_shift);
+      tile[ty * kTilePitch + tx] = (int16_t)r;
+    }
+    if (use24) {
+      // luma tap: sum over the co-sited luma samples of (source - denoised); the reference divides
+      // by the sample count (a power of two), the host undoes the scale exactly.
+      for (int e = tid; e < bh * bw; e += kGramThreads) {
+        const int yy = e / bw, xx = e - yy * bw;
+        const int y = y_o + yy, x = x_o + xx;
+        int l = 0;
+        if (y < ph && x < pw) {
+          for (int dy = 0; dy < (1 << sy); ++dy)
+            for (int dx = 0; dx < (1 << sx); ++dx) {
+              const int ly = (y << sy) + dy, lx = (x << sx) + dx;
+              l += load_sample8(fd.src[0], fd.src_stride[0], ly, lx, g.src_bytes, g.src_shift) -
+                   load_sample8(fd.den[0], fd.den_stride[0], ly, lx, g.den_bytes, g.den_shift);
+            }
+        }
+        tile[kTileElems + (yy + kLag) * kTilePitch + (xx + kLag)] = (int16_t)l;
+      }
+    }
+    __syncthreads();
+
+    // ---- per-block noise statistics over the frame-clipped block (get_block_mean / get_noise_var)
+    {
+      const int max_w = min(pw - x_o, bw), max_h = min(ph - y_o, bh);
+      int rs = 0;
+      unsigned rq = 0;
+      for (int e = tid; e < max_w * max_h; e += kGramThreads) {
+        const int yy = e / max_w, xx = e - yy * max_w;
+        const int r = tile[(yy + kLag) * kTilePitch + xx + kLag];
+        rs += r;
+        rq += (unsigned)(r * r);
+      }
+      unsigned ls = 0;
+      if (c == 0) {
+        const int lw = min(g.width - x_o, kBlock), lh = min(g.height - y_o, kBlock);
+        for (int e = tid; e < lw * lh; e += kGramThreads) {
+          const int yy = e / lw, xx = e - yy * lw;
+          ls += (unsigned)load_sample8(sp, ss, y_o + yy, x_o + xx, g.src_bytes, g.src_shift);
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        rs += __shfl_xor_sync(0xffffffffu, rs, o);
+        rq += __shfl_xor_sync(0xffffffffu, rq, o);
+        ls += __shfl_xor_sync(0xffffffffu, ls, o);
+      }
+      if ((tid & 31) == 0) {
+        red_i[tid >> 5] = rs;
+        red_u[tid >> 5] = rq;
+        red_l[tid >> 5] = ls;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int a = 0;
+        unsigned bq = 0, cl = 0;
+        for (int k = 0; k < kGramThreads / 32; ++k) {
+          a += red_i[k];
+          bq += red_u[k];
+          cl += red_l[k];
+        }
+        reinterpret_cast<int32_t *>(rec + rl.off_rsum)[c * g.nb + bidx] = a;
+        reinterpret_cast<uint32_t *>(rec + rl.off_rsq)[c * g.nb + bidx] = bq;
+        if (c == 0) reinterpret_cast<uint32_t *>(rec + rl.off_luma_sum)[bidx] = cl;
+      }
+    }
+
+    // ---- observation rectangle (add_block_observations)
+    const int y_start = (by > 0 && flat[bidx - g.nbw]) ? 0 : kLag;
+    const int x_start = (bx > 0 && flat[bidx - 1]) ? 0 : kLag;
+    const int y_end = min(ph - y_o, bh);
+    const int x_end = min(pw - x_o - kLag, (bx + 1 < g.nbw && flat[bidx + 1]) ? bw : bw - kLag);
+    if (y_end > y_start && x_end > x_start) {
+      nobs += (long long)(y_end - y_start) * (x_end - x_start);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (pi[q] < 0) continue;
+        if (!use24 && (pi[q] == 24 || pj[q] == 24)) continue;
+        int acc = 0;
+        for (int y = y_start; y < y_end; ++y) {
+          const int16_t *row = tile + (y + kLag) * kTilePitch + kLag;
+          for (int x = x_start; x < x_end; ++x) acc += (int)row[x + off_i[q]] * (int)row[x + off_j[q]];
+        }
+        acc64[q] += acc;
+      }
+    }
+    __syncthreads();
+  }
+
+  unsigned long long *gram = reinterpret_cast<unsigned long long *>(rec + rl.off_gram) + (size_t)c * kPairs;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int p = tid + q * kGramThreads;
+    if (p < kPairs && acc64[q] != 0) atomicAdd(&gram[p], (unsigned long long)acc64[q]);
+  }
+  if (tid == 0 && nobs)
+    atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + c, (unsigned long long)nobs);
+}
+
+void launch_gram_generic(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
+                         const RecordLayout &rl, cudaStream_t st) {
+  dim3 grid(g.nbh, g.planes, nframes);
+  gram_generic_kernel<<<grid, kGramThreads, 0, st>>>(frames, nframes, g, records, rl);
+}
+
+}  // namespace g1s

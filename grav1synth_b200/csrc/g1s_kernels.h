@@ -1,0 +1,59 @@
+// Device-side interface of the grain-estimation engine: data layout in HBM and the
+// kernel launchers.  Host code (g1s_engine.cpp) includes this; no CUDA types leak
+// beyond cudaStream_t.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace g1s {
+
+constexpr int kBlock = 32;         // BLOCK_SIZE of av1-grain's diff module (32x32 luma blocks)
+constexpr int kLag = 3;            // NOISE_MODEL_LAG
+constexpr int kTaps = 26;          // 24 AR taps + [24] luma tap (chroma only) + [25] centre sample
+constexpr int kPairs = kTaps * (kTaps + 1) / 2;  // 351 upper-triangular products
+
+// One frame pair as the kernels see it.  Pointers are device pointers; strides in bytes.
+struct FrameDesc {
+  const void *src[3];
+  const void *den[3];
+  uint32_t src_stride[3];
+  uint32_t den_stride[3];
+};
+
+// Stream geometry, constant for a handle.
+struct Geometry {
+  int width, height;      // luma samples
+  int ss_x, ss_y;         // chroma subsampling log2
+  int planes;             // 1 (monochrome) or 3
+  int src_shift, den_shift;  // bit_depth - 8: samples are reduced with a truncating >> (frame_into_u8)
+  int src_bytes, den_bytes;  // bytes per sample (1 or 2)
+  int nbw, nbh, nb;       // 32x32 luma block grid
+};
+
+// Constants of FlatBlockFinder::new computed once on the host in f64.
+struct FlatConsts {
+  double ata_inv[9];
+};
+
+// Per-frame result record, written by the kernels and copied back to the host.
+// Layout of one record (all offsets are 8-byte aligned), for nb blocks:
+//   int64  gram[3][kPairs]     upper-triangular integer Gram sums per plane
+//   int64  nobs[3]             observations per plane
+//   int64  num_flat            blocks with a non-zero flat flag
+//   uint32 luma_sum[nb]        sum of 8-bit source luma over each (frame-clipped) block
+//   int32  rsum[3][nb]         sum of the residual over each block, per plane
+//   uint32 rsq[3][nb]          sum of the squared residual over each block, per plane
+//   float  score[nb]           sigmoid flatness score (0 when var <= threshold)
+//   uint8  flat[nb]            0 / 1 / 255 flat flags (padded to 8 bytes)
+struct RecordLayout {
+  size_t off_gram, off_nobs, off_num_flat, off_luma_sum, off_rsum, off_rsq, off_score, off_flat, bytes;
+  static RecordLayout make(int nb);
+};
+
+void launch_flat_features(const FrameDesc *frames, int nframes, const Geometry &g, const FlatConsts &fc,
+                          uint8_t *records, const RecordLayout &rl, cudaStream_t st);
+void launch_flat_select(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, cudaStream_t st);
+void launch_gram_generic(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
+                         const RecordLayout &rl, cudaStream_t st);
+
+}  // namespace g1s

@@ -1,0 +1,518 @@
+// Host noise model: restates av1-grain 0.4.2 `diff/solver.rs` (NoiseModel, NoiseStrengthSolver,
+// EquationSystem; lineage libaom aom_dsp/noise_model.c) downstream of the per-pixel sums.
+// Reached from the reference at /root/reference/src/main.rs:442 (diff_frame) and :524 (finish).
+// Must be compiled without FP contraction (-ffp-contract=off): the reference has none.
+#include "g1s_model.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "g1s_kernels.h"
+
+namespace g1s {
+
+namespace {
+constexpr double kTiny = 1.0e-16;
+constexpr double kNorm2 = 255.0 * 255.0;  // BLOCK_NORMALIZATION^2
+constexpr int kNumBins = 20;
+constexpr uint16_t kDefaultGrainSeed = 10956;
+
+// util.rs::linsolve (libaom mathutils.h): elimination with adjacent-row pivot bubbling.
+bool gauss_solve(int n, double *A, double *b, double *x) {
+  for (int k = 0; k + 1 < n; ++k) {
+    for (int i = n - 1; i > k; --i) {
+      if (std::fabs(A[(i - 1) * n + k]) < std::fabs(A[i * n + k])) {
+        std::swap_ranges(A + i * n, A + i * n + n, A + (i - 1) * n);
+        std::swap(b[i], b[i - 1]);
+      }
+    }
+    for (int i = k; i + 1 < n; ++i) {
+      if (std::fabs(A[k * n + k]) < kTiny) return false;
+      const double c = A[(i + 1) * n + k] / A[k * n + k];
+      for (int j = 0; j < n; ++j) A[(i + 1) * n + j] -= c * A[k * n + j];
+      b[i + 1] -= c * b[k];
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    if (std::fabs(A[i * n + i]) < kTiny) return false;
+    double c = 0;
+    for (int j = i + 1; j < n; ++j) c += A[i * n + j] * x[j];
+    x[i] = (b[i] - c) / A[i * n + i];
+  }
+  return true;
+}
+
+inline int pair_index(int i, int j) {  // i <= j, row-major upper triangle of a 26x26 matrix
+  return i * kTaps - i * (i - 1) / 2 + (j - i);
+}
+inline int64_t gram_at(const int64_t *g, int i, int j) { return i <= j ? g[pair_index(i, j)] : g[pair_index(j, i)]; }
+
+inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+}  // namespace
+
+// ------------------------------------------------------------------ LinearSystem
+void LinearSystem::reset(int n_) {
+  n = n_;
+  A.assign((size_t)n * n, 0.0);
+  b.assign(n, 0.0);
+  x.assign(n, 0.0);
+}
+void LinearSystem::clear() {
+  std::fill(A.begin(), A.end(), 0.0);
+  std::fill(b.begin(), b.end(), 0.0);
+  std::fill(x.begin(), x.end(), 0.0);
+}
+bool LinearSystem::solve() {
+  std::vector<double> Ac(A), bc(b);
+  return gauss_solve(n, Ac.data(), bc.data(), x.data());
+}
+void LinearSystem::add(const LinearSystem &o) {
+  for (size_t i = 0; i < A.size(); ++i) A[i] += o.A[i];
+  for (size_t i = 0; i < b.size(); ++i) b[i] += o.b[i];
+}
+void LinearSystem::copy_from(const LinearSystem &o) {
+  A = o.A;
+  b = o.b;
+  x = o.x;
+}
+
+// ---------------------------------------------------------------- StrengthSolver
+StrengthSolver::StrengthSolver() : eqns(kNumBins), num_bins(kNumBins) {}
+void StrengthSolver::clear() {
+  eqns.clear();
+  num_equations = 0;
+  total = 0;
+}
+double StrengthSolver::bin_index(double v) const {
+  const double val = v < min_intensity ? min_intensity : (v > max_intensity ? max_intensity : v);
+  const double range = max_intensity - min_intensity;
+  return (num_bins - 1) * (val - min_intensity) / range;
+}
+double StrengthSolver::bin_center(int i) const {
+  const double range = max_intensity - min_intensity;
+  return ((double)i) / (num_bins - 1) * range + min_intensity;
+}
+double StrengthSolver::value_at(double intensity) const {
+  const double bin = bin_index(intensity);
+  const int i0 = (int)std::floor(bin);
+  const int i1 = std::min(num_bins - 1, i0 + 1);
+  const double a = bin - i0;
+  return (1.0 - a) * eqns.x[i0] + a * eqns.x[i1];
+}
+void StrengthSolver::add_measurement(double block_mean, double noise_std) {
+  const double bin = bin_index(block_mean);
+  const int i0 = (int)std::floor(bin);
+  const int i1 = std::min(num_bins - 1, i0 + 1);
+  const double a = bin - i0;
+  const int n = num_bins;
+  eqns.A[i0 * n + i0] += (1.0 - a) * (1.0 - a);
+  eqns.A[i1 * n + i0] += a * (1.0 - a);
+  eqns.A[i1 * n + i1] += a * a;
+  eqns.A[i0 * n + i1] += a * (1.0 - a);
+  eqns.b[i0] += (1.0 - a) * noise_std;
+  eqns.b[i1] += a * noise_std;
+  total += noise_std;
+  num_equations++;
+}
+bool StrengthSolver::solve() {
+  // Regularised copy of A; b keeps the ridge term (the reference modifies b in place).
+  const int n = num_bins;
+  const double alpha = 2.0 * (double)num_equations / n;
+  std::vector<double> saved(eqns.A);
+  for (int i = 0; i < n; ++i) {
+    const int lo = std::max(0, i - 1), hi = std::min(n - 1, i + 1);
+    eqns.A[i * n + lo] -= alpha;
+    eqns.A[i * n + i] += 2 * alpha;
+    eqns.A[i * n + hi] -= alpha;
+  }
+  const double mean = total / num_equations;
+  for (int i = 0; i < n; ++i) {
+    eqns.A[i * n + i] += 1.0 / 8192.;
+    eqns.b[i] += mean / 8192.;
+  }
+  const bool ok = eqns.solve();
+  eqns.A.swap(saved);
+  return ok;
+}
+void StrengthSolver::add(const StrengthSolver &o) {
+  eqns.add(o.eqns);
+  num_equations += o.num_equations;
+  total += o.total;
+}
+void StrengthSolver::update_residual(const std::vector<std::pair<double, double>> &pts,
+                                     std::vector<double> &residual, int start, int end) const {
+  const double dx = 255. / num_bins;
+  const int npts = (int)pts.size();
+  for (int i = std::max(start, 1); i < std::min(end, npts - 1); ++i) {
+    const int lower = std::max(0, (int)std::floor(bin_index(pts[i - 1].first)));
+    const int upper = std::min(num_bins - 1, (int)std::ceil(bin_index(pts[i + 1].first)));
+    double r = 0;
+    for (int j = lower; j <= upper; ++j) {
+      const double x = bin_center(j);
+      if (x < pts[i - 1].first) continue;
+      if (x >= pts[i + 1].first) continue;
+      const double y = eqns.x[j];
+      const double a = (x - pts[i - 1].first) / (pts[i + 1].first - pts[i - 1].first);
+      const double est = pts[i - 1].second * (1.0 - a) + pts[i + 1].second * a;
+      r += std::fabs(y - est);
+    }
+    residual[i] = r * dx;
+  }
+}
+std::vector<std::pair<double, double>> StrengthSolver::fit_piecewise(int max_points) const {
+  const double tol = max_intensity * 0.00625 / 255.0;
+  std::vector<std::pair<double, double>> pts(num_bins);
+  for (int i = 0; i < num_bins; ++i) pts[i] = {bin_center(i), eqns.x[i]};
+  std::vector<double> residual(num_bins, 0.0);
+  update_residual(pts, residual, 0, num_bins);
+  while (pts.size() > 2) {
+    int min_index = 1;
+    for (int j = 1; j + 1 < (int)pts.size(); ++j)
+      if (residual[j] < residual[min_index]) min_index = j;
+    const double dx = pts[min_index + 1].first - pts[min_index - 1].first;
+    const double avg = residual[min_index] / dx;
+    if ((int)pts.size() <= max_points && avg > tol) break;
+    pts.erase(pts.begin() + min_index);
+    residual.erase(residual.begin() + min_index);
+    update_residual(pts, residual, min_index - 1, min_index + 1);
+  }
+  return pts;
+}
+
+// ------------------------------------------------------------------ ChannelState
+bool ChannelState::solve_ar(bool is_chroma) {
+  const bool ok = eqns.solve();
+  ar_gain = 1.0;
+  if (!ok) return false;
+  const int n = eqns.n, m = n - (is_chroma ? 1 : 0);
+  const double nobs = (double)num_observations;
+  double var = 0;
+  for (int i = 0; i < m; ++i) var += eqns.A[i * n + i] / nobs;
+  var /= m;
+  double sum_covar = 0;
+  for (int i = 0; i < m; ++i) {
+    double bi = eqns.b[i];
+    if (is_chroma) bi -= eqns.A[i * n + (n - 1)] * eqns.x[n - 1];
+    sum_covar += (bi * eqns.x[i]) / nobs;
+  }
+  const double noise_var = std::fmax(var - sum_covar, 1e-6);
+  ar_gain = std::fmax(1, std::sqrt(std::fmax(var / noise_var, 1e-6)));
+  return true;
+}
+
+static void chroma_fallback(LinearSystem &e) {
+  const int last = e.n - 1;
+  std::fill(e.x.begin(), e.x.end(), 0.0);
+  if (std::fabs(e.A[last * e.n + last]) > 1e-6) e.x[last] = e.b[last] / e.A[last * e.n + last];
+}
+
+// -------------------------------------------------------------------- NoiseModel
+NoiseModel::NoiseModel(const StreamGeometry &g)
+    : latest{ChannelState(24), ChannelState(25), ChannelState(25)},
+      combined{ChannelState(24), ChannelState(25), ChannelState(25)},
+      g_(g) {}
+
+// Integer Gram -> the f64 normal equations add_block_observations would hold: every entry is
+// (exact sum) / (tap scale, a power of two) / 255^2 with a single rounding.
+void NoiseModel::load_equations(int c, const FrameRecordView &rec) {
+  ChannelState &st = latest[c];
+  const int n = st.eqns.n;
+  const int64_t *G = rec.gram + (size_t)c * kPairs;
+  const double nss = c ? (double)(1 << (g_.ss_x + g_.ss_y)) : 1.0;
+  for (int i = 0; i < n; ++i) {
+    const double si = i == 24 ? nss : 1.0;
+    for (int j = 0; j < n; ++j) {
+      const double sj = j == 24 ? nss : 1.0;
+      st.eqns.A[i * n + j] += ((double)gram_at(G, i, j) / (si * sj)) / kNorm2;
+    }
+    st.eqns.b[i] += ((double)gram_at(G, i, 25) / si) / kNorm2;
+  }
+  st.num_observations += rec.nobs[c];
+}
+
+void NoiseModel::add_strength_measurements(int c, const FrameRecordView &rec) {
+  const int sx = c ? g_.ss_x : 0, sy = c ? g_.ss_y : 0;
+  const int bw = kBlock >> sx, bh = kBlock >> sy;
+  const int pw = g_.width >> sx, ph = g_.height >> sy;
+  StrengthSolver &solver = latest[c].strength;
+  const StrengthSolver &luma = latest[0].strength;
+  const double luma_gain = latest[0].ar_gain;
+  const double noise_gain = latest[c].ar_gain;
+  const double corr = c > 0 ? latest[c].eqns.x[24] : 0;
+  for (int by = 0; by < g_.nbh; ++by) {
+    for (int bx = 0; bx < g_.nbw; ++bx) {
+      const int b = by * g_.nbw + bx;
+      if (!rec.flat[b]) continue;
+      const int ns_h = std::min(ph - by * bh, bh), ns_w = std::min(pw - bx * bw, bw);
+      if (ns_w * ns_h > kBlock) {
+        const int lw = std::min(g_.width - bx * kBlock, kBlock), lh = std::min(g_.height - by * kBlock, kBlock);
+        const double block_mean = (double)rec.luma_sum[b] / (lw * lh);
+        const int cnt = ns_w * ns_h;
+        const double noise_mean = (double)rec.rsum[(size_t)c * g_.nb + b] / cnt;
+        const double noise_var = (double)rec.rsq[(size_t)c * g_.nb + b] / cnt - noise_mean * noise_mean;
+        const double luma_strength = c > 0 ? luma_gain * luma.value_at(block_mean) : 0;
+        const double t = corr * luma_strength;
+        const double uncorr_std = std::sqrt(std::fmax(noise_var / 16, noise_var - t * t));
+        solver.add_measurement(block_mean, uncorr_std / noise_gain);
+      }
+    }
+  }
+}
+
+bool NoiseModel::is_different() const {
+  const LinearSystem &lx = latest[0].eqns, &cx = combined[0].eqns;
+  double c = 0, a_len = 0, b_len = 0;
+  for (int i = 0; i < cx.n; ++i) {
+    a_len += lx.x[i] * lx.x[i];
+    b_len += cx.x[i] * cx.x[i];
+    c += lx.x[i] * cx.x[i];
+  }
+  const double corr = c / (std::sqrt(a_len) * std::sqrt(b_len));
+  if (corr < 0.9) return true;
+  const LinearSystem &le = latest[0].strength.eqns, &ce = combined[0].strength.eqns;
+  const double dx = 1.0 / latest[0].strength.num_bins;
+  double diff = 0, total_weight = 0;
+  for (int j = 0; j < le.n; ++j) {
+    double weight = 0;
+    for (int i = 0; i < le.n; ++i) weight += le.A[i * le.n + j];
+    weight = std::sqrt(weight);
+    diff += weight * std::fabs(le.x[j] - ce.x[j]);
+    total_weight += weight;
+  }
+  return diff * dx / total_weight > 0.005;
+}
+
+NoiseStatus NoiseModel::update(const FrameRecordView &rec) {
+  for (auto &s : latest) {
+    s.eqns.clear();
+    s.num_observations = 0;
+    s.strength.clear();
+  }
+  if (rec.num_flat <= 1) {
+    err_ = "Not enough flat blocks to update noise estimate";
+    return NoiseStatus::Error;
+  }
+  bool y_model_different = false;
+  for (int c = 0; c < g_.planes; ++c) {
+    const bool is_chroma = c != 0;
+    load_equations(c, rec);
+    if (!latest[c].solve_ar(is_chroma)) {
+      if (is_chroma) {
+        chroma_fallback(latest[c].eqns);
+      } else {
+        err_ = "Solving latest noise equation system failed 0!";
+        return NoiseStatus::Error;
+      }
+    }
+    add_strength_measurements(c, rec);
+    if (!latest[c].strength.solve()) {
+      err_ = "Solving latest noise strength failed!";
+      return NoiseStatus::Error;
+    }
+    if (c == 0 && combined[0].strength.num_equations > 0 && is_different()) y_model_different = true;
+    if (y_model_different) continue;
+
+    combined[c].num_observations += latest[c].num_observations;
+    combined[c].eqns.add(latest[c].eqns);
+    if (!combined[c].solve_ar(is_chroma)) {
+      if (is_chroma) {
+        chroma_fallback(combined[c].eqns);
+      } else {
+        err_ = "Solving combined noise equation system failed 0!";
+        return NoiseStatus::Error;
+      }
+    }
+    combined[c].strength.add(latest[c].strength);
+    if (!combined[c].strength.solve()) {
+      err_ = "Solving combined noise strength failed!";
+      return NoiseStatus::Error;
+    }
+  }
+  return y_model_different ? NoiseStatus::DifferentType : NoiseStatus::Ok;
+}
+
+void NoiseModel::save_latest() {
+  for (int c = 0; c < 3; ++c) {
+    combined[c].eqns.copy_from(latest[c].eqns);
+    combined[c].strength.eqns.copy_from(latest[c].strength.eqns);
+    combined[c].strength.num_equations = latest[c].strength.num_equations;
+    combined[c].num_observations = latest[c].num_observations;
+    combined[c].ar_gain = latest[c].ar_gain;
+  }
+}
+
+void NoiseModel::grain_parameters(uint64_t start_ts, uint64_t end_ts, g1s_segment *seg) const {
+  std::memset(seg, 0, sizeof(*seg));
+  seg->start_time = start_ts;
+  seg->end_time = end_ts;
+  seg->random_seed = start_ts == 0 ? kDefaultGrainSeed : 0;
+  seg->ar_coeff_lag = kLag;
+
+  std::vector<std::pair<double, double>> sp[3] = {combined[0].strength.fit_piecewise(G1S_NUM_Y_POINTS),
+                                                  combined[1].strength.fit_piecewise(G1S_NUM_UV_POINTS),
+                                                  combined[2].strength.fit_piecewise(G1S_NUM_UV_POINTS)};
+  double max_scaling_value = 1e-4;
+  for (auto &pts : sp)
+    for (auto &p : pts) {
+      p.first = std::fmin(255, p.first / 1.0);
+      p.second = std::fmin(255, p.second / 1.0);
+      max_scaling_value = std::fmax(p.second, max_scaling_value);
+    }
+  const int max_log2 = clampi((int)std::floor(std::log2(max_scaling_value) + 1), 2, 5);
+  seg->scaling_shift = (uint8_t)(5 + (8 - max_log2));
+  const double scale_factor = (double)(1 << (8 - max_log2));
+  seg->num_y_points = (uint8_t)sp[0].size();
+  seg->num_cb_points = (uint8_t)sp[1].size();
+  seg->num_cr_points = (uint8_t)sp[2].size();
+  uint8_t(*dst[3])[2] = {seg->scaling_points_y, seg->scaling_points_cb, seg->scaling_points_cr};
+  for (int c = 0; c < 3; ++c)
+    for (size_t i = 0; i < sp[c].size(); ++i) {
+      dst[c][i][0] = (uint8_t)(int)(sp[c][i].first + 0.5);
+      dst[c][i][1] = (uint8_t)clampi((int)(scale_factor * sp[c][i].second + 0.5), 0, 255);
+    }
+
+  const int n_coeff = combined[0].eqns.n;
+  double max_coeff = 1e-4, min_coeff = -1e-4;
+  double y_corr[2] = {0, 0};
+  double avg_luma_strength = 0;
+  for (int c = 0; c < 3; ++c) {
+    const LinearSystem &e = combined[c].eqns;
+    for (int i = 0; i < n_coeff; ++i) {
+      max_coeff = std::fmax(max_coeff, e.x[i]);
+      min_coeff = std::fmin(min_coeff, e.x[i]);
+    }
+    const LinearSystem &se = combined[c].strength.eqns;
+    double average_strength = 0, total_weight = 0;
+    for (int i = 0; i < se.n; ++i) {
+      double w = 0;
+      for (int j = 0; j < se.n; ++j) w += se.A[i * se.n + j];
+      w = std::sqrt(w);
+      average_strength += se.x[i] * w;
+      total_weight += w;
+    }
+    if (total_weight == 0)
+      average_strength = 1;
+    else
+      average_strength /= total_weight;
+    if (c == 0) {
+      avg_luma_strength = average_strength;
+    } else {
+      y_corr[c - 1] = avg_luma_strength * e.x[n_coeff] / average_strength;
+      max_coeff = std::fmax(max_coeff, y_corr[c - 1]);
+      min_coeff = std::fmin(min_coeff, y_corr[c - 1]);
+    }
+  }
+  seg->ar_coeff_shift = (uint8_t)clampi(
+      7 - (int)std::fmax(1 + std::floor(std::log2(max_coeff)), std::ceil(std::log2(-min_coeff))), 6, 9);
+  const double scale_ar = (double)(1 << seg->ar_coeff_shift);
+  int8_t *ar[3] = {seg->ar_coeffs_y, seg->ar_coeffs_cb, seg->ar_coeffs_cr};
+  for (int c = 0; c < 3; ++c) {
+    const LinearSystem &e = combined[c].eqns;
+    for (int i = 0; i < n_coeff; ++i) ar[c][i] = (int8_t)clampi((int)std::round(scale_ar * e.x[i]), -128, 127);
+    if (c > 0) ar[c][n_coeff] = (int8_t)clampi((int)std::round(scale_ar * y_corr[c - 1]), -128, 127);
+  }
+  seg->cb_mult = 128;
+  seg->cb_luma_mult = 192;
+  seg->cb_offset = 256;
+  seg->cr_mult = 128;
+  seg->cr_luma_mult = 192;
+  seg->cr_offset = 256;
+  seg->chroma_scaling_from_luma = 0;
+  seg->grain_scale_shift = 0;
+  seg->overlap_flag = 1;
+}
+
+// ----------------------------------------------------------------- DiffSequencer
+DiffSequencer::DiffSequencer(int64_t fps_num, int64_t fps_den, const StreamGeometry &g)
+    : fps_num_(fps_num), fps_den_(fps_den), model_(g) {}
+
+void DiffSequencer::consume(const FrameRecordView &rec) {
+  // NoiseStatus::Error is swallowed, as in the crate (status is only compared to DifferentType).
+  if (model_.update(rec) == NoiseStatus::DifferentType) {
+    const uint64_t cur = (uint64_t)frame_count_ * 10000000ull * (uint64_t)fps_den_ / (uint64_t)fps_num_;
+    g1s_segment seg;
+    model_.grain_parameters(prev_timestamp_, cur, &seg);
+    table_.push_back(seg);
+    model_.save_latest();
+    prev_timestamp_ = cur;
+  }
+  ++frame_count_;
+}
+
+std::vector<g1s_segment> DiffSequencer::finish() {
+  std::vector<g1s_segment> out(table_);
+  g1s_segment seg;
+  model_.grain_parameters(prev_timestamp_, (uint64_t)INT64_MAX, &seg);
+  out.push_back(seg);
+  return out;
+}
+
+// ---------------------------------------------------------------- misc host math
+void flat_block_ata_inv(double out[9]) {
+  // FlatBlockFinder::new: A rows are [yd, xd, 1] with d = (i - 16) / 16; (A^T A)^-1 by three solves.
+  LinearSystem e(3);
+  for (int y = 0; y < kBlock; ++y) {
+    const double yd = ((double)y - 16.0) / 16.0;
+    for (int x = 0; x < kBlock; ++x) {
+      const double xd = ((double)x - 16.0) / 16.0;
+      const double c[3] = {yd, xd, 1.0};
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) e.A[3 * i + j] += c[i] * c[j];
+    }
+  }
+  for (int i = 0; i < 3; ++i) {
+    std::fill(e.b.begin(), e.b.end(), 0.0);
+    e.b[i] = 1.0;
+    e.solve();
+    for (int j = 0; j < 3; ++j) out[j * 3 + i] = e.x[j];
+  }
+}
+
+std::string format_grain_table(const g1s_segment *segs, size_t n) {
+  std::string s = "filmgrn1\n";
+  char buf[256];
+  for (size_t k = 0; k < n; ++k) {
+    const g1s_segment &p = segs[k];
+    std::snprintf(buf, sizeof buf, "E %llu %llu 1 %u 1\n", (unsigned long long)p.start_time,
+                  (unsigned long long)p.end_time, (unsigned)p.random_seed);
+    s += buf;
+    std::snprintf(buf, sizeof buf, "\tp %u %u %u %u %u %u %u %u %u %u %u %u\n", p.ar_coeff_lag, p.ar_coeff_shift,
+                  p.grain_scale_shift, p.scaling_shift, p.chroma_scaling_from_luma ? 1 : 0, p.overlap_flag ? 1 : 0,
+                  p.cb_mult, p.cb_luma_mult, p.cb_offset, p.cr_mult, p.cr_luma_mult, p.cr_offset);
+    s += buf;
+    auto points = [&](const char *tag, const uint8_t(*pts)[2], int cnt, bool trailing_space) {
+      s += tag;
+      s += std::to_string(cnt);
+      if (trailing_space) s += ' ';  // src/main.rs:659 writes "\tsY {} " (extra space), :665/:671 do not
+      for (int i = 0; i < cnt; ++i) {
+        s += ' ';
+        s += std::to_string(pts[i][0]);
+        s += ' ';
+        s += std::to_string(pts[i][1]);
+      }
+      s += '\n';
+    };
+    points("\tsY ", p.scaling_points_y, p.num_y_points, true);
+    points("\tsCb ", p.scaling_points_cb, p.num_cb_points, false);
+    points("\tsCr ", p.scaling_points_cr, p.num_cr_points, false);
+    auto coeffs = [&](const char *tag, const int8_t *v, int cnt) {
+      s += tag;
+      for (int i = 0; i < cnt; ++i) {
+        s += ' ';
+        s += std::to_string((int)v[i]);
+      }
+      s += '\n';
+    };
+    // coefficient counts follow the lag (AV1 5.9.30): 2*lag*(lag+1) luma, one more for chroma
+    const int lag = std::min<int>(p.ar_coeff_lag, 3);
+    const int ny = 2 * lag * (lag + 1);
+    coeffs("\tcY", p.ar_coeffs_y, ny);
+    coeffs("\tcCb", p.ar_coeffs_cb, ny + 1);
+    coeffs("\tcCr", p.ar_coeffs_cr, ny + 1);
+  }
+  return s;
+}
+
+}  // namespace g1s

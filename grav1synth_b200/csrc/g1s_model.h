@@ -1,0 +1,116 @@
+// Host side of the grain-estimation path: everything av1-grain's NoiseModel does AFTER
+// the per-pixel sums exist (the "tiny f64 solves" of SURVEY.md section 8a rows a7, a9-a12).
+// Input is one integer FrameRecord per frame pair, produced by the CUDA kernels; this
+// file never touches pixels.  Strictly sequential across frames, as in the reference.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/g1s.h"
+
+namespace g1s {
+
+struct StreamGeometry {
+  int width = 0, height = 0, ss_x = 1, ss_y = 1, planes = 3;
+  int nbw = 0, nbh = 0, nb = 0;
+};
+
+// View over one per-frame record in host memory (see RecordLayout in g1s_kernels.h).
+struct FrameRecordView {
+  const int64_t *gram;       // [3][351]
+  const int64_t *nobs;       // [3]
+  int64_t num_flat;
+  const uint32_t *luma_sum;  // [nb]
+  const int32_t *rsum;       // [3][nb]
+  const uint32_t *rsq;       // [3][nb]
+  const uint8_t *flat;       // [nb]
+};
+
+enum class NoiseStatus { Ok, DifferentType, Error };
+
+class LinearSystem {
+ public:
+  explicit LinearSystem(int n = 0) { reset(n); }
+  void reset(int n);
+  void clear();
+  bool solve();  // Gaussian elimination on copies of A and b (EquationSystem::solve)
+  void add(const LinearSystem &o);
+  void copy_from(const LinearSystem &o);
+  int n = 0;
+  std::vector<double> A, b, x;
+};
+
+class StrengthSolver {
+ public:
+  StrengthSolver();
+  void clear();
+  void add_measurement(double block_mean, double noise_std);
+  bool solve();
+  double value_at(double intensity) const;
+  double bin_center(int i) const;
+  void add(const StrengthSolver &o);
+  // (intensity, strength) points after greedy simplification (fit_piecewise)
+  std::vector<std::pair<double, double>> fit_piecewise(int max_points) const;
+  LinearSystem eqns;
+  int num_bins;
+  int num_equations = 0;
+  double total = 0;
+  double min_intensity = 0, max_intensity = 255;
+
+ private:
+  double bin_index(double v) const;
+  void update_residual(const std::vector<std::pair<double, double>> &pts, std::vector<double> &residual, int start,
+                       int end) const;
+};
+
+struct ChannelState {
+  explicit ChannelState(int n = 24) : eqns(n) {}
+  LinearSystem eqns;
+  double ar_gain = 1.0;
+  int64_t num_observations = 0;
+  StrengthSolver strength;
+  bool solve_ar(bool is_chroma);
+};
+
+class NoiseModel {
+ public:
+  explicit NoiseModel(const StreamGeometry &g);
+  NoiseStatus update(const FrameRecordView &rec);
+  void save_latest();
+  void grain_parameters(uint64_t start_ts, uint64_t end_ts, g1s_segment *seg) const;
+  const std::string &last_error() const { return err_; }
+  ChannelState latest[3], combined[3];
+
+ private:
+  void load_equations(int c, const FrameRecordView &rec);
+  void add_strength_measurements(int c, const FrameRecordView &rec);
+  bool is_different() const;
+  StreamGeometry g_;
+  std::string err_;
+};
+
+// DiffGenerator minus the pixels: frame counter, timestamps, segment list.
+class DiffSequencer {
+ public:
+  DiffSequencer(int64_t fps_num, int64_t fps_den, const StreamGeometry &g);
+  void consume(const FrameRecordView &rec);
+  std::vector<g1s_segment> finish();
+  int64_t frames() const { return frame_count_; }
+  NoiseModel &model() { return model_; }
+
+ private:
+  int64_t fps_num_, fps_den_;
+  int64_t frame_count_ = 0;
+  uint64_t prev_timestamp_ = 0;
+  NoiseModel model_;
+  std::vector<g1s_segment> table_;
+};
+
+// (A^T A)^-1 of FlatBlockFinder::new, row-major 3x3.
+void flat_block_ata_inv(double out[9]);
+
+// `filmgrn1` text, src/main.rs:525-530 + 631-696.
+std::string format_grain_table(const g1s_segment *segs, size_t n);
+
+}  // namespace g1s

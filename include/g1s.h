@@ -1,0 +1,185 @@
+/*
+ * g1s.h — C ABI of the B200 film-grain estimation engine (grav1synth `diff` hot path).
+ *
+ * This is the drop-in boundary: every entry point below replaces one call the
+ * reference makes into `av1_grain::DiffGenerator` (crate av1-grain 0.4.2, pinned in
+ * /root/reference/Cargo.toml:15, Cargo.lock:92-104) from its `Commands::Diff` arm.
+ * Plain pointers and sizes only; no torch / CUDA types cross this boundary.
+ *
+ *   reference call site (src/main.rs)                      entry point here
+ *   -----------------------------------------------------  -------------------------
+ *   DiffGenerator::new(fps, src_bd, den_bd)      :420-427  g1s_diff_create
+ *   differ.diff_frame(&src, &den)?  :442 / 462 / 482 / 502  g1s_diff_push_frame
+ *   differ.finish() -> Vec<GrainTableSegment>        :524  g1s_diff_finish
+ *   (drop of `differ`)                                      g1s_diff_destroy
+ *   anyhow::Error text (propagated by `?`)           :442  g1s_diff_last_error
+ *   writeln!("filmgrn1") + write_film_grain_segment
+ *                                        :525-530, 631-696  g1s_write_grain_table
+ *   GrainTableSegment / FilmGrainParams
+ *                 src/main.rs:698-713, parser/grain.rs:21-81  g1s_segment
+ *
+ * Threading: one handle is one stream of frame pairs; calls on a handle must be
+ * serialised by the caller (the reference loop src/main.rs:432-521 is single
+ * threaded too).  The engine itself is asynchronous: `push_frame` copies the
+ * borrowed planes into a pinned staging ring and returns; an error raised while
+ * processing frame k may therefore surface on a later push or on finish.
+ *
+ * There is NO CPU fallback: if no CUDA device is usable every call fails with
+ * G1S_E_CUDA.
+ */
+#ifndef G1S_H_
+#define G1S_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G1S_ABI_VERSION 1
+
+/* Capacities fixed by the AV1 film-grain syntax; av1_grain::NUM_Y_POINTS etc. as
+ * imported at /root/reference/src/parser/grain.rs:2 and used at :26-49. */
+#define G1S_NUM_Y_POINTS 14
+#define G1S_NUM_UV_POINTS 10
+#define G1S_NUM_Y_COEFFS 24
+#define G1S_NUM_UV_COEFFS 25
+
+enum g1s_status {
+  G1S_OK = 0,
+  G1S_E_ARG = -1,         /* bad argument / unsupported configuration            */
+  G1S_E_DIMS = -2,        /* source and denoised frame dimensions differ          */
+  G1S_E_CUDA = -3,        /* CUDA runtime failure or no device (no CPU fallback)  */
+  G1S_E_NCCL = -4,        /* reserved for the multi-process merge                 */
+  G1S_E_NOMEM = -5,
+  G1S_E_STATE = -6,       /* call after finish, or capacity too small             */
+  G1S_E_IO = -7
+};
+
+/* One grain-table segment: field-for-field the data carried by
+ * av1_grain::GrainTableSegment as consumed at src/parser/grain.rs:108-133 and
+ * src/main.rs:705-713.  POD, caller-allocated. */
+typedef struct g1s_segment {
+  uint64_t start_time; /* 1e-7 s units */
+  uint64_t end_time;
+  uint8_t num_y_points, num_cb_points, num_cr_points;
+  uint8_t scaling_shift;      /* 8..=11 */
+  uint8_t ar_coeff_lag;       /* always 3 on this path */
+  uint8_t ar_coeff_shift;     /* 6..=9 */
+  uint8_t grain_scale_shift;
+  uint8_t overlap_flag;
+  uint8_t chroma_scaling_from_luma;
+  uint8_t cb_mult, cb_luma_mult, cr_mult, cr_luma_mult;
+  uint8_t reserved_[3];
+  uint16_t cb_offset, cr_offset;
+  uint16_t random_seed;
+  uint16_t reserved2_;
+  uint8_t scaling_points_y[G1S_NUM_Y_POINTS][2];
+  uint8_t scaling_points_cb[G1S_NUM_UV_POINTS][2];
+  uint8_t scaling_points_cr[G1S_NUM_UV_POINTS][2];
+  int8_t ar_coeffs_y[G1S_NUM_Y_COEFFS];
+  int8_t ar_coeffs_cb[G1S_NUM_UV_COEFFS];
+  int8_t ar_coeffs_cr[G1S_NUM_UV_COEFFS];
+} g1s_segment;
+
+/* A borrowed planar frame (what `&Frame<T>` is at src/main.rs:442): Y, Cb, Cr.
+ * Samples are uint8_t when the stream's bit depth is 8, little-endian uint16_t
+ * when it is 9..16 (src/reader.rs:51-67).  Strides are in BYTES.  For monochrome
+ * streams plane[1] and plane[2] are NULL.  width/height are the luma size of THIS
+ * frame: the reference checks source against denoised per call
+ * (verify_dimensions_match) and fails the call when they differ. */
+typedef struct g1s_frame {
+  const void *plane[3];
+  size_t stride_bytes[3];
+  int32_t width, height;
+} g1s_frame;
+
+/* How a handle is used.  FULL is the drop-in for DiffGenerator.  The other two split
+ * it for frame-sharded multi-GPU runs: every rank runs a PRODUCER (kernels only; the
+ * per-frame integer records leave through the record tap), the records are exchanged
+ * (NCCL) and ONE rank feeds them, in frame order, to a CONSUMER (host model only, no
+ * device work) with g1s_diff_consume_record. */
+enum g1s_mode { G1S_MODE_FULL = 0, G1S_MODE_PRODUCER = 1, G1S_MODE_CONSUMER = 2 };
+
+typedef struct g1s_diff_config {
+  int64_t fps_num, fps_den;     /* Rational64 passed to DiffGenerator::new           */
+  int32_t src_bit_depth;        /* 8..16, bit depth of the source stream             */
+  int32_t den_bit_depth;        /* 8..16, bit depth of the denoised stream           */
+  int32_t width, height;        /* luma size in samples                              */
+  int32_t ss_x, ss_y;           /* chroma subsampling log2 (4:2:0 = 1,1)             */
+  int32_t monochrome;           /* non-zero: only plane[0] is read                   */
+  int32_t device;               /* CUDA device ordinal                               */
+  int32_t batch_frames;         /* frames per device launch; 0 = engine default      */
+  int32_t mode;                 /* enum g1s_mode                                     */
+  int32_t reserved_[6];
+} g1s_diff_config;
+
+typedef struct g1s_diff g1s_diff;
+
+/* DiffGenerator::new — src/main.rs:420-427. */
+int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out);
+
+/* DiffGenerator::diff_frame — src/main.rs:442.  Planes are borrowed only until
+ * the call returns. */
+int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *denoised);
+
+/* Same as push_frame but the planes are DEVICE pointers (already resident in HBM,
+ * same layout); used by the benchmark's device-resident arm and by callers that
+ * decode on the GPU.  The memory must stay valid until the next g1s_diff_flush /
+ * g1s_diff_finish returns. */
+int g1s_diff_push_frame_device(g1s_diff *d, const g1s_frame *source, const g1s_frame *denoised);
+
+/* Drains everything queued so far (blocks until the device and the host model have
+ * consumed every pushed frame).  Optional; finish implies it. */
+int g1s_diff_flush(g1s_diff *d);
+
+/* DiffGenerator::finish — src/main.rs:524.  Writes up to `cap` segments, stores the
+ * number of segments in *n.  Returns G1S_E_STATE if cap is too small (then *n is the
+ * required capacity and the call may be repeated). */
+int g1s_diff_finish(g1s_diff *d, g1s_segment *out, size_t cap, size_t *n);
+
+void g1s_diff_destroy(g1s_diff *d);
+
+/* Text of the last error on this handle (or of the last failed create when d is
+ * NULL).  Never NULL. */
+const char *g1s_diff_last_error(const g1s_diff *d);
+
+/* Number of frames accepted so far. */
+int64_t g1s_diff_frames_pushed(const g1s_diff *d);
+
+/* Timing/launch counters of the device pipeline, for the benchmark harness:
+ * out[0] = kernels launched, out[1] = total device ms spent in the fused
+ * residual+autocorrelation kernel (CUDA events on the engine stream),
+ * out[2] = its launch count, out[3] = device ms of the flat-block kernel,
+ * out[4] = its launch count, out[5] = frames fully processed. */
+int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n);
+
+/* ---- per-frame records (the unit exchanged between GPUs) -------------------------
+ * One record holds everything the host model needs from one frame pair, all integers
+ * except the f32 flatness scores: gram[3][351] int64 (upper triangle over 26 taps:
+ * 0..23 AR taps, 24 luma tap x 2^(ss_x+ss_y), 25 centre sample), nobs[3] int64,
+ * num_flat int64, luma_sum[nb] u32, rsum[3][nb] i32, rsq[3][nb] u32, score[nb] f32,
+ * flat[nb] u8.  g1s_record_layout fills off[0..7] with the byte offsets of those eight
+ * arrays in that order and returns the record size. */
+size_t g1s_record_layout(int32_t num_blocks, size_t off[8]);
+size_t g1s_diff_record_bytes(const g1s_diff *d);
+typedef void (*g1s_record_fn)(void *user, int64_t frame_index, const void *record, size_t bytes);
+/* Called on the caller's thread (inside push/flush/finish) once per frame, in frame
+ * order, before the record is folded into the model. */
+int g1s_diff_set_record_tap(g1s_diff *d, g1s_record_fn fn, void *user);
+/* CONSUMER handles: fold one record (next frame in order) into the model. */
+int g1s_diff_consume_record(g1s_diff *d, const void *record, size_t bytes);
+
+/* `filmgrn1` writer — src/main.rs:525-530 and 631-696, byte for byte. */
+int g1s_write_grain_table(const g1s_segment *segs, size_t n, const char *path);
+/* Same, into a caller buffer.  Returns the number of bytes needed (excluding the
+ * terminating NUL) or a negative status. */
+int64_t g1s_format_grain_table(const g1s_segment *segs, size_t n, char *buf, size_t cap);
+
+int g1s_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G1S_H_ */
