@@ -1,0 +1,204 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bit-exact bar: flat flags, f32 flatness scores (bit patterns), integer Gram sums, observation
+counts, per-block noise statistics and the final grain tables must all be identical.
+Nothing here reads /root/reference.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import CORPUS, ROOT, corpus_frames, gram_to_pairs, numpy_record
+from grav1synth_b200 import diff as D
+from grav1synth_b200.synth import SynthSpec, make_pair_numpy
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_run(spec, fps, frames, batch=0, src_bd=None, den_bd=None):
+    g = D.DiffGenerator(fps[0], fps[1], src_bd or spec.bit_depth, den_bd or spec.bit_depth, spec.width, spec.height,
+                        spec.ss_x, spec.ss_y, batch_frames=batch)
+    recs = []
+    g.set_record_tap(lambda i, r: recs.append((i, r)))
+    for s, d in frames:
+        g.diff_frame(s, d)
+    segs = g.finish()
+    assert [i for i, _ in recs] == list(range(len(frames)))
+    rl = D.RecordLayout(g.num_blocks)
+    return segs, [rl.unpack(r) for _, r in recs], g
+
+
+def oracle_run(spec, fps, frames, src_bd=None, den_bd=None):
+    o = O.OracleDiffGenerator(fps[0], fps[1], src_bd or spec.bit_depth, den_bd or spec.bit_depth, O.GRAM_EXACT_INT,
+                              O.EXP_FIXED, spec.ss_x, spec.ss_y)
+    per = []
+    for s, d in frames:
+        o.diff_frame(s, d)
+        flat, scores, feat = o.last_flat()
+        per.append(dict(flat=flat, scores=scores, gram=[o.last_gram(c) for c in range(3)], status=o.last_status))
+    return o.finish(), per
+
+
+def compare_records(spec, frames, got, want, src_bd=None, den_bd=None):
+    for k, ((s, d), g, w) in enumerate(zip(frames, got, want)):
+        assert np.array_equal(g["flat"], w["flat"]), f"frame {k}: flat flags differ"
+        assert np.array_equal(g["score"].view(np.uint32), w["scores"].view(np.uint32)), f"frame {k}: scores differ"
+        assert g["num_flat"] == int((w["flat"] != 0).sum())
+        if g["num_flat"] <= 1:
+            continue
+        ref = numpy_record(s, d, src_bd or spec.bit_depth, den_bd or spec.bit_depth, spec.ss_x, spec.ss_y, w["flat"])
+        for c in range(3):
+            G, nobs = w["gram"][c]
+            assert int(g["nobs"][c]) == nobs, f"frame {k} plane {c}: nobs"
+            assert np.array_equal(D.gram_pairs_to_matrix(g["gram"][c]), G), f"frame {k} plane {c}: Gram"
+            m = w["flat"] != 0
+            assert np.array_equal(g["rsum"][c][m], ref["rsum"][c][m])
+            assert np.array_equal(g["rsq"][c][m], ref["rsq"][c][m])
+        assert np.array_equal(g["luma_sum"][w["flat"] != 0], ref["luma_sum"][w["flat"] != 0])
+
+
+@pytest.mark.parametrize("name", list(CORPUS))
+def test_corpus_bit_exact(name):
+    spec, fps, frames = corpus_frames(name)
+    segs, recs, _ = gpu_run(spec, fps, frames)
+    want, per = oracle_run(spec, fps, frames)
+    compare_records(spec, frames, recs, per)
+    assert segs == want
+    with open(os.path.join(ROOT, "tests", "golden", name + ".tbl")) as f:
+        assert D.format_grain_table(segs) == f.read()
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3])
+def test_batching_does_not_change_results(batch):
+    spec, fps, frames = corpus_frames("c2_small_8bit")
+    a, ra, _ = gpu_run(spec, fps, frames, batch=batch)
+    b, rb, _ = gpu_run(spec, fps, frames, batch=0)
+    assert a == b
+    for x, y in zip(ra, rb):
+        for key in ("gram", "nobs", "flat", "score", "rsum", "rsq", "luma_sum"):
+            assert np.array_equal(x[key], y[key])
+
+
+def test_mixed_bit_depths():
+    spec, fps, frames = corpus_frames("c3_small_10bit")
+    frames = [(s, [(p >> 2).astype(np.uint8) for p in d]) for s, d in frames]
+    segs, recs, _ = gpu_run(spec, fps, frames, src_bd=10, den_bd=8)
+    want, per = oracle_run(spec, fps, frames, src_bd=10, den_bd=8)
+    compare_records(spec, frames, recs, per, 10, 8)
+    assert segs == want
+
+
+def test_device_resident_frames_equal_host_frames():
+    import torch
+    spec, fps, frames = corpus_frames("c3_small_10bit")
+    host, _, _ = gpu_run(spec, fps, frames)
+    g = D.DiffGenerator(fps[0], fps[1], spec.bit_depth, spec.bit_depth, spec.width, spec.height, spec.ss_x, spec.ss_y)
+    keep = []
+    for s, d in frames:
+        ts = [torch.from_numpy(p.view(np.int16)).cuda() for p in s]
+        td = [torch.from_numpy(p.view(np.int16)).cuda() for p in d]
+        keep += ts + td
+        g.diff_frame_device([t.data_ptr() for t in ts], [t.stride(0) * 2 for t in ts],
+                            [t.data_ptr() for t in td], [t.stride(0) * 2 for t in td])
+    torch.cuda.synchronize()
+    assert g.finish() == host
+
+
+def test_saturated_residual_and_zero_residual():
+    # |r| = 255 everywhere in one half (int8 overflow territory for any packed path), zero in the other
+    rng = np.random.default_rng(5)
+    h, w = 128, 192
+    den = [np.zeros((h, w), np.uint8), np.zeros((h // 2, w // 2), np.uint8), np.full((h // 2, w // 2), 255, np.uint8)]
+    src = [np.full((h, w), 255, np.uint8), np.full((h // 2, w // 2), 255, np.uint8), np.zeros((h // 2, w // 2), np.uint8)]
+    src[0][:, : w // 2] = rng.integers(0, 256, (h, w // 2), dtype=np.uint8)
+    den[0][:, : w // 2] = rng.integers(0, 256, (h, w // 2), dtype=np.uint8)
+    spec = SynthSpec(w, h, 8)
+    frames = [(src, den), (den, src)]
+    segs, recs, _ = gpu_run(spec, (24, 1), frames)
+    want, per = oracle_run(spec, (24, 1), frames)
+    compare_records(spec, frames, recs, per)
+    assert segs == want
+
+
+def test_flat_everything_rule_and_error_swallowing():
+    y = np.full((96, 128), 100, np.uint8)
+    c = np.full((48, 64), 128, np.uint8)
+    spec = SynthSpec(128, 96, 8)
+    segs, recs, _ = gpu_run(spec, (24, 1), [([y, c, c], [y, c, c])])
+    assert np.all(recs[0]["flat"] == 1) and np.all(recs[0]["score"] == 0)
+    want, _ = oracle_run(spec, (24, 1), [([y, c, c], [y, c, c])])
+    assert segs == want
+
+
+def test_single_block_frame_not_enough_flat_blocks():
+    rng = np.random.default_rng(0)
+    y = rng.integers(0, 255, (32, 32), dtype=np.uint8)
+    c = np.full((16, 16), 128, np.uint8)
+    spec = SynthSpec(32, 32, 8)
+    segs, recs, _ = gpu_run(spec, (24, 1), [([y, c, c], [y, c, c])])
+    want, _ = oracle_run(spec, (24, 1), [([y, c, c], [y, c, c])])
+    assert recs[0]["num_flat"] <= 1 and segs == want
+
+
+def test_dimension_mismatch_raises():
+    g = D.DiffGenerator(24, 1, 8, 8, 64, 64)
+    a = [np.zeros((64, 64), np.uint8), np.zeros((32, 32), np.uint8), np.zeros((32, 32), np.uint8)]
+    b = [np.zeros((64, 96), np.uint8), np.zeros((32, 48), np.uint8), np.zeros((32, 48), np.uint8)]
+    with pytest.raises(ValueError):
+        g.diff_frame(a, b)
+
+
+def test_monochrome():
+    spec, fps, frames = corpus_frames("c2_small_8bit")
+    g = D.DiffGenerator(fps[0], fps[1], 8, 8, spec.width, spec.height, monochrome=True)
+    o = O.OracleDiffGenerator(fps[0], fps[1], 8, 8)
+    for s, d in frames:
+        g.diff_frame(s[:1], d[:1])
+        o.diff_frame(s[:1], d[:1])
+    assert g.finish() == o.finish()
+
+
+def test_segment_cut_on_gpu():
+    a = SynthSpec(256, 192, 8, textured=0.0, sigma0=1.0, sigma1=0.5, ar_strength=0.0, seed=1)
+    b = SynthSpec(256, 192, 8, textured=0.0, sigma0=2.2, sigma1=0.5, ar_strength=0.6, seed=2)
+    frames = [make_pair_numpy(a, k) for k in range(3)] + [make_pair_numpy(b, k) for k in range(3)]
+    segs, _, _ = gpu_run(a, (30000, 1001), frames, batch=2)
+    want, _ = oracle_run(a, (30000, 1001), frames)
+    assert len(want) >= 2 and segs == want
+
+
+def test_full_size_4k_10bit_frame_against_oracle():
+    """BASELINE configs[2] geometry: one 3840x2160 10-bit 4:2:0 pair, full record vs the oracle."""
+    spec = SynthSpec(3840, 2160, 10, textured=0.1, sigma0=1.0, sigma1=1.5, seed=2026)
+    frames = [make_pair_numpy(spec, 0)]
+    segs, recs, g = gpu_run(spec, (24, 1), frames)
+    want, per = oracle_run(spec, (24, 1), frames)
+    compare_records(spec, frames, recs, per)
+    assert segs == want
+    c = g.counters()
+    assert c["gram_launches"] >= 1 and c["flat_launches"] >= 1 and c["frames_done"] == 1
+
+
+def test_full_size_properties_1080p_batch():
+    """BASELINE configs[1] geometry, 6 frames: determinism, frame-order independence of records, and
+    the closed-form observation count implied by the flat mask."""
+    from helpers import obs_rects
+    spec = SynthSpec(1920, 1080, 8, textured=0.2, sigma0=1.0, sigma1=1.5, seed=99)
+    frames = [make_pair_numpy(spec, k) for k in range(6)]
+    _, r1, _ = gpu_run(spec, (24, 1), frames, batch=4)
+    _, r2, _ = gpu_run(spec, (24, 1), frames[::-1], batch=6)
+    for a, b in zip(r1, r2[::-1]):
+        for key in ("gram", "nobs", "flat", "score", "rsum", "rsq", "luma_sum"):
+            assert np.array_equal(a[key], b[key]), key
+    nbw, nbh = 60, 34
+    for rec in r1:
+        for c in range(3):
+            s = 1 if c else 0
+            n = sum(max(0, x1 - x0) * max(0, y1 - y0) if (x1 > x0 and y1 > y0) else 0
+                    for (_, _, x0, x1, y0, y1) in obs_rects(rec["flat"], nbw, nbh, 1920 >> s, 1080 >> s, 32 >> s, 32 >> s))
+            assert int(rec["nobs"][c]) == n
+        # centre-sample square sum over observations can never exceed the sum over whole flat blocks
+        G = D.gram_pairs_to_matrix(rec["gram"][0])
+        assert 0 < G[25, 25] <= int(rec["rsq"][0][rec["flat"] != 0].astype(np.int64).sum())

@@ -1,0 +1,86 @@
+"""world_size-2 gloo test (CPU) of the frame-sharded driver: dealing, record gather, in-order fold.
+The CUDA producer is replaced by a CPU record producer (oracle flat mask + numpy sums); the
+exchange and consumer code under test is the code the GPU run uses."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import ROOT, corpus_frames, gram_to_pairs, numpy_record
+
+
+class CpuRecordProducer:
+    def __init__(self, spec):
+        from grav1synth_b200.diff import RecordLayout
+        from oracle import oracle as O
+        self.spec = spec
+        self.o = O.OracleDiffGenerator(24, 1, spec.bit_depth, spec.bit_depth, ss_x=spec.ss_x, ss_y=spec.ss_y)
+        self.rl = RecordLayout(((spec.width + 31) // 32) * ((spec.height + 31) // 32))
+        self.pending, self.tap, self.count = [], None, 0
+
+    def set_record_tap(self, fn):
+        self.tap = fn
+
+    def diff_frame(self, s, d):
+        spec = self.spec
+        self.o.diff_frame(s, d)
+        flat, scores, _ = self.o.last_flat()
+        r = numpy_record(s, d, spec.bit_depth, spec.bit_depth, spec.ss_x, spec.ss_y, flat)
+        pairs = np.stack([gram_to_pairs(r["gram"][c]) for c in range(3)])
+        self.pending.append(self.rl.pack(pairs, r["nobs"], r["num_flat"], r["luma_sum"], r["rsum"], r["rsq"], scores, flat))
+
+    def flush(self):
+        for rec in self.pending:
+            self.tap(self.count, rec)
+            self.count += 1
+        self.pending.clear()
+
+
+def _worker(rank, world, port, name, B, out_path):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from grav1synth_b200.diff import format_grain_table
+    from grav1synth_b200.sharded import ShardedDiff, owner_of
+    spec, fps, frames = corpus_frames(name)
+    sd = ShardedDiff(fps[0], fps[1], spec.bit_depth, spec.bit_depth, spec.width, spec.height, spec.ss_x, spec.ss_y,
+                     frames_per_rank=B, producer_factory=lambda: CpuRecordProducer(spec))
+    n, base, folded = len(frames), 0, 0
+    while base < n:
+        for k in range(base, min(n, base + world * B)):
+            if owner_of(k, world, B) == rank:
+                sd.push_local(*frames[k])
+        folded += sd.exchange()
+        base += world * B
+    segs = sd.finish()
+    if rank == 0:
+        assert folded == n
+        with open(out_path, "w") as f:
+            f.write(format_grain_table(segs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,B", [("c2_small_8bit", 1), ("c2_small_8bit", 3), ("c3_small_10bit", 2)])
+def test_two_rank_gloo_matches_golden(name, B, tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "t.tbl")
+    mp.spawn(_worker, args=(2, port, name, B, out), nprocs=2, join=True)
+    with open(os.path.join(ROOT, "tests", "golden", name + ".tbl")) as f:
+        assert open(out).read() == f.read()
+
+
+def test_owner_dealing():
+    from grav1synth_b200.sharded import owner_of
+    assert [owner_of(k, 2, 2) for k in range(8)] == [0, 0, 1, 1, 0, 0, 1, 1]
+    assert [owner_of(k, 4, 1) for k in range(6)] == [0, 1, 2, 3, 0, 1]
