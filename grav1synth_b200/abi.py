@@ -82,7 +82,8 @@ class CDiffConfig(C.Structure):
         ("device", C.c_int32),
         ("batch_frames", C.c_int32),
         ("mode", C.c_int32),
-        ("reserved_", C.c_int32 * 6),
+        ("gram_kernel", C.c_int32),
+        ("reserved_", C.c_int32 * 5),
     ]
 
 

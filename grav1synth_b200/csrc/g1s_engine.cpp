@@ -112,13 +112,28 @@ int submit(g1s_diff *d, Slot &s) {
   CU_TRY(d, cudaEventRecord(s.k0_end, st));
   launch_flat_select(s.count, d->geom, s.d_records, d->rl, st);
   CU_TRY(d, cudaEventRecord(s.k1_beg, st));
-  launch_gram_generic(s.d_descs, s.count, d->geom, s.d_records, d->rl, st);
-  CU_TRY(d, cudaEventRecord(s.k1_end, st));
+  int gram_launches = 1;
+  if (d->cfg.gram_kernel == 0 && gram_imma_supported(d->geom)) {
+    // 64-bit vector loads need 8-byte aligned rows; otherwise the kernel falls back to scalar loads
+    bool aligned = true;
+    for (int i = 0; i < s.count && aligned; ++i)
+      for (int c = 0; c < d->geom.planes; ++c) {
+        const FrameDesc &fd = s.h_descs[i];
+        if (((uintptr_t)fd.src[c] | (uintptr_t)fd.den[c] | fd.src_stride[c] | fd.den_stride[c]) & 7) aligned = false;
+      }
+    launch_gram_imma(s.d_descs, s.count, d->geom, s.d_records, d->rl, aligned, st);
+    CU_TRY(d, cudaEventRecord(s.k1_end, st));
+    launch_gram_generic(s.d_descs, s.count, d->geom, s.d_records, d->rl, /*only_overflow=*/true, st);
+    gram_launches = 2;
+  } else {
+    launch_gram_generic(s.d_descs, s.count, d->geom, s.d_records, d->rl, /*only_overflow=*/false, st);
+    CU_TRY(d, cudaEventRecord(s.k1_end, st));
+  }
   CU_TRY(d, cudaGetLastError());
   CU_TRY(d, cudaMemcpyAsync(s.h_records, s.d_records, d->rl.bytes * s.count, cudaMemcpyDeviceToHost, st));
   CU_TRY(d, cudaEventRecord(s.done, st));
   s.in_flight = true;
-  d->kernels_launched += 3;
+  d->kernels_launched += 2 + gram_launches;
   d->k0_launches += 1;
   d->k1_launches += 1;
   return G1S_OK;

@@ -35,6 +35,8 @@ RecordLayout RecordLayout::make(int nb) {
   r.off_rsq = take(sizeof(uint32_t) * 3 * nb);
   r.off_score = take(sizeof(float) * nb);
   r.off_flat = take(nb);
+  r.off_ovf_count = take(sizeof(int64_t));
+  r.off_ovf = take(3 * (size_t)nb);
   r.bytes = (o + 15) & ~size_t(15);
   return r;
 }
@@ -301,7 +303,7 @@ constexpr int kTileElems = kTilePitch * kTileRows;
 
 __global__ void __launch_bounds__(kGramThreads)
 gram_generic_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, uint8_t *__restrict__ records,
-                    RecordLayout rl) {
+                    RecordLayout rl, int only_overflow) {
   __shared__ int16_t tile[2 * kTileElems];  // [0]: residual with halo, [1]: luma tap (same geometry)
   __shared__ int red_i[kGramThreads / 32];
   __shared__ unsigned red_u[kGramThreads / 32];
@@ -314,6 +316,8 @@ gram_generic_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry 
   const FrameDesc fd = frames[f];
   uint8_t *rec = records + (size_t)f * rl.bytes;
   const uint8_t *flat = rec + rl.off_flat;
+  const uint8_t *ovf = rec + rl.off_ovf + (size_t)c * g.nb;
+  if (only_overflow && *reinterpret_cast<const int64_t *>(rec + rl.off_ovf_count) == 0) return;
 
   const int sx = c ? g.ss_x : 0, sy = c ? g.ss_y : 0;
   const int bw = kBlock >> sx, bh = kBlock >> sy;
@@ -360,6 +364,7 @@ gram_generic_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry 
   for (int bx = 0; bx < g.nbw; ++bx) {
     const int bidx = by * g.nbw + bx;
     if (!flat[bidx]) continue;
+    if (only_overflow && !ovf[bidx]) continue;
     const int x_o = bx * bw, y_o = by * bh;
     // ---- stage residual tile: tile(ty, tx) <-> plane (y_o - 3 + ty, x_o - 3 + tx)
     for (int e = tid; e < kTileRows * (bw + 2 * kLag); e += kGramThreads) {
@@ -391,7 +396,7 @@ gram_generic_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry 
     __syncthreads();
 
     // ---- per-block noise statistics over the frame-clipped block (get_block_mean / get_noise_var)
-    {
+    if (!only_overflow) {
       const int max_w = min(pw - x_o, bw), max_h = min(ph - y_o, bh);
       int rs = 0;
       unsigned rq = 0;
@@ -467,9 +472,9 @@ gram_generic_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry 
 }
 
 void launch_gram_generic(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
-                         const RecordLayout &rl, cudaStream_t st) {
+                         const RecordLayout &rl, bool only_overflow, cudaStream_t st) {
   dim3 grid(g.nbh, g.planes, nframes);
-  gram_generic_kernel<<<grid, kGramThreads, 0, st>>>(frames, nframes, g, records, rl);
+  gram_generic_kernel<<<grid, kGramThreads, 0, st>>>(frames, nframes, g, records, rl, only_overflow ? 1 : 0);
 }
 
 }  // namespace g1s

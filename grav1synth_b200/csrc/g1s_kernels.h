@@ -45,15 +45,24 @@ struct FlatConsts {
 //   uint32 rsq[3][nb]          sum of the squared residual over each block, per plane
 //   float  score[nb]           sigmoid flatness score (0 when var <= threshold)
 //   uint8  flat[nb]            0 / 1 / 255 flat flags (padded to 8 bytes)
+//   int64  ovf_count           blocks whose residual tile left the int8 range (device bookkeeping)
+//   uint8  ovf[3][nb]          per plane: block must be accumulated by the generic (int32) kernel
 struct RecordLayout {
-  size_t off_gram, off_nobs, off_num_flat, off_luma_sum, off_rsum, off_rsq, off_score, off_flat, bytes;
+  size_t off_gram, off_nobs, off_num_flat, off_luma_sum, off_rsum, off_rsq, off_score, off_flat, off_ovf_count,
+      off_ovf, bytes;
   static RecordLayout make(int nb);
 };
 
 void launch_flat_features(const FrameDesc *frames, int nframes, const Geometry &g, const FlatConsts &fc,
                           uint8_t *records, const RecordLayout &rl, cudaStream_t st);
 void launch_flat_select(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, cudaStream_t st);
+// only_overflow = false: every flat block, statistics included (any subsampling, any alignment).
+// only_overflow = true: just the blocks the tensor-core kernel flagged, Gram sums only.
 void launch_gram_generic(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
-                         const RecordLayout &rl, cudaStream_t st);
+                         const RecordLayout &rl, bool only_overflow, cudaStream_t st);
+// int8 tensor-core (mma.sync m16n8k32) Gram kernel for 4:2:0 / monochrome streams.
+bool gram_imma_supported(const Geometry &g);
+void launch_gram_imma(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
+                      const RecordLayout &rl, bool aligned, cudaStream_t st);
 
 }  // namespace g1s

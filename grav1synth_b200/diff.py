@@ -129,13 +129,14 @@ class DiffGenerator:
 
     def __init__(self, fps_num: int, fps_den: int, source_bit_depth: int, denoised_bit_depth: int, width: int,
                  height: int, ss_x: int = 1, ss_y: int = 1, monochrome: bool = False, device: int = 0,
-                 batch_frames: int = 0, mode: int = abi.MODE_FULL):
+                 batch_frames: int = 0, mode: int = abi.MODE_FULL, gram_kernel: int = 0):
         self._L = lib()
         cfg = CDiffConfig()
         cfg.fps_num, cfg.fps_den = fps_num, fps_den
         cfg.src_bit_depth, cfg.den_bit_depth = source_bit_depth, denoised_bit_depth
         cfg.width, cfg.height, cfg.ss_x, cfg.ss_y = width, height, ss_x, ss_y
         cfg.monochrome, cfg.device, cfg.batch_frames, cfg.mode = int(monochrome), device, batch_frames, mode
+        cfg.gram_kernel = gram_kernel
         self.cfg = cfg
         h = C.c_void_p()
         rc = self._L.g1s_diff_create(C.byref(cfg), C.byref(h))

@@ -112,7 +112,9 @@ typedef struct g1s_diff_config {
   int32_t device;               /* CUDA device ordinal                               */
   int32_t batch_frames;         /* frames per device launch; 0 = engine default      */
   int32_t mode;                 /* enum g1s_mode                                     */
-  int32_t reserved_[6];
+  int32_t gram_kernel;          /* 0 = auto (int8 tensor-core kernel when the stream
+                                   allows it), 1 = force the generic int32 kernel    */
+  int32_t reserved_[5];
 } g1s_diff_config;
 
 typedef struct g1s_diff g1s_diff;

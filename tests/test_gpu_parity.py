@@ -17,9 +17,9 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def gpu_run(spec, fps, frames, batch=0, src_bd=None, den_bd=None):
+def gpu_run(spec, fps, frames, batch=0, src_bd=None, den_bd=None, gram_kernel=0):
     g = D.DiffGenerator(fps[0], fps[1], src_bd or spec.bit_depth, den_bd or spec.bit_depth, spec.width, spec.height,
-                        spec.ss_x, spec.ss_y, batch_frames=batch)
+                        spec.ss_x, spec.ss_y, batch_frames=batch, gram_kernel=gram_kernel)
     recs = []
     g.set_record_tap(lambda i, r: recs.append((i, r)))
     for s, d in frames:
@@ -59,10 +59,11 @@ def compare_records(spec, frames, got, want, src_bd=None, den_bd=None):
         assert np.array_equal(g["luma_sum"][w["flat"] != 0], ref["luma_sum"][w["flat"] != 0])
 
 
+@pytest.mark.parametrize("gram_kernel", [0, 1], ids=["tensorcore", "generic"])
 @pytest.mark.parametrize("name", list(CORPUS))
-def test_corpus_bit_exact(name):
+def test_corpus_bit_exact(name, gram_kernel):
     spec, fps, frames = corpus_frames(name)
-    segs, recs, _ = gpu_run(spec, fps, frames)
+    segs, recs, _ = gpu_run(spec, fps, frames, gram_kernel=gram_kernel)
     want, per = oracle_run(spec, fps, frames)
     compare_records(spec, frames, recs, per)
     assert segs == want
@@ -120,6 +121,44 @@ def test_saturated_residual_and_zero_residual():
     want, per = oracle_run(spec, (24, 1), frames)
     compare_records(spec, frames, recs, per)
     assert segs == want
+
+
+def test_sparse_int8_overflow_falls_back_per_block():
+    # ordinary grain everywhere, plus a few isolated |r| > 127 samples: only the touched super-units may take
+    # the generic kernel, and the sums must still be exact
+    spec, fps, frames = corpus_frames("c2_small_8bit")
+    frames = [([p.copy() for p in s], [p.copy() for p in d]) for s, d in frames]
+    for k, (s, d) in enumerate(frames):
+        s[0][37 + k, 70], d[0][37 + k, 70] = 255, 3       # luma, +252
+        s[1][50, 101], d[1][50, 101] = 0, 200             # Cb, -200
+        s[2][5, 3], d[2][5, 3] = 129, 0                   # Cr, +129 (just outside int8)
+        s[0][100, 200], d[0][100, 200] = 0, 128           # luma, -128 (still inside int8)
+    segs, recs, _ = gpu_run(spec, fps, frames)
+    want, per = oracle_run(spec, fps, frames)
+    compare_records(spec, frames, recs, per)
+    assert segs == want
+
+
+def test_unaligned_device_planes():
+    # device planes whose base address / stride are not 8-byte aligned take the scalar-load variant
+    import torch
+    spec, fps, frames = corpus_frames("c2_small_8bit")
+    host, _, _ = gpu_run(spec, fps, frames)
+    g = D.DiffGenerator(fps[0], fps[1], 8, 8, spec.width, spec.height)
+    keep = []
+
+    def odd(p):
+        h, w = p.shape
+        buf = torch.zeros((h, w + 13), dtype=torch.uint8, device="cuda")
+        buf[:, 3:3 + w] = torch.from_numpy(p).cuda()
+        keep.append(buf)
+        return buf.data_ptr() + 3, w + 13
+
+    for s, d in frames:
+        sp, dp = [odd(p) for p in s], [odd(p) for p in d]
+        g.diff_frame_device([a for a, _ in sp], [b for _, b in sp], [a for a, _ in dp], [b for _, b in dp])
+    torch.cuda.synchronize()
+    assert g.finish() == host
 
 
 def test_flat_everything_rule_and_error_swallowing():
