@@ -11,18 +11,22 @@
 // 16x16 Cb and Cr blocks, so every sample of both frames is read from HBM once here: the luma
 // residual tile also provides the chroma "luma tap" (sum of the co-sited 2x2 luma residuals).
 // A CTA of 6 warps walks a run of super-units of one block row:
-//   staging  all warps: 64-bit loads of source and denoised, >> (bd-8), subtract, pack to s8
-//            words in shared memory (tile origin 4 samples left of the unit so loads are aligned),
-//            per-block sum r / sum r^2 / sum luma while the values are in registers;
-//   Gram     warps 0-3: the two luma blocks (half the rows each); warp 4: Cb pair; warp 5: Cb pair.
+//   staging  all warps: 64-bit loads of source and denoised, >> (bd-8) and subtract two samples
+//            per 32-bit op (16-bit SIMD lanes), pack to s8 words in shared memory (tile origin
+//            4 samples left of the unit so loads are aligned); per-block sum r / sum r^2 /
+//            sum luma by dp4a while the values are in registers;
+//   Gram     warps 0-3: the two luma blocks (half the rows each); warp 4: Cb pair; warp 5: Cr pair.
 //            One k-step = 32 pixels of one row.  X[k][a] = residual at pixel k shifted by tap a;
 //            D += X^T X over the upper block-triangle (6 m16n8k32 MMAs).  Tap a = 8q+g with
 //            g = cx+3 (lane group), q = cy+3: a thread's four taps are the SAME column offset on
-//            four consecutive rows, so its operand words slide down by one row per k-step and
-//            only one new 32-bit window (two LDS + funnel shift) per half is fetched.
+//            four consecutive rows, so its operands slide down one row per k-step: one new
+//            32-bit window (two LDS + funnel shift) per half is fetched, the B operand of a row
+//            is a register pair and the A operand of two consecutive rows a register quad that
+//            serves as the lower m-tile now and as the upper m-tile two steps later.
 //            The observation mask (block margins, frame clipping) is a byte mask on k applied
 //            to the operand words (mask^2 = mask, so masking both A and B is exact).
-//   epilogue int32 accumulators (bounded: <= 32 units * 16 k-steps * 32 * 2^14 * 4 warps < 2^31)
+//            Chroma adds one n-tile whose columns 0/1 are the luma tap split as 8*hi + lo.
+//   epilogue int32 accumulators (bounded: <= 30 units * 16 k-steps * 32 * 2^14 * 4 warps < 2^31)
 //            -> int64 global atomics, one per tap pair per CTA per plane.
 #include "g1s_kernels.h"
 
@@ -49,61 +53,75 @@ struct __align__(16) SuSmem {
   int ovf[3];
 };
 
-__device__ __forceinline__ void imma_16832(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                           uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
       "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// Four consecutive samples reduced to 8 bit (util.rs::frame_into_u8), zero outside [0,lim_w)x[0,lim_h).
-template <bool ALIGNED>
-__device__ __forceinline__ void load4(const void *base, uint32_t stride, int y, int x, int bytes, int shift,
-                                      int lim_w, int lim_h, int (&v)[4]) {
-  v[0] = v[1] = v[2] = v[3] = 0;
-  if (y < 0 || y >= lim_h || x < 0 || x >= lim_w) return;
-  const uint8_t *row = reinterpret_cast<const uint8_t *>(base) + (size_t)y * stride;
-  if (ALIGNED && x + 3 < lim_w) {
-    if (bytes == 2) {
-      const uint2 p = __ldg(reinterpret_cast<const uint2 *>(row + 2 * x));
-      v[0] = ((p.x & 0xFFFFu) >> shift) & 0xFF;
-      v[1] = ((p.x >> 16) >> shift) & 0xFF;
-      v[2] = ((p.y & 0xFFFFu) >> shift) & 0xFF;
-      v[3] = ((p.y >> 16) >> shift) & 0xFF;
-    } else {
-      const uint32_t p = __ldg(reinterpret_cast<const uint32_t *>(row + x));
-      v[0] = p & 0xFF;
-      v[1] = (p >> 8) & 0xFF;
-      v[2] = (p >> 16) & 0xFF;
-      v[3] = p >> 24;
-    }
-    return;
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (x + i < lim_w) {
-      v[i] = bytes == 2 ? ((reinterpret_cast<const uint16_t *>(row)[x + i] >> shift) & 0xFF) : row[x + i];
-    }
+// ------------------------------------------------------------------------------ staging
+//
+// Fast path (interior unit, 8-byte aligned rows): four samples of each plane arrive in one
+// vector load and are reduced to 8 bit two at a time in 16-bit lanes.
+
+// Four consecutive samples as two words of two 16-bit lanes each, values 0..255
+// (util.rs::frame_into_u8: truncating shift, then `as u8`).
+template <int BYTES>
+__device__ __forceinline__ void load4_lanes(const uint8_t *p, int shift, uint32_t &lo2, uint32_t &hi2) {
+  if (BYTES == 2) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+    lo2 = (v.x >> shift) & 0x00FF00FFu;
+    hi2 = (v.y >> shift) & 0x00FF00FFu;
+  } else {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(p));
+    lo2 = __byte_perm(v, 0u, 0x4140);
+    hi2 = __byte_perm(v, 0u, 0x4342);
   }
 }
 
-// Residual word for 4 samples: returns packed s8, accumulates statistics, reports overflow.
-template <bool ALIGNED>
-__device__ __forceinline__ uint32_t residual_word(const void *sp, uint32_t ss, const void *dp, uint32_t ds, int y,
-                                                  int x, const Geometry &g, int lim_w, int lim_h, int &rs,
-                                                  unsigned &rq, unsigned &ls, bool &ovf) {
-  int s[4], d[4];
-  load4<ALIGNED>(sp, ss, y, x, g.src_bytes, g.src_shift, lim_w, lim_h, s);
-  load4<ALIGNED>(dp, ds, y, x, g.den_bytes, g.den_shift, lim_w, lim_h, d);
+// Packed s8 residual word of four samples + running statistics.  The statistics use the s8 word,
+// so they are exact only when no sample overflowed; overflowed blocks are redone (statistics
+// included) by the generic kernel.
+template <int SB, int DB, bool STATS, bool LUMA_SUM>
+__device__ __forceinline__ uint32_t residual4(const uint8_t *sp, const uint8_t *dp, int sshift, int dshift, int &rs,
+                                              int &rq, unsigned &ls, uint32_t &ovf) {
+  uint32_t s0, s1, d0, d1;
+  load4_lanes<SB>(sp, sshift, s0, s1);
+  load4_lanes<DB>(dp, dshift, d0, d1);
+  const uint32_t b0 = (s0 | 0x01000100u) - d0;  // per lane: r + 256, never borrows across lanes
+  const uint32_t b1 = (s1 | 0x01000100u) - d1;
+  ovf |= ((b0 - 0x00800080u) | (b1 - 0x00800080u)) & 0xFF00FF00u;  // lane outside [128, 383] <=> r outside int8
+  const uint32_t w = __byte_perm(b0, b1, 0x6420);
+  if (STATS) {
+    rs = __dp4a((int)w, 0x01010101, rs);
+    rq = __dp4a((int)w, (int)w, rq);
+    if (LUMA_SUM) ls = __dp4a(__byte_perm(s0, s1, 0x6420), 0x01010101u, ls);
+  }
+  return w;
+}
+
+// Slow path (frame edges, unaligned rows): scalar, bounds-checked, zero outside [0,lim_w)x[0,lim_h).
+__device__ __forceinline__ uint32_t residual4_slow(const void *sp, uint32_t ss, const void *dp, uint32_t ds, int y,
+                                                   int x, const Geometry &g, int lim_w, int lim_h, bool stats,
+                                                   int &rs, int &rq, unsigned &ls, uint32_t &ovf) {
   uint32_t w = 0;
+  if (y < 0 || y >= lim_h) return 0;
+  const uint8_t *srow = reinterpret_cast<const uint8_t *>(sp) + (size_t)y * ss;
+  const uint8_t *drow = reinterpret_cast<const uint8_t *>(dp) + (size_t)y * ds;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int r = s[i] - d[i];
-    ovf |= (r < -128) | (r > 127);
-    rs += r;
-    rq += (unsigned)(r * r);
-    ls += (unsigned)s[i];
+    const int xx = x + i;
+    if (xx < 0 || xx >= lim_w) continue;
+    const int s = g.src_bytes == 2 ? ((reinterpret_cast<const uint16_t *>(srow)[xx] >> g.src_shift) & 0xFF) : srow[xx];
+    const int d = g.den_bytes == 2 ? ((reinterpret_cast<const uint16_t *>(drow)[xx] >> g.den_shift) & 0xFF) : drow[xx];
+    const int r = s - d;
+    if (r < -128 || r > 127) ovf |= 1u;
+    if (stats) {
+      rs += r;
+      rq += r * r;
+      ls += (unsigned)s;
+    }
     w |= (uint32_t)(r & 0xFF) << (8 * i);
   }
   return w;
@@ -117,118 +135,154 @@ __device__ __forceinline__ uint32_t byte_mask(int first, int lo, int hi) {
   return m;
 }
 
-// The k-loop of one warp over rows [ys, ye) of a 32-pixel-wide unit.
+// ------------------------------------------------------------------------------ k-loops
+//
 //   tile/pitch : s8 residual tile, row r <-> plane row (unit origin - 3 + r), col 0 <-> origin - 4
 //   colw       : word column of this lane's window for half 0 ( = unit word base + t + ((g+1)>>2) )
 //   sh         : funnel shift in bits ( = 8 * ((g+1) & 3) )
 //   mx[h]      : byte mask of the observed pixels of half h (x margins, frame clip, block not flat)
-//   y0h[h]     : first observed row of half h (rows below it are masked at use; chroma pairs only)
-template <bool CHROMA>
-__device__ __forceinline__ void gram_rows(const uint32_t *__restrict__ tile, int pitch, int colw, int sh, int ys,
-                                          int ye, const uint32_t (&mx)[2], const int (&y0h)[2],
-                                          const uint32_t *__restrict__ special, bool is_special, int t,
-                                          int (&acc)[6][4]) {
-  uint32_t W[4][2];
-  auto window = [&](int row, int h) -> uint32_t {
-    const uint32_t *p = tile + row * pitch + colw + 4 * h;
-    return __funnelshift_r(p[0], p[1], sh) & mx[h];
-  };
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    W[q][0] = window(ys + q, 0);
-    W[q][1] = window(ys + q, 1);
-  }
-#pragma unroll 4
-  for (int y = ys; y < ye; ++y) {
-    W[3][0] = window(y + 3, 0);
-    W[3][1] = window(y + 3, 1);
-    uint32_t u3[2] = {W[3][0], W[3][1]};
-    if (CHROMA) {
-      // lanes g = 4 / 5 carry the luma-tap hi / lo bytes in their (otherwise unused) cy = 0 slot
-      const uint32_t x0 = special[y * 8 + t] & mx[0];
-      const uint32_t x1 = special[y * 8 + 4 + t] & mx[1];
-      u3[0] = is_special ? x0 : u3[0];
-      u3[1] = is_special ? x1 : u3[1];
-    }
-    uint32_t A[4][2];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      A[q][0] = W[q][0];
-      A[q][1] = W[q][1];
-    }
-    A[3][0] = u3[0];
-    A[3][1] = u3[1];
-    if (CHROMA) {
-      // rows above a block's first observed row contribute nothing for that half
-      const uint32_t r0 = y >= y0h[0] ? 0xFFFFFFFFu : 0u, r1 = y >= y0h[1] ? 0xFFFFFFFFu : 0u;
-      uint32_t B[4][2];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        B[q][0] = A[q][0] & r0;
-        B[q][1] = A[q][1] & r1;
-      }
-      imma_16832(acc[0], A[0][0], A[1][0], A[0][1], A[1][1], B[0][0], B[0][1]);
-      imma_16832(acc[1], A[0][0], A[1][0], A[0][1], A[1][1], B[1][0], B[1][1]);
-      imma_16832(acc[2], A[0][0], A[1][0], A[0][1], A[1][1], B[2][0], B[2][1]);
-      imma_16832(acc[3], A[0][0], A[1][0], A[0][1], A[1][1], B[3][0], B[3][1]);
-      imma_16832(acc[4], A[2][0], A[3][0], A[2][1], A[3][1], B[2][0], B[2][1]);
-      imma_16832(acc[5], A[2][0], A[3][0], A[2][1], A[3][1], B[3][0], B[3][1]);
-    } else {
-      imma_16832(acc[0], A[0][0], A[1][0], A[0][1], A[1][1], A[0][0], A[0][1]);
-      imma_16832(acc[1], A[0][0], A[1][0], A[0][1], A[1][1], A[1][0], A[1][1]);
-      imma_16832(acc[2], A[0][0], A[1][0], A[0][1], A[1][1], A[2][0], A[2][1]);
-      imma_16832(acc[3], A[0][0], A[1][0], A[0][1], A[1][1], A[3][0], A[3][1]);
-      imma_16832(acc[4], A[2][0], A[3][0], A[2][1], A[3][1], A[2][0], A[2][1]);
-      imma_16832(acc[5], A[2][0], A[3][0], A[2][1], A[3][1], A[3][0], A[3][1]);
-    }
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      W[q][0] = W[q + 1][0];
-      W[q][1] = W[q + 1][1];
-    }
-  }
+// Row slots are indexed by (row - ys) & 3; P[s] is the operand pair of a row, Q[s] the operand
+// quad of rows (s, s+1).
+
+struct Window {
+  uint32_t Q[4][4];
+  uint32_t P[4][2];
+};
+
+// x & m, emitted as a distinct instruction per TAG.  A window word is consumed from three different
+// operand tuples (the row's B pair, the upper half of one A quad, the lower half of the next) and
+// mma.sync needs each tuple in consecutive aligned registers; without distinct values ptxas keeps one
+// copy and rebuilds the quads with ~12 moves per k-step.  Three ANDs per word is the minimum.
+template <int TAG>
+__device__ __forceinline__ uint32_t and_tag(uint32_t x, uint32_t m) {
+  uint32_t r;
+  if (TAG == 0) asm("lop3.b32 %0, %1, %2, 0, 0xC0;" : "=r"(r) : "r"(x), "r"(m));
+  if (TAG == 1) asm("lop3.b32 %0, %1, %2, 1, 0xC0;" : "=r"(r) : "r"(x), "r"(m));
+  if (TAG == 2) asm("lop3.b32 %0, %1, %2, 2, 0xC0;" : "=r"(r) : "r"(x), "r"(m));
+  return r;
 }
 
-// MMA tap index a = 8q+g  ->  record tap index (0..23 AR taps, 25 centre), -1 unused, -2/-3 luma-tap hi/lo.
+// Fetches the lane's window of one tile row (p: word of half 0; half 1 is 4 words = 16 pixels further)
+// and files it as: B pair of the row, upper row of quad `qprev`, lower row of quad `qthis`.
+__device__ __forceinline__ void fetch_row(const uint32_t *__restrict__ p, int sh, const uint32_t (&mx)[2],
+                                          uint32_t (&pair)[2], uint32_t (&qprev)[4], uint32_t (&qthis)[4]) {
+  const uint32_t r0 = __funnelshift_r(p[0], p[1], sh);
+  const uint32_t r1 = __funnelshift_r(p[4], p[5], sh);
+  pair[0] = and_tag<0>(r0, mx[0]);
+  pair[1] = and_tag<0>(r1, mx[1]);
+  qprev[1] = and_tag<1>(r0, mx[0]);
+  qprev[3] = and_tag<1>(r1, mx[1]);
+  qthis[0] = and_tag<2>(r0, mx[0]);
+  qthis[2] = and_tag<2>(r1, mx[1]);
+}
+
+// Rows ys, ys+1, ys+2 -> slots 0, 1, 2 (quad 3's upper row is scratch here).
+template <int PITCH>
+__device__ __forceinline__ void window_init(Window &w, const uint32_t *__restrict__ p, int sh,
+                                            const uint32_t (&mx)[2]) {
+  fetch_row(p, sh, mx, w.P[0], w.Q[3], w.Q[0]);
+  fetch_row(p + PITCH, sh, mx, w.P[1], w.Q[0], w.Q[1]);
+  fetch_row(p + 2 * PITCH, sh, mx, w.P[2], w.Q[1], w.Q[2]);
+}
+
+// One k-step of the six common tiles; K is the (compile-time) slot of the step's first row,
+// pnew the lane's window word in the tile row three below it.
+template <int K>
+__device__ __forceinline__ void step6(Window &w, const uint32_t *__restrict__ pnew, int sh, const uint32_t (&mx)[2],
+                                      int (&acc)[8][4]) {
+  fetch_row(pnew, sh, mx, w.P[(K + 3) & 3], w.Q[(K + 2) & 3], w.Q[(K + 3) & 3]);
+  imma_16832(acc[0], w.Q[K & 3], w.P[K & 3]);
+  imma_16832(acc[1], w.Q[K & 3], w.P[(K + 1) & 3]);
+  imma_16832(acc[2], w.Q[K & 3], w.P[(K + 2) & 3]);
+  imma_16832(acc[3], w.Q[K & 3], w.P[(K + 3) & 3]);
+  imma_16832(acc[4], w.Q[(K + 2) & 3], w.P[(K + 2) & 3]);
+  imma_16832(acc[5], w.Q[(K + 2) & 3], w.P[(K + 3) & 3]);
+}
+
+// p0: the lane's window word in tile row ys (the first observed row's cy = -3 tap row).
+__device__ __forceinline__ void luma_rows(const uint32_t *__restrict__ p0, int sh, int nrows,
+                                          const uint32_t (&mx)[2], int (&acc)[8][4]) {
+  Window w;
+  window_init<kPL>(w, p0, sh, mx);
+  const uint32_t *p = p0 + 3 * kPL;
+  int n = nrows;
+  for (; n >= 4; n -= 4, p += 4 * kPL) {
+    step6<0>(w, p, sh, mx, acc);
+    step6<1>(w, p + kPL, sh, mx, acc);
+    step6<2>(w, p + 2 * kPL, sh, mx, acc);
+    step6<3>(w, p + 3 * kPL, sh, mx, acc);
+  }
+  if (n > 0) step6<0>(w, p, sh, mx, acc);
+  if (n > 1) step6<1>(w, p + kPL, sh, mx, acc);
+  if (n > 2) step6<2>(w, p + 2 * kPL, sh, mx, acc);
+}
+
+// Chroma: the same six tiles plus n-tile 4 whose column 0 is the luma tap's high part (hs) and
+// column 1 its low part (ls); the three luma-tap self products are summed with dp4a.
+// hp / lp: the lane's word of hs / ls in the step's row (half 0; half 1 is 4 words further).
+template <int K>
+__device__ __forceinline__ void step8(Window &w, const uint32_t *__restrict__ pnew, const uint32_t *__restrict__ hp,
+                                      const uint32_t *__restrict__ lp, int sh, const uint32_t (&mx)[2], int gq,
+                                      int (&acc)[8][4], int (&self)[3]) {
+  step6<K>(w, pnew, sh, mx, acc);
+  const uint32_t h0 = hp[0] & mx[0], h1 = hp[4] & mx[1];
+  const uint32_t l0 = lp[0] & mx[0], l1 = lp[4] & mx[1];
+  self[0] = __dp4a((int)h0, (int)h0, __dp4a((int)h1, (int)h1, self[0]));
+  self[1] = __dp4a((int)h0, (int)l0, __dp4a((int)h1, (int)l1, self[1]));
+  self[2] = __dp4a((int)l0, (int)l0, __dp4a((int)l1, (int)l1, self[2]));
+  const uint32_t S[2] = {gq == 0 ? h0 : (gq == 1 ? l0 : 0u), gq == 0 ? h1 : (gq == 1 ? l1 : 0u)};
+  imma_16832(acc[6], w.Q[K & 3], S);
+  imma_16832(acc[7], w.Q[(K + 2) & 3], S);
+}
+
+__device__ __forceinline__ void chroma_rows(const uint32_t *__restrict__ p0, const uint32_t *__restrict__ hp,
+                                            const uint32_t *__restrict__ lp, int sh, int nrows,
+                                            const uint32_t (&mx)[2], int gq, int (&acc)[8][4], int (&self)[3]) {
+  Window w;
+  window_init<kPC>(w, p0, sh, mx);
+  const uint32_t *p = p0 + 3 * kPC;
+  int n = nrows;
+  for (; n >= 4; n -= 4, p += 4 * kPC, hp += 32, lp += 32) {
+    step8<0>(w, p, hp, lp, sh, mx, gq, acc, self);
+    step8<1>(w, p + kPC, hp + 8, lp + 8, sh, mx, gq, acc, self);
+    step8<2>(w, p + 2 * kPC, hp + 16, lp + 16, sh, mx, gq, acc, self);
+    step8<3>(w, p + 3 * kPC, hp + 24, lp + 24, sh, mx, gq, acc, self);
+  }
+  if (n > 0) step8<0>(w, p, hp, lp, sh, mx, gq, acc, self);
+  if (n > 1) step8<1>(w, p + kPC, hp + 8, lp + 8, sh, mx, gq, acc, self);
+  if (n > 2) step8<2>(w, p + 2 * kPC, hp + 16, lp + 16, sh, mx, gq, acc, self);
+}
+
+// MMA tap index a = 8q+g  ->  record tap index (0..23 AR taps, 25 centre sample), -1 unused.
 __device__ __forceinline__ int record_tap(int a) {
   const int q = a >> 3, g = a & 7;
   if (g == 7) return -1;
   if (q < 3) return 7 * q + g;
   if (g < 3) return 21 + g;
   if (g == 3) return 25;
-  if (g == 4) return -2;
-  if (g == 5) return -3;
   return -1;
 }
 
 __device__ __forceinline__ int pair_index(int i, int j) { return i * kTaps - i * (i - 1) / 2 + (j - i); }
 
-// Adds one accumulator element D[a][b] into the plane's 351-entry int64 Gram (global atomics).
-__device__ __forceinline__ void emit(unsigned long long *gram, int a, int b, long long v, bool chroma) {
-  if (a > b || v == 0) return;  // the mirrored element is always covered by another tile
-  int ia = record_tap(a), ib = record_tap(b);
-  if (ia == -1 || ib == -1) return;
-  long long wgt = 1;
-  if (ia < -1 || ib < -1) {
-    if (!chroma) return;
-    if (ia < -1) {
-      wgt *= ia == -2 ? 8 : 1;
-      ia = 24;
-    }
-    if (ib < -1) {
-      wgt *= ib == -2 ? 8 : 1;
-      ib = 24;
-    }
-    if (a != b && ia == 24 && ib == 24) wgt *= 2;  // (hi,lo) appears once (a<b) but counts twice in (8h+l)^2
-  }
-  const int i = min(ia, ib), j = max(ia, ib);
-  atomicAdd(&gram[pair_index(i, j)], (unsigned long long)(v * wgt));
+// Adds accumulator element D[a][b] (a <= b: the mirrored element is covered by another tile).
+__device__ __forceinline__ void emit(unsigned long long *gram, int a, int b, int v) {
+  if (a > b || v == 0) return;
+  const int ia = record_tap(a), ib = record_tap(b);
+  if (ia < 0 || ib < 0) return;
+  atomicAdd(&gram[pair_index(min(ia, ib), max(ia, ib))], (unsigned long long)(long long)v);
+}
+// D[a][luma tap part]: weight 8 for the high part, 1 for the low part.
+__device__ __forceinline__ void emit_luma_tap(unsigned long long *gram, int a, int v, int weight) {
+  const int ia = record_tap(a);
+  if (ia < 0 || v == 0) return;
+  atomicAdd(&gram[pair_index(min(ia, 24), max(ia, 24))], (unsigned long long)((long long)v * weight));
 }
 
-template <bool ALIGNED>
-__global__ void __launch_bounds__(kSuThreads)
+template <int SB, int DB>
+__global__ void __launch_bounds__(kSuThreads, 3)
 gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__restrict__ records, RecordLayout rl,
-                 int runs_per_row) {
+                 int runs_per_row, int aligned) {
   __shared__ SuSmem sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, t = lane & 3;  // mma "groupID" (= cx + 3) and thread-in-group
@@ -243,13 +297,16 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
   const int W = g.width, H = g.height, pw = W >> 1, ph = H >> 1;
   const int nsu = (g.nbw + 1) >> 1;
   const int u_beg = run * kSuRun, u_end = min(nsu, u_beg + kSuRun);
+  const int Y0 = 32 * by, CY0 = 16 * by;
+  const bool rows_inside = Y0 >= 3 && Y0 + 32 <= H && (!has_chroma || CY0 + 16 <= ph);
 
-  int acc[6][4];
+  int acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int r = 0; r < 4; ++r) acc[i][r] = 0;
-  long long nobs[3] = {0, 0, 0};  // thread 0 only
+  int self[3] = {0, 0, 0};
+  long long nobs = 0;  // luma: lane 0 of warps 0 and 2; chroma: lane 0 of warps 4 / 5
 
   for (int i = tid; i < (int)(sizeof(SuSmem) / 4); i += kSuThreads) reinterpret_cast<uint32_t *>(&sm)[i] = 0;
   __syncthreads();
@@ -264,27 +321,40 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
     const bool fl0 = flat[b0] != 0, fl1 = ex1 && flat[b0 + 1] != 0;
     if (!fl0 && !fl1) continue;  // uniform across the CTA
 
-    // ------------------------------------------------------------------ staging
     if (tid < 6) {
       sm.st_rs[tid] = 0;
       sm.st_rq[tid] = 0;
       if (tid < 2) sm.st_ls[tid] = 0;
       if (tid < 3) sm.ovf[tid] = 0;
     }
-    __syncthreads();  // previous unit's Gram loops are done with the tiles; stats zeroed
-    const int X0 = 64 * u, Y0 = 32 * by, CX0 = 32 * u, CY0 = 16 * by;
-    {
-      // luma main words: two tile rows per warp pass, lanes 0-15 / 16-31, word w = 1 + (lane & 15)
-      for (int p = warp; p < 18; p += 6) {
-        const int ty = 2 * p + (lane >> 4), w = 1 + (lane & 15);
-        int rs = 0;
-        unsigned rq = 0, ls = 0;
-        bool ov = false;
-        if (ty < kLumaRows) {
-          const uint32_t word = residual_word<ALIGNED>(fd.src[0], fd.src_stride[0], fd.den[0], fd.den_stride[0],
-                                                       Y0 - 3 + ty, X0 - 4 + 4 * w, g, W, H, rs, rq, ls, ov);
-          sm.luma[ty * kPL + w] = word;
-          if (ty < 3) rs = 0, rq = 0, ls = 0;  // halo rows belong to the block above
+    __syncthreads();  // previous unit's k-loops are done with the tiles; statistics zeroed
+
+    // ------------------------------------------------------------------ staging
+    const int X0 = 64 * u, CX0 = 32 * u;
+    const bool fast = aligned && rows_inside && X0 >= 4 && X0 + 68 <= W && (!has_chroma || CX0 + 36 <= pw);
+    if (fast) {
+      uint32_t ov = 0;
+      {
+        // luma main words: two tile rows per pass (lanes 0-15 / 16-31), rows warp*2 + 12*pass
+        int rs = 0, rq = 0;
+        unsigned ls = 0;
+        const int ty0 = 2 * warp + (lane >> 4), w = 1 + (lane & 15);
+        const uint8_t *sp = static_cast<const uint8_t *>(fd.src[0]) + (size_t)(Y0 - 3 + ty0) * fd.src_stride[0] +
+                            (size_t)(X0 - 4 + 4 * w) * SB;
+        const uint8_t *dp = static_cast<const uint8_t *>(fd.den[0]) + (size_t)(Y0 - 3 + ty0) * fd.den_stride[0] +
+                            (size_t)(X0 - 4 + 4 * w) * DB;
+        uint32_t *dst = &sm.luma[ty0 * kPL + w];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const int ty = ty0 + 12 * p;
+          if (ty < kLumaRows) {
+            int trs = 0, trq = 0;
+            unsigned tls = 0;
+            dst[12 * p * kPL] = residual4<SB, DB, true, true>(sp + (size_t)12 * p * fd.src_stride[0],
+                                                              dp + (size_t)12 * p * fd.den_stride[0], g.src_shift,
+                                                              g.den_shift, trs, trq, tls, ov);
+            if (ty >= 3) rs += trs, rq += trq, ls += tls;  // halo rows belong to the block above
+          }
         }
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {
@@ -295,59 +365,118 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
         if ((lane & 7) == 0) {
           const int blk = (lane >> 3) & 1;
           atomicAdd(&sm.st_rs[blk], rs);
-          atomicAdd(&sm.st_rq[blk], rq);
+          atomicAdd(&sm.st_rq[blk], (unsigned)rq);
           atomicAdd(&sm.st_ls[blk], ls);
         }
-        if (__any_sync(0xffffffffu, ov) && lane == 0) sm.ovf[0] = 1;
+        if (__any_sync(0xffffffffu, ov != 0) && lane == 0) sm.ovf[0] = 1;
       }
-      // luma halo words 0 and 17 (70 items), chroma halo words 0 and 9 (2 planes x 38 items)
-      if (tid < 70) {
-        const int ty = tid >> 1, w = (tid & 1) * 17;
-        int rs = 0;
-        unsigned rq = 0, ls = 0;
-        bool ov = false;
-        sm.luma[ty * kPL + w] = residual_word<ALIGNED>(fd.src[0], fd.src_stride[0], fd.den[0], fd.den_stride[0],
-                                                       Y0 - 3 + ty, X0 - 4 + 4 * w, g, W, H, rs, rq, ls, ov);
-        if (ov) sm.ovf[0] = 1;
-      } else if (has_chroma && tid < 70 + 76) {
-        const int idx = tid - 70, c = idx / 38, rem = idx - c * 38;
-        const int ty = rem >> 1, w = (rem & 1) * 9;
-        int rs = 0;
-        unsigned rq = 0, ls = 0;
-        bool ov = false;
-        sm.chroma[c][ty * kPC + w] =
-            residual_word<ALIGNED>(fd.src[1 + c], fd.src_stride[1 + c], fd.den[1 + c], fd.den_stride[1 + c],
-                                   CY0 - 3 + ty, CX0 - 4 + 4 * w, g, pw, ph, rs, rq, ls, ov);
-        if (ov) sm.ovf[1 + c] = 1;
-      }
-      // chroma main words: four tile rows per warp pass, word w = 1 + (lane & 7)
       if (has_chroma) {
-        for (int pp = warp; pp < 10; pp += 6) {
-          const int c = pp / 5, p = pp - 5 * c;
-          const int ty = 4 * p + (lane >> 3), w = 1 + (lane & 7);
-          int rs = 0;
-          unsigned rq = 0, ls = 0;
-          bool ov = false;
-          if (ty < kChromaRows) {
-            const uint32_t word =
-                residual_word<ALIGNED>(fd.src[1 + c], fd.src_stride[1 + c], fd.den[1 + c], fd.den_stride[1 + c],
-                                       CY0 - 3 + ty, CX0 - 4 + 4 * w, g, pw, ph, rs, rq, ls, ov);
-            sm.chroma[c][ty * kPC + w] = word;
-            if (ty < 3) rs = 0, rq = 0;
-          }
+        // chroma main words: warps 0-2 Cb, 3-5 Cr; four tile rows per pass, rows 4*(warp%3) + 12*pass
+        const int c = warp >= 3 ? 1 : 0, wk = warp - 3 * c;
+        int rs = 0, rq = 0;
+        unsigned ls = 0;
+        uint32_t ovc = 0;
+        const int ty0 = 4 * wk + (lane >> 3), w = 1 + (lane & 7);
+        const uint32_t sstr = fd.src_stride[1 + c], dstr = fd.den_stride[1 + c];
+        const uint8_t *sp = static_cast<const uint8_t *>(fd.src[1 + c]) + (size_t)(CY0 - 3 + ty0) * sstr +
+                            (size_t)(CX0 - 4 + 4 * w) * SB;
+        const uint8_t *dp = static_cast<const uint8_t *>(fd.den[1 + c]) + (size_t)(CY0 - 3 + ty0) * dstr +
+                            (size_t)(CX0 - 4 + 4 * w) * DB;
+        uint32_t *dst = &sm.chroma[c][ty0 * kPC + w];
 #pragma unroll
-          for (int o = 1; o < 4; o <<= 1) {
-            rs += __shfl_xor_sync(0xffffffffu, rs, o);
-            rq += __shfl_xor_sync(0xffffffffu, rq, o);
+        for (int p = 0; p < 2; ++p) {
+          const int ty = ty0 + 12 * p;
+          if (ty < kChromaRows) {
+            int trs = 0, trq = 0;
+            dst[12 * p * kPC] = residual4<SB, DB, true, false>(sp + (size_t)12 * p * sstr, dp + (size_t)12 * p * dstr,
+                                                               g.src_shift, g.den_shift, trs, trq, ls, ovc);
+            if (ty >= 3) rs += trs, rq += trq;
           }
-          if ((lane & 3) == 0) {
-            const int blk = (lane >> 2) & 1;
-            atomicAdd(&sm.st_rs[2 + 2 * c + blk], rs);
-            atomicAdd(&sm.st_rq[2 + 2 * c + blk], rq);
-          }
-          if (__any_sync(0xffffffffu, ov) && lane == 0) sm.ovf[1 + c] = 1;
+        }
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+          rs += __shfl_xor_sync(0xffffffffu, rs, o);
+          rq += __shfl_xor_sync(0xffffffffu, rq, o);
+        }
+        if ((lane & 3) == 0) {
+          const int blk = (lane >> 2) & 1;
+          atomicAdd(&sm.st_rs[2 + 2 * c + blk], rs);
+          atomicAdd(&sm.st_rq[2 + 2 * c + blk], (unsigned)rq);
+        }
+        if (__any_sync(0xffffffffu, ovc != 0) && lane == 0) sm.ovf[1 + c] = 1;
+      }
+      // halo words: luma 0 and 17 (70 items), chroma 0 and 9 (2 planes x 38 items)
+      {
+        int rs = 0, rq = 0;
+        unsigned ls = 0;
+        uint32_t ovh = 0;
+        if (tid < 70) {
+          const int ty = tid >> 1, w = (tid & 1) * 17;
+          const uint8_t *sp = static_cast<const uint8_t *>(fd.src[0]) + (size_t)(Y0 - 3 + ty) * fd.src_stride[0] +
+                              (size_t)(X0 - 4 + 4 * w) * SB;
+          const uint8_t *dp = static_cast<const uint8_t *>(fd.den[0]) + (size_t)(Y0 - 3 + ty) * fd.den_stride[0] +
+                              (size_t)(X0 - 4 + 4 * w) * DB;
+          sm.luma[ty * kPL + w] = residual4<SB, DB, false, false>(sp, dp, g.src_shift, g.den_shift, rs, rq, ls, ovh);
+          if (ovh) sm.ovf[0] = 1;
+        } else if (has_chroma && tid < 70 + 76) {
+          const int idx = tid - 70, c = idx >= 38 ? 1 : 0, rem = idx - 38 * c;
+          const int ty = rem >> 1, w = (rem & 1) * 9;
+          const uint8_t *sp = static_cast<const uint8_t *>(fd.src[1 + c]) +
+                              (size_t)(CY0 - 3 + ty) * fd.src_stride[1 + c] + (size_t)(CX0 - 4 + 4 * w) * SB;
+          const uint8_t *dp = static_cast<const uint8_t *>(fd.den[1 + c]) +
+                              (size_t)(CY0 - 3 + ty) * fd.den_stride[1 + c] + (size_t)(CX0 - 4 + 4 * w) * DB;
+          sm.chroma[c][ty * kPC + w] =
+              residual4<SB, DB, false, false>(sp, dp, g.src_shift, g.den_shift, rs, rq, ls, ovh);
+          if (ovh) sm.ovf[1 + c] = 1;
         }
       }
+    } else {
+      // frame-edge or unaligned unit: scalar bounds-checked loads, same tile contents
+      int rs[6] = {0, 0, 0, 0, 0, 0}, rq[6] = {0, 0, 0, 0, 0, 0};
+      unsigned ls[2] = {0, 0};
+      uint32_t ov[3] = {0, 0, 0};
+      for (int e = tid; e < kLumaRows * 18; e += kSuThreads) {
+        const int ty = e / 18, w = e - 18 * ty;
+        const bool st = ty >= 3 && w >= 1 && w <= 16;
+        const int blk = w > 8 ? 1 : 0;
+        int a = 0, b = 0;
+        unsigned l = 0;
+        sm.luma[ty * kPL + w] = residual4_slow(fd.src[0], fd.src_stride[0], fd.den[0], fd.den_stride[0], Y0 - 3 + ty,
+                                               X0 - 4 + 4 * w, g, W, H, st, a, b, l, ov[0]);
+        if (blk) rs[1] += a, rq[1] += b, ls[1] += l;
+        else rs[0] += a, rq[0] += b, ls[0] += l;
+      }
+      if (has_chroma) {
+        for (int e = tid; e < 2 * kChromaRows * 10; e += kSuThreads) {
+          const int c = e >= kChromaRows * 10 ? 1 : 0, r = e - c * kChromaRows * 10;
+          const int ty = r / 10, w = r - 10 * ty;
+          const bool st = ty >= 3 && w >= 1 && w <= 8;
+          const int blk = w > 4 ? 1 : 0;
+          int a = 0, b = 0;
+          unsigned l = 0;
+          const uint32_t word =
+              residual4_slow(fd.src[1 + c], fd.src_stride[1 + c], fd.den[1 + c], fd.den_stride[1 + c], CY0 - 3 + ty,
+                             CX0 - 4 + 4 * w, g, pw, ph, st, a, b, l, c ? ov[2] : ov[1]);
+          sm.chroma[c][ty * kPC + w] = word;
+          if (c) {
+            if (blk) rs[5] += a, rq[5] += b;
+            else rs[4] += a, rq[4] += b;
+          } else {
+            if (blk) rs[3] += a, rq[3] += b;
+            else rs[2] += a, rq[2] += b;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        if (rs[k]) atomicAdd(&sm.st_rs[k], rs[k]);
+        if (rq[k]) atomicAdd(&sm.st_rq[k], (unsigned)rq[k]);
+      }
+      if (ls[0]) atomicAdd(&sm.st_ls[0], ls[0]);
+      if (ls[1]) atomicAdd(&sm.st_ls[1], ls[1]);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (ov[k]) sm.ovf[k] = 1;
     }
     __syncthreads();  // tiles + statistics + overflow flags complete
 
@@ -356,13 +485,14 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
       const int cy = tid >> 3, w = tid & 7;
       const uint32_t *r0 = &sm.luma[(3 + 2 * cy) * kPL + 1 + 2 * w];
       const uint32_t *r1 = r0 + kPL;
+      const uint32_t a0 = r0[0], a1 = r0[1], c0 = r1[0], c1 = r1[1];
       uint32_t hw = 0, lw = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const uint32_t a = (i < 2 ? r0[0] : r0[1]) >> (16 * (i & 1));
-        const uint32_t b = (i < 2 ? r1[0] : r1[1]) >> (16 * (i & 1));
-        const int l4 = (int)(int8_t)(a & 0xFF) + (int)(int8_t)((a >> 8) & 0xFF) + (int)(int8_t)(b & 0xFF) +
-                       (int)(int8_t)((b >> 8) & 0xFF);
+        const uint32_t a = (i < 2 ? a0 : a1) >> (16 * (i & 1));
+        const uint32_t b = (i < 2 ? c0 : c1) >> (16 * (i & 1));
+        // four s8 bytes summed with one dp4a against 1,1,1,1 after gathering them into one word
+        const int l4 = __dp4a((int)__byte_perm(a, b, 0x5410), 0x01010101, 0);
         hw |= (uint32_t)((l4 >> 3) & 0xFF) << (8 * i);
         lw |= (uint32_t)(l4 & 7) << (8 * i);
       }
@@ -371,7 +501,7 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
     }
     // statistics and overflow flags out (each block belongs to exactly one CTA)
     const bool ovl = sm.ovf[0] != 0;
-    const bool ovc[2] = {ovl || sm.ovf[1] != 0, ovl || sm.ovf[2] != 0};  // the luma tap needs an exact luma tile
+    const bool ovcb = ovl || sm.ovf[1] != 0, ovcr = ovl || sm.ovf[2] != 0;  // the luma tap needs an exact luma tile
     if (tid < 6) {
       const int c = tid >> 1, blk = tid & 1;
       const bool fl = blk ? fl1 : fl0;
@@ -379,7 +509,7 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
         reinterpret_cast<int32_t *>(rec + rl.off_rsum)[c * g.nb + b0 + blk] = sm.st_rs[tid];
         reinterpret_cast<uint32_t *>(rec + rl.off_rsq)[c * g.nb + b0 + blk] = sm.st_rq[tid];
         if (c == 0) reinterpret_cast<uint32_t *>(rec + rl.off_luma_sum)[b0 + blk] = sm.st_ls[blk];
-        const bool o = c == 0 ? ovl : ovc[c - 1];
+        const bool o = c == 0 ? ovl : (c == 1 ? ovcb : ovcr);
         if (o) {
           ovf_out[(size_t)c * g.nb + b0 + blk] = 1;
           atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_ovf_count), 1ull);
@@ -392,52 +522,55 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
     // add_block_observations: margins of 3 unless the neighbour block is flat too
     const bool up0 = by > 0 && flat[b0 - g.nbw], up1 = by > 0 && ex1 && flat[b0 + 1 - g.nbw];
     const bool lf0 = bx0 > 0 && flat[b0 - 1], rt1 = bx0 + 2 < g.nbw && flat[b0 + 2];
-    int xs[2], ys0[2];
-    xs[0] = lf0 ? 0 : kLag;
-    xs[1] = fl0 ? 0 : kLag;
-    ys0[0] = up0 ? 0 : kLag;
-    ys0[1] = up1 ? 0 : kLag;
-    const bool rn[2] = {fl1, rt1};  // right neighbour flat
+    const int xs0 = lf0 ? 0 : kLag, xs1 = fl0 ? 0 : kLag;
+    const int ysb0 = up0 ? 0 : kLag, ysb1 = up1 ? 0 : kLag;
 
     if (warp < 4) {
       const int j = warp >> 1;
       const bool fl = j ? fl1 : fl0;
       if (fl && !ovl) {
-        const int x_o = 32 * (bx0 + j);
-        const int x1 = min(W - x_o - kLag, rn[j] ? 32 : 32 - kLag);
+        const int xs = j ? xs1 : xs0, y0 = j ? ysb1 : ysb0;
+        const bool rn = j ? rt1 : fl1;  // right neighbour flat
+        const int x1 = min(W - 32 * (bx0 + j) - kLag, rn ? 32 : 32 - kLag);
         const int y1 = min(H - Y0, 32);
-        const int y0 = ys0[j];
-        if (x1 > xs[j] && y1 > y0) {
-          if (tid == 0 || tid == 64) nobs[0] += (long long)(x1 - xs[j]) * (y1 - y0);
-          const int mid = y0 + ((y1 - y0 + 1) >> 1);
-          const int ys = (warp & 1) ? mid : y0, ye = (warp & 1) ? y1 : mid;
-          const uint32_t mx[2] = {byte_mask(4 * t, xs[j], x1), byte_mask(16 + 4 * t, xs[j], x1)};
-          const int y0h[2] = {0, 0};
-          gram_rows<false>(sm.luma, kPL, 8 * j + t + dxw, sh, ys, ye, mx, y0h, nullptr, false, t, acc);
+        if (x1 > xs && y1 > y0) {
+          if ((warp & 1) == 0 && lane == 0) nobs += (long long)(x1 - xs) * (y1 - y0);
+          // first warp of the block takes a multiple of four rows so only one warp has a ragged tail
+          const int n = y1 - y0, na = min(n, ((n >> 1) + 3) & ~3);
+          const int ys = (warp & 1) ? y0 + na : y0, nr = (warp & 1) ? n - na : na;
+          const uint32_t mx[2] = {byte_mask(4 * t, xs, x1), byte_mask(16 + 4 * t, xs, x1)};
+          if (nr > 0) luma_rows(&sm.luma[ys * kPL + 8 * j + t + dxw], sh, nr, mx, acc);
         }
       }
     } else if (has_chroma) {
       const int c = warp - 4;
+      const bool ovc = c ? ovcr : ovcb;
       const int y1 = min(ph - CY0, 16);
-      uint32_t mx[2] = {0, 0};
-      int y0h[2] = {99, 99};
-      int ymin = 99;
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const bool fl = j ? fl1 : fl0;
-        if (!fl || ovc[c]) continue;
-        const int x_o = 16 * (bx0 + j);
-        const int x1 = min(pw - x_o - kLag, rn[j] ? 16 : 16 - kLag);
-        if (x1 > xs[j] && y1 > ys0[j]) {
-          mx[j] = byte_mask(4 * t, xs[j], x1);
-          y0h[j] = ys0[j];
-          ymin = min(ymin, ys0[j]);
-          if (lane == 0) nobs[1 + c] += (long long)(x1 - xs[j]) * (y1 - ys0[j]);
+      // half 0 <-> chroma block bx0, half 1 <-> block bx0 + 1
+      const int x1a = min(pw - 16 * bx0 - kLag, fl1 ? 16 : 16 - kLag);
+      const int x1b = min(pw - 16 * (bx0 + 1) - kLag, rt1 ? 16 : 16 - kLag);
+      const bool on0 = fl0 && !ovc && x1a > xs0 && y1 > ysb0;
+      const bool on1 = fl1 && !ovc && x1b > xs1 && y1 > ysb1;
+      if (lane == 0) {
+        if (on0) nobs += (long long)(x1a - xs0) * (y1 - ysb0);
+        if (on1) nobs += (long long)(x1b - xs1) * (y1 - ysb1);
+      }
+      const uint32_t m0 = on0 ? byte_mask(4 * t, xs0, x1a) : 0u, m1 = on1 ? byte_mask(4 * t, xs1, x1b) : 0u;
+      const int ya = on0 ? ysb0 : 99, yb = on1 ? ysb1 : 99;
+      const int ylo = min(ya, yb), yhi = min(max(ya, yb), y1);
+      if (ylo < y1) {
+        // rows where only one block of the pair is observed (its top margin is 0, the other's is 3)
+        if (yhi > ylo) {
+          const uint32_t mx[2] = {ya <= ylo ? m0 : 0u, yb <= ylo ? m1 : 0u};
+          chroma_rows(&sm.chroma[c][ylo * kPC + t + dxw], &sm.hs[ylo * 8 + t], &sm.ls[ylo * 8 + t], sh, yhi - ylo, mx,
+                      gq, acc, self);
+        }
+        if (y1 > yhi) {
+          const uint32_t mx[2] = {m0, m1};
+          chroma_rows(&sm.chroma[c][yhi * kPC + t + dxw], &sm.hs[yhi * 8 + t], &sm.ls[yhi * 8 + t], sh, y1 - yhi, mx,
+                      gq, acc, self);
         }
       }
-      if (ymin < y1)
-        gram_rows<true>(sm.chroma[c], kPC, t + dxw, sh, ymin, y1, mx, y0h, gq == 4 ? sm.hs : sm.ls,
-                        gq == 4 || gq == 5, t, acc);
     }
   }
 
@@ -451,26 +584,40 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
         if (acc[i][r]) atomicAdd(&sm.dl[(i * 4 + r) * 32 + lane], acc[i][r]);
   }
   __syncthreads();
-  if (warp == 0 || warp >= 4) {
+  if (warp == 0 || (warp >= 4 && has_chroma)) {
     const int plane = warp == 0 ? 0 : warp - 3;
-    if (plane == 0 || has_chroma) {
-      unsigned long long *gram = reinterpret_cast<unsigned long long *>(rec + rl.off_gram) + (size_t)plane * kPairs;
+    unsigned long long *gram = reinterpret_cast<unsigned long long *>(rec + rl.off_gram) + (size_t)plane * kPairs;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int mrow = i >= 4 ? 16 : 0;
-        const int ncol = i >= 4 ? 8 * (i - 2) : 8 * i;
+    for (int i = 0; i < 6; ++i) {
+      const int mrow = i >= 4 ? 16 : 0;
+      const int ncol = i >= 4 ? 8 * (i - 2) : 8 * i;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int v = warp == 0 ? sm.dl[(i * 4 + r) * 32 + lane] : acc[i][r];
-          emit(gram, mrow + gq + 8 * (r >> 1), ncol + 2 * t + (r & 1), (long long)v, plane > 0);
+      for (int r = 0; r < 4; ++r) {
+        const int v = warp == 0 ? sm.dl[(i * 4 + r) * 32 + lane] : acc[i][r];
+        emit(gram, mrow + gq + 8 * (r >> 1), ncol + 2 * t + (r & 1), v);
+      }
+    }
+    if (plane > 0) {
+      if (t == 0) {  // columns 0 / 1 of n-tile 4: luma tap high / low part
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int a = 16 * i + gq;
+          emit_luma_tap(gram, a, acc[6 + i][0], 8);
+          emit_luma_tap(gram, a, acc[6 + i][1], 1);
+          emit_luma_tap(gram, a + 8, acc[6 + i][2], 8);
+          emit_luma_tap(gram, a + 8, acc[6 + i][3], 1);
         }
+      }
+      if (gq == 0) {  // (8h + l)^2 = 64 hh + 16 hl + ll, lanes t = 0..3 hold disjoint pixels
+        const long long v = 64ll * self[0] + 16ll * self[1] + (long long)self[2];
+        if (v) atomicAdd(&gram[pair_index(24, 24)], (unsigned long long)v);
       }
     }
   }
-  // observation counts: thread 0 (luma block 0), thread 64 (luma block 1), lanes 0 of warps 4 / 5
-  if (nobs[0]) atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs), (unsigned long long)nobs[0]);
-  if (nobs[1]) atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + 1, (unsigned long long)nobs[1]);
-  if (nobs[2]) atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + 2, (unsigned long long)nobs[2]);
+  if (nobs) {
+    const int plane = warp < 4 ? 0 : warp - 3;
+    atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + plane, (unsigned long long)nobs);
+  }
 }
 
 }  // namespace
@@ -484,10 +631,15 @@ void launch_gram_imma(const FrameDesc *frames, int nframes, const Geometry &g, u
   const int nsu = (g.nbw + 1) / 2;
   const int runs = (nsu + kSuRun - 1) / kSuRun;
   dim3 grid(runs * g.nbh, nframes);
-  if (aligned)
-    gram_imma_kernel<true><<<grid, kSuThreads, 0, st>>>(frames, g, records, rl, runs);
+  const int al = aligned ? 1 : 0;
+  if (g.src_bytes == 2 && g.den_bytes == 2)
+    gram_imma_kernel<2, 2><<<grid, kSuThreads, 0, st>>>(frames, g, records, rl, runs, al);
+  else if (g.src_bytes == 2)
+    gram_imma_kernel<2, 1><<<grid, kSuThreads, 0, st>>>(frames, g, records, rl, runs, al);
+  else if (g.den_bytes == 2)
+    gram_imma_kernel<1, 2><<<grid, kSuThreads, 0, st>>>(frames, g, records, rl, runs, al);
   else
-    gram_imma_kernel<false><<<grid, kSuThreads, 0, st>>>(frames, g, records, rl, runs);
+    gram_imma_kernel<1, 1><<<grid, kSuThreads, 0, st>>>(frames, g, records, rl, runs, al);
 }
 
 }  // namespace g1s

@@ -395,8 +395,9 @@ gram_generic_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry 
     }
     __syncthreads();
 
-    // ---- per-block noise statistics over the frame-clipped block (get_block_mean / get_noise_var)
-    if (!only_overflow) {
+    // ---- per-block noise statistics over the frame-clipped block (get_block_mean / get_noise_var);
+    // also in overflow mode: the tensor-core kernel's dp4a statistics assume int8 residuals
+    {
       const int max_w = min(pw - x_o, bw), max_h = min(ph - y_o, bh);
       int rs = 0;
       unsigned rq = 0;

@@ -57,7 +57,7 @@ void launch_flat_features(const FrameDesc *frames, int nframes, const Geometry &
                           uint8_t *records, const RecordLayout &rl, cudaStream_t st);
 void launch_flat_select(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, cudaStream_t st);
 // only_overflow = false: every flat block, statistics included (any subsampling, any alignment).
-// only_overflow = true: just the blocks the tensor-core kernel flagged, Gram sums only.
+// only_overflow = true: just the blocks the tensor-core kernel flagged (Gram sums and statistics).
 void launch_gram_generic(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
                          const RecordLayout &rl, bool only_overflow, cudaStream_t st);
 // int8 tensor-core (mma.sync m16n8k32) Gram kernel for 4:2:0 / monochrome streams.
