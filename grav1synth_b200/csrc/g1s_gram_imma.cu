@@ -41,16 +41,31 @@ constexpr int kLumaRows = 35;     // 3 halo rows + 32
 constexpr int kPC = 12;           // chroma tile pitch in words (40 bytes used)
 constexpr int kChromaRows = 19;   // 3 halo rows + 16
 
+constexpr int kFlagCols = 2 * kSuRun + 2;  // flat flags of the run's blocks plus one neighbour each side
+
+// Everything one super-unit needs to know about its observation rectangles (add_block_observations:
+// margins of 3 unless the neighbouring block is flat too), computed once per unit by one thread.
+struct UnitInfo {
+  int xs0, xs1;      // first observed column of block 0 / 1 (block-local)
+  int y00, y01;      // first observed row of block 0 / 1
+  int x1l0, x1l1;    // luma: one past the last observed column of block 0 / 1
+  int x1c0, x1c1;    // chroma: the same in chroma samples
+  int y1l, y1c;      // one past the last observed row (frame clip), luma / chroma
+};
+
 struct __align__(16) SuSmem {
   uint32_t luma[kLumaRows * kPL];
   uint32_t chroma[2][kChromaRows * kPC];
-  uint32_t hs[16 * 8];   // luma tap >> 3, one s8 per chroma pixel of the unit (32 x 16)
-  uint32_t ls[16 * 8];   // luma tap & 7
-  int dl[6 * 4 * 32];    // luma accumulators reduced over warps 0-3
+  uint32_t hs[kChromaRows * kPC];        // luma tap >> 3 (s8 per chroma pixel), chroma-tile pitch, rows >= 16 stay 0
+  uint32_t ls[(kChromaRows + 1) * kPC];  // luma tap & 7, stored one row down (row -1 is readable and 0)
+  int dl[6 * 4 * 32];                    // luma accumulators reduced over warps 0-3
   int st_rs[6];
   unsigned st_rq[6];
   unsigned st_ls[2];
   int ovf[3];
+  int self[2][3];                        // per chroma plane: sum h*h, h*l, l*l over observed pixels
+  UnitInfo info;
+  uint8_t flat[2][kFlagCols + 2];        // [0] this block row, [1] the row above; column 0 <-> block 2*u_beg - 1
 };
 
 __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -189,7 +204,7 @@ __device__ __forceinline__ void window_init(Window &w, const uint32_t *__restric
 // pnew the lane's window word in the tile row three below it.
 template <int K>
 __device__ __forceinline__ void step6(Window &w, const uint32_t *__restrict__ pnew, int sh, const uint32_t (&mx)[2],
-                                      int (&acc)[8][4]) {
+                                      int (&acc)[6][4]) {
   fetch_row(pnew, sh, mx, w.P[(K + 3) & 3], w.Q[(K + 2) & 3], w.Q[(K + 3) & 3]);
   imma_16832(acc[0], w.Q[K & 3], w.P[K & 3]);
   imma_16832(acc[1], w.Q[K & 3], w.P[(K + 1) & 3]);
@@ -201,7 +216,7 @@ __device__ __forceinline__ void step6(Window &w, const uint32_t *__restrict__ pn
 
 // p0: the lane's window word in tile row ys (the first observed row's cy = -3 tap row).
 __device__ __forceinline__ void luma_rows(const uint32_t *__restrict__ p0, int sh, int nrows,
-                                          const uint32_t (&mx)[2], int (&acc)[8][4]) {
+                                          const uint32_t (&mx)[2], int (&acc)[6][4]) {
   Window w;
   window_init<kPL>(w, p0, sh, mx);
   const uint32_t *p = p0 + 3 * kPL;
@@ -217,40 +232,58 @@ __device__ __forceinline__ void luma_rows(const uint32_t *__restrict__ p0, int s
   if (n > 2) step6<2>(w, p + 2 * kPL, sh, mx, acc);
 }
 
-// Chroma: the same six tiles plus n-tile 4 whose column 0 is the luma tap's high part (hs) and
-// column 1 its low part (ls); the three luma-tap self products are summed with dp4a.
-// hp / lp: the lane's word of hs / ls in the step's row (half 0; half 1 is 4 words further).
-template <int K>
-__device__ __forceinline__ void step8(Window &w, const uint32_t *__restrict__ pnew, const uint32_t *__restrict__ hp,
-                                      const uint32_t *__restrict__ lp, int sh, const uint32_t (&mx)[2], int gq,
-                                      int (&acc)[8][4], int (&self)[3]) {
-  step6<K>(w, pnew, sh, mx, acc);
-  const uint32_t h0 = hp[0] & mx[0], h1 = hp[4] & mx[1];
-  const uint32_t l0 = lp[0] & mx[0], l1 = lp[4] & mx[1];
-  self[0] = __dp4a((int)h0, (int)h0, __dp4a((int)h1, (int)h1, self[0]));
-  self[1] = __dp4a((int)h0, (int)l0, __dp4a((int)h1, (int)l1, self[1]));
-  self[2] = __dp4a((int)l0, (int)l0, __dp4a((int)l1, (int)l1, self[2]));
-  const uint32_t S[2] = {gq == 0 ? h0 : (gq == 1 ? l0 : 0u), gq == 0 ? h1 : (gq == 1 ? l1 : 0u)};
-  imma_16832(acc[6], w.Q[K & 3], S);
-  imma_16832(acc[7], w.Q[(K + 2) & 3], S);
+// Chroma.  The luma tap (split as 8*hi + lo so both parts fit int8) rides in the otherwise unused lane
+// group g = 7: those lanes step through hs instead of the residual tile (same pitch, funnel shift 0), so
+// their A rows 7 / 15 of the lower m-tile are hi(y) / lo(y) and the four existing tiles (m0 x n0..n3)
+// deliver every (tap, luma tap) product for free.  The quad's upper row is a separate register from the
+// next quad's lower row, which is what lets it carry lo(y) instead of hi(y+1).
+//   p  : window word of the fetched tile row (g = 7: hs row of the same index)
+//   lp : ls word of the row above the fetched one (only g = 7 lanes use the value)
+__device__ __forceinline__ void fetch_row_c(const uint32_t *__restrict__ p, const uint32_t *__restrict__ lp, int sh,
+                                            bool is7, const uint32_t (&mx)[2], uint32_t (&pair)[2],
+                                            uint32_t (&qprev)[4], uint32_t (&qthis)[4]) {
+  const uint32_t r0 = __funnelshift_r(p[0], p[1], sh);
+  const uint32_t r1 = __funnelshift_r(p[4], p[5], sh);
+  const uint32_t x0 = is7 ? lp[0] : r0;
+  const uint32_t x1 = is7 ? lp[4] : r1;
+  pair[0] = and_tag<0>(r0, mx[0]);
+  pair[1] = and_tag<0>(r1, mx[1]);
+  qprev[1] = and_tag<1>(x0, mx[0]);
+  qprev[3] = and_tag<1>(x1, mx[1]);
+  qthis[0] = and_tag<2>(r0, mx[0]);
+  qthis[2] = and_tag<2>(r1, mx[1]);
 }
 
-__device__ __forceinline__ void chroma_rows(const uint32_t *__restrict__ p0, const uint32_t *__restrict__ hp,
-                                            const uint32_t *__restrict__ lp, int sh, int nrows,
-                                            const uint32_t (&mx)[2], int gq, int (&acc)[8][4], int (&self)[3]) {
+template <int K>
+__device__ __forceinline__ void step6c(Window &w, const uint32_t *__restrict__ pnew, const uint32_t *__restrict__ lp,
+                                       int sh, bool is7, const uint32_t (&mx)[2], int (&acc)[6][4]) {
+  fetch_row_c(pnew, lp, sh, is7, mx, w.P[(K + 3) & 3], w.Q[(K + 2) & 3], w.Q[(K + 3) & 3]);
+  imma_16832(acc[0], w.Q[K & 3], w.P[K & 3]);
+  imma_16832(acc[1], w.Q[K & 3], w.P[(K + 1) & 3]);
+  imma_16832(acc[2], w.Q[K & 3], w.P[(K + 2) & 3]);
+  imma_16832(acc[3], w.Q[K & 3], w.P[(K + 3) & 3]);
+  imma_16832(acc[4], w.Q[(K + 2) & 3], w.P[(K + 2) & 3]);
+  imma_16832(acc[5], w.Q[(K + 2) & 3], w.P[(K + 3) & 3]);
+}
+
+// p0 / lp0: the lane's words for tile row ys (lp0 already points one ls row above it).
+__device__ __forceinline__ void chroma_rows(const uint32_t *__restrict__ p0, const uint32_t *__restrict__ lp0, int sh,
+                                            bool is7, int nrows, const uint32_t (&mx)[2], int (&acc)[6][4]) {
   Window w;
-  window_init<kPC>(w, p0, sh, mx);
-  const uint32_t *p = p0 + 3 * kPC;
+  fetch_row_c(p0, lp0, sh, is7, mx, w.P[0], w.Q[3], w.Q[0]);
+  fetch_row_c(p0 + kPC, lp0 + kPC, sh, is7, mx, w.P[1], w.Q[0], w.Q[1]);
+  fetch_row_c(p0 + 2 * kPC, lp0 + 2 * kPC, sh, is7, mx, w.P[2], w.Q[1], w.Q[2]);
+  const uint32_t *p = p0 + 3 * kPC, *lp = lp0 + 3 * kPC;
   int n = nrows;
-  for (; n >= 4; n -= 4, p += 4 * kPC, hp += 32, lp += 32) {
-    step8<0>(w, p, hp, lp, sh, mx, gq, acc, self);
-    step8<1>(w, p + kPC, hp + 8, lp + 8, sh, mx, gq, acc, self);
-    step8<2>(w, p + 2 * kPC, hp + 16, lp + 16, sh, mx, gq, acc, self);
-    step8<3>(w, p + 3 * kPC, hp + 24, lp + 24, sh, mx, gq, acc, self);
+  for (; n >= 4; n -= 4, p += 4 * kPC, lp += 4 * kPC) {
+    step6c<0>(w, p, lp, sh, is7, mx, acc);
+    step6c<1>(w, p + kPC, lp + kPC, sh, is7, mx, acc);
+    step6c<2>(w, p + 2 * kPC, lp + 2 * kPC, sh, is7, mx, acc);
+    step6c<3>(w, p + 3 * kPC, lp + 3 * kPC, sh, is7, mx, acc);
   }
-  if (n > 0) step8<0>(w, p, hp, lp, sh, mx, gq, acc, self);
-  if (n > 1) step8<1>(w, p + kPC, hp + 8, lp + 8, sh, mx, gq, acc, self);
-  if (n > 2) step8<2>(w, p + 2 * kPC, hp + 16, lp + 16, sh, mx, gq, acc, self);
+  if (n > 0) step6c<0>(w, p, lp, sh, is7, mx, acc);
+  if (n > 1) step6c<1>(w, p + kPC, lp + kPC, sh, is7, mx, acc);
+  if (n > 2) step6c<2>(w, p + 2 * kPC, lp + 2 * kPC, sh, is7, mx, acc);
 }
 
 // MMA tap index a = 8q+g  ->  record tap index (0..23 AR taps, 25 centre sample), -1 unused.
@@ -272,11 +305,11 @@ __device__ __forceinline__ void emit(unsigned long long *gram, int a, int b, int
   if (ia < 0 || ib < 0) return;
   atomicAdd(&gram[pair_index(min(ia, ib), max(ia, ib))], (unsigned long long)(long long)v);
 }
-// D[a][luma tap part]: weight 8 for the high part, 1 for the low part.
-__device__ __forceinline__ void emit_luma_tap(unsigned long long *gram, int a, int v, int weight) {
-  const int ia = record_tap(a);
-  if (ia < 0 || v == 0) return;
-  atomicAdd(&gram[pair_index(min(ia, 24), max(ia, 24))], (unsigned long long)((long long)v * weight));
+// D[luma tap part][b]: weight 8 for the high part, 1 for the low part.
+__device__ __forceinline__ void emit_luma_tap(unsigned long long *gram, int b, int v, int weight) {
+  const int ib = record_tap(b);
+  if (ib < 0 || v == 0) return;
+  atomicAdd(&gram[pair_index(min(ib, 24), max(ib, 24))], (unsigned long long)((long long)v * weight));
 }
 
 template <int SB, int DB>
@@ -300,26 +333,36 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
   const int Y0 = 32 * by, CY0 = 16 * by;
   const bool rows_inside = Y0 >= 3 && Y0 + 32 <= H && (!has_chroma || CY0 + 16 <= ph);
 
-  int acc[8][4];
+  int acc[6][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int r = 0; r < 4; ++r) acc[i][r] = 0;
-  int self[3] = {0, 0, 0};
-  long long nobs = 0;  // luma: lane 0 of warps 0 and 2; chroma: lane 0 of warps 4 / 5
+  long long nobs[3] = {0, 0, 0};  // kept by the bookkeeping thread only
 
   for (int i = tid; i < (int)(sizeof(SuSmem) / 4); i += kSuThreads) reinterpret_cast<uint32_t *>(&sm)[i] = 0;
+  __syncthreads();
+  // flat flags of this run: this block row and the one above, one extra block on each side
+  const int fbase = 2 * u_beg - 1;
+  for (int i = tid; i < 2 * kFlagCols; i += kSuThreads) {
+    const int r = i >= kFlagCols ? 1 : 0, k = i - r * kFlagCols;
+    const int bx = fbase + k, yy = by - r;
+    uint8_t v = 0;
+    if (bx >= 0 && bx < g.nbw && yy >= 0) v = flat[yy * g.nbw + bx];
+    sm.flat[r][k] = v;
+  }
   __syncthreads();
 
   const int sh = 8 * ((gq + 1) & 3);
   const int dxw = (gq + 1) >> 2;
+  const bool is7 = gq == 7;
+  constexpr int kBook = kSuThreads - 1;  // bookkeeping thread (observation rectangles, counts, flags)
 
   for (int u = u_beg; u < u_end; ++u) {
-    const int bx0 = 2 * u;
-    const bool ex1 = bx0 + 1 < g.nbw;
-    const int b0 = by * g.nbw + bx0;
-    const bool fl0 = flat[b0] != 0, fl1 = ex1 && flat[b0 + 1] != 0;
+    const int bx0 = 2 * u, fk = bx0 - fbase;
+    const bool fl0 = sm.flat[0][fk] != 0, fl1 = sm.flat[0][fk + 1] != 0;
     if (!fl0 && !fl1) continue;  // uniform across the CTA
+    const int b0 = by * g.nbw + bx0;
 
     if (tid < 6) {
       sm.st_rs[tid] = 0;
@@ -327,21 +370,38 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
       if (tid < 2) sm.st_ls[tid] = 0;
       if (tid < 3) sm.ovf[tid] = 0;
     }
-    __syncthreads();  // previous unit's k-loops are done with the tiles; statistics zeroed
+    if (tid == kBook) {
+      const bool lf0 = sm.flat[0][fk - 1] != 0, rt1 = sm.flat[0][fk + 2] != 0;
+      const bool up0 = sm.flat[1][fk] != 0, up1 = sm.flat[1][fk + 1] != 0;
+      UnitInfo in;
+      in.xs0 = lf0 ? 0 : kLag;
+      in.xs1 = fl0 ? 0 : kLag;
+      in.y00 = up0 ? 0 : kLag;
+      in.y01 = up1 ? 0 : kLag;
+      in.x1l0 = min(W - 32 * bx0 - kLag, fl1 ? 32 : 32 - kLag);
+      in.x1l1 = min(W - 32 * (bx0 + 1) - kLag, rt1 ? 32 : 32 - kLag);
+      in.x1c0 = min(pw - 16 * bx0 - kLag, fl1 ? 16 : 16 - kLag);
+      in.x1c1 = min(pw - 16 * (bx0 + 1) - kLag, rt1 ? 16 : 16 - kLag);
+      in.y1l = min(H - Y0, 32);
+      in.y1c = min(ph - CY0, 16);
+      sm.info = in;
+    }
+    __syncthreads();  // previous unit's k-loops are done with the tiles; statistics zeroed; info written
 
     // ------------------------------------------------------------------ staging
     const int X0 = 64 * u, CX0 = 32 * u;
     const bool fast = aligned && rows_inside && X0 >= 4 && X0 + 68 <= W && (!has_chroma || CX0 + 36 <= pw);
     if (fast) {
-      uint32_t ov = 0;
       {
         // luma main words: two tile rows per pass (lanes 0-15 / 16-31), rows warp*2 + 12*pass
+        uint32_t ov = 0;
         int rs = 0, rq = 0;
         unsigned ls = 0;
         const int ty0 = 2 * warp + (lane >> 4), w = 1 + (lane & 15);
-        const uint8_t *sp = static_cast<const uint8_t *>(fd.src[0]) + (size_t)(Y0 - 3 + ty0) * fd.src_stride[0] +
+        const uint32_t sstr = fd.src_stride[0], dstr = fd.den_stride[0];
+        const uint8_t *sp = static_cast<const uint8_t *>(fd.src[0]) + (size_t)(Y0 - 3 + ty0) * sstr +
                             (size_t)(X0 - 4 + 4 * w) * SB;
-        const uint8_t *dp = static_cast<const uint8_t *>(fd.den[0]) + (size_t)(Y0 - 3 + ty0) * fd.den_stride[0] +
+        const uint8_t *dp = static_cast<const uint8_t *>(fd.den[0]) + (size_t)(Y0 - 3 + ty0) * dstr +
                             (size_t)(X0 - 4 + 4 * w) * DB;
         uint32_t *dst = &sm.luma[ty0 * kPL + w];
 #pragma unroll
@@ -350,11 +410,11 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
           if (ty < kLumaRows) {
             int trs = 0, trq = 0;
             unsigned tls = 0;
-            dst[12 * p * kPL] = residual4<SB, DB, true, true>(sp + (size_t)12 * p * fd.src_stride[0],
-                                                              dp + (size_t)12 * p * fd.den_stride[0], g.src_shift,
-                                                              g.den_shift, trs, trq, tls, ov);
+            dst[12 * p * kPL] = residual4<SB, DB, true, true>(sp, dp, g.src_shift, g.den_shift, trs, trq, tls, ov);
             if (ty >= 3) rs += trs, rq += trq, ls += tls;  // halo rows belong to the block above
           }
+          sp += (size_t)12 * sstr;
+          dp += (size_t)12 * dstr;
         }
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {
@@ -388,10 +448,11 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
           const int ty = ty0 + 12 * p;
           if (ty < kChromaRows) {
             int trs = 0, trq = 0;
-            dst[12 * p * kPC] = residual4<SB, DB, true, false>(sp + (size_t)12 * p * sstr, dp + (size_t)12 * p * dstr,
-                                                               g.src_shift, g.den_shift, trs, trq, ls, ovc);
+            dst[12 * p * kPC] = residual4<SB, DB, true, false>(sp, dp, g.src_shift, g.den_shift, trs, trq, ls, ovc);
             if (ty >= 3) rs += trs, rq += trq;
           }
+          sp += (size_t)12 * sstr;
+          dp += (size_t)12 * dstr;
         }
 #pragma unroll
         for (int o = 1; o < 4; o <<= 1) {
@@ -480,7 +541,12 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
     }
     __syncthreads();  // tiles + statistics + overflow flags complete
 
-    // luma tap of the chroma planes: sum of the co-sited 2x2 luma residuals = 8*hi + lo
+    const UnitInfo in = sm.info;
+    const bool ovl = sm.ovf[0] != 0;
+    const bool ovcb = ovl || sm.ovf[1] != 0, ovcr = ovl || sm.ovf[2] != 0;  // the luma tap needs an exact luma tile
+
+    // luma tap of the chroma planes: sum of the co-sited 2x2 luma residuals = 8*hi + lo, and its
+    // self products over the observed pixels (the only Gram entries the k-loops do not produce)
     if (has_chroma && tid < 128) {
       const int cy = tid >> 3, w = tid & 7;
       const uint32_t *r0 = &sm.luma[(3 + 2 * cy) * kPL + 1 + 2 * w];
@@ -491,23 +557,36 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
       for (int i = 0; i < 4; ++i) {
         const uint32_t a = (i < 2 ? a0 : a1) >> (16 * (i & 1));
         const uint32_t b = (i < 2 ? c0 : c1) >> (16 * (i & 1));
-        // four s8 bytes summed with one dp4a against 1,1,1,1 after gathering them into one word
         const int l4 = __dp4a((int)__byte_perm(a, b, 0x5410), 0x01010101, 0);
         hw |= (uint32_t)((l4 >> 3) & 0xFF) << (8 * i);
         lw |= (uint32_t)(l4 & 7) << (8 * i);
       }
-      sm.hs[cy * 8 + w] = hw;
-      sm.ls[cy * 8 + w] = lw;
+      sm.hs[cy * kPC + w] = hw;
+      sm.ls[(cy + 1) * kPC + w] = lw;
+      const int j = w >> 2;  // block of the pair
+      const bool flj = j ? fl1 : fl0;
+      const int xs = j ? in.xs1 : in.xs0, x1 = j ? in.x1c1 : in.x1c0, y0 = j ? in.y01 : in.y00;
+      const uint32_t m = (flj && cy >= y0 && cy < in.y1c) ? byte_mask(4 * (w & 3), xs, x1) : 0u;
+      const int hm = (int)(hw & m), lm = (int)(lw & m);
+      int hh = __dp4a(hm, hm, 0), hl = __dp4a(hm, lm, 0), ll = __dp4a(lm, lm, 0);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        hh += __shfl_xor_sync(0xffffffffu, hh, o);
+        hl += __shfl_xor_sync(0xffffffffu, hl, o);
+        ll += __shfl_xor_sync(0xffffffffu, ll, o);
+      }
+      if (lane == 0) {
+        if (!ovcb) atomicAdd(&sm.self[0][0], hh), atomicAdd(&sm.self[0][1], hl), atomicAdd(&sm.self[0][2], ll);
+        if (!ovcr) atomicAdd(&sm.self[1][0], hh), atomicAdd(&sm.self[1][1], hl), atomicAdd(&sm.self[1][2], ll);
+      }
     }
     // statistics and overflow flags out (each block belongs to exactly one CTA)
-    const bool ovl = sm.ovf[0] != 0;
-    const bool ovcb = ovl || sm.ovf[1] != 0, ovcr = ovl || sm.ovf[2] != 0;  // the luma tap needs an exact luma tile
-    if (tid < 6) {
-      const int c = tid >> 1, blk = tid & 1;
+    if (tid >= 128 && tid < 134) {
+      const int k = tid - 128, c = k >> 1, blk = k & 1;
       const bool fl = blk ? fl1 : fl0;
       if (fl && (c == 0 || has_chroma)) {
-        reinterpret_cast<int32_t *>(rec + rl.off_rsum)[c * g.nb + b0 + blk] = sm.st_rs[tid];
-        reinterpret_cast<uint32_t *>(rec + rl.off_rsq)[c * g.nb + b0 + blk] = sm.st_rq[tid];
+        reinterpret_cast<int32_t *>(rec + rl.off_rsum)[c * g.nb + b0 + blk] = sm.st_rs[k];
+        reinterpret_cast<uint32_t *>(rec + rl.off_rsq)[c * g.nb + b0 + blk] = sm.st_rq[k];
         if (c == 0) reinterpret_cast<uint32_t *>(rec + rl.off_luma_sum)[b0 + blk] = sm.st_ls[blk];
         const bool o = c == 0 ? ovl : (c == 1 ? ovcb : ovcr);
         if (o) {
@@ -516,25 +595,24 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
         }
       }
     }
+    if (tid == kBook) {  // observation counts of the blocks this kernel accumulates
+      const long long hl0 = (in.x1l0 > in.xs0 && in.y1l > in.y00) ? (long long)(in.x1l0 - in.xs0) * (in.y1l - in.y00) : 0;
+      const long long hl1 = (in.x1l1 > in.xs1 && in.y1l > in.y01) ? (long long)(in.x1l1 - in.xs1) * (in.y1l - in.y01) : 0;
+      const long long hc0 = (in.x1c0 > in.xs0 && in.y1c > in.y00) ? (long long)(in.x1c0 - in.xs0) * (in.y1c - in.y00) : 0;
+      const long long hc1 = (in.x1c1 > in.xs1 && in.y1c > in.y01) ? (long long)(in.x1c1 - in.xs1) * (in.y1c - in.y01) : 0;
+      if (!ovl) nobs[0] += (fl0 ? hl0 : 0) + (fl1 ? hl1 : 0);
+      if (has_chroma && !ovcb) nobs[1] += (fl0 ? hc0 : 0) + (fl1 ? hc1 : 0);
+      if (has_chroma && !ovcr) nobs[2] += (fl0 ? hc0 : 0) + (fl1 ? hc1 : 0);
+    }
     __syncthreads();  // hs / ls visible
 
-    // ------------------------------------------------------------------ observation rectangles
-    // add_block_observations: margins of 3 unless the neighbour block is flat too
-    const bool up0 = by > 0 && flat[b0 - g.nbw], up1 = by > 0 && ex1 && flat[b0 + 1 - g.nbw];
-    const bool lf0 = bx0 > 0 && flat[b0 - 1], rt1 = bx0 + 2 < g.nbw && flat[b0 + 2];
-    const int xs0 = lf0 ? 0 : kLag, xs1 = fl0 ? 0 : kLag;
-    const int ysb0 = up0 ? 0 : kLag, ysb1 = up1 ? 0 : kLag;
-
+    // ------------------------------------------------------------------ k-loops
     if (warp < 4) {
       const int j = warp >> 1;
       const bool fl = j ? fl1 : fl0;
       if (fl && !ovl) {
-        const int xs = j ? xs1 : xs0, y0 = j ? ysb1 : ysb0;
-        const bool rn = j ? rt1 : fl1;  // right neighbour flat
-        const int x1 = min(W - 32 * (bx0 + j) - kLag, rn ? 32 : 32 - kLag);
-        const int y1 = min(H - Y0, 32);
+        const int xs = j ? in.xs1 : in.xs0, y0 = j ? in.y01 : in.y00, x1 = j ? in.x1l1 : in.x1l0, y1 = in.y1l;
         if (x1 > xs && y1 > y0) {
-          if ((warp & 1) == 0 && lane == 0) nobs += (long long)(x1 - xs) * (y1 - y0);
           // first warp of the block takes a multiple of four rows so only one warp has a ragged tail
           const int n = y1 - y0, na = min(n, ((n >> 1) + 3) & ~3);
           const int ys = (warp & 1) ? y0 + na : y0, nr = (warp & 1) ? n - na : na;
@@ -545,30 +623,26 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
     } else if (has_chroma) {
       const int c = warp - 4;
       const bool ovc = c ? ovcr : ovcb;
-      const int y1 = min(ph - CY0, 16);
+      const int y1 = in.y1c;
       // half 0 <-> chroma block bx0, half 1 <-> block bx0 + 1
-      const int x1a = min(pw - 16 * bx0 - kLag, fl1 ? 16 : 16 - kLag);
-      const int x1b = min(pw - 16 * (bx0 + 1) - kLag, rt1 ? 16 : 16 - kLag);
-      const bool on0 = fl0 && !ovc && x1a > xs0 && y1 > ysb0;
-      const bool on1 = fl1 && !ovc && x1b > xs1 && y1 > ysb1;
-      if (lane == 0) {
-        if (on0) nobs += (long long)(x1a - xs0) * (y1 - ysb0);
-        if (on1) nobs += (long long)(x1b - xs1) * (y1 - ysb1);
-      }
-      const uint32_t m0 = on0 ? byte_mask(4 * t, xs0, x1a) : 0u, m1 = on1 ? byte_mask(4 * t, xs1, x1b) : 0u;
-      const int ya = on0 ? ysb0 : 99, yb = on1 ? ysb1 : 99;
+      const bool on0 = fl0 && !ovc && in.x1c0 > in.xs0 && y1 > in.y00;
+      const bool on1 = fl1 && !ovc && in.x1c1 > in.xs1 && y1 > in.y01;
+      const uint32_t m0 = on0 ? byte_mask(4 * t, in.xs0, in.x1c0) : 0u;
+      const uint32_t m1 = on1 ? byte_mask(4 * t, in.xs1, in.x1c1) : 0u;
+      const int ya = on0 ? in.y00 : 99, yb = on1 ? in.y01 : 99;
       const int ylo = min(ya, yb), yhi = min(max(ya, yb), y1);
+      // g = 7 lanes walk hs (and ls one row up) instead of the residual tile
+      const uint32_t *base = is7 ? &sm.hs[t] : &sm.chroma[c][t + dxw];
+      const uint32_t *lbase = &sm.ls[t];  // storage row r holds ls row r - 1
       if (ylo < y1) {
         // rows where only one block of the pair is observed (its top margin is 0, the other's is 3)
         if (yhi > ylo) {
           const uint32_t mx[2] = {ya <= ylo ? m0 : 0u, yb <= ylo ? m1 : 0u};
-          chroma_rows(&sm.chroma[c][ylo * kPC + t + dxw], &sm.hs[ylo * 8 + t], &sm.ls[ylo * 8 + t], sh, yhi - ylo, mx,
-                      gq, acc, self);
+          chroma_rows(base + ylo * kPC, lbase + ylo * kPC, sh, is7, yhi - ylo, mx, acc);
         }
         if (y1 > yhi) {
           const uint32_t mx[2] = {m0, m1};
-          chroma_rows(&sm.chroma[c][yhi * kPC + t + dxw], &sm.hs[yhi * 8 + t], &sm.ls[yhi * 8 + t], sh, y1 - yhi, mx,
-                      gq, acc, self);
+          chroma_rows(base + yhi * kPC, lbase + yhi * kPC, sh, is7, y1 - yhi, mx, acc);
         }
       }
     }
@@ -594,29 +668,23 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int v = warp == 0 ? sm.dl[(i * 4 + r) * 32 + lane] : acc[i][r];
-        emit(gram, mrow + gq + 8 * (r >> 1), ncol + 2 * t + (r & 1), v);
+        const int b = ncol + 2 * t + (r & 1);
+        if (plane > 0 && is7 && i < 4)
+          emit_luma_tap(gram, b, v, (r >> 1) ? 1 : 8);  // rows 7 / 15 of the lower m-tile: luma tap hi / lo
+        else
+          emit(gram, mrow + gq + 8 * (r >> 1), b, v);
       }
     }
-    if (plane > 0) {
-      if (t == 0) {  // columns 0 / 1 of n-tile 4: luma tap high / low part
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int a = 16 * i + gq;
-          emit_luma_tap(gram, a, acc[6 + i][0], 8);
-          emit_luma_tap(gram, a, acc[6 + i][1], 1);
-          emit_luma_tap(gram, a + 8, acc[6 + i][2], 8);
-          emit_luma_tap(gram, a + 8, acc[6 + i][3], 1);
-        }
-      }
-      if (gq == 0) {  // (8h + l)^2 = 64 hh + 16 hl + ll, lanes t = 0..3 hold disjoint pixels
-        const long long v = 64ll * self[0] + 16ll * self[1] + (long long)self[2];
-        if (v) atomicAdd(&gram[pair_index(24, 24)], (unsigned long long)v);
-      }
+    if (plane > 0 && lane == 0) {  // (8h + l)^2 = 64 hh + 16 hl + ll
+      const long long v = 64ll * sm.self[plane - 1][0] + 16ll * sm.self[plane - 1][1] + (long long)sm.self[plane - 1][2];
+      if (v) atomicAdd(&gram[pair_index(24, 24)], (unsigned long long)v);
     }
   }
-  if (nobs) {
-    const int plane = warp < 4 ? 0 : warp - 3;
-    atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + plane, (unsigned long long)nobs);
+  if (tid == kBook) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (nobs[c])
+        atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + c, (unsigned long long)nobs[c]);
   }
 }
 
