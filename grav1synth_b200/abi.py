@@ -83,7 +83,8 @@ class CDiffConfig(C.Structure):
         ("batch_frames", C.c_int32),
         ("mode", C.c_int32),
         ("gram_kernel", C.c_int32),
-        ("reserved_", C.c_int32 * 5),
+        ("host_threads", C.c_int32),
+        ("reserved_", C.c_int32 * 4),
     ]
 
 

@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         _nvcc(), "-shared", "-o", LIB,
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-        "-Xcompiler", "-fPIC,-O3,-ffp-contract=off,-Wall",
+        "-Xcompiler", "-fPIC,-O3,-ffp-contract=off,-fno-math-errno,-Wall,-pthread",
         "-Xptxas", "-v" if verbose else "-O3",
         "-I", os.path.join(HERE, "..", "include"),
     ] + [os.path.join(CSRC, f) for f in SOURCES]

@@ -11,7 +11,12 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -29,6 +34,74 @@ namespace {
 thread_local std::string g_create_error;
 
 constexpr int kSlots = 3;
+
+// Minimal fork-join pool for the per-frame (order independent) half of the host model.
+class HostPool {
+ public:
+  explicit HostPool(int threads) {
+    for (int i = 1; i < threads; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto &t : workers_) t.join();
+  }
+  // runs fn(0..n-1), the caller participates; returns when all are done
+  void parallel_for(int n, const std::function<void(int)> &fn) {
+    if (n <= 0) return;
+    if (workers_.empty() || n == 1) {
+      for (int i = 0; i < n; ++i) fn(i);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> l(m_);
+      fn_ = &fn;
+      n_ = n;
+      next_.store(0);
+      pending_ = n;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    run_items();
+    std::unique_lock<std::mutex> l(m_);
+    done_cv_.wait(l, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void run_items() {
+    for (;;) {
+      const int i = next_.fetch_add(1);
+      if (i >= n_) return;
+      (*fn_)(i);
+      std::lock_guard<std::mutex> l(m_);
+      if (--pending_ == 0) done_cv_.notify_all();
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return stop_ || epoch_ != seen; });
+        if (stop_) return;
+        seen = epoch_;
+      }
+      run_items();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int)> *fn_ = nullptr;
+  std::atomic<int> next_{0};
+  int n_ = 0, pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
 
 struct PlaneGeom {
   int w, h;          // storage size in samples
@@ -65,6 +138,8 @@ struct g1s_diff {
   int cur = 0;            // slot being filled
   int oldest = 0;         // oldest slot possibly in flight
   std::unique_ptr<DiffSequencer> seq;
+  std::unique_ptr<HostPool> pool;
+  std::vector<LatestFrame> latest;  // one per frame of a batch, reused
   std::string err;
   bool finished = false;
   int64_t pushed = 0;
@@ -98,6 +173,21 @@ FrameRecordView view_of(const g1s_diff *d, const uint8_t *rec) {
   v.rsq = reinterpret_cast<const uint32_t *>(rec + d->rl.off_rsq);
   v.flat = rec + d->rl.off_flat;
   return v;
+}
+
+// Per-frame model evaluation in parallel, then tap + merge in frame order.
+void fold_records(g1s_diff *d, const uint8_t *recs, int count, size_t stride) {
+  const bool model = d->cfg.mode != G1S_MODE_PRODUCER;
+  if (model) {
+    if ((int)d->latest.size() < count) d->latest.resize(count);
+    const NoiseModel &nm = d->seq->model();
+    d->pool->parallel_for(count, [&](int i) { nm.compute_latest(view_of(d, recs + (size_t)i * stride), d->latest[i]); });
+  }
+  for (int i = 0; i < count; ++i) {
+    if (d->tap) d->tap(d->tap_user, d->retired, recs + (size_t)i * stride, d->rl.bytes);
+    if (model) d->seq->consume_latest(d->latest[i]);
+    d->retired++;
+  }
 }
 
 int submit(g1s_diff *d, Slot &s) {
@@ -146,12 +236,7 @@ int retire(g1s_diff *d, Slot &s) {
   float ms = 0;
   if (cudaEventElapsedTime(&ms, s.k0_beg, s.k0_end) == cudaSuccess) d->k0_ms += ms;
   if (cudaEventElapsedTime(&ms, s.k1_beg, s.k1_end) == cudaSuccess) d->k1_ms += ms;
-  for (int i = 0; i < s.count; ++i) {
-    const uint8_t *rec = s.h_records + (size_t)i * d->rl.bytes;
-    if (d->tap) d->tap(d->tap_user, d->retired, rec, d->rl.bytes);
-    if (d->cfg.mode != G1S_MODE_PRODUCER) d->seq->consume(view_of(d, rec));
-    d->retired++;
-  }
+  fold_records(d, s.h_records, s.count, d->rl.bytes);
   d->frames_done += s.count;
   s.in_flight = false;
   s.count = 0;
@@ -280,6 +365,12 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   d->rl = RecordLayout::make(g.nb);
   flat_block_ata_inv(d->fc.ata_inv);
   d->seq.reset(new DiffSequencer(cfg->fps_num, cfg->fps_den, d->sgeom));
+  {
+    int threads = cfg->host_threads;
+    if (const char *e = std::getenv("G1S_HOST_THREADS")) threads = std::atoi(e);
+    if (threads <= 0) threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    d->pool.reset(new HostPool(cfg->mode == G1S_MODE_PRODUCER ? 1 : threads));
+  }
 
   size_t off = 0;
   for (int c = 0; c < g.planes; ++c) {
@@ -426,9 +517,25 @@ int g1s_diff_consume_record(g1s_diff *d, const void *record, size_t bytes) {
     d->err = "record size does not match this stream's geometry";
     return G1S_E_ARG;
   }
-  d->seq->consume(view_of(d, static_cast<const uint8_t *>(record)));
+  fold_records(d, static_cast<const uint8_t *>(record), 1, bytes);
   d->pushed++;
   d->frames_done += 1;
+  return G1S_OK;
+}
+
+int g1s_diff_consume_records(g1s_diff *d, const void *records, size_t count, size_t stride_bytes) {
+  if (!d || (!records && count)) return G1S_E_ARG;
+  if (d->cfg.mode != G1S_MODE_CONSUMER || d->finished) {
+    d->err = "consume_records needs an unfinished CONSUMER handle";
+    return G1S_E_STATE;
+  }
+  if (stride_bytes < d->rl.bytes) {
+    d->err = "record stride smaller than this stream's record size";
+    return G1S_E_ARG;
+  }
+  fold_records(d, static_cast<const uint8_t *>(records), (int)count, stride_bytes);
+  d->pushed += (int64_t)count;
+  d->frames_done += (double)count;
   return G1S_OK;
 }
 

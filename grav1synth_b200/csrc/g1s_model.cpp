@@ -210,14 +210,27 @@ static void chroma_fallback(LinearSystem &e) {
 
 // -------------------------------------------------------------------- NoiseModel
 NoiseModel::NoiseModel(const StreamGeometry &g)
-    : latest{ChannelState(24), ChannelState(25), ChannelState(25)},
-      combined{ChannelState(24), ChannelState(25), ChannelState(25)},
-      g_(g) {}
+    : combined{ChannelState(24), ChannelState(25), ChannelState(25)}, g_(g) {
+  // add_noise_std_observations keeps a block when it has more than 32 samples; luma and chroma agree on
+  // that for every block unless the frame ends in a sliver, in which case nothing is shared below.
+  same_blocks_ = true;
+  cnt_luma_.resize(g_.nb);
+  cnt_chroma_.resize(g_.nb);
+  for (int by = 0; by < g_.nbh; ++by)
+    for (int bx = 0; bx < g_.nbw; ++bx) {
+      const int lw = std::min(g_.width - bx * kBlock, kBlock), lh = std::min(g_.height - by * kBlock, kBlock);
+      const int bw = kBlock >> g_.ss_x, bh = kBlock >> g_.ss_y;
+      const int cw = std::min((g_.width >> g_.ss_x) - bx * bw, bw), ch = std::min((g_.height >> g_.ss_y) - by * bh, bh);
+      // samples of the (frame-clipped) block: max_w * max_h of get_block_mean / get_noise_var
+      cnt_luma_[by * g_.nbw + bx] = lw * lh;
+      cnt_chroma_[by * g_.nbw + bx] = cw * ch;
+      if ((lw * lh > kBlock) != (cw * ch > kBlock)) same_blocks_ = false;
+    }
+}
 
 // Integer Gram -> the f64 normal equations add_block_observations would hold: every entry is
 // (exact sum) / (tap scale, a power of two) / 255^2 with a single rounding.
-void NoiseModel::load_equations(int c, const FrameRecordView &rec) {
-  ChannelState &st = latest[c];
+void NoiseModel::load_equations(int c, const FrameRecordView &rec, ChannelState &st) const {
   const int n = st.eqns.n;
   const int64_t *G = rec.gram + (size_t)c * kPairs;
   const double nss = c ? (double)(1 << (g_.ss_x + g_.ss_y)) : 1.0;
@@ -232,37 +245,104 @@ void NoiseModel::load_equations(int c, const FrameRecordView &rec) {
   st.num_observations += rec.nobs[c];
 }
 
-void NoiseModel::add_strength_measurements(int c, const FrameRecordView &rec) {
-  const int sx = c ? g_.ss_x : 0, sy = c ? g_.ss_y : 0;
-  const int bw = kBlock >> sx, bh = kBlock >> sy;
-  const int pw = g_.width >> sx, ph = g_.height >> sy;
-  StrengthSolver &solver = latest[c].strength;
-  const StrengthSolver &luma = latest[0].strength;
-  const double luma_gain = latest[0].ar_gain;
-  const double noise_gain = latest[c].ar_gain;
-  const double corr = c > 0 ? latest[c].eqns.x[24] : 0;
-  for (int by = 0; by < g_.nbh; ++by) {
-    for (int bx = 0; bx < g_.nbw; ++bx) {
-      const int b = by * g_.nbw + bx;
-      if (!rec.flat[b]) continue;
-      const int ns_h = std::min(ph - by * bh, bh), ns_w = std::min(pw - bx * bw, bw);
-      if (ns_w * ns_h > kBlock) {
-        const int lw = std::min(g_.width - bx * kBlock, kBlock), lh = std::min(g_.height - by * kBlock, kBlock);
-        const double block_mean = (double)rec.luma_sum[b] / (lw * lh);
-        const int cnt = ns_w * ns_h;
-        const double noise_mean = (double)rec.rsum[(size_t)c * g_.nb + b] / cnt;
-        const double noise_var = (double)rec.rsq[(size_t)c * g_.nb + b] / cnt - noise_mean * noise_mean;
-        const double luma_strength = c > 0 ? luma_gain * luma.value_at(block_mean) : 0;
-        const double t = corr * luma_strength;
-        const double uncorr_std = std::sqrt(std::fmax(noise_var / 16, noise_var - t * t));
-        solver.add_measurement(block_mean, uncorr_std / noise_gain);
-      }
-    }
+namespace {
+// The per-block arithmetic of add_noise_std_observations (get_block_mean, get_noise_var, bin index,
+// uncorrelated-std formula) as flat loops over ALL blocks of the frame, so the compiler vectorises the
+// divides and square roots (IEEE results do not depend on the vector width).  Blocks that do not
+// contribute are computed too and simply never read.
+
+// NoiseStrengthSolver::get_bin_index(block_mean) -> integer bin and interpolation weight
+__attribute__((target_clones("avx2", "default"))) void block_bins(int n, const unsigned *__restrict__ luma_sum,
+                                                                  const int *__restrict__ cnt, int nbins,
+                                                                  int *__restrict__ bin0, double *__restrict__ frac) {
+  const double scale = (double)(nbins - 1);
+  for (int b = 0; b < n; ++b) {
+    const double block_mean = (double)luma_sum[b] / (double)cnt[b];
+    const double val = block_mean < 0.0 ? 0.0 : (block_mean > 255.0 ? 255.0 : block_mean);
+    const double bin = scale * (val - 0.0) / 255.0;
+    const int i0 = (int)bin;  // == floor: bin >= 0
+    bin0[b] = i0;
+    frac[b] = bin - (double)i0;
   }
 }
 
-bool NoiseModel::is_different() const {
-  const LinearSystem &lx = latest[0].eqns, &cx = combined[0].eqns;
+// luma_gain * NoiseStrengthSolver::get_value(luma, block_mean)
+__attribute__((target_clones("avx2", "default"))) void block_luma_strength(int n, const int *__restrict__ bin0,
+                                                                           const double *__restrict__ frac,
+                                                                           const double *__restrict__ x, int nbins,
+                                                                           double luma_gain, double *__restrict__ out) {
+  for (int b = 0; b < n; ++b) {
+    const int i0 = bin0[b], i1 = i0 + 1 < nbins - 1 ? i0 + 1 : nbins - 1;
+    const double a = frac[b];
+    out[b] = luma_gain * ((1.0 - a) * x[i0] + a * x[i1]);
+  }
+}
+
+__attribute__((target_clones("avx2", "default"))) void block_strengths(
+    int n, const int *__restrict__ rsum, const unsigned *__restrict__ rsq, const int *__restrict__ cnt,
+    const double *__restrict__ luma_strength, double corr, double noise_gain, double *__restrict__ out) {
+  for (int b = 0; b < n; ++b) {
+    const double c = (double)cnt[b];
+    const double noise_mean = (double)rsum[b] / c;
+    const double noise_var = (double)rsq[b] / c - noise_mean * noise_mean;
+    const double t = corr * luma_strength[b];
+    const double lo = noise_var / 16, hi = noise_var - t * t;
+    const double m = hi != hi ? lo : (lo > hi ? lo : hi);  // fmax(lo, hi), branch-free
+    out[b] = std::sqrt(m) / noise_gain;
+  }
+}
+}  // namespace
+
+void NoiseModel::add_strength_measurements(int c, const FrameRecordView &rec, LatestFrame &lf) const {
+  const int nb = g_.nb;
+  StrengthSolver &solver = lf.ch[c].strength;
+  const StrengthSolver &luma = lf.ch[0].strength;
+  const double corr = c > 0 ? lf.ch[c].eqns.x[24] : 0;
+  const int nbins = solver.num_bins;
+  const std::vector<int> &cnt = c ? cnt_chroma_ : cnt_luma_;
+
+  // pass 1 (once per frame): block mean -> bin index and interpolation weight, shared by all channels
+  if (c == 0) {
+    lf.bin0.resize(nb);
+    lf.frac.resize(nb);
+    lf.mean.resize(nb);
+    lf.strength.assign(nb, 0.0);
+    block_bins(nb, rec.luma_sum, cnt_luma_.data(), nbins, lf.bin0.data(), lf.frac.data());
+  } else {
+    block_luma_strength(nb, lf.bin0.data(), lf.frac.data(), luma.eqns.x.data(), nbins, lf.ch[0].ar_gain,
+                        lf.strength.data());
+  }
+  // pass 2: per-block adjusted strength of this channel
+  block_strengths(nb, rec.rsum + (size_t)c * nb, rec.rsq + (size_t)c * nb, cnt.data(), lf.strength.data(), corr,
+                  lf.ch[c].ar_gain, lf.mean.data());
+  // pass 3: NoiseStrengthSolver::add_measurement in block order (the sums are order dependent)
+  const bool reuse_A = c > 0 && same_blocks_;
+  double *A = solver.eqns.A.data(), *bv = solver.eqns.b.data();
+  const double *std_of = lf.mean.data();
+  double total = solver.total;
+  int m = 0;
+  for (int b = 0; b < nb; ++b) {
+    if (!rec.flat[b] || cnt[b] <= kBlock) continue;  // "> block_size samples" guard of the reference
+    const int i0 = lf.bin0[b], i1 = std::min(nbins - 1, i0 + 1);
+    const double a = lf.frac[b], s = std_of[b];
+    if (!reuse_A) {
+      A[i0 * nbins + i0] += (1.0 - a) * (1.0 - a);
+      A[i1 * nbins + i0] += a * (1.0 - a);
+      A[i1 * nbins + i1] += a * a;
+      A[i0 * nbins + i1] += a * (1.0 - a);
+    }
+    bv[i0] += (1.0 - a) * s;
+    bv[i1] += a * s;
+    total += s;
+    ++m;
+  }
+  if (reuse_A) solver.eqns.A = luma.eqns.A;  // same blocks, same weights, same order: identical sums
+  solver.total = total;
+  solver.num_equations += m;
+}
+
+bool NoiseModel::is_different(const LatestFrame &lf) const {
+  const LinearSystem &lx = lf.ch[0].eqns, &cx = combined[0].eqns;
   double c = 0, a_len = 0, b_len = 0;
   for (int i = 0; i < cx.n; ++i) {
     a_len += lx.x[i] * lx.x[i];
@@ -271,8 +351,8 @@ bool NoiseModel::is_different() const {
   }
   const double corr = c / (std::sqrt(a_len) * std::sqrt(b_len));
   if (corr < 0.9) return true;
-  const LinearSystem &le = latest[0].strength.eqns, &ce = combined[0].strength.eqns;
-  const double dx = 1.0 / latest[0].strength.num_bins;
+  const LinearSystem &le = lf.ch[0].strength.eqns, &ce = combined[0].strength.eqns;
+  const double dx = 1.0 / lf.ch[0].strength.num_bins;
   double diff = 0, total_weight = 0;
   for (int j = 0; j < le.n; ++j) {
     double weight = 0;
@@ -284,38 +364,63 @@ bool NoiseModel::is_different() const {
   return diff * dx / total_weight > 0.005;
 }
 
-NoiseStatus NoiseModel::update(const FrameRecordView &rec) {
-  for (auto &s : latest) {
+// The per-frame half of NoiseModel::update: clear latest, check the flat-block count, then per channel
+// add_block_observations (here: load the integer Gram), solve the AR system, add the strength
+// measurements and solve the strength system.  Stops at the first NoiseStatus::Error.
+void NoiseModel::compute_latest(const FrameRecordView &rec, LatestFrame &lf) const {
+  for (auto &s : lf.ch) {
     s.eqns.clear();
     s.num_observations = 0;
+    s.ar_gain = 1.0;
     s.strength.clear();
   }
-  if (rec.num_flat <= 1) {
+  lf.channels = 0;
+  lf.fail_channel = -1;
+  lf.fail_text = nullptr;
+  lf.enough_flat = rec.num_flat > 1;
+  if (!lf.enough_flat) return;
+  for (int c = 0; c < g_.planes; ++c) {
+    const bool is_chroma = c != 0;
+    lf.channels = c + 1;
+    load_equations(c, rec, lf.ch[c]);
+    if (!lf.ch[c].solve_ar(is_chroma)) {
+      if (is_chroma) {
+        chroma_fallback(lf.ch[c].eqns);
+      } else {
+        lf.fail_channel = c;
+        lf.fail_text = "Solving latest noise equation system failed 0!";
+        return;
+      }
+    }
+    add_strength_measurements(c, rec, lf);
+    if (!lf.ch[c].strength.solve()) {
+      lf.fail_channel = c;
+      lf.fail_text = "Solving latest noise strength failed!";
+      return;
+    }
+  }
+}
+
+// The sequential half: compare with / merge into the combined state, in the reference's statement
+// order (channel by channel, so an error in channel c leaves channels < c merged, as the reference does).
+NoiseStatus NoiseModel::fold(const LatestFrame &lf) {
+  last_ = &lf;
+  if (!lf.enough_flat) {
     err_ = "Not enough flat blocks to update noise estimate";
     return NoiseStatus::Error;
   }
   bool y_model_different = false;
   for (int c = 0; c < g_.planes; ++c) {
     const bool is_chroma = c != 0;
-    load_equations(c, rec);
-    if (!latest[c].solve_ar(is_chroma)) {
-      if (is_chroma) {
-        chroma_fallback(latest[c].eqns);
-      } else {
-        err_ = "Solving latest noise equation system failed 0!";
-        return NoiseStatus::Error;
-      }
-    }
-    add_strength_measurements(c, rec);
-    if (!latest[c].strength.solve()) {
-      err_ = "Solving latest noise strength failed!";
+    if (lf.fail_channel == c) {
+      err_ = lf.fail_text;
       return NoiseStatus::Error;
     }
-    if (c == 0 && combined[0].strength.num_equations > 0 && is_different()) y_model_different = true;
+    if (c == 0 && combined[0].strength.num_equations > 0 && is_different(lf)) y_model_different = true;
     if (y_model_different) continue;
 
-    combined[c].num_observations += latest[c].num_observations;
-    combined[c].eqns.add(latest[c].eqns);
+    combined[c].num_observations += lf.ch[c].num_observations;
+    combined[c].eqns.add(lf.ch[c].eqns);
     if (!combined[c].solve_ar(is_chroma)) {
       if (is_chroma) {
         chroma_fallback(combined[c].eqns);
@@ -324,7 +429,7 @@ NoiseStatus NoiseModel::update(const FrameRecordView &rec) {
         return NoiseStatus::Error;
       }
     }
-    combined[c].strength.add(latest[c].strength);
+    combined[c].strength.add(lf.ch[c].strength);
     if (!combined[c].strength.solve()) {
       err_ = "Solving combined noise strength failed!";
       return NoiseStatus::Error;
@@ -333,13 +438,19 @@ NoiseStatus NoiseModel::update(const FrameRecordView &rec) {
   return y_model_different ? NoiseStatus::DifferentType : NoiseStatus::Ok;
 }
 
+NoiseStatus NoiseModel::update(const FrameRecordView &rec) {
+  compute_latest(rec, scratch_);
+  return fold(scratch_);
+}
+
 void NoiseModel::save_latest() {
+  const LatestFrame &lf = *last_;
   for (int c = 0; c < 3; ++c) {
-    combined[c].eqns.copy_from(latest[c].eqns);
-    combined[c].strength.eqns.copy_from(latest[c].strength.eqns);
-    combined[c].strength.num_equations = latest[c].strength.num_equations;
-    combined[c].num_observations = latest[c].num_observations;
-    combined[c].ar_gain = latest[c].ar_gain;
+    combined[c].eqns.copy_from(lf.ch[c].eqns);
+    combined[c].strength.eqns.copy_from(lf.ch[c].strength.eqns);
+    combined[c].strength.num_equations = lf.ch[c].strength.num_equations;
+    combined[c].num_observations = lf.ch[c].num_observations;
+    combined[c].ar_gain = lf.ch[c].ar_gain;
   }
 }
 
@@ -428,9 +539,9 @@ void NoiseModel::grain_parameters(uint64_t start_ts, uint64_t end_ts, g1s_segmen
 DiffSequencer::DiffSequencer(int64_t fps_num, int64_t fps_den, const StreamGeometry &g)
     : fps_num_(fps_num), fps_den_(fps_den), model_(g) {}
 
-void DiffSequencer::consume(const FrameRecordView &rec) {
+void DiffSequencer::after_update(NoiseStatus st) {
   // NoiseStatus::Error is swallowed, as in the crate (status is only compared to DifferentType).
-  if (model_.update(rec) == NoiseStatus::DifferentType) {
+  if (st == NoiseStatus::DifferentType) {
     const uint64_t cur = (uint64_t)frame_count_ * 10000000ull * (uint64_t)fps_den_ / (uint64_t)fps_num_;
     g1s_segment seg;
     model_.grain_parameters(prev_timestamp_, cur, &seg);
@@ -440,6 +551,10 @@ void DiffSequencer::consume(const FrameRecordView &rec) {
   }
   ++frame_count_;
 }
+
+void DiffSequencer::consume(const FrameRecordView &rec) { after_update(model_.update(rec)); }
+
+void DiffSequencer::consume_latest(const LatestFrame &lf) { after_update(model_.fold(lf)); }
 
 std::vector<g1s_segment> DiffSequencer::finish() {
   std::vector<g1s_segment> out(table_);

@@ -73,21 +73,43 @@ struct ChannelState {
   bool solve_ar(bool is_chroma);
 };
 
+// Everything NoiseModel::update derives from ONE frame before it looks at the combined state: the
+// three "latest" channel states.  A pure function of the frame's record, so the frames of a batch
+// are evaluated in parallel (host thread pool) and only `fold` runs in frame order.
+struct LatestFrame {
+  LatestFrame() : ch{ChannelState(24), ChannelState(25), ChannelState(25)} {}
+  ChannelState ch[3];
+  bool enough_flat = false;
+  int channels = 0;       // channels evaluated (stops at the first failing one)
+  int fail_channel = -1;  // channel whose evaluation hit NoiseStatus::Error, -1 if none
+  const char *fail_text = nullptr;
+  // scratch reused across frames (per-block bin data shared by the three channels)
+  std::vector<int> bin0;
+  std::vector<double> frac, mean, strength;
+};
+
 class NoiseModel {
  public:
   explicit NoiseModel(const StreamGeometry &g);
+  // NoiseModel::update = compute_latest (thread-safe, const) + fold (sequential)
+  void compute_latest(const FrameRecordView &rec, LatestFrame &out) const;
+  NoiseStatus fold(const LatestFrame &lf);
   NoiseStatus update(const FrameRecordView &rec);
   void save_latest();
   void grain_parameters(uint64_t start_ts, uint64_t end_ts, g1s_segment *seg) const;
   const std::string &last_error() const { return err_; }
-  ChannelState latest[3], combined[3];
+  ChannelState combined[3];
 
  private:
-  void load_equations(int c, const FrameRecordView &rec);
-  void add_strength_measurements(int c, const FrameRecordView &rec);
-  bool is_different() const;
+  void load_equations(int c, const FrameRecordView &rec, ChannelState &st) const;
+  void add_strength_measurements(int c, const FrameRecordView &rec, LatestFrame &lf) const;
+  bool is_different(const LatestFrame &lf) const;
   StreamGeometry g_;
   std::string err_;
+  LatestFrame scratch_;        // used by update()
+  const LatestFrame *last_ = nullptr;  // the frame save_latest() copies from
+  bool same_blocks_;           // luma and chroma contribute the same blocks to the strength solver
+  std::vector<int> cnt_luma_, cnt_chroma_;  // samples per frame-clipped block
 };
 
 // DiffGenerator minus the pixels: frame counter, timestamps, segment list.
@@ -95,11 +117,13 @@ class DiffSequencer {
  public:
   DiffSequencer(int64_t fps_num, int64_t fps_den, const StreamGeometry &g);
   void consume(const FrameRecordView &rec);
+  void consume_latest(const LatestFrame &lf);  // same, for a frame whose latest state is already evaluated
   std::vector<g1s_segment> finish();
   int64_t frames() const { return frame_count_; }
   NoiseModel &model() { return model_; }
 
  private:
+  void after_update(NoiseStatus st);
   int64_t fps_num_, fps_den_;
   int64_t frame_count_ = 0;
   uint64_t prev_timestamp_ = 0;

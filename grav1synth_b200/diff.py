@@ -28,7 +28,7 @@ EXPORTS = [
     "g1s_abi_version", "g1s_diff_create", "g1s_diff_push_frame", "g1s_diff_push_frame_device", "g1s_diff_flush",
     "g1s_diff_finish", "g1s_diff_destroy", "g1s_diff_last_error", "g1s_diff_frames_pushed",
     "g1s_diff_get_counters", "g1s_record_layout", "g1s_diff_record_bytes", "g1s_diff_set_record_tap",
-    "g1s_diff_consume_record", "g1s_write_grain_table", "g1s_format_grain_table",
+    "g1s_diff_consume_record", "g1s_diff_consume_records", "g1s_write_grain_table", "g1s_format_grain_table",
 ]
 
 
@@ -65,6 +65,7 @@ def lib() -> C.CDLL:
         L.g1s_diff_record_bytes.restype = C.c_size_t
         L.g1s_diff_set_record_tap.argtypes = [C.c_void_p, RECORD_FN, C.c_void_p]
         L.g1s_diff_consume_record.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.g1s_diff_consume_records.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
         L.g1s_write_grain_table.argtypes = [C.POINTER(CSegment), C.c_size_t, C.c_char_p]
         L.g1s_format_grain_table.argtypes = [C.POINTER(CSegment), C.c_size_t, C.c_char_p, C.c_size_t]
         L.g1s_format_grain_table.restype = C.c_int64
@@ -129,7 +130,7 @@ class DiffGenerator:
 
     def __init__(self, fps_num: int, fps_den: int, source_bit_depth: int, denoised_bit_depth: int, width: int,
                  height: int, ss_x: int = 1, ss_y: int = 1, monochrome: bool = False, device: int = 0,
-                 batch_frames: int = 0, mode: int = abi.MODE_FULL, gram_kernel: int = 0):
+                 batch_frames: int = 0, mode: int = abi.MODE_FULL, gram_kernel: int = 0, host_threads: int = 0):
         self._L = lib()
         cfg = CDiffConfig()
         cfg.fps_num, cfg.fps_den = fps_num, fps_den
@@ -137,6 +138,7 @@ class DiffGenerator:
         cfg.width, cfg.height, cfg.ss_x, cfg.ss_y = width, height, ss_x, ss_y
         cfg.monochrome, cfg.device, cfg.batch_frames, cfg.mode = int(monochrome), device, batch_frames, mode
         cfg.gram_kernel = gram_kernel
+        cfg.host_threads = host_threads
         self.cfg = cfg
         h = C.c_void_p()
         rc = self._L.g1s_diff_create(C.byref(cfg), C.byref(h))
@@ -220,6 +222,12 @@ class DiffGenerator:
     def consume_record(self, rec: np.ndarray) -> None:
         rec = np.ascontiguousarray(rec.view(np.uint8))
         self._check(self._L.g1s_diff_consume_record(self._h, rec.ctypes.data, rec.size))
+
+    def consume_records(self, recs: np.ndarray) -> None:
+        """recs: (count, record_bytes) uint8, consecutive frames in order."""
+        recs = np.ascontiguousarray(recs.view(np.uint8))
+        assert recs.ndim == 2
+        self._check(self._L.g1s_diff_consume_records(self._h, recs.ctypes.data, recs.shape[0], recs.strides[0]))
 
     @property
     def frames_pushed(self) -> int:

@@ -81,10 +81,9 @@ class ShardedDiff:
                 if seen_short and c:
                     raise RuntimeError("frames are not contiguous across ranks in this super-batch")
                 seen_short |= c < self.B
-                arr = allbuf[r].numpy()
-                for i in range(c):
-                    self.consumer.consume_record(arr[i])
-                    folded += 1
+                if c:
+                    self.consumer.consume_records(allbuf[r].numpy()[:c])
+                    folded += c
         return folded
 
     def finish(self):

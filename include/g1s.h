@@ -114,7 +114,9 @@ typedef struct g1s_diff_config {
   int32_t mode;                 /* enum g1s_mode                                     */
   int32_t gram_kernel;          /* 0 = auto (int8 tensor-core kernel when the stream
                                    allows it), 1 = force the generic int32 kernel    */
-  int32_t reserved_[5];
+  int32_t host_threads;         /* threads evaluating the per-frame half of the host model;
+                                   0 = auto (half the cores, at most 8)              */
+  int32_t reserved_[4];
 } g1s_diff_config;
 
 typedef struct g1s_diff g1s_diff;
@@ -172,6 +174,9 @@ typedef void (*g1s_record_fn)(void *user, int64_t frame_index, const void *recor
 int g1s_diff_set_record_tap(g1s_diff *d, g1s_record_fn fn, void *user);
 /* CONSUMER handles: fold one record (next frame in order) into the model. */
 int g1s_diff_consume_record(g1s_diff *d, const void *record, size_t bytes);
+/* Same for `count` consecutive frames, record k at records + k * stride_bytes; the per-frame half of
+ * the model is evaluated on the handle's host threads, the merge stays in frame order. */
+int g1s_diff_consume_records(g1s_diff *d, const void *records, size_t count, size_t stride_bytes);
 
 /* `filmgrn1` writer — src/main.rs:525-530 and 631-696, byte for byte. */
 int g1s_write_grain_table(const g1s_segment *segs, size_t n, const char *path);
