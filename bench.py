@@ -39,7 +39,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k10", choices=list(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=16, help="frame pairs per step per GPU")
+    ap.add_argument("--frames", type=int, default=32, help="frame pairs per step per GPU")
+    ap.add_argument("--batch", type=int, default=8, help="frame pairs per kernel launch (engine batch)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the CPU-baseline sample")
@@ -192,7 +193,7 @@ def main():
     if world == 1:
         # single GPU: the drop-in handle itself (kernels + host model), frames pushed as device pointers
         sd = None
-        eng = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=F)
+        eng = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=args.batch)
 
         def step():
             for (sp, ss), (dp, ds) in dev_args:
@@ -239,7 +240,7 @@ def main():
     # dominant kernel: fused residual + Gram accumulation, CUDA events on the engine's stream
     gram_ms = (c1["gram_ms"] - c0["gram_ms"]) / max(1.0, c1["gram_launches"] - c0["gram_launches"])
     flat_ms = (c1["flat_ms"] - c0["flat_ms"]) / max(1.0, c1["flat_launches"] - c0["flat_launches"])
-    frames_per_launch = F
+    frames_per_launch = min(F, args.batch) if world == 1 else F
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -255,7 +256,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": wl["label"], "frames_per_step_per_gpu": F, "bytes_per_frame_pair": pair_bytes,
+        "config": {"workload": wl["label"], "frames_per_step_per_gpu": F, "frames_per_launch": frames_per_launch, "bytes_per_frame_pair": pair_bytes,
                    "l2": f"inputs larger than L2 ({F * pair_bytes / 1e6:.0f} MB per step per GPU)",
                    "parallelism": f"frame-sharded x{world}, NCCL all-gather of per-frame records",
                    "device_ms_flat_kernel": flat_ms, "device_ms_gram_kernel": gram_ms},
@@ -281,7 +282,7 @@ def main():
         np_frames = [([t.numpy().view(np.uint16) if bd > 8 else t.numpy() for t in hs],
                       [t.numpy().view(np.uint16) if bd > 8 else t.numpy() for t in hd]) for hs, hd in host]
         if world == 1:
-            g = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank)
+            g = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=args.batch)
             sd2 = None
 
             def e2e_step():

@@ -198,7 +198,10 @@ int submit(g1s_diff *d, Slot &s) {
   CU_TRY(d, cudaMemcpyAsync(s.d_descs, s.h_descs, sizeof(FrameDesc) * s.count, cudaMemcpyHostToDevice, st));
   CU_TRY(d, cudaMemsetAsync(s.d_records, 0, d->rl.bytes * s.count, st));
   CU_TRY(d, cudaEventRecord(s.k0_beg, st));
-  launch_flat_features(s.d_descs, s.count, d->geom, d->fc, s.d_records, d->rl, st);
+  bool luma16 = true;  // 16-byte aligned source-luma rows -> 128-bit loads in the flat-block kernel
+  for (int i = 0; i < s.count && luma16; ++i)
+    if (((uintptr_t)s.h_descs[i].src[0] | s.h_descs[i].src_stride[0]) & 15) luma16 = false;
+  launch_flat_features(s.d_descs, s.count, d->geom, d->fc, s.d_records, d->rl, luma16, st);
   CU_TRY(d, cudaEventRecord(s.k0_end, st));
   launch_flat_select(s.count, d->geom, s.d_records, d->rl, st);
   CU_TRY(d, cudaEventRecord(s.k1_beg, st));

@@ -90,45 +90,87 @@ __device__ __forceinline__ double exp_fixed(double x) {
 
 // ------------------------------------------------------------------- flat_features_kernel
 //
-// One thread per (frame, block).  The reference's sums are sequential f64 chains in
-// row-major pixel order, so the block is walked by one thread; parallelism comes from
-// the 8160 blocks per 4K frame times the frames of a batch.  The plane-fit residual
-// rows needed by the central differences live in a 3-row shared-memory ring laid out
-// [row][x][thread] (conflict-free: consecutive lanes touch consecutive doubles).
+// One thread per (frame, block).  The reference's sums are sequential f64 chains in row-major pixel
+// order, so a block is walked by one thread; parallelism comes from the 8160 blocks per 4K frame times
+// the frames of a batch.  What is exact-by-construction and therefore free to restructure:
+//   * pix / 255.0 comes from a 256-entry table (built with the IEEE divide) in shared memory;
+//   * gx = (r - l) / 2 is an exact scaling, so sum (gx*gx) == 0.25 * sum ((r-l)*(r-l)) with identical
+//     roundings: the halvings are dropped and the three gradient sums are scaled by 0.25 at the end;
+//   * the plane-fit residual rows needed by the central differences live in a 2-row shared-memory
+//     ring laid out [row][x][thread] (conflict-free: consecutive lanes touch consecutive doubles);
+//     row y+1 is produced on the fly and overwrites row y-1 in the same step that reads it.
 
 constexpr int kFlatThreads = 128;
 
+// Eight consecutive source-luma samples reduced to 8 bit; coordinates clamped to the frame
+// (FlatBlockFinder::extract_block clamps, it does not pad).
+template <int SB>
+__device__ __forceinline__ void load8(const uint8_t *__restrict__ row, int x0, int w, int shift, bool vec_ok,
+                                      int (&p)[8]) {
+  if (vec_ok && x0 + 8 <= w) {
+    if (SB == 2) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + 2 * x0));
+      const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        p[2 * i] = ((q[i] & 0xFFFFu) >> shift) & 0xFF;
+        p[2 * i + 1] = ((q[i] >> 16) >> shift) & 0xFF;
+      }
+    } else {
+      const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row + x0));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        p[i] = (v.x >> (8 * i)) & 0xFF;
+        p[4 + i] = (v.y >> (8 * i)) & 0xFF;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int x = min(x0 + i, w - 1);
+      p[i] = SB == 2 ? ((reinterpret_cast<const uint16_t *>(row)[x] >> shift) & 0xFF) : row[x];
+    }
+  }
+}
+
+template <int SB>
 __global__ void __launch_bounds__(kFlatThreads)
 flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, FlatConsts fc,
-                     uint8_t *__restrict__ records, RecordLayout rl) {
-  extern __shared__ double ring[];  // [3][32][kFlatThreads]
+                     uint8_t *__restrict__ records, RecordLayout rl, int aligned) {
+  extern __shared__ double fsm[];  // lut[256] | ring[2][32][kFlatThreads]
+  double *lut = fsm;
+  double *ring = fsm + 256;
+  for (int i = threadIdx.x; i < 256; i += kFlatThreads) lut[i] = __ddiv_rn((double)i, 255.0);
+  __syncthreads();
+
   const int gid = blockIdx.x * kFlatThreads + threadIdx.x;
   const int total = nframes * g.nb;
-  const bool active = gid < total;
-  const int f = active ? gid / g.nb : 0;
-  const int b = active ? gid - f * g.nb : 0;
+  if (gid >= total) return;
+  const int f = gid / g.nb;
+  const int b = gid - f * g.nb;
   const int by = b / g.nbw, bx = b - by * g.nbw;
-  const void *src = frames[f].src[0];
+  const uint8_t *src = static_cast<const uint8_t *>(frames[f].src[0]);
   const uint32_t stride = frames[f].src_stride[0];
   const int w = g.width, h = g.height;
   const int x0 = bx * kBlock, y0 = by * kBlock;
   const int tid = threadIdx.x;
-
-  auto pix = [&](int yi, int xi) -> int {
-    const int y = min(y0 + yi, h - 1);
-    const int x = min(x0 + xi, w - 1);
-    return load_sample8(src, stride, y, x, g.src_bytes, g.src_shift);
-  };
+  const bool vec_ok = aligned != 0;
+  const int shift = g.src_shift;
 
   // --- A^T * block (multiply_mat(block, A, ., 1, 1024, 3)): three sequential chains
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  if (active) {
-    for (int yi = 0; yi < kBlock; ++yi) {
-      const double yd = (double)(yi - 16) * 0.0625;
-#pragma unroll 4
-      for (int xi = 0; xi < kBlock; ++xi) {
-        const double xd = (double)(xi - 16) * 0.0625;
-        const double v = div255(pix(yi, xi));
+#pragma unroll 1
+  for (int yi = 0; yi < kBlock; ++yi) {
+    const double yd = (double)(yi - 16) * 0.0625;
+    const uint8_t *row = src + (size_t)min(y0 + yi, h - 1) * stride;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int p[8];
+      load8<SB>(row, x0 + 8 * c, w, shift, vec_ok, p);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double xd = (double)(8 * c + i - 16) * 0.0625;
+        const double v = lut[p[i]];
         s0 = __dadd_rn(s0, __dmul_rn(v, yd));
         s1 = __dadd_rn(s1, __dmul_rn(v, xd));
         s2 = __dadd_rn(s2, v);  // v * 1.0 is exact
@@ -144,51 +186,71 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
     s = __dadd_rn(s, __dmul_rn(fc.ata_inv[r * 3 + 2], s2));
     pc[r] = s;
   }
-  // block[i] -= (A * plane_coords)[i], row by row into the ring
-  auto fill_row = [&](int yi) {
-    const double yd = (double)(yi - 16) * 0.0625;
-    const double ty = __dadd_rn(0.0, __dmul_rn(yd, pc[0]));
-    double *dst = ring + ((size_t)(yi % 3) * kBlock) * kFlatThreads + tid;
-#pragma unroll 4
-    for (int xi = 0; xi < kBlock; ++xi) {
-      const double xd = (double)(xi - 16) * 0.0625;
-      double fit = __dadd_rn(ty, __dmul_rn(xd, pc[1]));
-      fit = __dadd_rn(fit, pc[2]);  // 1.0 * pc[2] is exact
-      dst[(size_t)xi * kFlatThreads] = __dsub_rn(div255(pix(yi, xi)), fit);
-    }
+  // block[i] - (A * plane_coords)[i] for one sample
+  auto resid = [&](int pv, double ty, int xi) -> double {
+    const double xd = (double)(xi - 16) * 0.0625;
+    double fit = __dadd_rn(ty, __dmul_rn(xd, pc[1]));
+    fit = __dadd_rn(fit, pc[2]);  // 1.0 * pc[2] is exact
+    return __dsub_rn(lut[pv], fit);
   };
-  double Gxx = 0, Gxy = 0, Gyy = 0, var = 0, mean = 0;
-  if (active) {
-    fill_row(0);
-    fill_row(1);
-    for (int yi = 1; yi < kBlock - 1; ++yi) {
-      fill_row(yi + 1);
-      const double *up = ring + ((size_t)((yi - 1) % 3) * kBlock) * kFlatThreads + tid;
-      const double *cur = ring + ((size_t)(yi % 3) * kBlock) * kFlatThreads + tid;
-      const double *dn = ring + ((size_t)((yi + 1) % 3) * kBlock) * kFlatThreads + tid;
-      double left = cur[0], mid = cur[kFlatThreads];
-#pragma unroll 2
-      for (int xi = 1; xi < kBlock - 1; ++xi) {
-        const double right = cur[(size_t)(xi + 1) * kFlatThreads];
-        const double gx = __dmul_rn(__dsub_rn(right, left), 0.5);
-        const double gy = __dmul_rn(__dsub_rn(dn[(size_t)xi * kFlatThreads], up[(size_t)xi * kFlatThreads]), 0.5);
-        Gxx = __dadd_rn(Gxx, __dmul_rn(gx, gx));
-        Gxy = __dadd_rn(Gxy, __dmul_rn(gx, gy));
-        Gyy = __dadd_rn(Gyy, __dmul_rn(gy, gy));
-        mean = __dadd_rn(mean, mid);
-        var = __dadd_rn(var, __dmul_rn(mid, mid));
-        left = mid;
-        mid = right;
+  auto row_ty = [&](int yi) -> double {
+    const double yd = (double)(yi - 16) * 0.0625;
+    return __dadd_rn(0.0, __dmul_rn(yd, pc[0]));
+  };
+  // rows 0 and 1 into the ring
+#pragma unroll 1
+  for (int yi = 0; yi < 2; ++yi) {
+    const double ty = row_ty(yi);
+    const uint8_t *row = src + (size_t)min(y0 + yi, h - 1) * stride;
+    double *dst = ring + ((size_t)yi * kBlock) * kFlatThreads + tid;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int p[8];
+      load8<SB>(row, x0 + 8 * c, w, shift, vec_ok, p);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[(size_t)(8 * c + i) * kFlatThreads] = resid(p[i], ty, 8 * c + i);
+    }
+  }
+  // sums of (r-l)^2, (r-l)(d-u), (d-u)^2: the reference's Gxx, Gxy, Gyy are exactly 0.25 times these
+  double Dxx = 0, Dxy = 0, Dyy = 0, var = 0, mean = 0;
+#pragma unroll 1
+  for (int yi = 1; yi < kBlock - 1; ++yi) {
+    const double ty = row_ty(yi + 1);
+    const uint8_t *row = src + (size_t)min(y0 + yi + 1, h - 1) * stride;
+    const double *cur = ring + ((size_t)(yi & 1) * kBlock) * kFlatThreads + tid;
+    double *oth = ring + ((size_t)((yi + 1) & 1) * kBlock) * kFlatThreads + tid;  // row yi-1, becomes row yi+1
+    double left = cur[0], mid = cur[kFlatThreads];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int p[8];
+      load8<SB>(row, x0 + 8 * c, w, shift, vec_ok, p);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int xi = 8 * c + i;
+        const double dn = resid(p[i], ty, xi);
+        if (xi >= 1 && xi <= kBlock - 2) {
+          const double right = cur[(size_t)(xi + 1) * kFlatThreads];
+          const double up = oth[(size_t)xi * kFlatThreads];
+          const double dx = __dsub_rn(right, left);
+          const double dy = __dsub_rn(dn, up);
+          Dxx = __dadd_rn(Dxx, __dmul_rn(dx, dx));
+          Dxy = __dadd_rn(Dxy, __dmul_rn(dx, dy));
+          Dyy = __dadd_rn(Dyy, __dmul_rn(dy, dy));
+          mean = __dadd_rn(mean, mid);
+          var = __dadd_rn(var, __dmul_rn(mid, mid));
+          left = mid;
+          mid = right;
+        }
+        oth[(size_t)xi * kFlatThreads] = dn;
       }
     }
   }
-  if (!active) return;
 
   const double nf = 900.0;  // (BLOCK_SIZE - 2)^2
   mean = __ddiv_rn(mean, nf);
-  Gxx = __ddiv_rn(Gxx, nf);
-  Gxy = __ddiv_rn(Gxy, nf);
-  Gyy = __ddiv_rn(Gyy, nf);
+  const double Gxx = __ddiv_rn(__dmul_rn(Dxx, 0.25), nf);
+  const double Gxy = __ddiv_rn(__dmul_rn(Dxy, 0.25), nf);
+  const double Gyy = __ddiv_rn(__dmul_rn(Dyy, 0.25), nf);
   var = __dsub_rn(__ddiv_rn(var, nf), __dmul_rn(mean, mean));
 
   const double trace = __dadd_rn(Gxx, Gyy);
@@ -215,16 +277,20 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
 }
 
 void launch_flat_features(const FrameDesc *frames, int nframes, const Geometry &g, const FlatConsts &fc,
-                          uint8_t *records, const RecordLayout &rl, cudaStream_t st) {
+                          uint8_t *records, const RecordLayout &rl, bool aligned, cudaStream_t st) {
   const int total = nframes * g.nb;
   const int grid = (total + kFlatThreads - 1) / kFlatThreads;
-  const size_t smem = sizeof(double) * 3 * kBlock * kFlatThreads;
+  const size_t smem = sizeof(double) * (256 + 2 * kBlock * kFlatThreads);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(flat_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flat_features_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(flat_features_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  flat_features_kernel<<<grid, kFlatThreads, smem, st>>>(frames, nframes, g, fc, records, rl);
+  if (g.src_bytes == 2)
+    flat_features_kernel<2><<<grid, kFlatThreads, smem, st>>>(frames, nframes, g, fc, records, rl, aligned ? 1 : 0);
+  else
+    flat_features_kernel<1><<<grid, kFlatThreads, smem, st>>>(frames, nframes, g, fc, records, rl, aligned ? 1 : 0);
 }
 
 // --------------------------------------------------------------------- flat_select_kernel

@@ -53,8 +53,9 @@ struct RecordLayout {
   static RecordLayout make(int nb);
 };
 
+// aligned: every source-luma row start is 16-byte aligned (vector loads allowed).
 void launch_flat_features(const FrameDesc *frames, int nframes, const Geometry &g, const FlatConsts &fc,
-                          uint8_t *records, const RecordLayout &rl, cudaStream_t st);
+                          uint8_t *records, const RecordLayout &rl, bool aligned, cudaStream_t st);
 void launch_flat_select(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, cudaStream_t st);
 // only_overflow = false: every flat block, statistics included (any subsampling, any alignment).
 // only_overflow = true: just the blocks the tensor-core kernel flagged (Gram sums and statistics).
