@@ -116,7 +116,7 @@ struct Slot {
   FrameDesc *h_descs = nullptr;  // pinned
   uint8_t *d_records = nullptr;
   uint8_t *h_records = nullptr;  // pinned
-  cudaEvent_t done = nullptr, k0_beg = nullptr, k0_end = nullptr, k1_beg = nullptr, k1_end = nullptr;
+  cudaEvent_t done = nullptr, k0_beg = nullptr, k0_end = nullptr, k1_beg = nullptr, k1_end = nullptr, copied = nullptr;
   int count = 0;                 // frames staged
   int host_frames = 0;           // of which need the H2D copy (contiguous prefix is not required)
   bool in_flight = false;
@@ -133,7 +133,8 @@ struct g1s_diff {
   PlaneGeom pg[3]{};
   size_t pair_bytes = 0;
   int batch = 1;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // kernels + record read-back
+  cudaStream_t copy_stream = nullptr;  // per-frame host->device copies, overlapping the staging of the next frame
   Slot slots[kSlots];
   int cur = 0;            // slot being filled
   int oldest = 0;         // oldest slot possibly in flight
@@ -193,8 +194,10 @@ void fold_records(g1s_diff *d, const uint8_t *recs, int count, size_t stride) {
 int submit(g1s_diff *d, Slot &s) {
   if (s.count == 0) return G1S_OK;
   cudaStream_t st = d->stream;
-  if (s.host_frames > 0)
-    CU_TRY(d, cudaMemcpyAsync(s.d_frames, s.h_frames, (size_t)s.count * d->pair_bytes, cudaMemcpyHostToDevice, st));
+  if (s.host_frames > 0) {  // frames were sent one by one on the copy stream as they were pushed
+    CU_TRY(d, cudaEventRecord(s.copied, d->copy_stream));
+    CU_TRY(d, cudaStreamWaitEvent(st, s.copied, 0));
+  }
   CU_TRY(d, cudaMemcpyAsync(s.d_descs, s.h_descs, sizeof(FrameDesc) * s.count, cudaMemcpyHostToDevice, st));
   CU_TRY(d, cudaMemsetAsync(s.d_records, 0, d->rl.bytes * s.count, st));
   CU_TRY(d, cudaEventRecord(s.k0_beg, st));
@@ -372,7 +375,7 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     int threads = cfg->host_threads;
     if (const char *e = std::getenv("G1S_HOST_THREADS")) threads = std::atoi(e);
     if (threads <= 0) threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
-    d->pool.reset(new HostPool(cfg->mode == G1S_MODE_PRODUCER ? 1 : threads));
+    d->pool.reset(new HostPool(threads));
   }
 
   size_t off = 0;
@@ -398,6 +401,7 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     return G1S_OK;
   }
   CU_NEW(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  CU_NEW(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
   for (Slot &s : d->slots) {
     CU_NEW(cudaMalloc(&s.d_frames, (size_t)batch * d->pair_bytes));
     CU_NEW(cudaMallocHost(&s.h_frames, (size_t)batch * d->pair_bytes));
@@ -406,6 +410,7 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     CU_NEW(cudaMalloc(&s.d_records, d->rl.bytes * batch));
     CU_NEW(cudaMallocHost(&s.h_records, d->rl.bytes * batch));
     CU_NEW(cudaEventCreate(&s.done));
+    CU_NEW(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
     CU_NEW(cudaEventCreate(&s.k0_beg));
     CU_NEW(cudaEventCreate(&s.k0_end));
     CU_NEW(cudaEventCreate(&s.k1_beg));
@@ -430,6 +435,16 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
   std::memset(&fd, 0, sizeof fd);
   const g1s_frame *fr[2] = {source, denoised};
   const int bytes[2] = {d->geom.src_bytes, d->geom.den_bytes};
+  // The borrowed planes are copied into the pinned staging slot by the host threads, in row chunks of
+  // about 1 MiB, so the copy runs at memory bandwidth rather than at one core's memcpy speed.
+  struct CopyTask {
+    uint8_t *dst;
+    const uint8_t *src;
+    size_t dst_pitch, src_pitch, row_bytes;
+    int rows;
+  };
+  CopyTask tasks[96];
+  int ntasks = 0;
   for (int c = 0; c < d->geom.planes; ++c) {
     const PlaneGeom &p = d->pg[c];
     for (int k = 0; k < 2; ++k) {
@@ -440,11 +455,11 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
       }
       uint8_t *dst = s.h_frames + base + p.off[k];
       const uint8_t *src = static_cast<const uint8_t *>(fr[k]->plane[c]);
-      if (fr[k]->stride_bytes[c] == p.pitch[k]) {
-        std::memcpy(dst, src, p.pitch[k] * (size_t)(p.h - 1) + row_bytes);
-      } else {
-        for (int y = 0; y < p.h; ++y) std::memcpy(dst + (size_t)y * p.pitch[k], src + (size_t)y * fr[k]->stride_bytes[c], row_bytes);
-      }
+      const int chunks = (int)std::min<size_t>(16, std::max<size_t>(1, (row_bytes * p.h) >> 20));
+      const int rows_per = (p.h + chunks - 1) / chunks;
+      for (int r0 = 0; r0 < p.h; r0 += rows_per)
+        tasks[ntasks++] = {dst + (size_t)r0 * p.pitch[k], src + (size_t)r0 * fr[k]->stride_bytes[c], p.pitch[k],
+                           fr[k]->stride_bytes[c], row_bytes, std::min(rows_per, p.h - r0)};
       const void *dev = s.d_frames + base + p.off[k];
       if (k == 0) {
         fd.src[c] = dev;
@@ -455,6 +470,16 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
       }
     }
   }
+  d->pool->parallel_for(ntasks, [&](int i) {
+    const CopyTask &t = tasks[i];
+    if (t.dst_pitch == t.src_pitch) {
+      std::memcpy(t.dst, t.src, t.dst_pitch * (size_t)(t.rows - 1) + t.row_bytes);
+    } else {
+      for (int y = 0; y < t.rows; ++y) std::memcpy(t.dst + (size_t)y * t.dst_pitch, t.src + (size_t)y * t.src_pitch, t.row_bytes);
+    }
+  });
+  CU_TRY(d, cudaMemcpyAsync(s.d_frames + base, s.h_frames + base, d->pair_bytes, cudaMemcpyHostToDevice,
+                            d->copy_stream));
   s.count++;
   s.host_frames++;
   d->pushed++;
@@ -563,6 +588,7 @@ int g1s_diff_finish(g1s_diff *d, g1s_segment *out, size_t cap, size_t *n) {
 
 void g1s_diff_destroy(g1s_diff *d) {
   if (!d) return;
+  if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
   if (d->stream) cudaStreamSynchronize(d->stream);
   for (Slot &s : d->slots) {
     if (s.d_frames) cudaFree(s.d_frames);
@@ -571,10 +597,11 @@ void g1s_diff_destroy(g1s_diff *d) {
     if (s.h_descs) cudaFreeHost(s.h_descs);
     if (s.d_records) cudaFree(s.d_records);
     if (s.h_records) cudaFreeHost(s.h_records);
-    for (cudaEvent_t e : {s.done, s.k0_beg, s.k0_end, s.k1_beg, s.k1_end})
+    for (cudaEvent_t e : {s.done, s.k0_beg, s.k0_end, s.k1_beg, s.k1_end, s.copied})
       if (e) cudaEventDestroy(e);
   }
   if (d->stream) cudaStreamDestroy(d->stream);
+  if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
   delete d;
 }
 
