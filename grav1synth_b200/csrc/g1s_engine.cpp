@@ -8,6 +8,7 @@
 // Three slots rotate, so the caller fills slot k+1 while the device works on slot k and
 // the records of slot k-1 are folded into the model.  There is no CPU fallback: every
 // device failure is reported as G1S_E_CUDA.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -114,6 +115,8 @@ struct Slot {
   uint8_t *h_frames = nullptr;   // pinned mirror
   FrameDesc *d_descs = nullptr;
   FrameDesc *h_descs = nullptr;  // pinned
+  CUtensorMap *d_tmaps = nullptr;  // [B][6] TMA descriptors of the batch's planes
+  CUtensorMap *h_tmaps = nullptr;  // pinned
   uint8_t *d_records = nullptr;
   uint8_t *h_records = nullptr;  // pinned
   cudaEvent_t done = nullptr, k0_beg = nullptr, k0_end = nullptr, k1_beg = nullptr, k1_end = nullptr, copied = nullptr;
@@ -147,6 +150,12 @@ struct g1s_diff {
   int64_t retired = 0;
   g1s_record_fn tap = nullptr;
   void *tap_user = nullptr;
+  // cuTensorMapEncodeTiled, fetched through the runtime so libcuda is not a link dependency
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeTiledFn encode_tiled = nullptr;
+  double tma_batches = 0;
   // counters
   double kernels_launched = 0, k1_ms = 0, k1_launches = 0, k0_ms = 0, k0_launches = 0, frames_done = 0;
 };
@@ -191,6 +200,42 @@ void fold_records(g1s_diff *d, const uint8_t *recs, int count, size_t stride) {
   }
 }
 
+// Builds the six TMA descriptors of every frame of the batch.  Returns false when a plane is not
+// 16-byte aligned (base or pitch) or the driver entry point is missing: the kernel then stages with
+// per-thread loads instead.
+bool build_tensor_maps(g1s_diff *d, Slot &s) {
+  if (!d->encode_tiled || std::getenv("G1S_NO_TMA")) return false;
+  const Geometry &g = d->geom;
+  for (int i = 0; i < s.count; ++i) {
+    const FrameDesc &fd = s.h_descs[i];
+    for (int c = 0; c < g.planes; ++c)
+      if (((uintptr_t)fd.src[c] | (uintptr_t)fd.den[c] | fd.src_stride[c] | fd.den_stride[c]) & 15) return false;
+  }
+  for (int i = 0; i < s.count; ++i) {
+    const FrameDesc &fd = s.h_descs[i];
+    for (int c = 0; c < g.planes; ++c) {
+      for (int k = 0; k < 2; ++k) {
+        const int bytes = k ? g.den_bytes : g.src_bytes;
+        int lw, lh, cw, ch;
+        gram_imma_tma_boxes(bytes, &lw, &lh, &cw, &ch);
+        // extents are the LOOP extents (floor for chroma): everything beyond reads as zero, like the scalar path
+        const cuuint64_t dims[2] = {(cuuint64_t)(c ? g.width >> 1 : g.width), (cuuint64_t)(c ? g.height >> 1 : g.height)};
+        const cuuint64_t strides[1] = {(cuuint64_t)(k ? fd.den_stride[c] : fd.src_stride[c])};
+        const cuuint32_t box[2] = {(cuuint32_t)(c ? cw : lw), (cuuint32_t)(c ? ch : lh)};
+        const cuuint32_t estr[2] = {1, 1};
+        void *base = const_cast<void *>(k ? fd.den[c] : fd.src[c]);
+        const CUresult r = d->encode_tiled(&s.h_tmaps[(size_t)i * 6 + 2 * c + k],
+                                           bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                                           base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+      }
+    }
+  }
+  return true;
+}
+
 int submit(g1s_diff *d, Slot &s) {
   if (s.count == 0) return G1S_OK;
   cudaStream_t st = d->stream;
@@ -217,7 +262,13 @@ int submit(g1s_diff *d, Slot &s) {
         const FrameDesc &fd = s.h_descs[i];
         if (((uintptr_t)fd.src[c] | (uintptr_t)fd.den[c] | fd.src_stride[c] | fd.den_stride[c]) & 7) aligned = false;
       }
-    launch_gram_imma(s.d_descs, s.count, d->geom, s.d_records, d->rl, aligned, st);
+    const void *tmaps = nullptr;
+    if (d->geom.width >= 8 && d->geom.height >= 8 && build_tensor_maps(d, s)) {
+      CU_TRY(d, cudaMemcpyAsync(s.d_tmaps, s.h_tmaps, sizeof(CUtensorMap) * 6 * s.count, cudaMemcpyHostToDevice, st));
+      tmaps = s.d_tmaps;
+      d->tma_batches += 1;
+    }
+    launch_gram_imma(s.d_descs, s.count, d->geom, s.d_records, d->rl, aligned, tmaps, st);
     CU_TRY(d, cudaEventRecord(s.k1_end, st));
     launch_gram_generic(s.d_descs, s.count, d->geom, s.d_records, d->rl, /*only_overflow=*/true, st);
     gram_launches = 2;
@@ -400,11 +451,22 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     *out = d.release();
     return G1S_OK;
   }
+  {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      d->encode_tiled = reinterpret_cast<g1s_diff::EncodeTiledFn>(fn);
+    else
+      (void)cudaGetLastError();
+  }
   CU_NEW(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   CU_NEW(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
   for (Slot &s : d->slots) {
     CU_NEW(cudaMalloc(&s.d_frames, (size_t)batch * d->pair_bytes));
     CU_NEW(cudaMallocHost(&s.h_frames, (size_t)batch * d->pair_bytes));
+    CU_NEW(cudaMalloc(&s.d_tmaps, sizeof(CUtensorMap) * 6 * batch));
+    CU_NEW(cudaMallocHost(&s.h_tmaps, sizeof(CUtensorMap) * 6 * batch));
     CU_NEW(cudaMalloc(&s.d_descs, sizeof(FrameDesc) * batch));
     CU_NEW(cudaMallocHost(&s.h_descs, sizeof(FrameDesc) * batch));
     CU_NEW(cudaMalloc(&s.d_records, d->rl.bytes * batch));
@@ -593,6 +655,8 @@ void g1s_diff_destroy(g1s_diff *d) {
   for (Slot &s : d->slots) {
     if (s.d_frames) cudaFree(s.d_frames);
     if (s.h_frames) cudaFreeHost(s.h_frames);
+    if (s.d_tmaps) cudaFree(s.d_tmaps);
+    if (s.h_tmaps) cudaFreeHost(s.h_tmaps);
     if (s.d_descs) cudaFree(s.d_descs);
     if (s.h_descs) cudaFreeHost(s.h_descs);
     if (s.d_records) cudaFree(s.d_records);
@@ -611,8 +675,9 @@ int64_t g1s_diff_frames_pushed(const g1s_diff *d) { return d ? d->pushed : 0; }
 
 int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n) {
   if (!d || !out) return G1S_E_ARG;
-  const double v[6] = {d->kernels_launched, d->k1_ms, d->k1_launches, d->k0_ms, d->k0_launches, d->frames_done};
-  for (size_t i = 0; i < n && i < 6; ++i) out[i] = v[i];
+  const double v[7] = {d->kernels_launched, d->k1_ms,      d->k1_launches, d->k0_ms,
+                       d->k0_launches,      d->frames_done, d->tma_batches};
+  for (size_t i = 0; i < n && i < 7; ++i) out[i] = v[i];
   return G1S_OK;
 }
 

@@ -82,14 +82,14 @@ __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], 
 
 // Four consecutive samples as two words of two 16-bit lanes each, values 0..255
 // (util.rs::frame_into_u8: truncating shift, then `as u8`).
-template <int BYTES>
+template <int BYTES, bool SMEM>
 __device__ __forceinline__ void load4_lanes(const uint8_t *p, int shift, uint32_t &lo2, uint32_t &hi2) {
   if (BYTES == 2) {
-    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+    const uint2 v = SMEM ? *reinterpret_cast<const uint2 *>(p) : __ldg(reinterpret_cast<const uint2 *>(p));
     lo2 = (v.x >> shift) & 0x00FF00FFu;
     hi2 = (v.y >> shift) & 0x00FF00FFu;
   } else {
-    const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(p));
+    const uint32_t v = SMEM ? *reinterpret_cast<const uint32_t *>(p) : __ldg(reinterpret_cast<const uint32_t *>(p));
     lo2 = __byte_perm(v, 0u, 0x4140);
     hi2 = __byte_perm(v, 0u, 0x4342);
   }
@@ -98,12 +98,12 @@ __device__ __forceinline__ void load4_lanes(const uint8_t *p, int shift, uint32_
 // Packed s8 residual word of four samples + running statistics.  The statistics use the s8 word,
 // so they are exact only when no sample overflowed; overflowed blocks are redone (statistics
 // included) by the generic kernel.
-template <int SB, int DB, bool STATS, bool LUMA_SUM>
+template <int SB, int DB, bool STATS, bool LUMA_SUM, bool SMEM = false>
 __device__ __forceinline__ uint32_t residual4(const uint8_t *sp, const uint8_t *dp, int sshift, int dshift, int &rs,
                                               int &rq, unsigned &ls, uint32_t &ovf) {
   uint32_t s0, s1, d0, d1;
-  load4_lanes<SB>(sp, sshift, s0, s1);
-  load4_lanes<DB>(dp, dshift, d0, d1);
+  load4_lanes<SB, SMEM>(sp, sshift, s0, s1);
+  load4_lanes<DB, SMEM>(dp, dshift, d0, d1);
   const uint32_t b0 = (s0 | 0x01000100u) - d0;  // per lane: r + 256, never borrows across lanes
   const uint32_t b1 = (s1 | 0x01000100u) - d1;
   ovf |= ((b0 - 0x00800080u) | (b1 - 0x00800080u)) & 0xFF00FF00u;  // lane outside [128, 383] <=> r outside int8
@@ -312,11 +312,73 @@ __device__ __forceinline__ void emit_luma_tap(unsigned long long *gram, int b, i
   atomicAdd(&gram[pair_index(min(ib, 24), max(ib, 24))], (unsigned long long)((long long)v * weight));
 }
 
+// ------------------------------------------------------------------------------ TMA staging
+//
+// With 16-byte aligned planes the raw source / denoised tiles of a super-unit are fetched by the TMA
+// engine (cp.async.bulk.tensor.2d, SASS UTMALDG) straight into shared memory: six boxes per unit, one
+// elected thread, no per-thread address arithmetic, frame edges zero-filled by the hardware, and the
+// fetch of the NEXT unit overlaps the k-loops of the current one (single mbarrier, phase per unit).
+// The innermost box coordinate must be a multiple of 16 BYTES (anything else raises an illegal-instruction
+// fault, tools/tma_probe.cu), so the box starts 16 bytes left of the unit (8 or 16 samples, of which the
+// tile uses the last 4), and its width keeps the inner extent a multiple of 16 bytes.
+__host__ __device__ constexpr int tma_origin(int bytes) { return 16 / bytes; }
+__host__ __device__ constexpr int luma_box_w(int bytes) { return bytes == 2 ? 80 : 96; }    // >= origin + 64 + 3
+__host__ __device__ constexpr int chroma_box_w(int bytes) { return bytes == 2 ? 48 : 64; }  // >= origin + 32 + 3
+__host__ __device__ constexpr int align128(int v) { return (v + 127) & ~127; }
+
 template <int SB, int DB>
+struct RawLayout {
+  static constexpr int kLumaS = 0;
+  static constexpr int kLumaSBytes = kLumaRows * luma_box_w(SB) * SB;
+  static constexpr int kLumaD = kLumaS + align128(kLumaSBytes);
+  static constexpr int kLumaDBytes = kLumaRows * luma_box_w(DB) * DB;
+  static constexpr int kChromaSBytes = kChromaRows * chroma_box_w(SB) * SB;
+  static constexpr int kChromaDBytes = kChromaRows * chroma_box_w(DB) * DB;
+  static constexpr int kCbS = kLumaD + align128(kLumaDBytes);
+  static constexpr int kCbD = kCbS + align128(kChromaSBytes);
+  static constexpr int kCrS = kCbD + align128(kChromaDBytes);
+  static constexpr int kCrD = kCrS + align128(kChromaSBytes);
+  static constexpr int kBytes = kCrD + align128(kChromaDBytes);
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "G1S_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra G1S_DONE;\n"
+      "bra G1S_WAIT;\n"
+      "G1S_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, int y, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int SB, int DB, bool TMA>
 __global__ void __launch_bounds__(kSuThreads, 3)
 gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__restrict__ records, RecordLayout rl,
-                 int runs_per_row, int aligned) {
+                 int runs_per_row, int aligned, const uint8_t *__restrict__ tmaps) {
   __shared__ SuSmem sm;
+  using RL = RawLayout<SB, DB>;
+  __shared__ __align__(128) uint8_t raw[TMA ? RL::kBytes : 16];
+  __shared__ __align__(8) uint64_t raw_bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, t = lane & 3;  // mma "groupID" (= cx + 3) and thread-in-group
   const int by = blockIdx.x / runs_per_row;
@@ -358,10 +420,40 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
   const bool is7 = gq == 7;
   constexpr int kBook = kSuThreads - 1;  // bookkeeping thread (observation rectangles, counts, flags)
 
-  for (int u = u_beg; u < u_end; ++u) {
+  // next super-unit of the run with at least one flat block (uniform across the CTA)
+  auto next_flat = [&](int u) {
+    while (u < u_end && !(sm.flat[0][2 * u - fbase] | sm.flat[0][2 * u - fbase + 1])) ++u;
+    return u;
+  };
+  // one elected thread asks the TMA engine for the six raw tiles of a unit
+  const uint8_t *fmaps = TMA ? tmaps + (size_t)f * 6 * 128 : nullptr;
+  auto issue_tma = [&](int u) {
+    const int X0 = 64 * u, CX0 = 32 * u;
+    const uint32_t bytes = RL::kLumaSBytes + RL::kLumaDBytes + (has_chroma ? 2 * (RL::kChromaSBytes + RL::kChromaDBytes) : 0);
+    mbar_expect_tx(&raw_bar, bytes);
+    tma_load_2d(raw + RL::kLumaS, fmaps + 0 * 128, X0 - tma_origin(SB), Y0 - 3, &raw_bar);
+    tma_load_2d(raw + RL::kLumaD, fmaps + 1 * 128, X0 - tma_origin(DB), Y0 - 3, &raw_bar);
+    if (has_chroma) {
+      tma_load_2d(raw + RL::kCbS, fmaps + 2 * 128, CX0 - tma_origin(SB), CY0 - 3, &raw_bar);
+      tma_load_2d(raw + RL::kCbD, fmaps + 3 * 128, CX0 - tma_origin(DB), CY0 - 3, &raw_bar);
+      tma_load_2d(raw + RL::kCrS, fmaps + 4 * 128, CX0 - tma_origin(SB), CY0 - 3, &raw_bar);
+      tma_load_2d(raw + RL::kCrD, fmaps + 5 * 128, CX0 - tma_origin(DB), CY0 - 3, &raw_bar);
+    }
+  };
+  int u = next_flat(u_beg);
+  uint32_t raw_phase = 0;
+  if (TMA) {
+    if (tid == 0) {
+      mbar_init(&raw_bar, 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (u < u_end) issue_tma(u);
+    }
+    __syncthreads();
+  }
+
+  while (u < u_end) {
     const int bx0 = 2 * u, fk = bx0 - fbase;
     const bool fl0 = sm.flat[0][fk] != 0, fl1 = sm.flat[0][fk + 1] != 0;
-    if (!fl0 && !fl1) continue;  // uniform across the CTA
     const int b0 = by * g.nbw + bx0;
 
     if (tid < 6) {
@@ -391,7 +483,97 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
     // ------------------------------------------------------------------ staging
     const int X0 = 64 * u, CX0 = 32 * u;
     const bool fast = aligned && rows_inside && X0 >= 4 && X0 + 68 <= W && (!has_chroma || CX0 + 36 <= pw);
-    if (fast) {
+    if (TMA) {
+      // raw tiles of this unit were requested one unit ago; each thread converts the words it owns
+      mbar_wait(&raw_bar, raw_phase);
+      raw_phase ^= 1;
+      constexpr int kLpS = luma_box_w(SB) * SB, kLpD = luma_box_w(DB) * DB;        // raw row pitches in bytes
+      constexpr int kCpS = chroma_box_w(SB) * SB, kCpD = chroma_box_w(DB) * DB;
+      constexpr int kOs = (tma_origin(SB) - 4) * SB, kOd = (tma_origin(DB) - 4) * DB;  // tile column 0 inside a raw row
+      {
+        uint32_t ov = 0;
+        int rs = 0, rq = 0;
+        unsigned ls = 0;
+        const int ty0 = 2 * warp + (lane >> 4), w = 1 + (lane & 15);
+        const uint8_t *sp = raw + RL::kLumaS + ty0 * kLpS + kOs + 4 * w * SB;
+        const uint8_t *dp = raw + RL::kLumaD + ty0 * kLpD + kOd + 4 * w * DB;
+        uint32_t *dst = &sm.luma[ty0 * kPL + w];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const int ty = ty0 + 12 * p;
+          if (ty < kLumaRows) {
+            int trs = 0, trq = 0;
+            unsigned tls = 0;
+            dst[12 * p * kPL] = residual4<SB, DB, true, true, true>(sp + 12 * p * kLpS, dp + 12 * p * kLpD, g.src_shift,
+                                                                    g.den_shift, trs, trq, tls, ov);
+            if (ty >= 3) rs += trs, rq += trq, ls += tls;  // halo rows belong to the block above
+          }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          rs += __shfl_xor_sync(0xffffffffu, rs, o);
+          rq += __shfl_xor_sync(0xffffffffu, rq, o);
+          ls += __shfl_xor_sync(0xffffffffu, ls, o);
+        }
+        if ((lane & 7) == 0) {
+          const int blk = (lane >> 3) & 1;
+          atomicAdd(&sm.st_rs[blk], rs);
+          atomicAdd(&sm.st_rq[blk], (unsigned)rq);
+          atomicAdd(&sm.st_ls[blk], ls);
+        }
+        if (__any_sync(0xffffffffu, ov != 0) && lane == 0) sm.ovf[0] = 1;
+      }
+      if (has_chroma) {
+        const int c = warp >= 3 ? 1 : 0, wk = warp - 3 * c;
+        int rs = 0, rq = 0;
+        unsigned ls = 0;
+        uint32_t ovc = 0;
+        const int ty0 = 4 * wk + (lane >> 3), w = 1 + (lane & 7);
+        const uint8_t *sp = raw + (c ? RL::kCrS : RL::kCbS) + ty0 * kCpS + kOs + 4 * w * SB;
+        const uint8_t *dp = raw + (c ? RL::kCrD : RL::kCbD) + ty0 * kCpD + kOd + 4 * w * DB;
+        uint32_t *dst = &sm.chroma[c][ty0 * kPC + w];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const int ty = ty0 + 12 * p;
+          if (ty < kChromaRows) {
+            int trs = 0, trq = 0;
+            dst[12 * p * kPC] = residual4<SB, DB, true, false, true>(sp + 12 * p * kCpS, dp + 12 * p * kCpD, g.src_shift,
+                                                                     g.den_shift, trs, trq, ls, ovc);
+            if (ty >= 3) rs += trs, rq += trq;
+          }
+        }
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+          rs += __shfl_xor_sync(0xffffffffu, rs, o);
+          rq += __shfl_xor_sync(0xffffffffu, rq, o);
+        }
+        if ((lane & 3) == 0) {
+          const int blk = (lane >> 2) & 1;
+          atomicAdd(&sm.st_rs[2 + 2 * c + blk], rs);
+          atomicAdd(&sm.st_rq[2 + 2 * c + blk], (unsigned)rq);
+        }
+        if (__any_sync(0xffffffffu, ovc != 0) && lane == 0) sm.ovf[1 + c] = 1;
+      }
+      {
+        int rs = 0, rq = 0;
+        unsigned ls = 0;
+        uint32_t ovh = 0;
+        if (tid < 70) {
+          const int ty = tid >> 1, w = (tid & 1) * 17;
+          sm.luma[ty * kPL + w] = residual4<SB, DB, false, false, true>(
+              raw + RL::kLumaS + ty * kLpS + kOs + 4 * w * SB, raw + RL::kLumaD + ty * kLpD + kOd + 4 * w * DB, g.src_shift,
+              g.den_shift, rs, rq, ls, ovh);
+          if (ovh) sm.ovf[0] = 1;
+        } else if (has_chroma && tid < 70 + 76) {
+          const int idx = tid - 70, c = idx >= 38 ? 1 : 0, rem = idx - 38 * c;
+          const int ty = rem >> 1, w = (rem & 1) * 9;
+          sm.chroma[c][ty * kPC + w] = residual4<SB, DB, false, false, true>(
+              raw + (c ? RL::kCrS : RL::kCbS) + ty * kCpS + kOs + 4 * w * SB,
+              raw + (c ? RL::kCrD : RL::kCbD) + ty * kCpD + kOd + 4 * w * DB, g.src_shift, g.den_shift, rs, rq, ls, ovh);
+          if (ovh) sm.ovf[1 + c] = 1;
+        }
+      }
+    } else if (fast) {
       {
         // luma main words: two tile rows per pass (lanes 0-15 / 16-31), rows warp*2 + 12*pass
         uint32_t ov = 0;
@@ -539,7 +721,12 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
       for (int k = 0; k < 3; ++k)
         if (ov[k]) sm.ovf[k] = 1;
     }
-    __syncthreads();  // tiles + statistics + overflow flags complete
+    __syncthreads();  // tiles + statistics + overflow flags complete (and the raw tiles are free again)
+    const int u_next = next_flat(u + 1);
+    if (TMA && tid == 0 && u_next < u_end) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of raw before the async refill
+      issue_tma(u_next);
+    }
 
     const UnitInfo in = sm.info;
     const bool ovl = sm.ovf[0] != 0;
@@ -646,6 +833,7 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
         }
       }
     }
+    u = u_next;
   }
 
   // ---------------------------------------------------------------------- epilogue
@@ -694,20 +882,36 @@ bool gram_imma_supported(const Geometry &g) {
   return (g.planes == 1) || (g.planes == 3 && g.ss_x == 1 && g.ss_y == 1);
 }
 
+void gram_imma_tma_boxes(int bytes, int *luma_w, int *luma_h, int *chroma_w, int *chroma_h) {
+  *luma_w = luma_box_w(bytes);
+  *luma_h = kLumaRows;
+  *chroma_w = chroma_box_w(bytes);
+  *chroma_h = kChromaRows;
+}
+
 void launch_gram_imma(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
-                      const RecordLayout &rl, bool aligned, cudaStream_t st) {
+                      const RecordLayout &rl, bool aligned, const void *tmaps, cudaStream_t st) {
   const int nsu = (g.nbw + 1) / 2;
   const int runs = (nsu + kSuRun - 1) / kSuRun;
   dim3 grid(runs * g.nbh, nframes);
   const int al = aligned ? 1 : 0;
+  const uint8_t *tm = static_cast<const uint8_t *>(tmaps);
+#define G1S_LAUNCH(SB, DB)                                                                                   \
+  do {                                                                                                       \
+    if (tm)                                                                                                  \
+      gram_imma_kernel<SB, DB, true><<<grid, kSuThreads, 0, st>>>(frames, g, records, rl, runs, al, tm);     \
+    else                                                                                                     \
+      gram_imma_kernel<SB, DB, false><<<grid, kSuThreads, 0, st>>>(frames, g, records, rl, runs, al, tm);    \
+  } while (0)
   if (g.src_bytes == 2 && g.den_bytes == 2)
-    gram_imma_kernel<2, 2><<<grid, kSuThreads, 0, st>>>(frames, g, records, rl, runs, al);
+    G1S_LAUNCH(2, 2);
   else if (g.src_bytes == 2)
-    gram_imma_kernel<2, 1><<<grid, kSuThreads, 0, st>>>(frames, g, records, rl, runs, al);
+    G1S_LAUNCH(2, 1);
   else if (g.den_bytes == 2)
-    gram_imma_kernel<1, 2><<<grid, kSuThreads, 0, st>>>(frames, g, records, rl, runs, al);
+    G1S_LAUNCH(1, 2);
   else
-    gram_imma_kernel<1, 1><<<grid, kSuThreads, 0, st>>>(frames, g, records, rl, runs, al);
+    G1S_LAUNCH(1, 1);
+#undef G1S_LAUNCH
 }
 
 }  // namespace g1s

@@ -63,7 +63,10 @@ void launch_gram_generic(const FrameDesc *frames, int nframes, const Geometry &g
                          const RecordLayout &rl, bool only_overflow, cudaStream_t st);
 // int8 tensor-core (mma.sync m16n8k32) Gram kernel for 4:2:0 / monochrome streams.
 bool gram_imma_supported(const Geometry &g);
+// tmaps: device array of CUtensorMap[nframes][6] (source/denoised x Y,Cb,Cr; boxes from
+// gram_imma_tma_boxes) -> the raw tiles are staged by the TMA engine; nullptr -> per-thread loads.
 void launch_gram_imma(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
-                      const RecordLayout &rl, bool aligned, cudaStream_t st);
+                      const RecordLayout &rl, bool aligned, const void *tmaps, cudaStream_t st);
+void gram_imma_tma_boxes(int bytes_per_sample, int *luma_w, int *luma_h, int *chroma_w, int *chroma_h);
 
 }  // namespace g1s

@@ -234,9 +234,9 @@ class DiffGenerator:
         return int(self._L.g1s_diff_frames_pushed(self._h))
 
     def counters(self) -> dict:
-        out = (C.c_double * 6)()
-        self._check(self._L.g1s_diff_get_counters(self._h, out, 6))
-        k = ("kernels_launched", "gram_ms", "gram_launches", "flat_ms", "flat_launches", "frames_done")
+        out = (C.c_double * 7)()
+        self._check(self._L.g1s_diff_get_counters(self._h, out, 7))
+        k = ("kernels_launched", "gram_ms", "gram_launches", "flat_ms", "flat_launches", "frames_done", "tma_batches")
         return dict(zip(k, [float(v) for v in out]))
 
 

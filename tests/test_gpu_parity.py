@@ -59,11 +59,17 @@ def compare_records(spec, frames, got, want, src_bd=None, den_bd=None):
         assert np.array_equal(g["luma_sum"][w["flat"] != 0], ref["luma_sum"][w["flat"] != 0])
 
 
-@pytest.mark.parametrize("gram_kernel", [0, 1], ids=["tensorcore", "generic"])
+@pytest.mark.parametrize("path", ["tensorcore-tma", "tensorcore-ldg", "generic"])
 @pytest.mark.parametrize("name", list(CORPUS))
-def test_corpus_bit_exact(name, gram_kernel):
+def test_corpus_bit_exact(name, path, monkeypatch):
+    """Every Gram path against the oracle: int8 tensor cores with TMA-staged tiles, the same with per-thread
+    loads (what unaligned planes get), and the generic int32 kernel."""
+    if path == "tensorcore-ldg":
+        monkeypatch.setenv("G1S_NO_TMA", "1")
     spec, fps, frames = corpus_frames(name)
-    segs, recs, _ = gpu_run(spec, fps, frames, gram_kernel=gram_kernel)
+    segs, recs, g = gpu_run(spec, fps, frames, gram_kernel=1 if path == "generic" else 0)
+    if spec.ss_x == 1 and spec.ss_y == 1:
+        assert (g.counters()["tma_batches"] > 0) == (path == "tensorcore-tma")
     want, per = oracle_run(spec, fps, frames)
     compare_records(spec, frames, recs, per)
     assert segs == want
