@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k10", choices=list(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=32, help="frame pairs per step per GPU")
+    ap.add_argument("--frames", type=int, default=64, help="frame pairs per step per GPU")
     ap.add_argument("--batch", type=int, default=8, help="frame pairs per kernel launch (engine batch)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -26,7 +26,7 @@
 //            The observation mask (block margins, frame clipping) is a byte mask on k applied
 //            to the operand words (mask^2 = mask, so masking both A and B is exact).
 //            Chroma adds one n-tile whose columns 0/1 are the luma tap split as 8*hi + lo.
-//   epilogue int32 accumulators (bounded: <= 30 units * 16 k-steps * 32 * 2^14 * 4 warps < 2^31)
+//   epilogue int32 accumulators (bounded: <= 12 units * 16 k-steps * 32 * 2^14 * 4 warps < 2^31)
 //            -> int64 global atomics, one per tap pair per CTA per plane.
 #include "g1s_kernels.h"
 
@@ -35,7 +35,7 @@ namespace g1s {
 namespace {
 
 constexpr int kSuThreads = 192;
-constexpr int kSuRun = 30;        // super-units per CTA (bounds the int32 accumulators, see above)
+constexpr int kSuRun = 12;        // super-units per CTA (bounds the int32 accumulators, see above)
 constexpr int kPL = 20;           // luma tile pitch in 32-bit words (72 bytes used)
 constexpr int kLumaRows = 35;     // 3 halo rows + 32
 constexpr int kPC = 12;           // chroma tile pitch in words (40 bytes used)
@@ -372,7 +372,7 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, 
 }
 
 template <int SB, int DB, bool TMA>
-__global__ void __launch_bounds__(kSuThreads, 3)
+__global__ void __launch_bounds__(kSuThreads, 4)
 gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__restrict__ records, RecordLayout rl,
                  int runs_per_row, int aligned, const uint8_t *__restrict__ tmaps) {
   __shared__ SuSmem sm;
