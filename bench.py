@@ -39,8 +39,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k10", choices=list(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=64, help="frame pairs per step per GPU")
-    ap.add_argument("--batch", type=int, default=8, help="frame pairs per kernel launch (engine batch)")
+    ap.add_argument("--frames", type=int, default=60, help="frame pairs per step per GPU (3 engine batches at 4K)")
+    ap.add_argument("--batch", type=int, default=0, help="frame pairs per kernel launch (engine batch)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the CPU-baseline sample")
@@ -240,7 +240,7 @@ def main():
     # dominant kernel: fused residual + Gram accumulation, CUDA events on the engine's stream
     gram_ms = (c1["gram_ms"] - c0["gram_ms"]) / max(1.0, c1["gram_launches"] - c0["gram_launches"])
     flat_ms = (c1["flat_ms"] - c0["flat_ms"]) / max(1.0, c1["flat_launches"] - c0["flat_launches"])
-    frames_per_launch = min(F, args.batch) if world == 1 else F
+    frames_per_launch = (c1["frames_done"] - c0["frames_done"]) / max(1.0, c1["gram_launches"] - c0["gram_launches"])
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <condition_variable>
 #include <cstdio>
 #include <functional>
@@ -442,9 +443,21 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     }
   }
   d->pair_bytes = off;
-  // default batch: about 384 MiB of frame pairs per slot, at most 64 frames
+  // Default batch: at most ~1 GiB of frame pairs per slot and 64 frames; within that, the size whose
+  // flat-block launch (one thread per block, 384 resident threads per SM) fills its last wave best.
   int batch = cfg->batch_frames;
-  if (batch <= 0) batch = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)384 << 20) / d->pair_bytes));
+  if (batch <= 0) {
+    const int cap = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)1 << 30) / d->pair_bytes));
+    int sms = 148;
+    if (!consumer) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    const double wave = 384.0 * sms;
+    double best = -1;
+    batch = cap;
+    for (int b = std::max(1, cap / 2); b <= cap; ++b) {
+      const double waves = (double)b * g.nb / wave, eff = waves / std::ceil(waves);
+      if (eff >= best) best = eff, batch = b;
+    }
+  }
   d->batch = batch;
 
   if (consumer) {
@@ -463,8 +476,8 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   CU_NEW(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   CU_NEW(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
   for (Slot &s : d->slots) {
-    CU_NEW(cudaMalloc(&s.d_frames, (size_t)batch * d->pair_bytes));
-    CU_NEW(cudaMallocHost(&s.h_frames, (size_t)batch * d->pair_bytes));
+    // the frame store (device) and its pinned mirror (host) are allocated on the first host push:
+    // streams whose frames are already in HBM never need them
     CU_NEW(cudaMalloc(&s.d_tmaps, sizeof(CUtensorMap) * 6 * batch));
     CU_NEW(cudaMallocHost(&s.h_tmaps, sizeof(CUtensorMap) * 6 * batch));
     CU_NEW(cudaMalloc(&s.d_descs, sizeof(FrameDesc) * batch));
@@ -492,6 +505,10 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
   int rc = check_frames(d, source, denoised);
   if (rc != G1S_OK) return rc;
   Slot &s = d->slots[d->cur];
+  if (!s.d_frames) {
+    CU_TRY(d, cudaMalloc(&s.d_frames, (size_t)d->batch * d->pair_bytes));
+    CU_TRY(d, cudaMallocHost(&s.h_frames, (size_t)d->batch * d->pair_bytes));
+  }
   const size_t base = (size_t)s.count * d->pair_bytes;
   FrameDesc &fd = s.h_descs[s.count];
   std::memset(&fd, 0, sizeof fd);

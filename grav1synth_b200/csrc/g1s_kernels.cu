@@ -102,6 +102,8 @@ __device__ __forceinline__ double exp_fixed(double x) {
 
 constexpr int kFlatThreads = 128;
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // Eight consecutive source-luma samples reduced to 8 bit; coordinates clamped to the frame
 // (FlatBlockFinder::extract_block clamps, it does not pad).
 template <int SB>
@@ -163,6 +165,7 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
   for (int yi = 0; yi < kBlock; ++yi) {
     const double yd = (double)(yi - 16) * 0.0625;
     const uint8_t *row = src + (size_t)min(y0 + yi, h - 1) * stride;
+    prefetch_l2(src + (size_t)min(y0 + yi + 4, h - 1) * stride + (size_t)min(x0, w - 1) * SB);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       int p[8];
@@ -217,6 +220,7 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
   for (int yi = 1; yi < kBlock - 1; ++yi) {
     const double ty = row_ty(yi + 1);
     const uint8_t *row = src + (size_t)min(y0 + yi + 1, h - 1) * stride;
+    prefetch_l2(src + (size_t)min(y0 + yi + 5, h - 1) * stride + (size_t)min(x0, w - 1) * SB);
     const double *cur = ring + ((size_t)(yi & 1) * kBlock) * kFlatThreads + tid;
     double *oth = ring + ((size_t)((yi + 1) & 1) * kBlock) * kFlatThreads + tid;  // row yi-1, becomes row yi+1
     double left = cur[0], mid = cur[kFlatThreads];
