@@ -35,7 +35,7 @@ METRIC = "diff_frames_per_sec_4k_10bit"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k10", choices=list(WORKLOADS))
@@ -64,7 +64,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                       "-lms", "200", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
@@ -196,11 +196,12 @@ def main():
         eng = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=args.batch)
 
         def step():
+            # one pass over the batch of F frame pairs; the engine pipelines launches and folds results
+            # asynchronously, the drain happens once at the end of the timed region (barrier())
             for (sp, ss), (dp, ds) in dev_args:
                 eng.diff_frame_device(sp, ss, dp, ds)
-            eng.flush()
     else:
-        sd = ShardedDiff(24, 1, bd, bd, W, H, 1, 1, frames_per_rank=F, device=local_rank)
+        sd = ShardedDiff(24, 1, bd, bd, W, H, 1, 1, frames_per_rank=F, device=local_rank, batch_frames=args.batch)
         eng = sd.producer
 
         def step():
@@ -209,6 +210,8 @@ def main():
             sd.exchange()
 
     def barrier():
+        if world == 1:
+            eng.flush()  # every pushed frame processed by the device AND folded into the host model
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -216,21 +219,22 @@ def main():
 
     for _ in range(args.warmup):
         step()
-    c0 = eng.counters()
     barrier()
+    c0 = eng.counters()
     clocks = ClockSampler(local_rank) if rank == 0 else None
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    # timed region: CUDA events on the engine's own kernel stream (torch events only see torch's stream),
+    # cross-checked against the host clock; the larger of the two is reported
+    eng.mark(0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     barrier()
+    eng.mark(1)
+    ev_ms = eng.marks_elapsed_ms()
     t1 = time.perf_counter()
-    ev1.record()
-    torch.cuda.synchronize()
     clk = clocks.stop() if clocks else None
     c1 = eng.counters()
-    elapsed = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    elapsed = torch.tensor([max(t1 - t0, ev_ms * 1e-3)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
     elapsed = float(elapsed.item())
@@ -258,7 +262,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": wl["label"], "frames_per_step_per_gpu": F, "frames_per_launch": frames_per_launch, "bytes_per_frame_pair": pair_bytes,
                    "l2": f"inputs larger than L2 ({F * pair_bytes / 1e6:.0f} MB per step per GPU)",
-                   "parallelism": f"frame-sharded x{world}, NCCL all-gather of per-frame records",
+                   "parallelism": f"frame-sharded x{world}, NCCL all-gather of per-frame model digests ({D.digest_bytes()} B/frame)",
                    "device_ms_flat_kernel": flat_ms, "device_ms_gram_kernel": gram_ms},
         "gpu_launches": int(c1["kernels_launched"] - c0["kernels_launched"]),
         "roofline": {"bound": "hbm", "kernel": "gram (fused residual + autocorrelation)", "achieved": achieved,
@@ -289,9 +293,8 @@ def main():
                 for k in range(F):
                     s, d = np_frames[k % nh]
                     g.diff_frame(s, d)
-                g.flush()
         else:
-            sd2 = ShardedDiff(24, 1, bd, bd, W, H, 1, 1, frames_per_rank=F, device=local_rank)
+            sd2 = ShardedDiff(24, 1, bd, bd, W, H, 1, 1, frames_per_rank=F, device=local_rank, batch_frames=args.batch)
             g = sd2.producer
 
             def e2e_step():
@@ -300,18 +303,23 @@ def main():
                     sd2.push_local(s, d)
                 sd2.exchange()
 
+        def e2e_barrier():
+            if world == 1:
+                g.flush()
+            barrier()
+
         e2e_step()
-        barrier()
+        e2e_barrier()
         t0 = time.perf_counter()
         n_e2e = max(1, min(args.steps, 3))
         for _ in range(n_e2e):
             e2e_step()
-        barrier()
+        e2e_barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         line["e2e"] = {"value": world * F * n_e2e / float(dt.item()), "unit": "frames/s",
-                       "h2d_bytes_per_step": F * pair_bytes, "d2h_bytes_per_step": F * g.record_bytes,
+                       "h2d_bytes_per_step": F * pair_bytes, "d2h_bytes_per_step": F * g.record_bytes, "records_bytes_per_frame": g.record_bytes,
                        "steps": n_e2e, "api": "g1s_diff_push_frame (C ABI) with host planes + g1s_diff_flush"}
         g.close()
 

@@ -138,6 +138,7 @@ struct g1s_diff {
   size_t pair_bytes = 0;
   int batch = 1;
   cudaStream_t stream = nullptr;       // kernels + record read-back
+  cudaEvent_t marks[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;  // per-frame host->device copies, overlapping the staging of the next frame
   Slot slots[kSlots];
   int cur = 0;            // slot being filled
@@ -151,6 +152,8 @@ struct g1s_diff {
   int64_t retired = 0;
   g1s_record_fn tap = nullptr;
   void *tap_user = nullptr;
+  double *sink = nullptr;  // digest sink (producer ranks)
+  size_t sink_cap = 0, sink_count = 0;
   // cuTensorMapEncodeTiled, fetched through the runtime so libcuda is not a link dependency
   typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -189,7 +192,7 @@ FrameRecordView view_of(const g1s_diff *d, const uint8_t *rec) {
 // Per-frame model evaluation in parallel, then tap + merge in frame order.
 void fold_records(g1s_diff *d, const uint8_t *recs, int count, size_t stride) {
   const bool model = d->cfg.mode != G1S_MODE_PRODUCER;
-  if (model) {
+  if (model || d->sink) {
     if ((int)d->latest.size() < count) d->latest.resize(count);
     const NoiseModel &nm = d->seq->model();
     d->pool->parallel_for(count, [&](int i) { nm.compute_latest(view_of(d, recs + (size_t)i * stride), d->latest[i]); });
@@ -197,6 +200,8 @@ void fold_records(g1s_diff *d, const uint8_t *recs, int count, size_t stride) {
   for (int i = 0; i < count; ++i) {
     if (d->tap) d->tap(d->tap_user, d->retired, recs + (size_t)i * stride, d->rl.bytes);
     if (model) d->seq->consume_latest(d->latest[i]);
+    if (d->sink && d->sink_count < d->sink_cap)
+      d->latest[i].to_digest(d->sink + LatestFrame::kDigestDoubles * d->sink_count++);
     d->retired++;
   }
 }
@@ -681,6 +686,8 @@ void g1s_diff_destroy(g1s_diff *d) {
     for (cudaEvent_t e : {s.done, s.k0_beg, s.k0_end, s.k1_beg, s.k1_end, s.copied})
       if (e) cudaEventDestroy(e);
   }
+  for (cudaEvent_t e : d->marks)
+    if (e) cudaEventDestroy(e);
   if (d->stream) cudaStreamDestroy(d->stream);
   if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
   delete d;
@@ -695,6 +702,63 @@ int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n) {
   const double v[7] = {d->kernels_launched, d->k1_ms,      d->k1_launches, d->k0_ms,
                        d->k0_launches,      d->frames_done, d->tma_batches};
   for (size_t i = 0; i < n && i < 7; ++i) out[i] = v[i];
+  return G1S_OK;
+}
+
+int g1s_diff_mark(g1s_diff *d, int which) {
+  if (!d || which < 0 || which > 1 || !d->stream) return G1S_E_ARG;
+  if (!d->marks[which]) CU_TRY(d, cudaEventCreate(&d->marks[which]));
+  CU_TRY(d, cudaEventRecord(d->marks[which], d->stream));
+  return G1S_OK;
+}
+
+double g1s_diff_marks_elapsed_ms(g1s_diff *d) {
+  if (!d || !d->marks[0] || !d->marks[1]) return -1.0;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(d->marks[1]) != cudaSuccess || cudaEventElapsedTime(&ms, d->marks[0], d->marks[1]) != cudaSuccess)
+    return -1.0;
+  return (double)ms;
+}
+
+size_t g1s_digest_bytes(void) { return LatestFrame::kDigestDoubles * sizeof(double); }
+
+int g1s_diff_set_digest_sink(g1s_diff *d, void *buffer, size_t capacity_frames) {
+  if (!d) return G1S_E_ARG;
+  d->sink = static_cast<double *>(buffer);
+  d->sink_cap = buffer ? capacity_frames : 0;
+  d->sink_count = 0;
+  return G1S_OK;
+}
+
+int64_t g1s_diff_digest_count(const g1s_diff *d) { return d ? (int64_t)d->sink_count : 0; }
+
+int g1s_diff_consume_digests(g1s_diff *d, const void *digests, size_t count) {
+  if (!d || (!digests && count)) return G1S_E_ARG;
+  if (d->cfg.mode != G1S_MODE_CONSUMER || d->finished) {
+    d->err = "consume_digests needs an unfinished CONSUMER handle";
+    return G1S_E_STATE;
+  }
+  if (d->latest.empty()) d->latest.resize(1);
+  const double *p = static_cast<const double *>(digests);
+  for (size_t i = 0; i < count; ++i) {
+    d->latest[0].from_digest(p + LatestFrame::kDigestDoubles * i);
+    d->seq->consume_latest(d->latest[0]);
+    d->retired++;
+  }
+  d->pushed += (int64_t)count;
+  d->frames_done += (double)count;
+  return G1S_OK;
+}
+
+int g1s_diff_digest_from_record(g1s_diff *d, const void *record, size_t bytes, void *digest_out) {
+  if (!d || !record || !digest_out) return G1S_E_ARG;
+  if (bytes != d->rl.bytes) {
+    d->err = "record size does not match this stream's geometry";
+    return G1S_E_ARG;
+  }
+  LatestFrame lf;
+  d->seq->model().compute_latest(view_of(d, static_cast<const uint8_t *>(record)), lf);
+  lf.to_digest(static_cast<double *>(digest_out));
   return G1S_OK;
 }
 

@@ -303,7 +303,7 @@ void launch_flat_features(const FrameDesc *frames, int nframes, const Geometry &
 // Scores are non-negative floats, so their bit patterns order like unsigned integers and
 // the k-th smallest is found by a 4-pass MSB-first radix select; one CTA per frame.
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 flat_select_kernel(int nframes, Geometry g, uint8_t *__restrict__ records, RecordLayout rl) {
   __shared__ unsigned hist[256];
   __shared__ unsigned s_prefix, s_k;
@@ -319,7 +319,7 @@ flat_select_kernel(int nframes, Geometry g, uint8_t *__restrict__ records, Recor
     s_count = 0;
   }
   for (int pass = 3; pass >= 0; --pass) {
-    hist[threadIdx.x] = 0;
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
     __syncthreads();
     const unsigned prefix = s_prefix;
     const unsigned himask = pass == 3 ? 0u : (0xFFFFFFFFu << (8 * (pass + 1)));
@@ -354,7 +354,7 @@ flat_select_kernel(int nframes, Geometry g, uint8_t *__restrict__ records, Recor
 }
 
 void launch_flat_select(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, cudaStream_t st) {
-  flat_select_kernel<<<nframes, 256, 0, st>>>(nframes, g, records, rl);
+  flat_select_kernel<<<nframes, 1024, 0, st>>>(nframes, g, records, rl);
 }
 
 // --------------------------------------------------------------------- gram_generic_kernel

@@ -208,6 +208,61 @@ static void chroma_fallback(LinearSystem &e) {
   if (std::fabs(e.A[last * e.n + last]) > 1e-6) e.x[last] = e.b[last] / e.A[last * e.n + last];
 }
 
+// ------------------------------------------------------------------- LatestFrame
+namespace {
+const char *const kFailTexts[3] = {nullptr, "Solving latest noise equation system failed 0!",
+                                   "Solving latest noise strength failed!"};
+}
+
+void LatestFrame::to_digest(double *out) const {
+  double *p = out;
+  *p++ = enough_flat ? 1.0 : 0.0;
+  *p++ = (double)channels;
+  *p++ = (double)fail_channel;
+  *p++ = fail_text == kFailTexts[1] ? 1.0 : (fail_text == kFailTexts[2] ? 2.0 : 0.0);
+  for (int c = 0; c < 3; ++c) {
+    const ChannelState &s = ch[c];
+    const int n = s.eqns.n;
+    std::memset(p, 0, sizeof(double) * (25 * 25 + 25 + 25));
+    std::memcpy(p, s.eqns.A.data(), sizeof(double) * n * n);
+    std::memcpy(p + 625, s.eqns.b.data(), sizeof(double) * n);
+    std::memcpy(p + 650, s.eqns.x.data(), sizeof(double) * n);
+    p += 675;
+    *p++ = s.ar_gain;
+    *p++ = (double)s.num_observations;  // exact: < 2^53
+    std::memcpy(p, s.strength.eqns.A.data(), sizeof(double) * 400);
+    std::memcpy(p + 400, s.strength.eqns.b.data(), sizeof(double) * 20);
+    std::memcpy(p + 420, s.strength.eqns.x.data(), sizeof(double) * 20);
+    p += 440;
+    *p++ = s.strength.total;
+    *p++ = (double)s.strength.num_equations;
+  }
+}
+
+void LatestFrame::from_digest(const double *in) {
+  const double *p = in;
+  enough_flat = *p++ != 0.0;
+  channels = (int)*p++;
+  fail_channel = (int)*p++;
+  fail_text = kFailTexts[(int)*p++];
+  for (int c = 0; c < 3; ++c) {
+    ChannelState &s = ch[c];
+    const int n = s.eqns.n;
+    std::memcpy(s.eqns.A.data(), p, sizeof(double) * n * n);
+    std::memcpy(s.eqns.b.data(), p + 625, sizeof(double) * n);
+    std::memcpy(s.eqns.x.data(), p + 650, sizeof(double) * n);
+    p += 675;
+    s.ar_gain = *p++;
+    s.num_observations = (int64_t)*p++;
+    std::memcpy(s.strength.eqns.A.data(), p, sizeof(double) * 400);
+    std::memcpy(s.strength.eqns.b.data(), p + 400, sizeof(double) * 20);
+    std::memcpy(s.strength.eqns.x.data(), p + 420, sizeof(double) * 20);
+    p += 440;
+    s.strength.total = *p++;
+    s.strength.num_equations = (int)*p++;
+  }
+}
+
 // -------------------------------------------------------------------- NoiseModel
 NoiseModel::NoiseModel(const StreamGeometry &g)
     : combined{ChannelState(24), ChannelState(25), ChannelState(25)}, g_(g) {
@@ -388,14 +443,14 @@ void NoiseModel::compute_latest(const FrameRecordView &rec, LatestFrame &lf) con
         chroma_fallback(lf.ch[c].eqns);
       } else {
         lf.fail_channel = c;
-        lf.fail_text = "Solving latest noise equation system failed 0!";
+        lf.fail_text = kFailTexts[1];
         return;
       }
     }
     add_strength_measurements(c, rec, lf);
     if (!lf.ch[c].strength.solve()) {
       lf.fail_channel = c;
-      lf.fail_text = "Solving latest noise strength failed!";
+      lf.fail_text = kFailTexts[2];
       return;
     }
   }

@@ -27,8 +27,9 @@ RECORD_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t)
 EXPORTS = [
     "g1s_abi_version", "g1s_diff_create", "g1s_diff_push_frame", "g1s_diff_push_frame_device", "g1s_diff_flush",
     "g1s_diff_finish", "g1s_diff_destroy", "g1s_diff_last_error", "g1s_diff_frames_pushed",
-    "g1s_diff_get_counters", "g1s_record_layout", "g1s_diff_record_bytes", "g1s_diff_set_record_tap",
-    "g1s_diff_consume_record", "g1s_diff_consume_records", "g1s_write_grain_table", "g1s_format_grain_table",
+    "g1s_diff_get_counters", "g1s_diff_mark", "g1s_diff_marks_elapsed_ms", "g1s_record_layout", "g1s_diff_record_bytes", "g1s_diff_set_record_tap",
+    "g1s_diff_consume_record", "g1s_diff_consume_records", "g1s_digest_bytes", "g1s_diff_set_digest_sink",
+    "g1s_diff_digest_count", "g1s_diff_consume_digests", "g1s_diff_digest_from_record", "g1s_write_grain_table", "g1s_format_grain_table",
 ]
 
 
@@ -59,6 +60,9 @@ def lib() -> C.CDLL:
         L.g1s_diff_frames_pushed.argtypes = [C.c_void_p]
         L.g1s_diff_frames_pushed.restype = C.c_int64
         L.g1s_diff_get_counters.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_size_t]
+        L.g1s_diff_mark.argtypes = [C.c_void_p, C.c_int]
+        L.g1s_diff_marks_elapsed_ms.argtypes = [C.c_void_p]
+        L.g1s_diff_marks_elapsed_ms.restype = C.c_double
         L.g1s_record_layout.argtypes = [C.c_int32, C.POINTER(C.c_size_t)]
         L.g1s_record_layout.restype = C.c_size_t
         L.g1s_diff_record_bytes.argtypes = [C.c_void_p]
@@ -66,6 +70,12 @@ def lib() -> C.CDLL:
         L.g1s_diff_set_record_tap.argtypes = [C.c_void_p, RECORD_FN, C.c_void_p]
         L.g1s_diff_consume_record.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.g1s_diff_consume_records.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+        L.g1s_digest_bytes.restype = C.c_size_t
+        L.g1s_diff_set_digest_sink.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.g1s_diff_digest_count.argtypes = [C.c_void_p]
+        L.g1s_diff_digest_count.restype = C.c_int64
+        L.g1s_diff_consume_digests.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.g1s_diff_digest_from_record.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.g1s_write_grain_table.argtypes = [C.POINTER(CSegment), C.c_size_t, C.c_char_p]
         L.g1s_format_grain_table.argtypes = [C.POINTER(CSegment), C.c_size_t, C.c_char_p, C.c_size_t]
         L.g1s_format_grain_table.restype = C.c_int64
@@ -229,15 +239,44 @@ class DiffGenerator:
         assert recs.ndim == 2
         self._check(self._L.g1s_diff_consume_records(self._h, recs.ctypes.data, recs.shape[0], recs.strides[0]))
 
+    # -- digests (multi-GPU exchange unit)
+    def set_digest_sink(self, ptr: int, capacity_frames: int) -> None:
+        """ptr: address of a buffer of capacity_frames * digest_bytes() bytes (e.g. a pinned torch tensor)."""
+        self._check(self._L.g1s_diff_set_digest_sink(self._h, ptr, capacity_frames))
+
+    @property
+    def digest_count(self) -> int:
+        return int(self._L.g1s_diff_digest_count(self._h))
+
+    def digest_from_record(self, rec: np.ndarray) -> np.ndarray:
+        rec = np.ascontiguousarray(rec.view(np.uint8))
+        out = np.zeros(digest_bytes() // 8, np.float64)
+        self._check(self._L.g1s_diff_digest_from_record(self._h, rec.ctypes.data, rec.size, out.ctypes.data))
+        return out
+
+    def consume_digests(self, ptr: int, count: int) -> None:
+        self._check(self._L.g1s_diff_consume_digests(self._h, ptr, count))
+
     @property
     def frames_pushed(self) -> int:
         return int(self._L.g1s_diff_frames_pushed(self._h))
+
+    def mark(self, which: int) -> None:
+        """CUDA event on the engine's kernel stream (benchmark timing)."""
+        self._check(self._L.g1s_diff_mark(self._h, which))
+
+    def marks_elapsed_ms(self) -> float:
+        return float(self._L.g1s_diff_marks_elapsed_ms(self._h))
 
     def counters(self) -> dict:
         out = (C.c_double * 7)()
         self._check(self._L.g1s_diff_get_counters(self._h, out, 7))
         k = ("kernels_launched", "gram_ms", "gram_launches", "flat_ms", "flat_launches", "frames_done", "tma_batches")
         return dict(zip(k, [float(v) for v in out]))
+
+
+def digest_bytes() -> int:
+    return int(lib().g1s_digest_bytes())
 
 
 def format_grain_table(segments: Sequence[GrainTableSegment]) -> str:

@@ -1,46 +1,52 @@
 """Frame-sharded multi-GPU driver (one process per GPU, torch.distributed for the plumbing).
 
 The path shards by frame: every per-pixel quantity is a function of one frame
-pair, and the only cross-frame logic is the small sequential model update.  So each rank runs a
-PRODUCER handle (kernels only) on its own frames, the fixed-size per-frame integer records are
-all-gathered (NCCL over NVLink on GPUs, gloo in the CPU tests) once per super-batch, and rank 0
-feeds them in global frame order to one CONSUMER handle.  A super-batch is world*B consecutive
-frames; rank r owns frames [base + r*B, base + (r+1)*B), so the rank-major gather result is
-already in frame order.  There is no data-path collective besides that record gather.
+pair, and the only cross-frame logic is the small sequential model merge.  So each rank runs a
+PRODUCER handle on its own frames: kernels, plus the per-frame half of the host model, whose result
+is a fixed-size ~27 KB digest per frame written straight into a pinned tensor.  Once per super-batch
+the digests are all-gathered (NCCL over NVLink on GPUs, gloo in the CPU tests) and rank 0 folds them
+in global frame order into one CONSUMER handle.  A super-batch is world*B consecutive frames; rank r
+owns frames [base + r*B, base + (r+1)*B), so the rank-major gather result is already in frame order.
+There is no data-path collective besides that gather.
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence
+from typing import Callable, Optional
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import abi
-from .diff import DiffGenerator, RecordLayout
+from .diff import DiffGenerator, digest_bytes
 
 
 class ShardedDiff:
     def __init__(self, fps_num: int, fps_den: int, source_bit_depth: int, denoised_bit_depth: int, width: int,
                  height: int, ss_x: int = 1, ss_y: int = 1, frames_per_rank: int = 8, device: Optional[int] = None,
-                 producer_factory: Optional[Callable[[], object]] = None, group=None):
+                 producer_factory: Optional[Callable[[], object]] = None, group=None, batch_frames: int = 0):
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.group = group
         self.B = frames_per_rank
-        self.nb = ((width + 31) // 32) * ((height + 31) // 32)
-        self.layout = RecordLayout(self.nb)
-        self._records: List[np.ndarray] = []
+        self.ndbl = digest_bytes() // 8
         args = (fps_num, fps_den, source_bit_depth, denoised_bit_depth, width, height, ss_x, ss_y)
-        if producer_factory is not None:          # tests inject a CPU record producer
+        if producer_factory is not None:          # tests inject a CPU digest producer
             self.producer = producer_factory()
         else:
-            self.producer = DiffGenerator(*args, device=device or 0, batch_frames=frames_per_rank,
+            self.producer = DiffGenerator(*args, device=device or 0, batch_frames=batch_frames,
                                           mode=abi.MODE_PRODUCER)
-        self.producer.set_record_tap(lambda i, r: self._records.append(r))
-        self.consumer = DiffGenerator(*args, mode=abi.MODE_CONSUMER) if self.rank == 0 else None
         backend = dist.get_backend(group) if dist.is_initialized() else "none"
-        self.comm_device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        self.on_gpu = backend == "nccl"
+        # the producer writes digests straight into this (pinned when a GPU is involved) tensor
+        self.sink = torch.zeros((self.B, self.ndbl), dtype=torch.float64)
+        if self.on_gpu:
+            self.sink = self.sink.pin_memory()
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self.dev_local = torch.empty((self.B + 1, self.ndbl), dtype=torch.float64, device=dev)
+            self.dev_all = torch.empty((self.world * (self.B + 1), self.ndbl), dtype=torch.float64, device=dev)
+            self.host_all = torch.empty((self.world * (self.B + 1), self.ndbl), dtype=torch.float64).pin_memory()
+        self.producer.set_digest_sink(self.sink.data_ptr(), self.B)
+        self.consumer = DiffGenerator(*args, mode=abi.MODE_CONSUMER) if self.rank == 0 else None
 
     # -- per super-batch --------------------------------------------------------------
     def push_local(self, source, denoised, device_resident: bool = False) -> None:
@@ -51,39 +57,39 @@ class ShardedDiff:
             self.producer.diff_frame(source, denoised)
 
     def exchange(self) -> int:
-        """Finish the super-batch: drain the local kernels, gather all ranks' records, fold them
+        """Finish the super-batch: drain the local kernels, gather all ranks' digests, fold them
         into the model on rank 0 in global frame order.  Returns the frames folded (rank 0)."""
         self.producer.flush()
-        n_local = len(self._records)
+        n_local = self.producer.digest_count
         if n_local > self.B:
             raise RuntimeError("more than frames_per_rank frames pushed in one super-batch")
-        buf = torch.zeros((self.B, self.layout.bytes), dtype=torch.uint8)
-        if n_local:
-            buf[:n_local] = torch.from_numpy(np.stack(self._records))
-        self._records.clear()
-        count = torch.tensor([n_local], dtype=torch.int64)
-        if self.world > 1:
-            buf = buf.to(self.comm_device)
-            count = count.to(self.comm_device)
-            allbuf = torch.empty((self.world * self.B, self.layout.bytes), dtype=torch.uint8, device=self.comm_device)
-            allcnt = torch.empty((self.world,), dtype=torch.int64, device=self.comm_device)
-            dist.all_gather_into_tensor(allbuf, buf, group=self.group)
-            dist.all_gather_into_tensor(allcnt, count, group=self.group)
-            allbuf, allcnt = allbuf.cpu().view(self.world, self.B, self.layout.bytes), allcnt.cpu()
-        else:
-            allbuf, allcnt = buf.unsqueeze(0), count.unsqueeze(0)
         folded = 0
+        if self.world > 1 and self.on_gpu:
+            # row B of every rank's block carries its frame count
+            self.dev_local[: self.B].copy_(self.sink, non_blocking=True)
+            self.dev_local[self.B].fill_(float(n_local))
+            dist.all_gather_into_tensor(self.dev_all, self.dev_local, group=self.group)
+            if self.consumer is not None:
+                self.host_all.copy_(self.dev_all, non_blocking=False)
+                allv = self.host_all.view(self.world, self.B + 1, self.ndbl)
+        elif self.world > 1:
+            local = torch.cat([self.sink, torch.full((1, self.ndbl), float(n_local), dtype=torch.float64)])
+            allbuf = torch.empty((self.world * (self.B + 1), self.ndbl), dtype=torch.float64)
+            dist.all_gather_into_tensor(allbuf, local, group=self.group)
+            allv = allbuf.view(self.world, self.B + 1, self.ndbl)
+        else:
+            allv = torch.cat([self.sink, torch.full((1, self.ndbl), float(n_local), dtype=torch.float64)]).unsqueeze(0)
         if self.consumer is not None:
-            counts = [int(c) for c in allcnt.view(-1)]
-            # a short rank may only be followed by empty ranks (tail of the stream)
             seen_short = False
-            for r, c in enumerate(counts):
-                if seen_short and c:
+            for r in range(self.world):
+                c = int(allv[r, self.B, 0].item())
+                if seen_short and c:  # a short rank may only be followed by empty ranks (tail of the stream)
                     raise RuntimeError("frames are not contiguous across ranks in this super-batch")
                 seen_short |= c < self.B
                 if c:
-                    self.consumer.consume_records(allbuf[r].numpy()[:c])
+                    self.consumer.consume_digests(allv[r].data_ptr(), c)
                     folded += c
+        self.producer.set_digest_sink(self.sink.data_ptr(), self.B)  # reset the count for the next super-batch
         return folded
 
     def finish(self):

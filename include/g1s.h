@@ -160,6 +160,11 @@ int64_t g1s_diff_frames_pushed(const g1s_diff *d);
  * raw tiles were staged by the TMA engine (0 when the planes are not 16-byte aligned). */
 int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n);
 
+/* Records CUDA event `which` (0 or 1) on the engine's kernel stream; g1s_diff_marks_elapsed_ms returns the
+ * device time between them (benchmark timing on the stream the kernels are launched on). */
+int g1s_diff_mark(g1s_diff *d, int which);
+double g1s_diff_marks_elapsed_ms(g1s_diff *d);
+
 /* ---- per-frame records (the unit exchanged between GPUs) -------------------------
  * One record holds everything the host model needs from one frame pair, all integers
  * except the f32 flatness scores: gram[3][351] int64 (upper triangle over 26 taps:
@@ -178,6 +183,23 @@ int g1s_diff_consume_record(g1s_diff *d, const void *record, size_t bytes);
 /* Same for `count` consecutive frames, record k at records + k * stride_bytes; the per-frame half of
  * the model is evaluated on the handle's host threads, the merge stays in frame order. */
 int g1s_diff_consume_records(g1s_diff *d, const void *records, size_t count, size_t stride_bytes);
+
+/* ---- per-frame digests (what scales across GPUs) ------------------------------------
+ * The host model splits into a per-frame half (a pure function of one record: AR solve, strength
+ * measurements, strength solve) and a sequential merge.  A PRODUCER handle with a digest sink runs
+ * the per-frame half itself and writes one fixed-size digest (g1s_digest_bytes(), ~27 KB, independent
+ * of the frame size) per retired frame into the caller's buffer, in frame order; the rank that owns
+ * the model folds them with g1s_diff_consume_digests.  Same results as exchanging the full records,
+ * 10x less traffic and no per-frame work left on the sequential rank but the merge itself. */
+size_t g1s_digest_bytes(void);
+/* buffer must hold capacity_frames digests and stay valid while it is the sink; resets the count. */
+int g1s_diff_set_digest_sink(g1s_diff *d, void *buffer, size_t capacity_frames);
+/* digests written into the sink since it was (re)set. */
+int64_t g1s_diff_digest_count(const g1s_diff *d);
+int g1s_diff_consume_digests(g1s_diff *d, const void *digests, size_t count);
+/* Evaluates the per-frame half for one record without touching the model (any handle of the stream's
+ * geometry; no device work) and writes its digest. */
+int g1s_diff_digest_from_record(g1s_diff *d, const void *record, size_t bytes, void *digest_out);
 
 /* `filmgrn1` writer — src/main.rs:525-530 and 631-696, byte for byte. */
 int g1s_write_grain_table(const g1s_segment *segs, size_t n, const char *path);

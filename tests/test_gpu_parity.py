@@ -195,6 +195,26 @@ def test_dimension_mismatch_raises():
         g.diff_frame(a, b)
 
 
+def test_producer_digests_fold_to_the_same_table():
+    """PRODUCER handle (kernels + per-frame model half, digests into a sink) -> CONSUMER handle: the
+    multi-GPU data flow on one GPU must reproduce the FULL handle's table."""
+    import torch
+    from grav1synth_b200 import abi
+    spec, fps, frames = corpus_frames("c3_small_10bit")
+    full, _, _ = gpu_run(spec, fps, frames)
+    args = (fps[0], fps[1], spec.bit_depth, spec.bit_depth, spec.width, spec.height, spec.ss_x, spec.ss_y)
+    prod = D.DiffGenerator(*args, mode=abi.MODE_PRODUCER, batch_frames=2)
+    cons = D.DiffGenerator(*args, mode=abi.MODE_CONSUMER)
+    sink = torch.zeros((len(frames), D.digest_bytes() // 8), dtype=torch.float64).pin_memory()
+    prod.set_digest_sink(sink.data_ptr(), len(frames))
+    for s, d in frames:
+        prod.diff_frame(s, d)
+    prod.flush()
+    assert prod.digest_count == len(frames)
+    cons.consume_digests(sink.data_ptr(), len(frames))
+    assert cons.finish() == full
+
+
 def test_monochrome():
     spec, fps, frames = corpus_frames("c2_small_8bit")
     g = D.DiffGenerator(fps[0], fps[1], 8, 8, spec.width, spec.height, monochrome=True)

@@ -15,16 +15,28 @@ from helpers import ROOT, corpus_frames, gram_to_pairs, numpy_record
 
 
 class CpuRecordProducer:
-    def __init__(self, spec):
-        from grav1synth_b200.diff import RecordLayout
+    """Stand-in for the CUDA producer: per-frame record from the oracle's flat mask + numpy sums, turned into a
+    digest by the product's own per-frame model code (g1s_diff_digest_from_record), written into the sink."""
+
+    def __init__(self, spec, fps):
+        import ctypes as C
+        from grav1synth_b200 import abi
+        from grav1synth_b200.diff import DiffGenerator, RecordLayout, digest_bytes
         from oracle import oracle as O
         self.spec = spec
         self.o = O.OracleDiffGenerator(24, 1, spec.bit_depth, spec.bit_depth, ss_x=spec.ss_x, ss_y=spec.ss_y)
         self.rl = RecordLayout(((spec.width + 31) // 32) * ((spec.height + 31) // 32))
-        self.pending, self.tap, self.count = [], None, 0
+        self.helper = DiffGenerator(fps[0], fps[1], spec.bit_depth, spec.bit_depth, spec.width, spec.height, spec.ss_x,
+                                    spec.ss_y, mode=abi.MODE_CONSUMER)
+        self.pending, self.sink, self.cap, self.count, self.C = [], None, 0, 0, C
+        self.ndbl = digest_bytes() // 8
 
-    def set_record_tap(self, fn):
-        self.tap = fn
+    def set_digest_sink(self, ptr, cap):
+        self.sink, self.cap, self.count = ptr, cap, 0
+
+    @property
+    def digest_count(self):
+        return self.count
 
     def diff_frame(self, s, d):
         spec = self.spec
@@ -36,7 +48,9 @@ class CpuRecordProducer:
 
     def flush(self):
         for rec in self.pending:
-            self.tap(self.count, rec)
+            dg = self.helper.digest_from_record(rec)
+            dst = (self.C.c_double * self.ndbl).from_address(self.sink + 8 * self.ndbl * self.count)
+            np.frombuffer(dst, np.float64)[:] = dg
             self.count += 1
         self.pending.clear()
 
@@ -51,7 +65,7 @@ def _worker(rank, world, port, name, B, out_path):
     from grav1synth_b200.sharded import ShardedDiff, owner_of
     spec, fps, frames = corpus_frames(name)
     sd = ShardedDiff(fps[0], fps[1], spec.bit_depth, spec.bit_depth, spec.width, spec.height, spec.ss_x, spec.ss_y,
-                     frames_per_rank=B, producer_factory=lambda: CpuRecordProducer(spec))
+                     frames_per_rank=B, producer_factory=lambda: CpuRecordProducer(spec, fps))
     n, base, folded = len(frames), 0, 0
     while base < n:
         for k in range(base, min(n, base + world * B)):

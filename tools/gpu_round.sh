@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 ( timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tail -5 ) > gpurun_out/bench.log
 cat gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/bench.log
 if [ "$1" == "prof" ]; then
-CMD="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --frames 16 --batch 8"
+CMD="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --frames 20"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"flat_|gram_" -c 80 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gram_imma -s 1 -c 1 -f -o gpurun_out/prof_gram $CMD > gpurun_out/ncu_gram.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:flat_features -s 1 -c 1 -f -o gpurun_out/prof_flat $CMD > gpurun_out/ncu_flat.log 2>&1
