@@ -21,6 +21,7 @@
 #include <thread>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <string>
 #include <vector>
@@ -105,6 +106,62 @@ class HostPool {
   bool stop_ = false;
 };
 
+// The sequential half of the host model (merge into the combined state, segment cuts) runs on its own
+// thread, strictly in submission order, so neither the kernels' launches nor the caller wait for it.
+class FoldQueue {
+ public:
+  FoldQueue() : th_([this] { loop(); }) {}
+  ~FoldQueue() {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    th_.join();
+  }
+  uint64_t push(std::function<void()> fn) {
+    std::lock_guard<std::mutex> l(m_);
+    q_.push_back(std::move(fn));
+    cv_.notify_all();
+    return ++submitted_;
+  }
+  void wait(uint64_t ticket) {
+    std::unique_lock<std::mutex> l(m_);
+    done_cv_.wait(l, [&] { return done_ >= ticket; });
+  }
+  void wait_all() { wait(submitted_snapshot()); }
+
+ private:
+  uint64_t submitted_snapshot() {
+    std::lock_guard<std::mutex> l(m_);
+    return submitted_;
+  }
+  void loop() {
+    for (;;) {
+      std::function<void()> fn;
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return stop_ || !q_.empty(); });
+        if (q_.empty()) return;
+        fn = std::move(q_.front());
+        q_.pop_front();
+      }
+      fn();
+      {
+        std::lock_guard<std::mutex> l(m_);
+        ++done_;
+      }
+      done_cv_.notify_all();
+    }
+  }
+  std::mutex m_;
+  std::condition_variable cv_, done_cv_;
+  std::deque<std::function<void()>> q_;
+  uint64_t submitted_ = 0, done_ = 0;
+  bool stop_ = false;
+  std::thread th_;
+};
+
 struct PlaneGeom {
   int w, h;          // storage size in samples
   size_t pitch[2];   // [0] source, [1] denoised: bytes per row in the HBM frame store
@@ -124,6 +181,8 @@ struct Slot {
   int count = 0;                 // frames staged
   int host_frames = 0;           // of which need the H2D copy (contiguous prefix is not required)
   bool in_flight = false;
+  std::vector<LatestFrame> latest;  // per-frame model state of the batch, owned until its fold job is done
+  uint64_t fold_ticket = 0;
 };
 
 }  // namespace
@@ -145,7 +204,8 @@ struct g1s_diff {
   int oldest = 0;         // oldest slot possibly in flight
   std::unique_ptr<DiffSequencer> seq;
   std::unique_ptr<HostPool> pool;
-  std::vector<LatestFrame> latest;  // one per frame of a batch, reused
+  std::unique_ptr<FoldQueue> folder;
+  std::vector<LatestFrame> latest;  // scratch for the single-record entry points
   std::string err;
   bool finished = false;
   int64_t pushed = 0;
@@ -190,20 +250,28 @@ FrameRecordView view_of(const g1s_diff *d, const uint8_t *rec) {
 }
 
 // Per-frame model evaluation in parallel, then tap + merge in frame order.
-void fold_records(g1s_diff *d, const uint8_t *recs, int count, size_t stride) {
+// Per-frame model half in parallel on the host pool, taps / digests on the caller's thread in frame
+// order, then the sequential merge is queued for the fold thread.  `store` must stay untouched until the
+// returned ticket is done (0: nothing queued).
+uint64_t fold_records(g1s_diff *d, const uint8_t *recs, int count, size_t stride, std::vector<LatestFrame> &store) {
   const bool model = d->cfg.mode != G1S_MODE_PRODUCER;
   if (model || d->sink) {
-    if ((int)d->latest.size() < count) d->latest.resize(count);
+    if ((int)store.size() < count) store.resize(count);
     const NoiseModel &nm = d->seq->model();
-    d->pool->parallel_for(count, [&](int i) { nm.compute_latest(view_of(d, recs + (size_t)i * stride), d->latest[i]); });
+    d->pool->parallel_for(count, [&](int i) { nm.compute_latest(view_of(d, recs + (size_t)i * stride), store[i]); });
   }
   for (int i = 0; i < count; ++i) {
     if (d->tap) d->tap(d->tap_user, d->retired, recs + (size_t)i * stride, d->rl.bytes);
-    if (model) d->seq->consume_latest(d->latest[i]);
     if (d->sink && d->sink_count < d->sink_cap)
-      d->latest[i].to_digest(d->sink + LatestFrame::kDigestDoubles * d->sink_count++);
+      store[i].to_digest(d->sink + LatestFrame::kDigestDoubles * d->sink_count++);
     d->retired++;
   }
+  if (!model) return 0;
+  DiffSequencer *seq = d->seq.get();
+  LatestFrame *frames = store.data();
+  return d->folder->push([seq, frames, count] {
+    for (int i = 0; i < count; ++i) seq->consume_latest(frames[i]);
+  });
 }
 
 // Builds the six TMA descriptors of every frame of the batch.  Returns false when a plane is not
@@ -299,7 +367,8 @@ int retire(g1s_diff *d, Slot &s) {
   float ms = 0;
   if (cudaEventElapsedTime(&ms, s.k0_beg, s.k0_end) == cudaSuccess) d->k0_ms += ms;
   if (cudaEventElapsedTime(&ms, s.k1_beg, s.k1_end) == cudaSuccess) d->k1_ms += ms;
-  fold_records(d, s.h_records, s.count, d->rl.bytes);
+  d->folder->wait(s.fold_ticket);  // the slot's previous batch must have left the fold thread
+  s.fold_ticket = fold_records(d, s.h_records, s.count, d->rl.bytes, s.latest);
   d->frames_done += s.count;
   s.in_flight = false;
   s.count = 0;
@@ -330,6 +399,7 @@ int drain(g1s_diff *d) {
     d->oldest = (d->oldest + 1) % kSlots;
   }
   d->oldest = d->cur;
+  d->folder->wait_all();
   return G1S_OK;
 }
 
@@ -433,6 +503,7 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     if (const char *e = std::getenv("G1S_HOST_THREADS")) threads = std::atoi(e);
     if (threads <= 0) threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
     d->pool.reset(new HostPool(threads));
+    d->folder.reset(new FoldQueue());
   }
 
   size_t off = 0;
@@ -596,7 +667,10 @@ int g1s_diff_push_frame_device(g1s_diff *d, const g1s_frame *source, const g1s_f
 
 int g1s_diff_flush(g1s_diff *d) {
   if (!d) return G1S_E_ARG;
-  if (d->cfg.mode == G1S_MODE_CONSUMER) return G1S_OK;
+  if (d->cfg.mode == G1S_MODE_CONSUMER) {
+    d->folder->wait_all();
+    return G1S_OK;
+  }
   return drain(d);
 }
 
@@ -629,7 +703,10 @@ int g1s_diff_consume_record(g1s_diff *d, const void *record, size_t bytes) {
     d->err = "record size does not match this stream's geometry";
     return G1S_E_ARG;
   }
-  fold_records(d, static_cast<const uint8_t *>(record), 1, bytes);
+  auto blk = std::make_shared<std::vector<LatestFrame>>(1);
+  const uint64_t t = fold_records(d, static_cast<const uint8_t *>(record), 1, bytes, *blk);
+  d->folder->push([blk] {});  // keeps the block alive until the fold job before it has run
+  (void)t;
   d->pushed++;
   d->frames_done += 1;
   return G1S_OK;
@@ -645,7 +722,9 @@ int g1s_diff_consume_records(g1s_diff *d, const void *records, size_t count, siz
     d->err = "record stride smaller than this stream's record size";
     return G1S_E_ARG;
   }
-  fold_records(d, static_cast<const uint8_t *>(records), (int)count, stride_bytes);
+  auto blk = std::make_shared<std::vector<LatestFrame>>(count);
+  fold_records(d, static_cast<const uint8_t *>(records), (int)count, stride_bytes, *blk);
+  d->folder->push([blk] {});  // keeps the block alive until the fold job before it has run
   d->pushed += (int64_t)count;
   d->frames_done += (double)count;
   return G1S_OK;
@@ -659,6 +738,7 @@ int g1s_diff_finish(g1s_diff *d, g1s_segment *out, size_t cap, size_t *n) {
   }
   int rc = d->cfg.mode == G1S_MODE_CONSUMER ? G1S_OK : drain(d);
   if (rc != G1S_OK) return rc;
+  d->folder->wait_all();
   std::vector<g1s_segment> segs = d->seq->finish();
   *n = segs.size();
   if (cap < segs.size() || !out) {
@@ -672,6 +752,7 @@ int g1s_diff_finish(g1s_diff *d, g1s_segment *out, size_t cap, size_t *n) {
 
 void g1s_diff_destroy(g1s_diff *d) {
   if (!d) return;
+  d->folder.reset();  // runs the queued folds to completion, then joins
   if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
   if (d->stream) cudaStreamSynchronize(d->stream);
   for (Slot &s : d->slots) {
@@ -738,13 +819,18 @@ int g1s_diff_consume_digests(g1s_diff *d, const void *digests, size_t count) {
     d->err = "consume_digests needs an unfinished CONSUMER handle";
     return G1S_E_STATE;
   }
-  if (d->latest.empty()) d->latest.resize(1);
-  const double *p = static_cast<const double *>(digests);
-  for (size_t i = 0; i < count; ++i) {
-    d->latest[0].from_digest(p + LatestFrame::kDigestDoubles * i);
-    d->seq->consume_latest(d->latest[0]);
-    d->retired++;
-  }
+  // the digests are copied (the caller's buffer is free on return) and folded asynchronously, in order
+  auto blk = std::make_shared<std::vector<double>>(static_cast<const double *>(digests),
+                                                   static_cast<const double *>(digests) + LatestFrame::kDigestDoubles * count);
+  DiffSequencer *seq = d->seq.get();
+  d->folder->push([blk, seq, count] {
+    LatestFrame lf;
+    for (size_t i = 0; i < count; ++i) {
+      lf.from_digest(blk->data() + LatestFrame::kDigestDoubles * i);
+      seq->consume_latest(lf);
+    }
+  });
+  d->retired += (int64_t)count;
   d->pushed += (int64_t)count;
   d->frames_done += (double)count;
   return G1S_OK;

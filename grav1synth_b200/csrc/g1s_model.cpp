@@ -20,7 +20,8 @@ constexpr int kNumBins = 20;
 constexpr uint16_t kDefaultGrainSeed = 10956;
 
 // util.rs::linsolve (libaom mathutils.h): elimination with adjacent-row pivot bubbling.
-bool gauss_solve(int n, double *A, double *b, double *x) {
+// (row updates are element-wise independent, so wider vectors change nothing but the speed)
+__attribute__((target_clones("avx2", "default"))) bool gauss_solve(int n, double *A, double *b, double *x) {
   for (int k = 0; k + 1 < n; ++k) {
     for (int i = n - 1; i > k; --i) {
       if (std::fabs(A[(i - 1) * n + k]) < std::fabs(A[i * n + k])) {
@@ -65,7 +66,10 @@ void LinearSystem::clear() {
   std::fill(x.begin(), x.end(), 0.0);
 }
 bool LinearSystem::solve() {
-  std::vector<double> Ac(A), bc(b);
+  // elimination works on copies (EquationSystem::solve); the scratch is per thread, not per call
+  static thread_local std::vector<double> Ac, bc;
+  Ac.assign(A.begin(), A.end());
+  bc.assign(b.begin(), b.end());
   return gauss_solve(n, Ac.data(), bc.data(), x.data());
 }
 void LinearSystem::add(const LinearSystem &o) {
@@ -120,21 +124,21 @@ bool StrengthSolver::solve() {
   // Regularised copy of A; b keeps the ridge term (the reference modifies b in place).
   const int n = num_bins;
   const double alpha = 2.0 * (double)num_equations / n;
-  std::vector<double> saved(eqns.A);
+  static thread_local std::vector<double> Ar, br;
+  Ar.assign(eqns.A.begin(), eqns.A.end());
   for (int i = 0; i < n; ++i) {
     const int lo = std::max(0, i - 1), hi = std::min(n - 1, i + 1);
-    eqns.A[i * n + lo] -= alpha;
-    eqns.A[i * n + i] += 2 * alpha;
-    eqns.A[i * n + hi] -= alpha;
+    Ar[i * n + lo] -= alpha;
+    Ar[i * n + i] += 2 * alpha;
+    Ar[i * n + hi] -= alpha;
   }
   const double mean = total / num_equations;
   for (int i = 0; i < n; ++i) {
-    eqns.A[i * n + i] += 1.0 / 8192.;
+    Ar[i * n + i] += 1.0 / 8192.;
     eqns.b[i] += mean / 8192.;
   }
-  const bool ok = eqns.solve();
-  eqns.A.swap(saved);
-  return ok;
+  br.assign(eqns.b.begin(), eqns.b.end());  // elimination consumes its inputs
+  return gauss_solve(n, Ar.data(), br.data(), eqns.x.data());
 }
 void StrengthSolver::add(const StrengthSolver &o) {
   eqns.add(o.eqns);
