@@ -212,6 +212,8 @@ def main():
     def barrier():
         if world == 1:
             eng.flush()  # every pushed frame processed by the device AND folded into the host model
+        else:
+            sd.exchange(final=True)  # drain kernels, gather the outstanding digests, fold them on rank 0
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -306,7 +308,11 @@ def main():
         def e2e_barrier():
             if world == 1:
                 g.flush()
-            barrier()
+            else:
+                sd2.exchange(final=True)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
 
         e2e_step()
         e2e_barrier()

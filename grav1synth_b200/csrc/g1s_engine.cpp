@@ -262,8 +262,8 @@ uint64_t fold_records(g1s_diff *d, const uint8_t *recs, int count, size_t stride
   }
   for (int i = 0; i < count; ++i) {
     if (d->tap) d->tap(d->tap_user, d->retired, recs + (size_t)i * stride, d->rl.bytes);
-    if (d->sink && d->sink_count < d->sink_cap)
-      store[i].to_digest(d->sink + LatestFrame::kDigestDoubles * d->sink_count++);
+    if (d->sink && d->sink_cap)
+      store[i].to_digest(d->sink + LatestFrame::kDigestDoubles * (d->sink_count++ % d->sink_cap));
     d->retired++;
   }
   if (!model) return 0;
@@ -812,6 +812,17 @@ int g1s_diff_set_digest_sink(g1s_diff *d, void *buffer, size_t capacity_frames) 
 }
 
 int64_t g1s_diff_digest_count(const g1s_diff *d) { return d ? (int64_t)d->sink_count : 0; }
+
+int g1s_diff_wait_retired(g1s_diff *d, int64_t frames) {
+  if (!d) return G1S_E_ARG;
+  if (d->cfg.mode == G1S_MODE_CONSUMER) return G1S_OK;
+  while (d->retired < frames && d->slots[d->oldest].in_flight) {
+    const int rc = retire(d, d->slots[d->oldest]);
+    if (rc != G1S_OK) return rc;
+    d->oldest = (d->oldest + 1) % kSlots;
+  }
+  return G1S_OK;
+}
 
 int g1s_diff_consume_digests(g1s_diff *d, const void *digests, size_t count) {
   if (!d || (!digests && count)) return G1S_E_ARG;

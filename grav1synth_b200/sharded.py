@@ -3,11 +3,13 @@
 The path shards by frame: every per-pixel quantity is a function of one frame
 pair, and the only cross-frame logic is the small sequential model merge.  So each rank runs a
 PRODUCER handle on its own frames: kernels, plus the per-frame half of the host model, whose result
-is a fixed-size ~27 KB digest per frame written straight into a pinned tensor.  Once per super-batch
+is a fixed-size ~27 KB digest per frame written straight into a pinned ring.  Once per super-batch
 the digests are all-gathered (NCCL over NVLink on GPUs, gloo in the CPU tests) and rank 0 folds them
-in global frame order into one CONSUMER handle.  A super-batch is world*B consecutive frames; rank r
-owns frames [base + r*B, base + (r+1)*B), so the rank-major gather result is already in frame order.
-There is no data-path collective besides that gather.
+in global frame order into one CONSUMER handle (asynchronously, on the handle's own thread).
+A super-batch is world*B consecutive frames; rank r owns frames [base + r*B, base + (r+1)*B), so the
+rank-major gather result is already in frame order.  The gather of super-batch k is issued after the
+frames of super-batch k+1 have been queued, so it overlaps the kernels.  There is no data-path
+collective besides that gather.
 """
 from __future__ import annotations
 
@@ -18,6 +20,8 @@ import torch.distributed as dist
 
 from . import abi
 from .diff import DiffGenerator, digest_bytes
+
+RING = 4  # super-batches the digest ring holds
 
 
 class ShardedDiff:
@@ -37,16 +41,21 @@ class ShardedDiff:
                                           mode=abi.MODE_PRODUCER)
         backend = dist.get_backend(group) if dist.is_initialized() else "none"
         self.on_gpu = backend == "nccl"
-        # the producer writes digests straight into this (pinned when a GPU is involved) tensor
-        self.sink = torch.zeros((self.B, self.ndbl), dtype=torch.float64)
+        # the producer writes digests straight into this ring (pinned when a GPU is involved)
+        self.ring = torch.zeros((RING * self.B, self.ndbl), dtype=torch.float64)
+        rows = self.B + 1  # + one row carrying the rank's frame count of the super-batch
         if self.on_gpu:
-            self.sink = self.sink.pin_memory()
+            self.ring = self.ring.pin_memory()
             dev = torch.device("cuda", torch.cuda.current_device())
-            self.dev_local = torch.empty((self.B + 1, self.ndbl), dtype=torch.float64, device=dev)
-            self.dev_all = torch.empty((self.world * (self.B + 1), self.ndbl), dtype=torch.float64, device=dev)
-            self.host_all = torch.empty((self.world * (self.B + 1), self.ndbl), dtype=torch.float64).pin_memory()
-        self.producer.set_digest_sink(self.sink.data_ptr(), self.B)
+            self.dev_local = torch.empty((rows, self.ndbl), dtype=torch.float64, device=dev)
+            self.dev_all = torch.empty((self.world * rows, self.ndbl), dtype=torch.float64, device=dev)
+            self.host_all = torch.empty((self.world * rows, self.ndbl), dtype=torch.float64).pin_memory()
+        self.producer.set_digest_sink(self.ring.data_ptr(), RING * self.B)
         self.consumer = DiffGenerator(*args, mode=abi.MODE_CONSUMER) if self.rank == 0 else None
+        self.pushed = 0        # local frames pushed
+        self.sb_pushed = []    # local frame count of every super-batch closed so far
+        self.sb_done = 0       # super-batches exchanged
+        self.folded = 0        # frames handed to the consumer (rank 0)
 
     # -- per super-batch --------------------------------------------------------------
     def push_local(self, source, denoised, device_resident: bool = False) -> None:
@@ -55,30 +64,36 @@ class ShardedDiff:
             self.producer.diff_frame_device(*source, *denoised)
         else:
             self.producer.diff_frame(source, denoised)
+        self.pushed += 1
 
-    def exchange(self) -> int:
-        """Finish the super-batch: drain the local kernels, gather all ranks' digests, fold them
-        into the model on rank 0 in global frame order.  Returns the frames folded (rank 0)."""
-        self.producer.flush()
-        n_local = self.producer.digest_count
-        if n_local > self.B:
-            raise RuntimeError("more than frames_per_rank frames pushed in one super-batch")
-        folded = 0
+    def _exchange_one(self, final: bool) -> None:
+        k = self.sb_done
+        n_local = self.sb_pushed[k]
+        first = sum(self.sb_pushed[:k])
+        if final:
+            self.producer.flush()
+        else:
+            self.producer.wait_retired(first + n_local)
+        if self.producer.digest_count < first + n_local:
+            raise RuntimeError("digests of the super-batch are not complete")
+        lo = (k % RING) * self.B
+        local = self.ring[lo:lo + self.B]
+        rows = self.B + 1
         if self.world > 1 and self.on_gpu:
-            # row B of every rank's block carries its frame count
-            self.dev_local[: self.B].copy_(self.sink, non_blocking=True)
+            self.dev_local[: self.B].copy_(local, non_blocking=True)
             self.dev_local[self.B].fill_(float(n_local))
             dist.all_gather_into_tensor(self.dev_all, self.dev_local, group=self.group)
+            allv = None
             if self.consumer is not None:
                 self.host_all.copy_(self.dev_all, non_blocking=False)
-                allv = self.host_all.view(self.world, self.B + 1, self.ndbl)
+                allv = self.host_all.view(self.world, rows, self.ndbl)
         elif self.world > 1:
-            local = torch.cat([self.sink, torch.full((1, self.ndbl), float(n_local), dtype=torch.float64)])
-            allbuf = torch.empty((self.world * (self.B + 1), self.ndbl), dtype=torch.float64)
-            dist.all_gather_into_tensor(allbuf, local, group=self.group)
-            allv = allbuf.view(self.world, self.B + 1, self.ndbl)
+            mine = torch.cat([local, torch.full((1, self.ndbl), float(n_local), dtype=torch.float64)])
+            allbuf = torch.empty((self.world * rows, self.ndbl), dtype=torch.float64)
+            dist.all_gather_into_tensor(allbuf, mine, group=self.group)
+            allv = allbuf.view(self.world, rows, self.ndbl)
         else:
-            allv = torch.cat([self.sink, torch.full((1, self.ndbl), float(n_local), dtype=torch.float64)]).unsqueeze(0)
+            allv = torch.cat([local, torch.full((1, self.ndbl), float(n_local), dtype=torch.float64)]).unsqueeze(0)
         if self.consumer is not None:
             seen_short = False
             for r in range(self.world):
@@ -87,13 +102,29 @@ class ShardedDiff:
                     raise RuntimeError("frames are not contiguous across ranks in this super-batch")
                 seen_short |= c < self.B
                 if c:
-                    self.consumer.consume_digests(allv[r].data_ptr(), c)
-                    folded += c
-        self.producer.set_digest_sink(self.sink.data_ptr(), self.B)  # reset the count for the next super-batch
-        return folded
+                    self.consumer.consume_digests(allv[r].data_ptr(), c)  # copied, folded asynchronously
+                    self.folded += c
+        self.sb_done += 1
+
+    def exchange(self, final: bool = False) -> int:
+        """Close the current super-batch.  Unless `final`, only the super-batch BEFORE it is gathered now
+        (its kernels finished while this one was being queued), so the gather overlaps compute.  With
+        `final` everything outstanding is drained, gathered and folded.  Returns frames folded so far."""
+        closed = self.pushed - sum(self.sb_pushed)
+        if closed > self.B:
+            raise RuntimeError("more than frames_per_rank frames pushed in one super-batch")
+        self.sb_pushed.append(closed)
+        keep = 0 if final else 1
+        while len(self.sb_pushed) - self.sb_done > keep:
+            self._exchange_one(final)
+        if final and self.consumer is not None:
+            self.consumer.flush()
+        return self.folded
 
     def finish(self):
-        """rank 0: the grain table; other ranks: None."""
+        """rank 0: the grain table; other ranks: None.  Call exchange(final=True) first."""
+        if len(self.sb_pushed) != self.sb_done or self.pushed != sum(self.sb_pushed):
+            self.exchange(final=True)
         return self.consumer.finish() if self.consumer is not None else None
 
 

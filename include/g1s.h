@@ -192,10 +192,16 @@ int g1s_diff_consume_records(g1s_diff *d, const void *records, size_t count, siz
  * the model folds them with g1s_diff_consume_digests.  Same results as exchanging the full records,
  * 10x less traffic and no per-frame work left on the sequential rank but the merge itself. */
 size_t g1s_digest_bytes(void);
-/* buffer must hold capacity_frames digests and stay valid while it is the sink; resets the count. */
+/* buffer must hold capacity_frames digests and stay valid while it is the sink; resets the count.
+ * The sink is a ring: digest k (counted from the reset) lands in slot k % capacity_frames, so a reader
+ * that keeps up never has to reset it. */
 int g1s_diff_set_digest_sink(g1s_diff *d, void *buffer, size_t capacity_frames);
-/* digests written into the sink since it was (re)set. */
+/* digests written into the sink since it was (re)set (monotonic). */
 int64_t g1s_diff_digest_count(const g1s_diff *d);
+/* Blocks until at least `frames` frames (counted from creation) have left the device pipeline and, for
+ * sinks and taps, been delivered -- without forcing a partially filled batch out as flush does.
+ * Returns early if fewer frames are in flight. */
+int g1s_diff_wait_retired(g1s_diff *d, int64_t frames);
 int g1s_diff_consume_digests(g1s_diff *d, const void *digests, size_t count);
 /* Evaluates the per-frame half for one record without touching the model (any handle of the stream's
  * geometry; no device work) and writes its digest. */

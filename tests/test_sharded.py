@@ -49,10 +49,13 @@ class CpuRecordProducer:
     def flush(self):
         for rec in self.pending:
             dg = self.helper.digest_from_record(rec)
-            dst = (self.C.c_double * self.ndbl).from_address(self.sink + 8 * self.ndbl * self.count)
+            dst = (self.C.c_double * self.ndbl).from_address(self.sink + 8 * self.ndbl * (self.count % self.cap))
             np.frombuffer(dst, np.float64)[:] = dg
             self.count += 1
         self.pending.clear()
+
+    def wait_retired(self, frames):
+        self.flush()
 
 
 def _worker(rank, world, port, name, B, out_path):
@@ -71,8 +74,9 @@ def _worker(rank, world, port, name, B, out_path):
         for k in range(base, min(n, base + world * B)):
             if owner_of(k, world, B) == rank:
                 sd.push_local(*frames[k])
-        folded += sd.exchange()
+        sd.exchange()
         base += world * B
+    folded = sd.exchange(final=True)
     segs = sd.finish()
     if rank == 0:
         assert folded == n
