@@ -142,12 +142,12 @@ __device__ __forceinline__ uint32_t residual4_slow(const void *sp, uint32_t ss, 
   return w;
 }
 
+// Byte i of the result is 0xFF iff lo <= first + i < hi (i = 0..3).
 __device__ __forceinline__ uint32_t byte_mask(int first, int lo, int hi) {
-  uint32_t m = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (first + i >= lo && first + i < hi) m |= 0xFFu << (8 * i);
-  return m;
+  const int a = min(max(lo - first, 0), 4), b = min(max(hi - first, 0), 4);  // bytes [a, b) are on
+  const uint32_t below_b = b >= 4 ? 0xFFFFFFFFu : ((1u << (8 * b)) - 1u);
+  const uint32_t below_a = a >= 4 ? 0xFFFFFFFFu : ((1u << (8 * a)) - 1u);
+  return b > a ? (below_b & ~below_a) : 0u;
 }
 
 // ------------------------------------------------------------------------------ k-loops
@@ -401,6 +401,7 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
 #pragma unroll
     for (int r = 0; r < 4; ++r) acc[i][r] = 0;
   long long nobs[3] = {0, 0, 0};  // kept by the bookkeeping thread only
+  int selfp[2][3] = {{0, 0, 0}, {0, 0, 0}};  // luma-tap self products per chroma plane, threads 0..127
 
   for (int i = tid; i < (int)(sizeof(SuSmem) / 4); i += kSuThreads) reinterpret_cast<uint32_t *>(&sm)[i] = 0;
   __syncthreads();
@@ -755,17 +756,10 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
       const int xs = j ? in.xs1 : in.xs0, x1 = j ? in.x1c1 : in.x1c0, y0 = j ? in.y01 : in.y00;
       const uint32_t m = (flj && cy >= y0 && cy < in.y1c) ? byte_mask(4 * (w & 3), xs, x1) : 0u;
       const int hm = (int)(hw & m), lm = (int)(lw & m);
-      int hh = __dp4a(hm, hm, 0), hl = __dp4a(hm, lm, 0), ll = __dp4a(lm, lm, 0);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        hh += __shfl_xor_sync(0xffffffffu, hh, o);
-        hl += __shfl_xor_sync(0xffffffffu, hl, o);
-        ll += __shfl_xor_sync(0xffffffffu, ll, o);
-      }
-      if (lane == 0) {
-        if (!ovcb) atomicAdd(&sm.self[0][0], hh), atomicAdd(&sm.self[0][1], hl), atomicAdd(&sm.self[0][2], ll);
-        if (!ovcr) atomicAdd(&sm.self[1][0], hh), atomicAdd(&sm.self[1][1], hl), atomicAdd(&sm.self[1][2], ll);
-      }
+      // per thread and unit at most 4 * 128^2; summed over the run in registers, reduced once at the end
+      const int hh = __dp4a(hm, hm, 0), hl = __dp4a(hm, lm, 0), ll = __dp4a(lm, lm, 0);
+      if (!ovcb) selfp[0][0] += hh, selfp[0][1] += hl, selfp[0][2] += ll;
+      if (!ovcr) selfp[1][0] += hh, selfp[1][1] += hl, selfp[1][2] += ll;
     }
     // statistics and overflow flags out (each block belongs to exactly one CTA)
     if (tid >= 128 && tid < 134) {
@@ -837,6 +831,17 @@ gram_imma_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__re
   }
 
   // ---------------------------------------------------------------------- epilogue
+  if (has_chroma && warp < 4) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        int v = selfp[c][k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&sm.self[c][k], v);
+      }
+  }
   __syncthreads();
   if (warp < 4) {
 #pragma unroll

@@ -135,6 +135,41 @@ __device__ __forceinline__ void load8(const uint8_t *__restrict__ row, int x0, i
   }
 }
 
+// One 8-sample chunk as loaded (16 bytes of u16 or 8 bytes of u8); blocks that lie fully inside an
+// aligned frame run one chunk ahead of the arithmetic so the load latency hides behind ~200 instructions.
+template <int SB>
+struct RawChunk {
+  uint32_t q[SB == 2 ? 4 : 2];
+};
+template <int SB>
+__device__ __forceinline__ RawChunk<SB> fetch_chunk(const uint8_t *__restrict__ p) {
+  RawChunk<SB> r;
+  if (SB == 2) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    r.q[0] = v.x, r.q[1] = v.y, r.q[2] = v.z, r.q[3] = v.w;
+  } else {
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+    r.q[0] = v.x, r.q[1] = v.y;
+  }
+  return r;
+}
+template <int SB>
+__device__ __forceinline__ void unpack_chunk(const RawChunk<SB> &r, int shift, int (&p)[8]) {
+  if (SB == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      p[2 * i] = ((r.q[i] & 0xFFFFu) >> shift) & 0xFF;
+      p[2 * i + 1] = ((r.q[i] >> 16) >> shift) & 0xFF;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      p[i] = (r.q[0] >> (8 * i)) & 0xFF;
+      p[4 + i] = (r.q[1] >> (8 * i)) & 0xFF;
+    }
+  }
+}
+
 template <int SB>
 __global__ void __launch_bounds__(kFlatThreads)
 flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, FlatConsts fc,
@@ -161,15 +196,26 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
 
   // --- A^T * block (multiply_mat(block, A, ., 1, 1024, 3)): three sequential chains
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  const bool fastblk = vec_ok && x0 + kBlock <= w;  // every chunk is one aligned vector load
+  const uint8_t *blk0 = src + (size_t)x0 * SB;       // first sample of the block's columns in row 0 of the frame
+  RawChunk<SB> nxt;
+  if (fastblk) nxt = fetch_chunk<SB>(blk0 + (size_t)min(y0, h - 1) * stride);
 #pragma unroll 1
   for (int yi = 0; yi < kBlock; ++yi) {
     const double yd = (double)(yi - 16) * 0.0625;
     const uint8_t *row = src + (size_t)min(y0 + yi, h - 1) * stride;
+    const uint8_t *rown = blk0 + (size_t)min(y0 + min(yi + 1, kBlock - 1), h - 1) * stride;
     prefetch_l2(src + (size_t)min(y0 + yi + 4, h - 1) * stride + (size_t)min(x0, w - 1) * SB);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       int p[8];
-      load8<SB>(row, x0 + 8 * c, w, shift, vec_ok, p);
+      if (fastblk) {
+        const RawChunk<SB> cur = nxt;
+        nxt = fetch_chunk<SB>(c < 3 ? row + (size_t)(x0 + 8 * (c + 1)) * SB : rown);
+        unpack_chunk<SB>(cur, shift, p);
+      } else {
+        load8<SB>(row, x0 + 8 * c, w, shift, vec_ok, p);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const double xd = (double)(8 * c + i - 16) * 0.0625;
@@ -216,10 +262,12 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
   }
   // sums of (r-l)^2, (r-l)(d-u), (d-u)^2: the reference's Gxx, Gxy, Gyy are exactly 0.25 times these
   double Dxx = 0, Dxy = 0, Dyy = 0, var = 0, mean = 0;
+  if (fastblk) nxt = fetch_chunk<SB>(blk0 + (size_t)min(y0 + 2, h - 1) * stride);
 #pragma unroll 1
   for (int yi = 1; yi < kBlock - 1; ++yi) {
     const double ty = row_ty(yi + 1);
     const uint8_t *row = src + (size_t)min(y0 + yi + 1, h - 1) * stride;
+    const uint8_t *rown = blk0 + (size_t)min(y0 + min(yi + 2, kBlock - 1), h - 1) * stride;
     prefetch_l2(src + (size_t)min(y0 + yi + 5, h - 1) * stride + (size_t)min(x0, w - 1) * SB);
     const double *cur = ring + ((size_t)(yi & 1) * kBlock) * kFlatThreads + tid;
     double *oth = ring + ((size_t)((yi + 1) & 1) * kBlock) * kFlatThreads + tid;  // row yi-1, becomes row yi+1
@@ -227,7 +275,13 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       int p[8];
-      load8<SB>(row, x0 + 8 * c, w, shift, vec_ok, p);
+      if (fastblk) {
+        const RawChunk<SB> curc = nxt;
+        nxt = fetch_chunk<SB>(c < 3 ? row + (size_t)(x0 + 8 * (c + 1)) * SB : rown);
+        unpack_chunk<SB>(curc, shift, p);
+      } else {
+        load8<SB>(row, x0 + 8 * c, w, shift, vec_ok, p);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int xi = 8 * c + i;
