@@ -255,7 +255,8 @@ def main():
     achieved = frames_per_launch * pair_bytes / (gram_ms * 1e-3) / 1e9 if gram_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "gram_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.workload == "4k10" and abs(frames_per_launch - 20.0) < 1e-9:
+        # ncu --set full capture of one gram launch of exactly this configuration (20 frame pairs)
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
 
     line = {

@@ -581,15 +581,54 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
   int rc = check_frames(d, source, denoised);
   if (rc != G1S_OK) return rc;
   Slot &s = d->slots[d->cur];
-  if (!s.d_frames) {
-    CU_TRY(d, cudaMalloc(&s.d_frames, (size_t)d->batch * d->pair_bytes));
-    CU_TRY(d, cudaMallocHost(&s.h_frames, (size_t)d->batch * d->pair_bytes));
-  }
+  if (!s.d_frames) CU_TRY(d, cudaMalloc(&s.d_frames, (size_t)d->batch * d->pair_bytes));
   const size_t base = (size_t)s.count * d->pair_bytes;
   FrameDesc &fd = s.h_descs[s.count];
   std::memset(&fd, 0, sizeof fd);
   const g1s_frame *fr[2] = {source, denoised};
   const int bytes[2] = {d->geom.src_bytes, d->geom.den_bytes};
+
+  // Planes that already live in page-locked host memory go to the device directly (one 2-D DMA per plane at
+  // PCIe rate, no staging copy, no host cores); the call still returns only when the borrowed memory is no
+  // longer needed.  Pageable planes take the staged path below.
+  bool pinned = std::getenv("G1S_NO_DIRECT_H2D") == nullptr;
+  for (int c = 0; c < d->geom.planes && pinned; ++c)
+    for (int k = 0; k < 2 && pinned; ++k) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, fr[k]->plane[c]) != cudaSuccess || at.type != cudaMemoryTypeHost) {
+        (void)cudaGetLastError();
+        pinned = false;
+      }
+    }
+  if (pinned) {
+    for (int c = 0; c < d->geom.planes; ++c) {
+      const PlaneGeom &p = d->pg[c];
+      for (int k = 0; k < 2; ++k) {
+        const size_t row_bytes = (size_t)p.w * bytes[k];
+        if (fr[k]->stride_bytes[c] < row_bytes) {
+          d->err = "stride smaller than a row";
+          return G1S_E_ARG;
+        }
+        uint8_t *dev = s.d_frames + base + p.off[k];
+        CU_TRY(d, cudaMemcpy2DAsync(dev, p.pitch[k], fr[k]->plane[c], fr[k]->stride_bytes[c], row_bytes, p.h,
+                                    cudaMemcpyHostToDevice, d->copy_stream));
+        if (k == 0) {
+          fd.src[c] = dev;
+          fd.src_stride[c] = (uint32_t)p.pitch[k];
+        } else {
+          fd.den[c] = dev;
+          fd.den_stride[c] = (uint32_t)p.pitch[k];
+        }
+      }
+    }
+    CU_TRY(d, cudaStreamSynchronize(d->copy_stream));  // the planes are borrowed only until we return
+    s.count++;
+    s.host_frames++;
+    d->pushed++;
+    if (s.count == d->batch) return rotate(d);
+    return G1S_OK;
+  }
+  if (!s.h_frames) CU_TRY(d, cudaMallocHost(&s.h_frames, (size_t)d->batch * d->pair_bytes));
   // The borrowed planes are copied into the pinned staging slot by the host threads, in row chunks of
   // about 1 MiB, so the copy runs at memory bandwidth rather than at one core's memcpy speed.
   struct CopyTask {

@@ -215,6 +215,35 @@ def test_producer_digests_fold_to_the_same_table():
     assert cons.finish() == full
 
 
+def test_pinned_host_planes_take_the_direct_path():
+    import torch
+    spec, fps, frames = corpus_frames("c3_small_10bit")
+    want, _, _ = gpu_run(spec, fps, frames)
+    g = D.DiffGenerator(fps[0], fps[1], spec.bit_depth, spec.bit_depth, spec.width, spec.height, spec.ss_x, spec.ss_y)
+    keep = []
+    for s, d in frames:
+        ps = [torch.from_numpy(p.view(np.int16)).pin_memory() for p in s]
+        pd = [torch.from_numpy(p.view(np.int16)).pin_memory() for p in d]
+        keep += ps + pd
+        g.diff_frame([t.numpy().view(np.uint16) for t in ps], [t.numpy().view(np.uint16) for t in pd])
+    assert g.finish() == want
+
+
+def test_8k_two_scenes_cut_a_segment():
+    """BASELINE configs[4] geometry (7680x4320 10-bit 4:2:0): two frames with different grain must give the
+    oracle's table, segment cut included."""
+    a = SynthSpec(7680, 4320, 10, textured=0.1, sigma0=1.0, sigma1=0.5, ar_strength=0.0, seed=41)
+    b = SynthSpec(7680, 4320, 10, textured=0.1, sigma0=2.0, sigma1=0.5, ar_strength=0.6, seed=42)
+    frames = [make_pair_numpy(a, 0), make_pair_numpy(b, 0)]
+    segs, recs, _ = gpu_run(a, (60, 1), frames)
+    want, per = oracle_run(a, (60, 1), frames)
+    assert np.array_equal(recs[0]["flat"], per[0]["flat"]) and np.array_equal(recs[1]["flat"], per[1]["flat"])
+    for c in range(3):
+        for k in range(2):
+            assert np.array_equal(D.gram_pairs_to_matrix(recs[k]["gram"][c]), per[k]["gram"][c][0])
+    assert segs == want and len(segs) == 2 and segs[0].end_time == 10_000_000 // 60
+
+
 def test_monochrome():
     spec, fps, frames = corpus_frames("c2_small_8bit")
     g = D.DiffGenerator(fps[0], fps[1], 8, 8, spec.width, spec.height, monochrome=True)
