@@ -170,6 +170,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: this engine has no CPU fallback")
+    if world > 1 and "G1S_HOST_THREADS" not in os.environ:
+        # the per-frame half of the host model runs on every rank: share the host cores between the ranks
+        os.environ["G1S_HOST_THREADS"] = str(max(2, min(8, (os.cpu_count() or 16) // world)))
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -21,7 +21,7 @@ constexpr uint16_t kDefaultGrainSeed = 10956;
 
 // util.rs::linsolve (libaom mathutils.h): elimination with adjacent-row pivot bubbling.
 // (row updates are element-wise independent, so wider vectors change nothing but the speed)
-__attribute__((target_clones("avx2", "default"))) bool gauss_solve(int n, double *A, double *b, double *x) {
+__attribute__((target_clones("avx512f", "avx2", "default"))) bool gauss_solve(int n, double *A, double *b, double *x) {
   for (int k = 0; k + 1 < n; ++k) {
     for (int i = n - 1; i > k; --i) {
       if (std::fabs(A[(i - 1) * n + k]) < std::fabs(A[i * n + k])) {
@@ -275,14 +275,22 @@ NoiseModel::NoiseModel(const StreamGeometry &g)
   same_blocks_ = true;
   cnt_luma_.resize(g_.nb);
   cnt_chroma_.resize(g_.nb);
+  inv_luma_.resize(g_.nb);
+  inv_chroma_.resize(g_.nb);
   for (int by = 0; by < g_.nbh; ++by)
     for (int bx = 0; bx < g_.nbw; ++bx) {
       const int lw = std::min(g_.width - bx * kBlock, kBlock), lh = std::min(g_.height - by * kBlock, kBlock);
       const int bw = kBlock >> g_.ss_x, bh = kBlock >> g_.ss_y;
       const int cw = std::min((g_.width >> g_.ss_x) - bx * bw, bw), ch = std::min((g_.height >> g_.ss_y) - by * bh, bh);
       // samples of the (frame-clipped) block: max_w * max_h of get_block_mean / get_noise_var
-      cnt_luma_[by * g_.nbw + bx] = lw * lh;
-      cnt_chroma_[by * g_.nbw + bx] = cw * ch;
+      const int b = by * g_.nbw + bx;
+      cnt_luma_[b] = lw * lh;
+      cnt_chroma_[b] = cw * ch;
+      auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+      inv_luma_[b] = pow2(lw * lh) ? 1.0 / (lw * lh) : 1.0;
+      inv_chroma_[b] = pow2(cw * ch) ? 1.0 / (cw * ch) : 1.0;
+      if (!pow2(lw * lh)) odd_luma_.push_back(b);
+      if (!pow2(cw * ch) && cw * ch > 0) odd_chroma_.push_back(b);
       if ((lw * lh > kBlock) != (cw * ch > kBlock)) same_blocks_ = false;
     }
 }
@@ -311,12 +319,12 @@ namespace {
 // contribute are computed too and simply never read.
 
 // NoiseStrengthSolver::get_bin_index(block_mean) -> integer bin and interpolation weight
-__attribute__((target_clones("avx2", "default"))) void block_bins(int n, const unsigned *__restrict__ luma_sum,
-                                                                  const int *__restrict__ cnt, int nbins,
+__attribute__((target_clones("avx512f", "avx2", "default"))) void block_bins(int n, const unsigned *__restrict__ luma_sum,
+                                                                  const double *__restrict__ inv_cnt, int nbins,
                                                                   int *__restrict__ bin0, double *__restrict__ frac) {
   const double scale = (double)(nbins - 1);
   for (int b = 0; b < n; ++b) {
-    const double block_mean = (double)luma_sum[b] / (double)cnt[b];
+    const double block_mean = (double)luma_sum[b] * inv_cnt[b];  // == / cnt: cnt is a power of two here
     const double val = block_mean < 0.0 ? 0.0 : (block_mean > 255.0 ? 255.0 : block_mean);
     const double bin = scale * (val - 0.0) / 255.0;
     const int i0 = (int)bin;  // == floor: bin >= 0
@@ -326,7 +334,7 @@ __attribute__((target_clones("avx2", "default"))) void block_bins(int n, const u
 }
 
 // luma_gain * NoiseStrengthSolver::get_value(luma, block_mean)
-__attribute__((target_clones("avx2", "default"))) void block_luma_strength(int n, const int *__restrict__ bin0,
+__attribute__((target_clones("avx512f", "avx2", "default"))) void block_luma_strength(int n, const int *__restrict__ bin0,
                                                                            const double *__restrict__ frac,
                                                                            const double *__restrict__ x, int nbins,
                                                                            double luma_gain, double *__restrict__ out) {
@@ -337,13 +345,13 @@ __attribute__((target_clones("avx2", "default"))) void block_luma_strength(int n
   }
 }
 
-__attribute__((target_clones("avx2", "default"))) void block_strengths(
-    int n, const int *__restrict__ rsum, const unsigned *__restrict__ rsq, const int *__restrict__ cnt,
+__attribute__((target_clones("avx512f", "avx2", "default"))) void block_strengths(
+    int n, const int *__restrict__ rsum, const unsigned *__restrict__ rsq, const double *__restrict__ inv_cnt,
     const double *__restrict__ luma_strength, double corr, double noise_gain, double *__restrict__ out) {
   for (int b = 0; b < n; ++b) {
-    const double c = (double)cnt[b];
-    const double noise_mean = (double)rsum[b] / c;
-    const double noise_var = (double)rsq[b] / c - noise_mean * noise_mean;
+    const double ic = inv_cnt[b];  // exact reciprocal of a power-of-two sample count: x * ic == x / cnt bit for bit
+    const double noise_mean = (double)rsum[b] * ic;
+    const double noise_var = (double)rsq[b] * ic - noise_mean * noise_mean;
     const double t = corr * luma_strength[b];
     const double lo = noise_var / 16, hi = noise_var - t * t;
     const double m = hi != hi ? lo : (lo > hi ? lo : hi);  // fmax(lo, hi), branch-free
@@ -366,14 +374,28 @@ void NoiseModel::add_strength_measurements(int c, const FrameRecordView &rec, La
     lf.frac.resize(nb);
     lf.mean.resize(nb);
     lf.strength.assign(nb, 0.0);
-    block_bins(nb, rec.luma_sum, cnt_luma_.data(), nbins, lf.bin0.data(), lf.frac.data());
+    block_bins(nb, rec.luma_sum, inv_luma_.data(), nbins, lf.bin0.data(), lf.frac.data());
+    for (int b : odd_luma_) {  // frame-edge blocks whose sample count is not a power of two: true division
+      const double block_mean = (double)rec.luma_sum[b] / (double)cnt_luma_[b];
+      const double val = block_mean < 0.0 ? 0.0 : (block_mean > 255.0 ? 255.0 : block_mean);
+      const double bin = (double)(nbins - 1) * (val - 0.0) / 255.0;
+      lf.bin0[b] = (int)bin;
+      lf.frac[b] = bin - (double)lf.bin0[b];
+    }
   } else {
     block_luma_strength(nb, lf.bin0.data(), lf.frac.data(), luma.eqns.x.data(), nbins, lf.ch[0].ar_gain,
                         lf.strength.data());
   }
   // pass 2: per-block adjusted strength of this channel
-  block_strengths(nb, rec.rsum + (size_t)c * nb, rec.rsq + (size_t)c * nb, cnt.data(), lf.strength.data(), corr,
-                  lf.ch[c].ar_gain, lf.mean.data());
+  block_strengths(nb, rec.rsum + (size_t)c * nb, rec.rsq + (size_t)c * nb, (c ? inv_chroma_ : inv_luma_).data(),
+                  lf.strength.data(), corr, lf.ch[c].ar_gain, lf.mean.data());
+  for (int b : (c ? odd_chroma_ : odd_luma_)) {  // non-power-of-two sample counts: true division
+    const double cn = (double)cnt[b];
+    const double noise_mean = (double)rec.rsum[(size_t)c * nb + b] / cn;
+    const double noise_var = (double)rec.rsq[(size_t)c * nb + b] / cn - noise_mean * noise_mean;
+    const double t = corr * lf.strength[b];
+    lf.mean[b] = std::sqrt(std::fmax(noise_var / 16, noise_var - t * t)) / lf.ch[c].ar_gain;
+  }
   // pass 3: NoiseStrengthSolver::add_measurement in block order (the sums are order dependent)
   const bool reuse_A = c > 0 && same_blocks_;
   double *A = solver.eqns.A.data(), *bv = solver.eqns.b.data();

@@ -116,6 +116,8 @@ class NoiseModel {
   const LatestFrame *last_ = nullptr;  // the frame save_latest() copies from
   bool same_blocks_;           // luma and chroma contribute the same blocks to the strength solver
   std::vector<int> cnt_luma_, cnt_chroma_;  // samples per frame-clipped block
+  std::vector<double> inv_luma_, inv_chroma_;  // exact reciprocals where the count is a power of two
+  std::vector<int> odd_luma_, odd_chroma_;  // blocks whose count is not (frame-edge slivers)
 };
 
 // DiffGenerator minus the pixels: frame counter, timestamps, segment list.
