@@ -1,0 +1,76 @@
+"""`python -m grav1synth_b200 diff SOURCE DENOISED -o OUT [-y]` — the reference's `diff` sub-command
+(/root/reference/src/main.rs:347-533, arguments :846-871) over the B200 engine, reading .y4m clips
+instead of going through FFmpeg.  Same checks and messages as the reference's Diff arm; the per-pixel
+work goes through the C ABI (g1s_diff_create / push_frame / finish) and the table through
+g1s_write_grain_table.  Only `diff` exists: the other sub-commands never touch pixels and are out of
+scope.
+"""
+from __future__ import annotations
+
+import argparse
+import logging
+import os
+import sys
+
+log = logging.getLogger("grav1synth")
+
+
+def main(argv=None) -> int:
+    logging.basicConfig(level=os.environ.get("G1S_LOG", "INFO"), format=" %(levelname)-5s %(name)s > %(message)s")
+    ap = argparse.ArgumentParser(prog="grav1synth_b200", description="Grain Synth analyzer: B200 `diff` path")
+    sub = ap.add_subparsers(dest="command", required=True)
+    d = sub.add_parser("diff", help="Compares a source video to a denoised video and generates a film grain table")
+    d.add_argument("source", help="The untouched source file to inspect (.y4m).")
+    d.add_argument("denoised", help="The denoised file to inspect (.y4m).")
+    d.add_argument("-o", "--output", required=True, help="The path to the output film grain table.")
+    d.add_argument("-y", "--overwrite", action="store_true", help="Overwrite the output file without prompting.")
+    d.add_argument("-f", "--filters", default=None, help="(not supported by this build: crop/resize filter chain)")
+    d.add_argument("--device", type=int, default=0)
+    args = ap.parse_args(argv)
+
+    # src/main.rs:354-368
+    if os.path.abspath(args.source) == os.path.abspath(args.output) or \
+            os.path.abspath(args.denoised) == os.path.abspath(args.output):
+        log.error("Input and output paths are the same. This is probably a typo, because this would overwrite "
+                  "your input. Exiting.")
+        return 0
+    if os.path.abspath(args.source) == os.path.abspath(args.denoised):
+        log.error("Source and denoised paths are the same. This is probably a typo, because this would always "
+                  "compute an empty diff. Exiting.")
+        return 0
+    if args.filters:
+        log.error("Invalid filter chain: --filters is not supported by this build")
+        return 0
+    # src/main.rs:382-393
+    if os.path.exists(args.output) and not args.overwrite:
+        if not sys.stdin.isatty() or input(f"File {args.output} exists. Overwrite? [y/n] ").strip().lower() != "y":
+            log.warning("Not overwriting existing file. Exiting.")
+            return 0
+
+    from .diff import DiffGenerator, write_grain_table
+    from .y4m import Y4MReader
+    src, den = Y4MReader(args.source), Y4MReader(args.denoised)
+    sd, dd = src.get_video_details(), den.get_video_details()
+    for bd in (sd.bit_depth, dd.bit_depth):
+        if not 8 <= bd <= 16:
+            raise SystemExit("Bit depths not between 8-16 are not currently supported")  # src/main.rs:516
+    differ = DiffGenerator(sd.fps_num, sd.fps_den, sd.bit_depth, dd.bit_depth, sd.width, sd.height, sd.ss_x, sd.ss_y,
+                           monochrome=sd.monochrome, device=args.device)
+    frames = 0
+    while True:  # src/main.rs:432-521
+        s, d_ = src.get_frame(), den.get_frame()
+        if s is None and d_ is None:
+            break
+        if s is None or d_ is None:
+            log.warning("Videos did not have equal frame counts. Resulting grain table may not be as expected.")
+            break
+        differ.diff_frame(s, d_)  # raises ValueError on a dimension mismatch, like `?` on diff_frame
+        frames += 1
+    write_grain_table(differ.finish(), args.output)
+    log.info("Computed diff for %d frames", frames)
+    log.info("Done, wrote output file to %s", args.output)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
