@@ -244,6 +244,23 @@ def test_8k_two_scenes_cut_a_segment():
     assert segs == want and len(segs) == 2 and segs[0].end_time == 10_000_000 // 60
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_random_geometries(seed):
+    """Random sizes (odd, not multiples of 32/64, narrow last block columns), bit depths and texture fractions:
+    every record field against the oracle.  Exercises super-unit edges, the TMA zero fill and the margin logic."""
+    rng = np.random.default_rng(1000 + seed)
+    w = int(rng.integers(40, 420))
+    h = int(rng.integers(40, 260))
+    bd = int(rng.choice([8, 10, 12]))
+    spec = SynthSpec(w, h, bd, textured=float(rng.choice([0.0, 0.3, 0.6, 0.9])), sigma0=float(rng.uniform(0.8, 2.5)),
+                     sigma1=float(rng.uniform(0.0, 2.0)), ar_strength=float(rng.uniform(0, 0.5)), seed=seed)
+    frames = [make_pair_numpy(spec, k) for k in range(2)]
+    segs, recs, _ = gpu_run(spec, (24, 1), frames)
+    want, per = oracle_run(spec, (24, 1), frames)
+    compare_records(spec, frames, recs, per)
+    assert segs == want
+
+
 def test_monochrome():
     spec, fps, frames = corpus_frames("c2_small_8bit")
     g = D.DiffGenerator(fps[0], fps[1], 8, 8, spec.width, spec.height, monochrome=True)
