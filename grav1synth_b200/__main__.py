@@ -24,7 +24,9 @@ def main(argv=None) -> int:
     d.add_argument("denoised", help="The denoised file to inspect (.y4m).")
     d.add_argument("-o", "--output", required=True, help="The path to the output film grain table.")
     d.add_argument("-y", "--overwrite", action="store_true", help="Overwrite the output file without prompting.")
-    d.add_argument("-f", "--filters", default=None, help="(not supported by this build: crop/resize filter chain)")
+    d.add_argument("-f", "--filters", default=None,
+                   help='A semicolon-separated list of filters to apply to the source before running the diff, e.g. '
+                        '"crop:top=42,left=64" (resize is parsed but not available in this build).')
     d.add_argument("--device", type=int, default=0)
     args = ap.parse_args(argv)
 
@@ -38,8 +40,11 @@ def main(argv=None) -> int:
         log.error("Source and denoised paths are the same. This is probably a typo, because this would always "
                   "compute an empty diff. Exiting.")
         return 0
-    if args.filters:
-        log.error("Invalid filter chain: --filters is not supported by this build")
+    from .filters import FilterChain, FilterError
+    try:  # src/main.rs:370-380
+        chain = FilterChain(args.filters) if args.filters else None
+    except FilterError as e:
+        log.error("Invalid filter chain: %s", e)
         return 0
     # src/main.rs:382-393
     if os.path.exists(args.output) and not args.overwrite:
@@ -54,7 +59,8 @@ def main(argv=None) -> int:
     for bd in (sd.bit_depth, dd.bit_depth):
         if not 8 <= bd <= 16:
             raise SystemExit("Bit depths not between 8-16 are not currently supported")  # src/main.rs:516
-    differ = DiffGenerator(sd.fps_num, sd.fps_den, sd.bit_depth, dd.bit_depth, sd.width, sd.height, sd.ss_x, sd.ss_y,
+    # the engine is sized for the frames it will see: the denoised clip's size (the source is filtered to it)
+    differ = DiffGenerator(sd.fps_num, sd.fps_den, sd.bit_depth, dd.bit_depth, dd.width, dd.height, sd.ss_x, sd.ss_y,
                            monochrome=sd.monochrome, device=args.device)
     frames = 0
     while True:  # src/main.rs:432-521
@@ -64,6 +70,8 @@ def main(argv=None) -> int:
         if s is None or d_ is None:
             log.warning("Videos did not have equal frame counts. Resulting grain table may not be as expected.")
             break
+        if chain is not None:
+            s = chain.apply(s, sd.ss_x, sd.ss_y)  # source only, src/main.rs:621-624
         differ.diff_frame(s, d_)  # raises ValueError on a dimension mismatch, like `?` on diff_frame
         frames += 1
     write_grain_table(differ.finish(), args.output)
