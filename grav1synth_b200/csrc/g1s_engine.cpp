@@ -173,11 +173,12 @@ struct Slot {
   uint8_t *h_frames = nullptr;   // pinned mirror
   FrameDesc *d_descs = nullptr;
   FrameDesc *h_descs = nullptr;  // pinned
-  CUtensorMap *d_tmaps = nullptr;  // [B][6] TMA descriptors of the batch's planes
-  CUtensorMap *h_tmaps = nullptr;  // pinned
+  int8_t *d_res = nullptr;           // B * ResidualStore::frame_bytes: s8 residual + luma-tap planes (tensor-core path)
+  CUtensorMap *d_rmaps = nullptr;    // [B][kResidualMaps] TMA descriptors of d_res, built once
   uint8_t *d_records = nullptr;
   uint8_t *h_records = nullptr;  // pinned
-  cudaEvent_t done = nullptr, k0_beg = nullptr, k0_end = nullptr, k1_beg = nullptr, k1_end = nullptr, copied = nullptr;
+  cudaEvent_t done = nullptr, k0_beg = nullptr, k0_end = nullptr, kr_beg = nullptr, k1_beg = nullptr, k1_end = nullptr,
+              copied = nullptr;
   int count = 0;                 // frames staged
   int host_frames = 0;           // of which need the H2D copy (contiguous prefix is not required)
   bool in_flight = false;
@@ -219,9 +220,11 @@ struct g1s_diff {
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   EncodeTiledFn encode_tiled = nullptr;
-  double tma_batches = 0;
+  double tma_batches = 0, vector_batches = 0;
+  ResidualStore rstore{};
+  bool tensor_path = false;  // residual_kernel + gram_imma_kernel available for this stream
   // counters
-  double kernels_launched = 0, k1_ms = 0, k1_launches = 0, k0_ms = 0, k0_launches = 0, frames_done = 0;
+  double kernels_launched = 0, k1_ms = 0, k1_launches = 0, k0_ms = 0, k0_launches = 0, frames_done = 0, kr_ms = 0;
 };
 
 namespace {
@@ -274,37 +277,28 @@ uint64_t fold_records(g1s_diff *d, const uint8_t *recs, int count, size_t stride
   });
 }
 
-// Builds the six TMA descriptors of every frame of the batch.  Returns false when a plane is not
-// 16-byte aligned (base or pitch) or the driver entry point is missing: the kernel then stages with
-// per-thread loads instead.
-bool build_tensor_maps(g1s_diff *d, Slot &s) {
-  if (!d->encode_tiled || std::getenv("G1S_NO_TMA")) return false;
+// Builds (once per slot) the TMA descriptors of the slot's residual planes: per frame of the batch the s8
+// residual of Y, Cb, Cr and the two luma-tap halves.  Extents are the LOOP extents (floor for chroma), so
+// everything beyond reads as zero, like the reference's frame clipping.
+bool build_residual_maps(g1s_diff *d, Slot &s, std::vector<CUtensorMap> &host) {
   const Geometry &g = d->geom;
-  for (int i = 0; i < s.count; ++i) {
-    const FrameDesc &fd = s.h_descs[i];
-    for (int c = 0; c < g.planes; ++c)
-      if (((uintptr_t)fd.src[c] | (uintptr_t)fd.den[c] | fd.src_stride[c] | fd.den_stride[c]) & 15) return false;
-  }
-  for (int i = 0; i < s.count; ++i) {
-    const FrameDesc &fd = s.h_descs[i];
-    for (int c = 0; c < g.planes; ++c) {
-      for (int k = 0; k < 2; ++k) {
-        const int bytes = k ? g.den_bytes : g.src_bytes;
-        int lw, lh, cw, ch;
-        gram_imma_tma_boxes(bytes, &lw, &lh, &cw, &ch);
-        // extents are the LOOP extents (floor for chroma): everything beyond reads as zero, like the scalar path
-        const cuuint64_t dims[2] = {(cuuint64_t)(c ? g.width >> 1 : g.width), (cuuint64_t)(c ? g.height >> 1 : g.height)};
-        const cuuint64_t strides[1] = {(cuuint64_t)(k ? fd.den_stride[c] : fd.src_stride[c])};
-        const cuuint32_t box[2] = {(cuuint32_t)(c ? cw : lw), (cuuint32_t)(c ? ch : lh)};
-        const cuuint32_t estr[2] = {1, 1};
-        void *base = const_cast<void *>(k ? fd.den[c] : fd.src[c]);
-        const CUresult r = d->encode_tiled(&s.h_tmaps[(size_t)i * 6 + 2 * c + k],
-                                           bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
-                                           base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return false;
-      }
+  const ResidualStore &rs = d->rstore;
+  int box[kResidualMaps][2];
+  gram_imma_tma_boxes(box);
+  host.assign((size_t)d->batch * kResidualMaps, CUtensorMap{});
+  for (int i = 0; i < d->batch; ++i) {
+    int8_t *fb = s.d_res + (size_t)i * rs.frame_bytes;
+    for (int k = 0; k < (g.planes == 3 ? kResidualMaps : 1); ++k) {
+      const bool luma = k == 0;
+      const cuuint64_t dims[2] = {(cuuint64_t)(luma ? g.width : g.width >> 1), (cuuint64_t)(luma ? g.height : g.height >> 1)};
+      const cuuint64_t strides[1] = {(cuuint64_t)(luma ? rs.pitch_l : rs.pitch_c)};
+      const cuuint32_t bx[2] = {(cuuint32_t)box[k][0], (cuuint32_t)box[k][1]};
+      const cuuint32_t estr[2] = {1, 1};
+      void *base = fb + (k < 3 ? rs.off_res[k] : (k == 3 ? rs.off_hi : rs.off_lo));
+      const CUresult r = d->encode_tiled(&host[(size_t)i * kResidualMaps + k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims,
+                                         strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return false;
     }
   }
   return true;
@@ -326,27 +320,29 @@ int submit(g1s_diff *d, Slot &s) {
   launch_flat_features(s.d_descs, s.count, d->geom, d->fc, s.d_records, d->rl, luma16, st);
   CU_TRY(d, cudaEventRecord(s.k0_end, st));
   launch_flat_select(s.count, d->geom, s.d_records, d->rl, st);
-  CU_TRY(d, cudaEventRecord(s.k1_beg, st));
   int gram_launches = 1;
-  if (d->cfg.gram_kernel == 0 && gram_imma_supported(d->geom)) {
-    // 64-bit vector loads need 8-byte aligned rows; otherwise the kernel falls back to scalar loads
-    bool aligned = true;
+  if (d->tensor_path) {
+    // 128-bit loads need 16-byte aligned rows; otherwise the residual kernel falls back to scalar loads
+    bool aligned = !std::getenv("G1S_SCALAR_LOADS");
     for (int i = 0; i < s.count && aligned; ++i)
       for (int c = 0; c < d->geom.planes; ++c) {
         const FrameDesc &fd = s.h_descs[i];
-        if (((uintptr_t)fd.src[c] | (uintptr_t)fd.den[c] | fd.src_stride[c] | fd.den_stride[c]) & 7) aligned = false;
+        if (((uintptr_t)fd.src[c] | (uintptr_t)fd.den[c] | fd.src_stride[c] | fd.den_stride[c]) & 15) aligned = false;
       }
-    const void *tmaps = nullptr;
-    if (d->geom.width >= 8 && d->geom.height >= 8 && build_tensor_maps(d, s)) {
-      CU_TRY(d, cudaMemcpyAsync(s.d_tmaps, s.h_tmaps, sizeof(CUtensorMap) * 6 * s.count, cudaMemcpyHostToDevice, st));
-      tmaps = s.d_tmaps;
-      d->tma_batches += 1;
-    }
-    launch_gram_imma(s.d_descs, s.count, d->geom, s.d_records, d->rl, aligned, tmaps, st);
+    ResidualStore rs = d->rstore;
+    rs.base = s.d_res;
+    CU_TRY(d, cudaEventRecord(s.kr_beg, st));
+    launch_residual(s.d_descs, s.count, d->geom, rs, s.d_records, d->rl, aligned, st);
+    CU_TRY(d, cudaEventRecord(s.k1_beg, st));
+    launch_gram_imma(s.count, d->geom, s.d_records, d->rl, s.d_rmaps, st);
     CU_TRY(d, cudaEventRecord(s.k1_end, st));
     launch_gram_generic(s.d_descs, s.count, d->geom, s.d_records, d->rl, /*only_overflow=*/true, st);
-    gram_launches = 2;
+    gram_launches = 3;
+    d->tma_batches += 1;
+    if (aligned) d->vector_batches += 1;
   } else {
+    CU_TRY(d, cudaEventRecord(s.kr_beg, st));
+    CU_TRY(d, cudaEventRecord(s.k1_beg, st));
     launch_gram_generic(s.d_descs, s.count, d->geom, s.d_records, d->rl, /*only_overflow=*/false, st);
     CU_TRY(d, cudaEventRecord(s.k1_end, st));
   }
@@ -367,6 +363,7 @@ int retire(g1s_diff *d, Slot &s) {
   float ms = 0;
   if (cudaEventElapsedTime(&ms, s.k0_beg, s.k0_end) == cudaSuccess) d->k0_ms += ms;
   if (cudaEventElapsedTime(&ms, s.k1_beg, s.k1_end) == cudaSuccess) d->k1_ms += ms;
+  if (cudaEventElapsedTime(&ms, s.kr_beg, s.k1_beg) == cudaSuccess) d->kr_ms += ms;
   d->folder->wait(s.fold_ticket);  // the slot's previous batch must have left the fold thread
   s.fold_ticket = fold_records(d, s.h_records, s.count, d->rl.bytes, s.latest);
   d->frames_done += s.count;
@@ -551,11 +548,22 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   }
   CU_NEW(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   CU_NEW(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+  // int8 tensor-core path (residual_kernel + gram_imma_kernel): 4:2:0 / monochrome, TMA descriptors available
+  d->tensor_path = cfg->gram_kernel == 0 && gram_imma_supported(g) && d->encode_tiled != nullptr;
+  d->rstore = ResidualStore::make(g);
   for (Slot &s : d->slots) {
     // the frame store (device) and its pinned mirror (host) are allocated on the first host push:
     // streams whose frames are already in HBM never need them
-    CU_NEW(cudaMalloc(&s.d_tmaps, sizeof(CUtensorMap) * 6 * batch));
-    CU_NEW(cudaMallocHost(&s.h_tmaps, sizeof(CUtensorMap) * 6 * batch));
+    if (d->tensor_path) {
+      CU_NEW(cudaMalloc(&s.d_res, d->rstore.frame_bytes * batch));
+      CU_NEW(cudaMalloc(&s.d_rmaps, sizeof(CUtensorMap) * kResidualMaps * batch));
+      std::vector<CUtensorMap> host;
+      if (!build_residual_maps(d.get(), s, host)) {
+        d->err = "cuTensorMapEncodeTiled failed for the residual planes";
+        return fail(G1S_E_CUDA);
+      }
+      CU_NEW(cudaMemcpy(s.d_rmaps, host.data(), sizeof(CUtensorMap) * host.size(), cudaMemcpyHostToDevice));
+    }
     CU_NEW(cudaMalloc(&s.d_descs, sizeof(FrameDesc) * batch));
     CU_NEW(cudaMallocHost(&s.h_descs, sizeof(FrameDesc) * batch));
     CU_NEW(cudaMalloc(&s.d_records, d->rl.bytes * batch));
@@ -564,6 +572,7 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     CU_NEW(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
     CU_NEW(cudaEventCreate(&s.k0_beg));
     CU_NEW(cudaEventCreate(&s.k0_end));
+    CU_NEW(cudaEventCreate(&s.kr_beg));
     CU_NEW(cudaEventCreate(&s.k1_beg));
     CU_NEW(cudaEventCreate(&s.k1_end));
   }
@@ -797,13 +806,13 @@ void g1s_diff_destroy(g1s_diff *d) {
   for (Slot &s : d->slots) {
     if (s.d_frames) cudaFree(s.d_frames);
     if (s.h_frames) cudaFreeHost(s.h_frames);
-    if (s.d_tmaps) cudaFree(s.d_tmaps);
-    if (s.h_tmaps) cudaFreeHost(s.h_tmaps);
+    if (s.d_res) cudaFree(s.d_res);
+    if (s.d_rmaps) cudaFree(s.d_rmaps);
     if (s.d_descs) cudaFree(s.d_descs);
     if (s.h_descs) cudaFreeHost(s.h_descs);
     if (s.d_records) cudaFree(s.d_records);
     if (s.h_records) cudaFreeHost(s.h_records);
-    for (cudaEvent_t e : {s.done, s.k0_beg, s.k0_end, s.k1_beg, s.k1_end, s.copied})
+    for (cudaEvent_t e : {s.done, s.k0_beg, s.k0_end, s.kr_beg, s.k1_beg, s.k1_end, s.copied})
       if (e) cudaEventDestroy(e);
   }
   for (cudaEvent_t e : d->marks)
@@ -819,9 +828,9 @@ int64_t g1s_diff_frames_pushed(const g1s_diff *d) { return d ? d->pushed : 0; }
 
 int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n) {
   if (!d || !out) return G1S_E_ARG;
-  const double v[7] = {d->kernels_launched, d->k1_ms,      d->k1_launches, d->k0_ms,
-                       d->k0_launches,      d->frames_done, d->tma_batches};
-  for (size_t i = 0; i < n && i < 7; ++i) out[i] = v[i];
+  const double v[9] = {d->kernels_launched, d->k1_ms,       d->k1_launches, d->k0_ms,          d->k0_launches,
+                       d->frames_done,      d->tma_batches, d->kr_ms,       d->vector_batches};
+  for (size_t i = 0; i < n && i < 9; ++i) out[i] = v[i];
   return G1S_OK;
 }
 

@@ -61,12 +61,30 @@ void launch_flat_select(int nframes, const Geometry &g, uint8_t *records, const 
 // only_overflow = true: just the blocks the tensor-core kernel flagged (Gram sums and statistics).
 void launch_gram_generic(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
                          const RecordLayout &rl, bool only_overflow, cudaStream_t st);
-// int8 tensor-core (mma.sync m16n8k32) Gram kernel for 4:2:0 / monochrome streams.
+// Engine-owned s8 planes of a batch, written by residual_kernel and read (through TMA boxes) by
+// gram_imma_kernel: per frame the residual of Y, Cb, Cr and, for chroma's luma tap, the sum of the
+// co-sited 2x2 luma residuals split as 8*hi + lo.  Pitches are multiples of 16 bytes, plane offsets of 256.
+struct ResidualStore {
+  int8_t *base;            // frame f of the batch starts at base + f * frame_bytes
+  size_t frame_bytes;
+  size_t off_res[3];
+  size_t off_hi, off_lo;
+  uint32_t pitch_l, pitch_c;
+  static ResidualStore make(const Geometry &g);  // offsets / pitches only; base stays null
+};
+constexpr int kResidualMaps = 5;  // TMA descriptors per frame: res Y, Cb, Cr, tap hi, tap lo
+
+// int8 tensor-core (mma.sync m16n8k32) path for 4:2:0 / monochrome streams: residual_kernel then
+// gram_imma_kernel.
 bool gram_imma_supported(const Geometry &g);
-// tmaps: device array of CUtensorMap[nframes][6] (source/denoised x Y,Cb,Cr; boxes from
-// gram_imma_tma_boxes) -> the raw tiles are staged by the TMA engine; nullptr -> per-thread loads.
-void launch_gram_imma(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
-                      const RecordLayout &rl, bool aligned, const void *tmaps, cudaStream_t st);
-void gram_imma_tma_boxes(int bytes_per_sample, int *luma_w, int *luma_h, int *chroma_w, int *chroma_h);
+// aligned: every plane base and stride of every frame is 16-byte aligned (vector loads allowed).
+void launch_residual(const FrameDesc *frames, int nframes, const Geometry &g, const ResidualStore &rs,
+                     uint8_t *records, const RecordLayout &rl, bool aligned, cudaStream_t st);
+// tmaps: device array of CUtensorMap[nframes][kResidualMaps] over the ResidualStore planes (extents =
+// the loop extents W x H and (W>>1) x (H>>1), boxes from gram_imma_tma_boxes, zero fill).
+void launch_gram_imma(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, const void *tmaps,
+                      cudaStream_t st);
+// box[k] = {width, height} in bytes / rows for descriptor k of a frame
+void gram_imma_tma_boxes(int box[kResidualMaps][2]);
 
 }  // namespace g1s

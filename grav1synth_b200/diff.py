@@ -273,9 +273,10 @@ class DiffGenerator:
         return float(self._L.g1s_diff_marks_elapsed_ms(self._h))
 
     def counters(self) -> dict:
-        out = (C.c_double * 7)()
-        self._check(self._L.g1s_diff_get_counters(self._h, out, 7))
-        k = ("kernels_launched", "gram_ms", "gram_launches", "flat_ms", "flat_launches", "frames_done", "tma_batches")
+        out = (C.c_double * 9)()
+        self._check(self._L.g1s_diff_get_counters(self._h, out, 9))
+        k = ("kernels_launched", "gram_ms", "gram_launches", "flat_ms", "flat_launches", "frames_done", "tma_batches",
+             "residual_ms", "vector_batches")
         return dict(zip(k, [float(v) for v in out]))
 
 

@@ -156,8 +156,9 @@ int64_t g1s_diff_frames_pushed(const g1s_diff *d);
  * out[0] = kernels launched, out[1] = total device ms spent in the fused
  * residual+autocorrelation kernel (CUDA events on the engine stream),
  * out[2] = its launch count, out[3] = device ms of the flat-block kernel,
- * out[4] = its launch count, out[5] = frames fully processed, out[6] = batches whose
- * raw tiles were staged by the TMA engine (0 when the planes are not 16-byte aligned). */
+ * out[4] = its launch count, out[5] = frames fully processed, out[6] = batches that took
+ * the int8 tensor-core path (residual kernel + TMA-fed Gram kernel), out[7] = device ms of the
+ * residual kernel, out[8] = batches whose planes were 16-byte aligned (128-bit loads). */
 int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n);
 
 /* Records CUDA event `which` (0 or 1) on the engine's kernel stream; g1s_diff_marks_elapsed_ms returns the

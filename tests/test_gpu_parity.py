@@ -59,17 +59,20 @@ def compare_records(spec, frames, got, want, src_bd=None, den_bd=None):
         assert np.array_equal(g["luma_sum"][w["flat"] != 0], ref["luma_sum"][w["flat"] != 0])
 
 
-@pytest.mark.parametrize("path", ["tensorcore-tma", "tensorcore-ldg", "generic"])
+@pytest.mark.parametrize("path", ["tensorcore-vec", "tensorcore-scalar", "generic"])
 @pytest.mark.parametrize("name", list(CORPUS))
 def test_corpus_bit_exact(name, path, monkeypatch):
-    """Every Gram path against the oracle: int8 tensor cores with TMA-staged tiles, the same with per-thread
-    loads (what unaligned planes get), and the generic int32 kernel."""
-    if path == "tensorcore-ldg":
-        monkeypatch.setenv("G1S_NO_TMA", "1")
+    """Every Gram path against the oracle: residual kernel (128-bit loads) + TMA-fed int8 tensor-core Gram
+    kernel, the same with the residual kernel's scalar loads (what unaligned planes get), and the generic
+    int32 kernel."""
+    if path == "tensorcore-scalar":
+        monkeypatch.setenv("G1S_SCALAR_LOADS", "1")
     spec, fps, frames = corpus_frames(name)
     segs, recs, g = gpu_run(spec, fps, frames, gram_kernel=1 if path == "generic" else 0)
     if spec.ss_x == 1 and spec.ss_y == 1:
-        assert (g.counters()["tma_batches"] > 0) == (path == "tensorcore-tma")
+        c = g.counters()
+        assert (c["tma_batches"] > 0) == (path != "generic")
+        assert (c["vector_batches"] > 0) == (path == "tensorcore-vec")
     want, per = oracle_run(spec, fps, frames)
     compare_records(spec, frames, recs, per)
     assert segs == want
