@@ -178,7 +178,7 @@ struct Slot {
   uint8_t *d_records = nullptr;
   uint8_t *h_records = nullptr;  // pinned
   cudaEvent_t done = nullptr, k0_beg = nullptr, k0_end = nullptr, kr_beg = nullptr, k1_beg = nullptr, k1_end = nullptr,
-              copied = nullptr;
+              copied = nullptr, computed = nullptr;
   int count = 0;                 // frames staged
   int host_frames = 0;           // of which need the H2D copy (contiguous prefix is not required)
   bool in_flight = false;
@@ -200,6 +200,7 @@ struct g1s_diff {
   cudaStream_t stream = nullptr;       // kernels + record read-back
   cudaEvent_t marks[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;  // per-frame host->device copies, overlapping the staging of the next frame
+  cudaStream_t d2h_stream = nullptr;   // record read-back, overlapping the kernels of the next batch
   Slot slots[kSlots];
   int cur = 0;            // slot being filled
   int oldest = 0;         // oldest slot possibly in flight
@@ -347,8 +348,11 @@ int submit(g1s_diff *d, Slot &s) {
     CU_TRY(d, cudaEventRecord(s.k1_end, st));
   }
   CU_TRY(d, cudaGetLastError());
-  CU_TRY(d, cudaMemcpyAsync(s.h_records, s.d_records, d->rl.bytes * s.count, cudaMemcpyDeviceToHost, st));
-  CU_TRY(d, cudaEventRecord(s.done, st));
+  // the read-back rides its own stream so the next batch's kernels start right behind this batch's
+  CU_TRY(d, cudaEventRecord(s.computed, st));
+  CU_TRY(d, cudaStreamWaitEvent(d->d2h_stream, s.computed, 0));
+  CU_TRY(d, cudaMemcpyAsync(s.h_records, s.d_records, d->rl.bytes * s.count, cudaMemcpyDeviceToHost, d->d2h_stream));
+  CU_TRY(d, cudaEventRecord(s.done, d->d2h_stream));
   s.in_flight = true;
   d->kernels_launched += 2 + gram_launches;
   d->k0_launches += 1;
@@ -548,6 +552,7 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   }
   CU_NEW(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   CU_NEW(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+  CU_NEW(cudaStreamCreateWithFlags(&d->d2h_stream, cudaStreamNonBlocking));
   // int8 tensor-core path (residual_kernel + gram_imma_kernel): 4:2:0 / monochrome, TMA descriptors available
   d->tensor_path = cfg->gram_kernel == 0 && gram_imma_supported(g) && d->encode_tiled != nullptr;
   d->rstore = ResidualStore::make(g);
@@ -570,6 +575,7 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     CU_NEW(cudaMallocHost(&s.h_records, d->rl.bytes * batch));
     CU_NEW(cudaEventCreate(&s.done));
     CU_NEW(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    CU_NEW(cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
     CU_NEW(cudaEventCreate(&s.k0_beg));
     CU_NEW(cudaEventCreate(&s.k0_end));
     CU_NEW(cudaEventCreate(&s.kr_beg));
@@ -802,6 +808,7 @@ void g1s_diff_destroy(g1s_diff *d) {
   if (!d) return;
   d->folder.reset();  // runs the queued folds to completion, then joins
   if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
+  if (d->d2h_stream) cudaStreamSynchronize(d->d2h_stream);
   if (d->stream) cudaStreamSynchronize(d->stream);
   for (Slot &s : d->slots) {
     if (s.d_frames) cudaFree(s.d_frames);
@@ -812,13 +819,14 @@ void g1s_diff_destroy(g1s_diff *d) {
     if (s.h_descs) cudaFreeHost(s.h_descs);
     if (s.d_records) cudaFree(s.d_records);
     if (s.h_records) cudaFreeHost(s.h_records);
-    for (cudaEvent_t e : {s.done, s.k0_beg, s.k0_end, s.kr_beg, s.k1_beg, s.k1_end, s.copied})
+    for (cudaEvent_t e : {s.done, s.k0_beg, s.k0_end, s.kr_beg, s.k1_beg, s.k1_end, s.copied, s.computed})
       if (e) cudaEventDestroy(e);
   }
   for (cudaEvent_t e : d->marks)
     if (e) cudaEventDestroy(e);
   if (d->stream) cudaStreamDestroy(d->stream);
   if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
+  if (d->d2h_stream) cudaStreamDestroy(d->d2h_stream);
   delete d;
 }
 
