@@ -8,16 +8,19 @@
 // whatever the summation order.
 //
 // The kernel never touches the frames: residual_kernel left the s8 residual of Y / Cb / Cr and the two
-// halves of chroma's luma tap in engine-owned planes, and this kernel pulls tiles of them into shared
-// memory with the TMA engine (cp.async.bulk.tensor.2d, SASS UTMALDG; frame edges are zero-filled by the
-// hardware, so there is no edge path), through a kStages-deep ring of full / empty mbarriers.  Nothing but
-// k-loops runs on the SM: no conversion, no statistics, no CTA-wide barrier inside a run.
+// halves of chroma's luma tap in engine-owned planes, and every warp pulls the tiles of its own work items
+// into its own slice of shared memory with the TMA engine (cp.async.bulk.tensor.2d, SASS UTMALDG; frame
+// edges are zero-filled by the hardware, so there is no edge path), one or two items ahead of its k-loop.
 //
-// Work unit: eight horizontally adjacent 32x32 luma blocks plus their co-sited 16x16 Cb and Cr blocks.
-// Persistent CTAs of 12 warps (three per SM sub-partition, all with the same 32 k-steps per unit), two per
-// SM, each walking an equal contiguous share of the batch's units:
-//   warps 0-7   luma: block = warp
-//   warps 8-11  chroma: plane = (warp - 8) / 2, blocks 4 * ((warp - 8) % 2) .. + 3 as two block pairs
+// Why warps are autonomous.  Measured on the B200 (tools/imma_probe.cu, profiles/): the legacy IMMA path
+// holds a sub-partition's issue port for its whole 8.4 cycles, so a sub-partition's time is
+// 8.4 * IMMAs + (every other warp instruction it issues) -- nothing overlaps, polls and barrier spins are
+// paid in full.  So: no CTA barriers, no shared rings, no inter-warp waits.  A warp has a plane for life
+// (7 luma + 5 chroma warps per CTA, the measured 3:1:1 cost ratio of Y:Cb:Cr), an equal contiguous share
+// of that plane's blocks over the whole batch, its own mbarriers, and it adds its int32 accumulators to
+// the frame's int64 record directly when its share leaves a frame (about 330 atomics, once or twice per
+// warp per launch).
+//   work item   luma: one 32x32 block (32 k-steps); chroma: two adjacent 16x16 blocks (16 k-steps)
 //   One k-step = 32 pixels of one row.  X[k][a] = residual at pixel k shifted by tap a;
 //   D += X^T X over the upper block-triangle (6 m16n8k32 MMAs).  Tap a = 8q+g with g = cx+3 (lane
 //   group), q = cy+3: a thread's four taps are the SAME column offset on four consecutive rows, so its
@@ -26,8 +29,7 @@
 //   register quad that serves as the lower m-tile now and as the upper m-tile two steps later.
 //   The observation mask (block margins, frame clipping) is a byte mask on k applied to the operand
 //   words (mask^2 = mask, so masking both A and B is exact).  Chroma's luma tap rides in lane group 7.
-//   flush: int32 accumulators (bounded: <= 15 units * 32 k-steps * 32 * 2^14 * 8 warps < 2^31)
-//   -> shared-memory reduction -> int64 global atomics, one per tap pair per CTA per plane.
+//   int32 accumulators are bounded by the share: <= 96 blocks * 32 k-steps * 32 * 2^14 < 2^31.
 #include "g1s_kernels.h"
 
 #include <algorithm>
@@ -37,37 +39,39 @@ namespace g1s {
 
 namespace {
 
-constexpr int kUnitBlocks = 8;
-constexpr int kGramWarps = 12;
+#ifndef G1S_GRAM_WARPS
+#define G1S_GRAM_WARPS 12
+#define G1S_LUMA_WARPS 7
+#endif
+constexpr int kGramWarps = G1S_GRAM_WARPS;
 constexpr int kGramThreads = 32 * kGramWarps;
-constexpr int kFlushUnits = 15;   // units between accumulator flushes (bounds the int32 accumulators, see above)
-constexpr int kStages = 3;        // TMA ring depth (2 x (3 x 23.1 KB + 18.1 KB static) fits one SM with room to spare)
-constexpr int kRefillLag = 1;     // a stage is refilled this many iterations after its unit was consumed
-constexpr int kPL = 40;           // luma tile pitch in 32-bit words (160-byte box rows)
+constexpr int kLumaWarps = G1S_LUMA_WARPS;  // per CTA; the others are chroma warps (measured cost ratio Y : Cb : Cr about 3 : 1 : 1)
+constexpr int kMaxShare = 96;     // luma blocks per warp and launch: bounds the int32 accumulators
+constexpr int kWin = 30;          // blocks per flag window: one ballot holds blocks bx0-1 .. bx0+30
+constexpr int kPL = 16;           // tile pitch in 32-bit words (64-byte box rows), luma
+constexpr int kPC = 16;           // the same for chroma and the luma-tap tiles
 constexpr int kLumaRows = 35;     // 3 halo rows + 32
-constexpr int kPC = 40;           // chroma / tap tile pitch in words (160-byte box rows)
 constexpr int kChromaRows = 19;   // 3 halo rows + 16
 constexpr int kLoRows = 20;       // the lo tile starts one row higher (row -1 of the first step is read, never used)
-constexpr int kBoxW = 160;        // 16 + 128 + 16 samples: half a unit of luma, a whole unit of chroma
-// Boxes start 16 samples left of their first block (the innermost TMA coordinate must be a multiple of 16
-// bytes, tools/tma_probe.cu).  The k-loops address tiles whose column 0 is that block's origin - 4 samples:
+constexpr int kBoxW = 64;         // 16 + 32 + 16 samples: one luma block, or two chroma blocks
+// Boxes start 16 samples left of the item (the innermost TMA coordinate must be a multiple of 16 bytes,
+// tools/tma_probe.cu).  The k-loops address tiles whose column 0 is the item's origin - 4 samples:
 constexpr int kResCol0 = 3;       // word of that column inside a residual box row
-constexpr int kTapCol0 = 4;       // word of the unit's first sample inside a hi / lo box row
-constexpr int kLumaBytes = kLumaRows * kBoxW;      // 5600 (two of these per unit)
-constexpr int kChromaBytes = kChromaRows * kBoxW;  // 3040
-constexpr int kLoBytes = kLoRows * kBoxW;          // 3200
-constexpr int kLumaSlot = 5632, kChromaSlot = 3072;
-constexpr int kOffLuma = 0, kOffCb = 2 * kLumaSlot, kOffCr = kOffCb + kChromaSlot, kOffHi = kOffCr + kChromaSlot,
-              kOffLo = kOffHi + kChromaSlot;
-constexpr int kStageBytes = kOffLo + kLoBytes;     // 23680, every tile 128-byte aligned
-static_assert(kLumaBytes <= kLumaSlot && kChromaBytes <= kChromaSlot && kStageBytes % 128 == 0, "stage layout");
+constexpr int kTapCol0 = 4;       // word of the item's first sample inside a hi / lo box row
+constexpr int kLumaBytes = kLumaRows * kBoxW;      // 2240
+constexpr int kChromaBytes = kChromaRows * kBoxW;  // 1216
+constexpr int kLoBytes = kLoRows * kBoxW;          // 1280
+constexpr int kLumaSlot = 2304, kLumaStages = 3;   // per luma warp: 3 x 2304 = 6912 bytes
+constexpr int kOffHi = 1280, kOffLo = 2560, kChromaSlot = 3840, kChromaStages = 2;  // per chroma warp: 2 x 3840
+constexpr int kWarpSmem = 7680;
+constexpr int kMaxStages = 3;
+static_assert(kLumaBytes <= kLumaSlot && kChromaBytes <= kOffHi && kLumaSlot * kLumaStages <= kWarpSmem &&
+                  kChromaSlot * kChromaStages <= kWarpSmem && kLumaSlot % 128 == 0 && kOffHi % 128 == 0,
+              "per-warp tile layout");
 
 struct __align__(16) GramSmem {
-  int dl[2][3][6 * 4 * 32];        // [flush parity][plane]: accumulators reduced over the warps of a plane
-  int ll[2][2];                    // [flush parity][chroma plane]: sum lo*lo of the luma tap over observed pixels
-  int arrived[2];                  // [flush parity]: warps that have added their accumulators
-  uint64_t full[kStages], empty[kStages];
-  int prod[4];                     // producer cursor (thread 0 only): frame, block row, unit, units requested
+  uint64_t full[kGramWarps][kMaxStages];  // one mbarrier per warp and stage: the warp's own TMA completions
+  int4 fifo[kGramWarps][4];               // per warp: items requested from the TMA engine, not yet consumed
 };
 
 __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
@@ -303,263 +307,260 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 
 // MODE 0: the product.  MODE 1 / 2 are measurement aids (G1S_GRAM_MODE, wrong results by design):
-// 1 = TMA ring and waits only, no k-loops; 2 = k-loops on whatever is in shared memory, no TMA traffic.
+// 1 = TMA traffic and waits only, no k-loops; 2 = k-loops on whatever is in shared memory, no TMA traffic.
 template <int MODE>
 __global__ void __launch_bounds__(kGramThreads, 2)
 gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int nframes,
                  const uint8_t *__restrict__ tmaps) {
-  extern __shared__ __align__(128) uint8_t stages[];
+  extern __shared__ __align__(128) uint8_t tiles[];
   __shared__ GramSmem sm;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, t = lane & 3;  // mma "groupID" (= cx + 3) and thread-in-group
   const bool has_chroma = g.planes == 3;
   const int W = g.width, H = g.height, pw = W >> 1, ph = H >> 1;
-  const int nsu = (g.nbw + kUnitBlocks - 1) / kUnitBlocks;
-  // Persistent CTAs: the units of the whole batch in (frame, block row, unit) order, an equal contiguous
-  // share per CTA, so the TMA ring never drains and all CTAs finish together.
-  const int per_frame = g.nbh * nsu;
-  const long long total = (long long)nframes * per_frame;
-  const int L0 = (int)(total * blockIdx.x / gridDim.x), L1 = (int)(total * (blockIdx.x + 1) / gridDim.x);
-  if (L0 >= L1) return;
+
+  // ---- this warp's plane and its share of the plane's items
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  int plane, rank, nranks;
+  if (!has_chroma) {
+    plane = 0, rank = cta * kGramWarps + warp, nranks = ncta * kGramWarps;
+  } else if (warp < kLumaWarps) {
+    plane = 0, rank = cta * kLumaWarps + warp, nranks = ncta * kLumaWarps;
+  } else {
+    // chroma warps split evenly between Cb and Cr; with an odd count the extra warp alternates with the CTA's parity
+    constexpr int kC = kGramWarps - kLumaWarps, kHi = (kC + 1) / 2, kLo = kC / 2;
+    const int k = warp - kLumaWarps, ncb = (cta & 1) ? kLo : kHi;
+    const int even = (ncta + 1) >> 1, odd = ncta >> 1, e_before = (cta + 1) >> 1, o_before = cta >> 1;
+    if (k < ncb) plane = 1, rank = kHi * e_before + kLo * o_before + k, nranks = kHi * even + kLo * odd;
+    else plane = 2, rank = kLo * e_before + kHi * o_before + (k - ncb), nranks = kLo * even + kHi * odd;
+  }
+  const bool luma = plane == 0;
+  const int per_row = luma ? g.nbw : (g.nbw + 1) >> 1;  // items per block row: blocks, or chroma block pairs
+  const int per_win = luma ? kWin : kWin / 2;
+  const long long total = (long long)nframes * g.nbh * per_row;
+  const int i_lo = (int)(total * rank / nranks), i_hi = (int)(total * (rank + 1) / nranks);
+  if (i_lo >= i_hi) return;  // whole warp; nothing below synchronises across warps
+
+  uint8_t *const my_tiles = tiles + warp * kWarpSmem;
+  const int nstages = luma ? kLumaStages : kChromaStages;
+  const int slot = luma ? kLumaSlot : kChromaSlot;
+  if (lane == 0) {
+    for (int s = 0; s < kMaxStages; ++s) mbar_init(&sm.full[warp][s], 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
 
   int acc[6][4];
 #pragma unroll
   for (int i = 0; i < 6; ++i)
 #pragma unroll
     for (int r = 0; r < 4; ++r) acc[i][r] = 0;
-  int ll = 0;          // chroma warps, g = 7 lanes
-  int nobs = 0;        // observation count of this warp's blocks (<= kFlushUnits * 2 * 1024 between flushes)
-
-  for (int i = tid; i < 2 * 3 * 6 * 4 * 32 + 4 + 2; i += kGramThreads) (&sm.dl[0][0][0])[i] = 0;  // dl, ll, arrived are contiguous
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], kGramWarps);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
+  int ll = 0;    // chroma, g = 7 lanes: sum lo*lo of the luma tap over observed pixels
+  int nobs = 0;  // observations of the items accumulated since the last flush
 
   const int sh = 8 * ((gq + 1) & 3);
   const int dxw = (gq + 1) >> 2;
   const bool is7 = gq == 7;
-  const bool luma_warp = warp < 8;
-  const int plane_of_warp = luma_warp ? 0 : 1 + ((warp - 8) >> 1);
-  const int jblk = luma_warp ? warp : 4 * ((warp - 8) & 1);  // first block of the unit this warp works on
 
-  // one elected thread asks the TMA engine for the tiles of a unit
-  auto issue_tma = [&](int f, int by, int u, int s) {
-    const uint8_t *fmaps = tmaps + (size_t)f * kResidualMaps * 128;
-    uint8_t *st = stages + s * kStageBytes;
-    uint64_t *bar = &sm.full[s];
-    mbar_expect_tx(bar, 2 * kLumaBytes + (has_chroma ? 3 * kChromaBytes + kLoBytes : 0));
-    tma_load_2d(st + kOffLuma, fmaps + 0 * 128, 256 * u - 16, 32 * by - 3, bar);
-    tma_load_2d(st + kOffLuma + kLumaSlot, fmaps + 0 * 128, 256 * u + 112, 32 * by - 3, bar);
-    if (has_chroma) {
-      tma_load_2d(st + kOffCb, fmaps + 1 * 128, 128 * u - 16, 16 * by - 3, bar);
-      tma_load_2d(st + kOffCr, fmaps + 2 * 128, 128 * u - 16, 16 * by - 3, bar);
-      tma_load_2d(st + kOffHi, fmaps + 3 * 128, 128 * u - 16, 16 * by, bar);
-      tma_load_2d(st + kOffLo, fmaps + 4 * 128, 128 * u - 16, 16 * by - 1, bar);
-    }
-  };
-  auto advance = [&](int &f, int &by, int &u) {
-    if (++u == nsu) {
-      u = 0;
-      if (++by == g.nbh) by = 0, ++f;
-    }
-  };
-  // Flat / overflow flags a warp needs for a unit, one byte per lane, combined with a ballot:
-  //   luma   lanes 0-2: flat(by, bx-1 .. bx+1); 3: flat(by-1, bx); 4: ovf[0](by, bx)
-  //   chroma lanes 0-5: flat(by, bx0-1 .. bx0+4); 6-9: flat(by-1, bx0 .. bx0+3); 10-13: ovf[c](by, bx0 .. bx0+3)
-  auto load_flag = [&](int f, int by, int u) -> uint32_t {
-    const uint8_t *rec = records + (size_t)f * rl.bytes;
-    const int bx0 = kUnitBlocks * u + jblk;
-    int yy = by, xx = bx0;
-    const uint8_t *base = rec + rl.off_flat;
-    if (luma_warp) {
-      if (lane < 3) xx = bx0 - 1 + lane;
-      else if (lane == 3) yy = by - 1;
-      else if (lane == 4) base = rec + rl.off_ovf;
-      else return 0u;
-    } else {
-      if (lane < 6) xx = bx0 - 1 + lane;
-      else if (lane < 10) yy = by - 1, xx = bx0 + lane - 6;
-      else if (lane < 14) base = rec + rl.off_ovf + (size_t)plane_of_warp * g.nb, xx = bx0 + lane - 10;
-      else return 0u;
-    }
-    if (xx < 0 || xx >= g.nbw || yy < 0) return 0u;
-    return base[yy * g.nbw + xx];
-  };
-
-  // Accumulators out: int32 registers -> shared-memory sums per plane -> int64 global atomics into the
-  // frame's record.  Needed at frame changes, at the end, and every kFlushUnits units (int32 bound).
-  // No CTA barrier: every warp adds its registers to the buffer of the flush's parity and counts itself in;
-  // the warp that arrives last emits the buffer and re-zeroes it.  The buffer of one parity is reused two
-  // flushes later, by which time its emission is long over (warps are never more than kStages units apart).
-  int flush_gen = 0;
+  // Accumulators -> the frame's int64 record, straight from registers (every (lane, tile, element) owns one tap pair).
   auto flush = [&](int f) {
     uint8_t *rec = records + (size_t)f * rl.bytes;
-    const int pb = flush_gen & 1;
-    ++flush_gen;
-    if (luma_warp || has_chroma) {
+    unsigned long long *gram = reinterpret_cast<unsigned long long *>(rec + rl.off_gram) + (size_t)plane * kPairs;
 #pragma unroll
-      for (int i = 0; i < 6; ++i)
+    for (int i = 0; i < 6; ++i) {
+      const int mrow = i >= 4 ? 16 : 0;
+      const int ncol = i >= 4 ? 8 * (i - 2) : 8 * i;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          if (acc[i][r]) atomicAdd(&sm.dl[pb][plane_of_warp][(i * 4 + r) * 32 + lane], acc[i][r]);
-          acc[i][r] = 0;
+      for (int r = 0; r < 4; ++r) {
+        const int v = acc[i][r];
+        acc[i][r] = 0;
+        if (v == 0) continue;
+        const int b = ncol + 2 * t + (r & 1);
+        if (plane > 0 && is7 && i < 4) {
+          // rows 7 / 15 of the lower m-tile: luma tap hi / lo
+          if (b == 7)  // column 7 of the first n-tile is hi again: (8h + l)^2 = 64 hh + 16 hl + ll
+            atomicAdd(&gram[pair_index(24, 24)], (unsigned long long)((long long)v * ((r >> 1) ? 16 : 64)));
+          else
+            emit_luma_tap(gram, b, v, (r >> 1) ? 1 : 8);
+        } else {
+          emit(gram, mrow + gq + 8 * (r >> 1), b, v);
         }
-      if (!luma_warp && is7 && ll) atomicAdd(&sm.ll[pb][plane_of_warp - 1], ll);
+      }
+    }
+    if (plane > 0) {
+      int v = is7 ? ll : 0;
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (lane == 28 && v) atomicAdd(&gram[pair_index(24, 24)], (unsigned long long)(long long)v);
       ll = 0;
-      if (lane == 0 && nobs)
-        atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + plane_of_warp, (unsigned long long)(long long)nobs);
-      nobs = 0;
     }
-    __syncwarp();
-    int order = 0;
-    if (lane == 0) {
-      __threadfence_block();
-      order = atomicAdd(&sm.arrived[pb], 1);
-    }
-    order = __shfl_sync(0xffffffffu, order, 0);
-    if (order != kGramWarps - 1) return;
-    __threadfence_block();
-#pragma unroll 1
-    for (int plane = 0; plane < g.planes; ++plane) {
-      unsigned long long *gram = reinterpret_cast<unsigned long long *>(rec + rl.off_gram) + (size_t)plane * kPairs;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int mrow = i >= 4 ? 16 : 0;
-        const int ncol = i >= 4 ? 8 * (i - 2) : 8 * i;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          int *slot = &sm.dl[pb][plane][(i * 4 + r) * 32 + lane];
-          const int v = *slot;
-          if (v == 0) continue;
-          *slot = 0;
-          const int b = ncol + 2 * t + (r & 1);
-          if (plane > 0 && is7 && i < 4) {
-            // rows 7 / 15 of the lower m-tile: luma tap hi / lo
-            if (b == 7)  // column 7 of the first n-tile is hi again: (8h + l)^2 = 64 hh + 16 hl + ll
-              atomicAdd(&gram[pair_index(24, 24)], (unsigned long long)((long long)v * ((r >> 1) ? 16 : 64)));
-            else
-              emit_luma_tap(gram, b, v, (r >> 1) ? 1 : 8);
-          } else {
-            emit(gram, mrow + gq + 8 * (r >> 1), b, v);
-          }
-        }
-      }
-      if (plane > 0 && lane == 0 && sm.ll[pb][plane - 1]) {
-        atomicAdd(&gram[pair_index(24, 24)], (unsigned long long)(long long)sm.ll[pb][plane - 1]);
-        sm.ll[pb][plane - 1] = 0;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) sm.arrived[pb] = 0;
+    if (lane == 0 && nobs)
+      atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + plane, (unsigned long long)(long long)nobs);
+    nobs = 0;
   };
 
-  // unit cursors: consumers (all threads) and the producer (thread 0)
-  int f = L0 / per_frame, by, u;
+  // ---- producer side: scan the share for items with work, request their tiles, queue them
+  // position of the scan: frame, block row, first item of the current flag window, and the window's ballots
+  int pf, pby, pwx;
   {
-    const int r = L0 - f * per_frame;
-    by = r / nsu;
-    u = r - by * nsu;
+    const int per_frame = g.nbh * per_row;
+    pf = i_lo / per_frame;
+    const int r = i_lo - pf * per_frame;
+    pby = r / per_row;
+    pwx = ((r - pby * per_row) / per_win) * per_win;
   }
-  const int count = L1 - L0;
-  if (tid == 0 && MODE != 2) {
-    int pf = f, pby = by, pu = u, issued = 0;
-    for (; issued < kStages - kRefillLag && issued < count; ++issued) {
-      issue_tma(pf, pby, pu, issued);
-      advance(pf, pby, pu);
+  int pidx = ((pf * g.nbh + pby) * per_row) + pwx;  // global index of the window's first item
+  uint32_t m_flat = 0, m_up = 0, m_ovf = 0, m_todo = 0;  // bit l <-> block (window's first block - 1 + l); todo: items left in the window
+  auto load_window = [&]() {
+    const uint8_t *rec = records + (size_t)pf * rl.bytes;
+    const int bx = (luma ? pwx : 2 * pwx) - 1 + lane;
+    const bool in = bx >= 0 && bx < g.nbw;
+    const int b = pby * g.nbw + bx;
+    const uint8_t fl = in ? (rec + rl.off_flat)[b] : 0;
+    const uint8_t up = (in && pby > 0) ? (rec + rl.off_flat)[b - g.nbw] : 0;
+    const uint8_t ov = in ? (rec + rl.off_ovf)[(size_t)plane * g.nb + b] : 0;
+    m_flat = __ballot_sync(0xffffffffu, fl != 0);
+    m_up = __ballot_sync(0xffffffffu, up != 0);
+    m_ovf = __ballot_sync(0xffffffffu, ov != 0);
+    // items of the window that lie in the share, in the row, and have at least one flat, non-overflowed block
+    const uint32_t ok = m_flat & ~m_ovf;
+    uint32_t items = luma ? (ok >> 1) & ((1u << kWin) - 1u) : 0u;
+    if (!luma)
+      for (int k = 0; k < kWin / 2; ++k)
+        if ((ok >> (2 * k + 1)) & 3u) items |= 1u << k;
+    const int first = max(i_lo - pidx, 0), last = min(min(i_hi - pidx, per_row - pwx), per_win);  // [first, last)
+    const uint32_t keep = last > first ? (((last >= 32 ? 0u : (1u << last)) - 1u) & ~((1u << first) - 1u)) : 0u;
+    m_todo = items & keep;
+  };
+  bool scan_done = false;
+  auto next_window = [&]() {  // advance to the next window of the share; false when the share is exhausted
+    pwx += per_win;
+    pidx += per_win;
+    if (pwx >= per_row) {
+      pidx += per_row - pwx;  // the last window of a row is short
+      pwx = 0;
+      if (++pby == g.nbh) pby = 0, ++pf;
     }
-    sm.prod[0] = pf, sm.prod[1] = pby, sm.prod[2] = pu, sm.prod[3] = issued;
-  }
-  uint32_t flagv = load_flag(f, by, u);
+    return pidx < i_hi;
+  };
+  load_window();
 
-  for (int it = 0; it < count; ++it) {
-    const uint32_t bits = __ballot_sync(0xffffffffu, flagv != 0);
-    const bool last = it + 1 == count;
-    {
-      int nf = f, nby = by, nu = u;
-      advance(nf, nby, nu);
-      flagv = last ? 0u : load_flag(nf, nby, nu);  // next unit's flags travel behind this unit's k-loops
+  int head = 0, tail = 0;       // fifo positions (items requested / consumed)
+  int hstage = 0, tstage = 0;   // their stages ( = position % nstages, kept incrementally)
+  uint32_t phases = 0;          // bit s: parity to wait for on stage s
+  auto produce = [&]() {        // request the next item with work; false if there is none left
+    while (m_todo == 0) {
+      if (scan_done || !next_window()) {
+        scan_done = true;
+        return false;
+      }
+      load_window();
     }
-
-    const int s = it % kStages;
-    if (MODE != 2) mbar_wait(&sm.full[s], (uint32_t)(it / kStages) & 1u);
-    const uint8_t *st = stages + s * kStageBytes;
-    const int Y0 = 32 * by, CY0 = 16 * by;
-
-    if (MODE == 1) {
-    } else if (luma_warp) {
-      const int j = jblk;
-      if ((bits & 2u) && !(bits & 16u)) {
-        const int xs = (bits & 1u) ? 0 : kLag, y0 = (bits & 8u) ? 0 : kLag;
-        const int x1 = min(W - 32 * (kUnitBlocks * u + j) - kLag, (bits & 4u) ? 32 : 32 - kLag);
-        const int y1 = min(H - Y0, 32);
-        if (x1 > xs && y1 > y0) {
-          const uint32_t mx[2] = {byte_mask(4 * t, xs, x1), byte_mask(16 + 4 * t, xs, x1)};
-          const uint32_t *tile = reinterpret_cast<const uint32_t *>(st + kOffLuma + (j >> 2) * kLumaSlot);
-          luma_rows(tile + y0 * kPL + kResCol0 + 8 * (j & 3) + t + dxw, sh, y1 - y0, mx, acc);
-          nobs += (x1 - xs) * (y1 - y0);
+    const int k = __ffs(m_todo) - 1;
+    m_todo &= m_todo - 1;
+    // flags of the item's blocks, from the window ballots (bit l <-> block first - 1 + l)
+    uint32_t bits;
+    if (luma) {
+      const int l = k + 1;
+      bits = ((m_flat >> (l - 1)) & 1u) | (((m_flat >> (l + 1)) & 1u) << 1) | (((m_up >> l) & 1u) << 2);
+    } else {
+      const int l = 2 * k + 1;  // blocks l (half 0) and l + 1 (half 1)
+      bits = ((m_flat >> (l - 1)) & 15u)            // flat: left neighbour, A, B, right neighbour
+             | (((m_up >> l) & 3u) << 4)             // flat above A, B
+             | (((m_ovf >> l) & 3u) << 6);           // overflow A, B
+    }
+    const int stage = hstage;
+    if (++hstage == nstages) hstage = 0;
+    if (lane == 0) {
+      sm.fifo[warp][head & 3] = make_int4(pf, pby, pwx + k, (int)bits);
+      if (MODE != 2) {
+        const uint8_t *fmaps = tmaps + (size_t)pf * kResidualMaps * 128;
+        uint8_t *st = my_tiles + stage * slot;
+        uint64_t *bar = &sm.full[warp][stage];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this warp's reads of the stage precede the refill
+        if (luma) {
+          mbar_expect_tx(bar, kLumaBytes);
+          tma_load_2d(st, fmaps, 32 * (pwx + k) - 16, 32 * pby - 3, bar);
+        } else {
+          const int cx = 32 * (pwx + k) - 16, cy = 16 * pby;
+          mbar_expect_tx(bar, 2 * kChromaBytes + kLoBytes);
+          tma_load_2d(st, fmaps + plane * 128, cx, cy - 3, bar);
+          tma_load_2d(st + kOffHi, fmaps + 3 * 128, cx, cy, bar);
+          tma_load_2d(st + kOffLo, fmaps + 4 * 128, cx, cy - 1, bar);
         }
       }
-    } else if (has_chroma) {
-      const int c = plane_of_warp - 1;
-      const int y1 = min(ph - CY0, 16);
-#pragma unroll 1
-      for (int pr = 0; pr < 2; ++pr) {  // the two block pairs of this warp: blocks jblk + 2 pr (half 0) and + 1 (half 1)
-        const uint32_t fb = bits >> (2 * pr), ub = bits >> (6 + 2 * pr), ob = bits >> (10 + 2 * pr);
-        const int bxa = kUnitBlocks * u + jblk + 2 * pr;
-        const bool fla = (fb & 2u) && !(ob & 1u), flb = (fb & 4u) && !(ob & 2u);
-        const int xsa = (fb & 1u) ? 0 : kLag, xsb = (fb & 2u) ? 0 : kLag;
-        const int y0a = (ub & 1u) ? 0 : kLag, y0b = (ub & 2u) ? 0 : kLag;
-        const int x1a = min(pw - 16 * bxa - kLag, (fb & 4u) ? 16 : 16 - kLag);
-        const int x1b = min(pw - 16 * (bxa + 1) - kLag, (fb & 8u) ? 16 : 16 - kLag);
-        const bool on0 = fla && x1a > xsa && y1 > y0a;
-        const bool on1 = flb && x1b > xsb && y1 > y0b;
-        const uint32_t m0 = on0 ? byte_mask(4 * t, xsa, x1a) : 0u;
-        const uint32_t m1 = on1 ? byte_mask(4 * t, xsb, x1b) : 0u;
-        const int ya = on0 ? y0a : 99, yb = on1 ? y0b : 99;
-        const int ylo = min(ya, yb), yhi = min(max(ya, yb), y1);
-        const int wofs = 4 * jblk + 8 * pr + t;  // words from the unit's first sample to this lane's half 0
-        // g = 7 lanes walk the hi tile (and the lo tile one row up) instead of the residual tile
-        const uint32_t *base = is7 ? reinterpret_cast<const uint32_t *>(st + kOffHi) + kTapCol0 + wofs
-                                   : reinterpret_cast<const uint32_t *>(st + (c ? kOffCr : kOffCb)) + kResCol0 + wofs + dxw;
-        const uint32_t *lbase = reinterpret_cast<const uint32_t *>(st + kOffLo) + kTapCol0 + wofs;  // storage row r = lo row r - 1
-        if (ylo < y1) {
-          // rows where only one block of the pair is observed (its top margin is 0, the other's is 3)
-          if (yhi > ylo) {
-            const uint32_t mx[2] = {ya <= ylo ? m0 : 0u, yb <= ylo ? m1 : 0u};
-            chroma_rows(base + ylo * kPC, lbase + ylo * kPC, sh, is7, yhi - ylo, mx, acc, ll);
-          }
-          if (y1 > yhi) {
-            const uint32_t mx[2] = {m0, m1};
-            chroma_rows(base + yhi * kPC, lbase + yhi * kPC, sh, is7, y1 - yhi, mx, acc, ll);
-          }
-        }
-        nobs += (on0 ? (x1a - xsa) * (y1 - y0a) : 0) + (on1 ? (x1b - xsb) * (y1 - y0b) : 0);
-      }
     }
+    ++head;
+    return true;
+  };
 
+  int cf = -1;  // frame the accumulators belong to
+  for (;;) {
+    __syncwarp();  // every lane is done with the stage about to be refilled
+    while (head - tail < nstages && produce()) {
+    }
+    if (head == tail) break;
     __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[s]);  // this warp is done with the stage
-    if (MODE != 2 && tid == 0 && sm.prod[3] < count) {
-      // refill the stage consumed kRefillLag iterations ago (every warp has almost surely left it)
-      const int prev = sm.prod[3] - kStages;  // iteration whose stage the next requested unit reuses ( = it - kRefillLag )
-      if (prev >= 0) mbar_wait(&sm.empty[prev % kStages], (uint32_t)(prev / kStages) & 1u);
-      int pf = sm.prod[0], pby = sm.prod[1], pu = sm.prod[2];
-      issue_tma(pf, pby, pu, sm.prod[3] % kStages);
-      advance(pf, pby, pu);
-      sm.prod[0] = pf, sm.prod[1] = pby, sm.prod[2] = pu, sm.prod[3] += 1;
+    const int4 item = sm.fifo[warp][tail & 3];
+    const int stage = tstage;
+    if (++tstage == nstages) tstage = 0;
+    ++tail;
+    const int f = item.x, by = item.y, ix = item.z;
+    const uint32_t bits = (uint32_t)item.w;
+    if (f != cf) {
+      if (cf >= 0) flush(cf);
+      cf = f;
     }
-
-    // accumulators out at frame changes, at the end, and every kFlushUnits units (int32 bound)
-    const bool frame_end = u == nsu - 1 && by == g.nbh - 1;
-    if (last || frame_end || it % kFlushUnits == kFlushUnits - 1) flush(f);
-    advance(f, by, u);
+    if (MODE != 2) {
+      mbar_wait(&sm.full[warp][stage], (phases >> stage) & 1u);
+      phases ^= 1u << stage;
+    }
+    if (MODE == 1) continue;
+    const uint8_t *st = my_tiles + stage * slot;
+    if (luma) {
+      const int xs = (bits & 1u) ? 0 : kLag, y0 = (bits & 4u) ? 0 : kLag;
+      const int x1 = min(W - 32 * ix - kLag, (bits & 2u) ? 32 : 32 - kLag);
+      const int y1 = min(H - 32 * by, 32);
+      if (x1 > xs && y1 > y0) {
+        uint32_t mx[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (xs != 0 || x1 != 32) mx[0] = byte_mask(4 * t, xs, x1), mx[1] = byte_mask(16 + 4 * t, xs, x1);
+        luma_rows(reinterpret_cast<const uint32_t *>(st) + y0 * kPL + kResCol0 + t + dxw, sh, y1 - y0, mx, acc);
+        nobs += (x1 - xs) * (y1 - y0);
+      }
+    } else {
+      // blocks 2 ix (half 0) and 2 ix + 1 (half 1); bits: flat left, A, B, right | flat above A, B | overflow A, B
+      const int bxa = 2 * ix;
+      const int y1 = min(ph - 16 * by, 16);
+      const bool fla = (bits & 2u) && !(bits & 64u), flb = (bits & 4u) && !(bits & 128u);
+      const int xsa = (bits & 1u) ? 0 : kLag, xsb = (bits & 2u) ? 0 : kLag;
+      const int y0a = (bits & 16u) ? 0 : kLag, y0b = (bits & 32u) ? 0 : kLag;
+      const int x1a = min(pw - 16 * bxa - kLag, (bits & 4u) ? 16 : 16 - kLag);
+      const int x1b = min(pw - 16 * (bxa + 1) - kLag, (bits & 8u) ? 16 : 16 - kLag);
+      const bool on0 = fla && x1a > xsa && y1 > y0a;
+      const bool on1 = flb && x1b > xsb && y1 > y0b;
+      const uint32_t m0 = !on0 ? 0u : (xsa == 0 && x1a == 16) ? 0xFFFFFFFFu : byte_mask(4 * t, xsa, x1a);
+      const uint32_t m1 = !on1 ? 0u : (xsb == 0 && x1b == 16) ? 0xFFFFFFFFu : byte_mask(4 * t, xsb, x1b);
+      const int ya = on0 ? y0a : 99, yb = on1 ? y0b : 99;
+      const int ylo = min(ya, yb), yhi = min(max(ya, yb), y1);
+      // g = 7 lanes walk the hi tile (and the lo tile one row up) instead of the residual tile
+      const uint32_t *base = is7 ? reinterpret_cast<const uint32_t *>(st + kOffHi) + kTapCol0 + t
+                                 : reinterpret_cast<const uint32_t *>(st) + kResCol0 + t + dxw;
+      const uint32_t *lbase = reinterpret_cast<const uint32_t *>(st + kOffLo) + kTapCol0 + t;  // storage row r = lo row r - 1
+      if (ylo < y1) {
+        // rows where only one block of the pair is observed (its top margin is 0, the other's is 3)
+        if (yhi > ylo) {
+          const uint32_t mx[2] = {ya <= ylo ? m0 : 0u, yb <= ylo ? m1 : 0u};
+          chroma_rows(base + ylo * kPC, lbase + ylo * kPC, sh, is7, yhi - ylo, mx, acc, ll);
+        }
+        if (y1 > yhi) {
+          const uint32_t mx[2] = {m0, m1};
+          chroma_rows(base + yhi * kPC, lbase + yhi * kPC, sh, is7, y1 - yhi, mx, acc, ll);
+        }
+      }
+      nobs += (on0 ? (x1a - xsa) * (y1 - y0a) : 0) + (on1 ? (x1b - xsb) * (y1 - y0b) : 0);
+    }
   }
+  if (cf >= 0) flush(cf);
 }
 
 }  // namespace
@@ -577,10 +578,8 @@ void gram_imma_tma_boxes(int box[kResidualMaps][2]) {
 
 void launch_gram_imma(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, const void *tmaps,
                       cudaStream_t st) {
-  const int nsu = (g.nbw + kUnitBlocks - 1) / kUnitBlocks;
-  const long long total = (long long)nframes * g.nbh * nsu;
-  const int smem = kStages * kStageBytes;
-  static int slots = 0, mode = 0;  // resident CTAs on the device: the persistent grid is exactly one wave
+  const int smem = kGramWarps * kWarpSmem;
+  static int slots = 0, mode = 0;  // resident CTAs on the device: the persistent grid is one wave
   if (slots == 0) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
@@ -592,7 +591,10 @@ void launch_gram_imma(int nframes, const Geometry &g, uint8_t *records, const Re
     if (const char *e = std::getenv("G1S_GRAM_MODE")) mode = std::atoi(e);
     slots = sms * std::max(per_sm, 1);
   }
-  const int grid = (int)std::min<long long>(total, slots);
+  // A warp's share must stay below kMaxShare items (int32 accumulators): more CTAs than one wave if the batch is huge.
+  const long long blocks = (long long)nframes * g.nb;
+  const long long need = (blocks + (long long)kMaxShare * kLumaWarps - 1) / ((long long)kMaxShare * kLumaWarps);
+  const int grid = (int)std::max<long long>(std::min<long long>(slots, std::max<long long>(1, blocks / 8)), need);
   const uint8_t *tm = static_cast<const uint8_t *>(tmaps);
   if (mode == 1)
     gram_imma_kernel<1><<<grid, kGramThreads, smem, st>>>(g, records, rl, nframes, tm);

@@ -102,7 +102,12 @@ __device__ __forceinline__ double exp_fixed(double x) {
 
 constexpr int kFlatThreads = 128;
 
+#ifndef G1S_FLAT_PF
+#define G1S_FLAT_PF 0
+#endif
+// G1S_FLAT_PF: 0 = L2 prefetch four rows ahead; 1 = L1 prefetch two rows ahead; 2 = both
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Eight consecutive source-luma samples reduced to 8 bit; coordinates clamped to the frame
 // (FlatBlockFinder::extract_block clamps, it does not pad).
@@ -205,7 +210,8 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
     const double yd = (double)(yi - 16) * 0.0625;
     const uint8_t *row = src + (size_t)min(y0 + yi, h - 1) * stride;
     const uint8_t *rown = blk0 + (size_t)min(y0 + min(yi + 1, kBlock - 1), h - 1) * stride;
-    prefetch_l2(src + (size_t)min(y0 + yi + 4, h - 1) * stride + (size_t)min(x0, w - 1) * SB);
+    if (G1S_FLAT_PF != 1) prefetch_l2(src + (size_t)min(y0 + yi + 4, h - 1) * stride + (size_t)min(x0, w - 1) * SB);
+    if (G1S_FLAT_PF >= 1) prefetch_l1(src + (size_t)min(y0 + yi + 2, h - 1) * stride + (size_t)min(x0, w - 1) * SB);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       int p[8];
@@ -268,7 +274,8 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
     const double ty = row_ty(yi + 1);
     const uint8_t *row = src + (size_t)min(y0 + yi + 1, h - 1) * stride;
     const uint8_t *rown = blk0 + (size_t)min(y0 + min(yi + 2, kBlock - 1), h - 1) * stride;
-    prefetch_l2(src + (size_t)min(y0 + yi + 5, h - 1) * stride + (size_t)min(x0, w - 1) * SB);
+    if (G1S_FLAT_PF != 1) prefetch_l2(src + (size_t)min(y0 + yi + 5, h - 1) * stride + (size_t)min(x0, w - 1) * SB);
+    if (G1S_FLAT_PF >= 1) prefetch_l1(src + (size_t)min(y0 + yi + 3, h - 1) * stride + (size_t)min(x0, w - 1) * SB);
     const double *cur = ring + ((size_t)(yi & 1) * kBlock) * kFlatThreads + tid;
     double *oth = ring + ((size_t)((yi + 1) & 1) * kBlock) * kFlatThreads + tid;  // row yi-1, becomes row yi+1
     double left = cur[0], mid = cur[kFlatThreads];

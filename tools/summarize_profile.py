@@ -28,7 +28,7 @@ for r in rows:
     agg.setdefault(name, []).append(float(r[hdr.index("Metric Value")]))
 total = sum(sum(v) for v in agg.values())
 with open(os.path.join(out_dir, f"{tag}_launches.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'flat_|gram_' python bench.py ...\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'flat_|gram_|residual_' python bench.py ...\n")
     f.write("# kernel, launches, avg us, total us, share of the step\n")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         f.write(f"{k:50s} {len(v):4d} {sum(v) / len(v) / 1e3:10.1f} {sum(v) / 1e3:10.1f} {100 * sum(v) / total:6.1f}%\n")
@@ -45,7 +45,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio"]
-for kern in ("gram", "flat"):
+traffic = {}
+for kern in ("gram_imma", "residual", "flat_features"):
     rep = os.path.join(src_dir, f"prof_{kern}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -54,18 +55,23 @@ for kern in ("gram", "flat"):
     h, units, vals = rr[0], rr[1], rr[2]
     got = {}
     with open(os.path.join(out_dir, f"{tag}_{kern}_ncu.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{kern} (one launch), key metrics\n")
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{kern} (one launch, 20 frame pairs), key metrics\n")
         f.write(f"# kernel: {vals[h.index('Kernel Name')]}\n")
         for name, u, v in zip(h, units, vals):
             if name in WANT:
                 f.write(f"{name:90s} {u:12s} {v}\n")
                 got[name] = (u, v)
-    if kern == "gram":
-        def to_bytes(key):
-            u, v = got[key]
-            return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-        dur_u, dur_v = got["gpu__time_duration.sum"]
-        json.dump({"dram_bytes_per_launch": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),
-                   "dram_bytes_read": to_bytes("dram__bytes_read.sum"), "ncu_duration": f"{dur_v} {dur_u}",
-                   "source": f"profiles/{tag}_gram_ncu.txt"}, open(os.path.join(out_dir, "gram_traffic.json"), "w"), indent=1)
+
+    def to_bytes(key):
+        u, v = got[key]
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    traffic[kern] = {"dram_bytes_read": to_bytes("dram__bytes_read.sum"), "dram_bytes_write": to_bytes("dram__bytes_write.sum"),
+                     "ncu_duration": " ".join(reversed(got["gpu__time_duration.sum"]))}
+if "gram_imma" in traffic and "residual" in traffic:
+    # the roofline's `traffic`: DRAM bytes of one residual launch + one gram launch (the two launches that do
+    # the residual + autocorrelation work of a 20-frame batch)
+    tot = sum(traffic[k]["dram_bytes_read"] + traffic[k]["dram_bytes_write"] for k in ("gram_imma", "residual"))
+    json.dump({"dram_bytes_per_launch": tot, "per_kernel": traffic,
+               "source": f"profiles/{tag}_gram_imma_ncu.txt + profiles/{tag}_residual_ncu.txt"},
+              open(os.path.join(out_dir, "gram_traffic.json"), "w"), indent=1)
 print("wrote summaries for", tag)
