@@ -214,6 +214,8 @@ struct g1s_diff {
   int64_t retired = 0;
   g1s_record_fn tap = nullptr;
   void *tap_user = nullptr;
+  std::mutex digest_mu;    // consumer handles: recycled copies of incoming digest blocks
+  std::vector<std::shared_ptr<std::vector<double>>> digest_free;
   double *sink = nullptr;  // digest sink (producer ranks)
   size_t sink_cap = 0, sink_count = 0;
   // cuTensorMapEncodeTiled, fetched through the runtime so libcuda is not a link dependency
@@ -886,16 +888,28 @@ int g1s_diff_consume_digests(g1s_diff *d, const void *digests, size_t count) {
     d->err = "consume_digests needs an unfinished CONSUMER handle";
     return G1S_E_STATE;
   }
-  // the digests are copied (the caller's buffer is free on return) and folded asynchronously, in order
-  auto blk = std::make_shared<std::vector<double>>(static_cast<const double *>(digests),
-                                                   static_cast<const double *>(digests) + LatestFrame::kDigestDoubles * count);
+  // the digests are copied (the caller's buffer is free on return) and folded asynchronously, in order; the
+  // copies live in recycled buffers (a fresh 10+ MB allocation per exchange is mostly page faults)
+  std::shared_ptr<std::vector<double>> blk;
+  {
+    std::lock_guard<std::mutex> lk(d->digest_mu);
+    if (!d->digest_free.empty()) {
+      blk = std::move(d->digest_free.back());
+      d->digest_free.pop_back();
+    }
+  }
+  if (!blk) blk = std::make_shared<std::vector<double>>();
+  const double *src = static_cast<const double *>(digests);
+  blk->assign(src, src + LatestFrame::kDigestDoubles * count);
   DiffSequencer *seq = d->seq.get();
-  d->folder->push([blk, seq, count] {
+  d->folder->push([blk, seq, count, d] {
     LatestFrame lf;
     for (size_t i = 0; i < count; ++i) {
       lf.from_digest(blk->data() + LatestFrame::kDigestDoubles * i);
       seq->consume_latest(lf);
     }
+    std::lock_guard<std::mutex> lk(d->digest_mu);
+    if (d->digest_free.size() < 8) d->digest_free.push_back(blk);
   });
   d->retired += (int64_t)count;
   d->pushed += (int64_t)count;

@@ -120,8 +120,14 @@ void StrengthSolver::add_measurement(double block_mean, double noise_std) {
   total += noise_std;
   num_equations++;
 }
-bool StrengthSolver::solve() {
-  // Regularised copy of A; b keeps the ridge term (the reference modifies b in place).
+// The reference's solve regularises a COPY of A but adds the ridge term to b in place, so b depends on how many
+// times solve has run.  bump_b is that side effect alone; solve_bumped is the elimination on the current b.
+void StrengthSolver::bump_b() {
+  const int n = num_bins;
+  const double mean = total / num_equations;
+  for (int i = 0; i < n; ++i) eqns.b[i] += mean / 8192.;
+}
+bool StrengthSolver::solve_bumped() {
   const int n = num_bins;
   const double alpha = 2.0 * (double)num_equations / n;
   static thread_local std::vector<double> Ar, br;
@@ -132,13 +138,13 @@ bool StrengthSolver::solve() {
     Ar[i * n + i] += 2 * alpha;
     Ar[i * n + hi] -= alpha;
   }
-  const double mean = total / num_equations;
-  for (int i = 0; i < n; ++i) {
-    Ar[i * n + i] += 1.0 / 8192.;
-    eqns.b[i] += mean / 8192.;
-  }
+  for (int i = 0; i < n; ++i) Ar[i * n + i] += 1.0 / 8192.;
   br.assign(eqns.b.begin(), eqns.b.end());  // elimination consumes its inputs
   return gauss_solve(n, Ar.data(), br.data(), eqns.x.data());
+}
+bool StrengthSolver::solve() {
+  bump_b();
+  return solve_bumped();
 }
 void StrengthSolver::add(const StrengthSolver &o) {
   eqns.add(o.eqns);
@@ -502,15 +508,23 @@ NoiseStatus NoiseModel::fold(const LatestFrame &lf) {
 
     combined[c].num_observations += lf.ch[c].num_observations;
     combined[c].eqns.add(lf.ch[c].eqns);
-    if (!combined[c].solve_ar(is_chroma)) {
-      if (is_chroma) {
-        chroma_fallback(combined[c].eqns);
-      } else {
-        err_ = "Solving combined noise equation system failed 0!";
-        return NoiseStatus::Error;
-      }
-    }
     combined[c].strength.add(lf.ch[c].strength);
+    if (is_chroma) {
+      // The crate re-solves the combined chroma systems after every frame, but nothing reads those solutions
+      // until a segment is emitted (is_different looks at luma only): the eliminations are deferred to settle().
+      // What is NOT deferred is the strength solve's side effect on b (one ridge bump per frame, in frame order),
+      // so the deferred solve sees bit for bit the b the crate's last per-frame solve would.  The one observable
+      // difference would be the crate's early return when a combined chroma strength solve fails, which cannot
+      // happen: the system is a sum of PSD terms plus a 1/8192 ridge.  This takes two thirds of the sequential
+      // per-frame eliminations off the fold thread, which is what bounds the multi-GPU rate.
+      combined[c].strength.bump_b();
+      stale_[c] = true;
+      continue;
+    }
+    if (!combined[c].solve_ar(is_chroma)) {
+      err_ = "Solving combined noise equation system failed 0!";
+      return NoiseStatus::Error;
+    }
     if (!combined[c].strength.solve()) {
       err_ = "Solving combined noise strength failed!";
       return NoiseStatus::Error;
@@ -524,7 +538,17 @@ NoiseStatus NoiseModel::update(const FrameRecordView &rec) {
   return fold(scratch_);
 }
 
+void NoiseModel::settle() {
+  for (int c = 1; c < g_.planes; ++c) {
+    if (!stale_[c]) continue;
+    if (!combined[c].solve_ar(true)) chroma_fallback(combined[c].eqns);
+    combined[c].strength.solve_bumped();
+    stale_[c] = false;
+  }
+}
+
 void NoiseModel::save_latest() {
+  stale_[0] = stale_[1] = stale_[2] = false;
   const LatestFrame &lf = *last_;
   for (int c = 0; c < 3; ++c) {
     combined[c].eqns.copy_from(lf.ch[c].eqns);
@@ -625,6 +649,7 @@ void DiffSequencer::after_update(NoiseStatus st) {
   if (st == NoiseStatus::DifferentType) {
     const uint64_t cur = (uint64_t)frame_count_ * 10000000ull * (uint64_t)fps_den_ / (uint64_t)fps_num_;
     g1s_segment seg;
+    model_.settle();
     model_.grain_parameters(prev_timestamp_, cur, &seg);
     table_.push_back(seg);
     model_.save_latest();
@@ -640,6 +665,7 @@ void DiffSequencer::consume_latest(const LatestFrame &lf) { after_update(model_.
 std::vector<g1s_segment> DiffSequencer::finish() {
   std::vector<g1s_segment> out(table_);
   g1s_segment seg;
+  model_.settle();
   model_.grain_parameters(prev_timestamp_, (uint64_t)INT64_MAX, &seg);
   out.push_back(seg);
   return out;

@@ -46,7 +46,9 @@ class StrengthSolver {
   StrengthSolver();
   void clear();
   void add_measurement(double block_mean, double noise_std);
-  bool solve();
+  bool solve();         // = bump_b() + solve_bumped(), the reference's NoiseStrengthSolver::solve
+  void bump_b();        // its in-place side effect on b alone
+  bool solve_bumped();  // its elimination alone, on the current b
   double value_at(double intensity) const;
   double bin_center(int i) const;
   void add(const StrengthSolver &o);
@@ -102,6 +104,9 @@ class NoiseModel {
   NoiseStatus fold(const LatestFrame &lf);
   NoiseStatus update(const FrameRecordView &rec);
   void save_latest();
+  // Deferred work of fold(): the chroma solves of the combined state (see fold).  Must run before the
+  // combined chroma solutions are read (grain_parameters).
+  void settle();
   void grain_parameters(uint64_t start_ts, uint64_t end_ts, g1s_segment *seg) const;
   const std::string &last_error() const { return err_; }
   ChannelState combined[3];
@@ -114,6 +119,7 @@ class NoiseModel {
   std::string err_;
   LatestFrame scratch_;        // used by update()
   const LatestFrame *last_ = nullptr;  // the frame save_latest() copies from
+  bool stale_[3] = {false, false, false};  // combined[c] has sums newer than its solutions
   bool same_blocks_;           // luma and chroma contribute the same blocks to the strength solver
   std::vector<int> cnt_luma_, cnt_chroma_;  // samples per frame-clipped block
   std::vector<double> inv_luma_, inv_chroma_;  // exact reciprocals where the count is a power of two
