@@ -917,6 +917,27 @@ int g1s_diff_consume_digests(g1s_diff *d, const void *digests, size_t count) {
   return G1S_OK;
 }
 
+int g1s_diff_consume_digests_borrowed(g1s_diff *d, const void *digests, size_t count) {
+  if (!d || (!digests && count)) return G1S_E_ARG;
+  if (d->cfg.mode != G1S_MODE_CONSUMER || d->finished) {
+    d->err = "consume_digests needs an unfinished CONSUMER handle";
+    return G1S_E_STATE;
+  }
+  const double *src = static_cast<const double *>(digests);
+  DiffSequencer *seq = d->seq.get();
+  d->folder->push([src, seq, count] {
+    LatestFrame lf;
+    for (size_t i = 0; i < count; ++i) {
+      lf.from_digest(src + LatestFrame::kDigestDoubles * i);
+      seq->consume_latest(lf);
+    }
+  });
+  d->retired += (int64_t)count;
+  d->pushed += (int64_t)count;
+  d->frames_done += (double)count;
+  return G1S_OK;
+}
+
 int g1s_diff_digest_from_record(g1s_diff *d, const void *record, size_t bytes, void *digest_out) {
   if (!d || !record || !digest_out) return G1S_E_ARG;
   if (bytes != d->rl.bytes) {

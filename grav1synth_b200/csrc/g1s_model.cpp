@@ -224,6 +224,12 @@ const char *const kFailTexts[3] = {nullptr, "Solving latest noise equation syste
                                    "Solving latest noise strength failed!"};
 }
 
+// Digest layout (doubles): [enough_flat, channels, fail_channel, fail_text] then per channel
+//   AR system: upper triangle of A row-major in 325 slots (A is symmetric bit for bit: load_equations fills
+//   (i, j) and (j, i) from the same Gram entry), b[25], x[25], ar_gain, num_observations,
+//   strength system: diagonal[20], superdiagonal[20] (A is symmetric tridiagonal: add_measurement only touches
+//   (i0, i0), (i1, i0), (i1, i1), (i0, i1) with i1 <= i0 + 1, the mirrored entries with identical adds),
+//   b[20], x[20], total, num_equations.
 void LatestFrame::to_digest(double *out) const {
   double *p = out;
   *p++ = enough_flat ? 1.0 : 0.0;
@@ -233,17 +239,25 @@ void LatestFrame::to_digest(double *out) const {
   for (int c = 0; c < 3; ++c) {
     const ChannelState &s = ch[c];
     const int n = s.eqns.n;
-    std::memset(p, 0, sizeof(double) * (25 * 25 + 25 + 25));
-    std::memcpy(p, s.eqns.A.data(), sizeof(double) * n * n);
-    std::memcpy(p + 625, s.eqns.b.data(), sizeof(double) * n);
-    std::memcpy(p + 650, s.eqns.x.data(), sizeof(double) * n);
-    p += 675;
+    std::memset(p, 0, sizeof(double) * (325 + 25 + 25));
+    double *q = p;
+    for (int i = 0; i < n; ++i) {
+      std::memcpy(q, s.eqns.A.data() + i * n + i, sizeof(double) * (n - i));
+      q += n - i;
+    }
+    std::memcpy(p + 325, s.eqns.b.data(), sizeof(double) * n);
+    std::memcpy(p + 350, s.eqns.x.data(), sizeof(double) * n);
+    p += 375;
     *p++ = s.ar_gain;
     *p++ = (double)s.num_observations;  // exact: < 2^53
-    std::memcpy(p, s.strength.eqns.A.data(), sizeof(double) * 400);
-    std::memcpy(p + 400, s.strength.eqns.b.data(), sizeof(double) * 20);
-    std::memcpy(p + 420, s.strength.eqns.x.data(), sizeof(double) * 20);
-    p += 440;
+    const double *SA = s.strength.eqns.A.data();
+    for (int i = 0; i < 20; ++i) {
+      p[i] = SA[i * 20 + i];
+      p[20 + i] = i + 1 < 20 ? SA[i * 20 + i + 1] : 0.0;
+    }
+    std::memcpy(p + 40, s.strength.eqns.b.data(), sizeof(double) * 20);
+    std::memcpy(p + 60, s.strength.eqns.x.data(), sizeof(double) * 20);
+    p += 80;
     *p++ = s.strength.total;
     *p++ = (double)s.strength.num_equations;
   }
@@ -258,16 +272,27 @@ void LatestFrame::from_digest(const double *in) {
   for (int c = 0; c < 3; ++c) {
     ChannelState &s = ch[c];
     const int n = s.eqns.n;
-    std::memcpy(s.eqns.A.data(), p, sizeof(double) * n * n);
-    std::memcpy(s.eqns.b.data(), p + 625, sizeof(double) * n);
-    std::memcpy(s.eqns.x.data(), p + 650, sizeof(double) * n);
-    p += 675;
+    const double *q = p;
+    double *A = s.eqns.A.data();
+    for (int i = 0; i < n; ++i) {
+      std::memcpy(A + i * n + i, q, sizeof(double) * (n - i));
+      for (int j = i + 1; j < n; ++j) A[j * n + i] = q[j - i];
+      q += n - i;
+    }
+    std::memcpy(s.eqns.b.data(), p + 325, sizeof(double) * n);
+    std::memcpy(s.eqns.x.data(), p + 350, sizeof(double) * n);
+    p += 375;
     s.ar_gain = *p++;
     s.num_observations = (int64_t)*p++;
-    std::memcpy(s.strength.eqns.A.data(), p, sizeof(double) * 400);
-    std::memcpy(s.strength.eqns.b.data(), p + 400, sizeof(double) * 20);
-    std::memcpy(s.strength.eqns.x.data(), p + 420, sizeof(double) * 20);
-    p += 440;
+    double *SA = s.strength.eqns.A.data();
+    std::memset(SA, 0, sizeof(double) * 400);
+    for (int i = 0; i < 20; ++i) {
+      SA[i * 20 + i] = p[i];
+      if (i + 1 < 20) SA[i * 20 + i + 1] = SA[(i + 1) * 20 + i] = p[20 + i];
+    }
+    std::memcpy(s.strength.eqns.b.data(), p + 40, sizeof(double) * 20);
+    std::memcpy(s.strength.eqns.x.data(), p + 60, sizeof(double) * 20);
+    p += 80;
     s.strength.total = *p++;
     s.strength.num_equations = (int)*p++;
   }
@@ -402,16 +427,25 @@ void NoiseModel::add_strength_measurements(int c, const FrameRecordView &rec, La
     const double t = corr * lf.strength[b];
     lf.mean[b] = std::sqrt(std::fmax(noise_var / 16, noise_var - t * t)) / lf.ch[c].ar_gain;
   }
-  // pass 3: NoiseStrengthSolver::add_measurement in block order (the sums are order dependent)
+  // pass 3: NoiseStrengthSolver::add_measurement in block order (the sums are order dependent).  The blocks
+  // that contribute (flat, and more than block_size samples: the reference's guard) are listed once per
+  // frame, so the order-dependent loop has no data-dependent branch to mispredict.
   const bool reuse_A = c > 0 && same_blocks_;
+  if (c == 0 || !same_blocks_) {
+    lf.contrib.clear();
+    for (int b = 0; b < nb; ++b)
+      if (rec.flat[b] && cnt[b] > kBlock) lf.contrib.push_back(b);
+  }
   double *A = solver.eqns.A.data(), *bv = solver.eqns.b.data();
   const double *std_of = lf.mean.data();
   double total = solver.total;
-  int m = 0;
-  for (int b = 0; b < nb; ++b) {
-    if (!rec.flat[b] || cnt[b] <= kBlock) continue;  // "> block_size samples" guard of the reference
-    const int i0 = lf.bin0[b], i1 = std::min(nbins - 1, i0 + 1);
-    const double a = lf.frac[b], s = std_of[b];
+  const int m = (int)lf.contrib.size();
+  const int *bin0 = lf.bin0.data();
+  const double *frac = lf.frac.data();
+  for (int k = 0; k < m; ++k) {
+    const int b = lf.contrib[k];
+    const int i0 = bin0[b], i1 = std::min(nbins - 1, i0 + 1);
+    const double a = frac[b], s = std_of[b];
     if (!reuse_A) {
       A[i0 * nbins + i0] += (1.0 - a) * (1.0 - a);
       A[i1 * nbins + i0] += a * (1.0 - a);
@@ -421,7 +455,6 @@ void NoiseModel::add_strength_measurements(int c, const FrameRecordView &rec, La
     bv[i0] += (1.0 - a) * s;
     bv[i1] += a * s;
     total += s;
-    ++m;
   }
   if (reuse_A) solver.eqns.A = luma.eqns.A;  // same blocks, same weights, same order: identical sums
   solver.total = total;

@@ -87,11 +87,13 @@ struct LatestFrame {
   const char *fail_text = nullptr;
   // scratch reused across frames (per-block bin data shared by the three channels)
   std::vector<int> bin0;
+  std::vector<int> contrib;  // blocks that add a strength measurement (flat, more than block_size samples), in block order
   std::vector<double> frac, mean, strength;
 
   // Fixed-size little-endian image of the state above (the "digest"): what a producer rank sends to the
-  // rank that owns the sequential model, ~27 KB per frame whatever the frame size.
-  static constexpr size_t kDigestDoubles = 4 + 3 * (25 * 25 + 25 + 25 + 2 + 20 * 20 + 20 + 20 + 2);
+  // rank that owns the sequential model, 11.1 KB per frame whatever the frame size (symmetric systems are sent
+  // as their upper triangle, the tridiagonal strength system as two diagonals).
+  static constexpr size_t kDigestDoubles = 4 + 3 * (325 + 25 + 25 + 2 + 20 + 20 + 20 + 20 + 2);
   void to_digest(double *out) const;
   void from_digest(const double *in);
 };

@@ -29,7 +29,7 @@ EXPORTS = [
     "g1s_diff_finish", "g1s_diff_destroy", "g1s_diff_last_error", "g1s_diff_frames_pushed",
     "g1s_diff_get_counters", "g1s_diff_mark", "g1s_diff_marks_elapsed_ms", "g1s_record_layout", "g1s_diff_record_bytes", "g1s_diff_set_record_tap",
     "g1s_diff_consume_record", "g1s_diff_consume_records", "g1s_digest_bytes", "g1s_diff_set_digest_sink",
-    "g1s_diff_digest_count", "g1s_diff_wait_retired", "g1s_diff_consume_digests", "g1s_diff_digest_from_record", "g1s_write_grain_table", "g1s_format_grain_table",
+    "g1s_diff_digest_count", "g1s_diff_wait_retired", "g1s_diff_consume_digests", "g1s_diff_consume_digests_borrowed", "g1s_diff_digest_from_record", "g1s_write_grain_table", "g1s_format_grain_table",
 ]
 
 
@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
         L.g1s_diff_digest_count.restype = C.c_int64
         L.g1s_diff_wait_retired.argtypes = [C.c_void_p, C.c_int64]
         L.g1s_diff_consume_digests.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.g1s_diff_consume_digests_borrowed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.g1s_diff_digest_from_record.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.g1s_write_grain_table.argtypes = [C.POINTER(CSegment), C.c_size_t, C.c_char_p]
         L.g1s_format_grain_table.argtypes = [C.POINTER(CSegment), C.c_size_t, C.c_char_p, C.c_size_t]
@@ -258,8 +259,10 @@ class DiffGenerator:
         self._check(self._L.g1s_diff_digest_from_record(self._h, rec.ctypes.data, rec.size, out.ctypes.data))
         return out
 
-    def consume_digests(self, ptr: int, count: int) -> None:
-        self._check(self._L.g1s_diff_consume_digests(self._h, ptr, count))
+    def consume_digests(self, ptr: int, count: int, borrowed: bool = False) -> None:
+        """borrowed: no copy; the memory must stay valid until flush() on this handle has returned."""
+        fn = self._L.g1s_diff_consume_digests_borrowed if borrowed else self._L.g1s_diff_consume_digests
+        self._check(fn(self._h, ptr, count))
 
     @property
     def frames_pushed(self) -> int:

@@ -3,7 +3,7 @@
 The path shards by frame: every per-pixel quantity is a function of one frame
 pair, and the only cross-frame logic is the small sequential model merge.  So each rank runs a
 PRODUCER handle on its own frames: kernels, plus the per-frame half of the host model, whose result
-is a fixed-size ~27 KB digest per frame written straight into a pinned ring.  Once per super-batch
+is a fixed-size ~11 KB digest per frame written straight into a pinned ring.  Once per super-batch
 the digests are all-gathered (NCCL over NVLink on GPUs, gloo in the CPU tests) and rank 0 folds them
 in global frame order into one CONSUMER handle (asynchronously, on the handle's own thread).
 A super-batch is world*B consecutive frames; rank r owns frames [base + r*B, base + (r+1)*B), so the
@@ -48,8 +48,15 @@ class ShardedDiff:
             self.ring = self.ring.pin_memory()
             dev = torch.device("cuda", torch.cuda.current_device())
             self.dev_local = torch.empty((rows, self.ndbl), dtype=torch.float64, device=dev)
-            self.dev_all = torch.empty((self.world * rows, self.ndbl), dtype=torch.float64, device=dev)
-            self.host_all = torch.empty((self.world * rows, self.ndbl), dtype=torch.float64).pin_memory()
+            # two gather buffers: the device->host copy of exchange k runs while exchange k+1 is being gathered,
+            # and rank 0's fold thread reads the pinned copy in place (no second copy on the Python thread)
+            self.dev_all = [torch.empty((self.world * rows, self.ndbl), dtype=torch.float64, device=dev) for _ in range(2)]
+            if self.rank == 0:
+                self.host_all = [torch.empty((self.world * rows, self.ndbl), dtype=torch.float64).pin_memory()
+                                 for _ in range(2)]
+                self.copied = [torch.cuda.Event() for _ in range(2)]
+            self.pending = None            # gather slot whose digests have not been handed to the consumer yet
+            self.borrowed = [False, False]  # slot is (possibly still) being read by the consumer's fold thread
         self.producer.set_digest_sink(self.ring.data_ptr(), RING * self.B)
         self.consumer = DiffGenerator(*args, mode=abi.MODE_CONSUMER) if self.rank == 0 else None
         self.pushed = 0        # local frames pushed
@@ -80,13 +87,21 @@ class ShardedDiff:
         local = self.ring[lo:lo + self.B]
         rows = self.B + 1
         if self.world > 1 and self.on_gpu:
+            slot = k % 2
+            if self.consumer is not None and self.borrowed[slot]:
+                self.consumer.flush()  # the fold thread is done with what this slot held two exchanges ago
+                self.borrowed[slot] = False
             self.dev_local[: self.B].copy_(local, non_blocking=True)
             self.dev_local[self.B].fill_(float(n_local))
-            dist.all_gather_into_tensor(self.dev_all, self.dev_local, group=self.group)
-            allv = None
+            dist.all_gather_into_tensor(self.dev_all[slot], self.dev_local, group=self.group)
             if self.consumer is not None:
-                self.host_all.copy_(self.dev_all, non_blocking=False)
-                allv = self.host_all.view(self.world, rows, self.ndbl)
+                self.host_all[slot].copy_(self.dev_all[slot], non_blocking=True)
+                self.copied[slot].record()
+                prev, self.pending = self.pending, slot
+                if prev is not None:
+                    self._hand_over(prev)  # the previous exchange's digests: their copy finished long ago
+            self.sb_done += 1
+            return
         elif self.world > 1:
             mine = torch.cat([local, torch.full((1, self.ndbl), float(n_local), dtype=torch.float64)])
             allbuf = torch.empty((self.world * rows, self.ndbl), dtype=torch.float64)
@@ -95,16 +110,25 @@ class ShardedDiff:
         else:
             allv = torch.cat([local, torch.full((1, self.ndbl), float(n_local), dtype=torch.float64)]).unsqueeze(0)
         if self.consumer is not None:
-            seen_short = False
-            for r in range(self.world):
-                c = int(allv[r, self.B, 0].item())
-                if seen_short and c:  # a short rank may only be followed by empty ranks (tail of the stream)
-                    raise RuntimeError("frames are not contiguous across ranks in this super-batch")
-                seen_short |= c < self.B
-                if c:
-                    self.consumer.consume_digests(allv[r].data_ptr(), c)  # copied, folded asynchronously
-                    self.folded += c
+            self._fold_gathered(allv, borrowed=False)
         self.sb_done += 1
+
+    def _fold_gathered(self, allv, borrowed: bool) -> None:
+        seen_short = False
+        for r in range(self.world):
+            c = int(allv[r, self.B, 0].item())
+            if seen_short and c:  # a short rank may only be followed by empty ranks (tail of the stream)
+                raise RuntimeError("frames are not contiguous across ranks in this super-batch")
+            seen_short |= c < self.B
+            if c:
+                self.consumer.consume_digests(allv[r].data_ptr(), c, borrowed=borrowed)  # folded asynchronously
+                self.folded += c
+
+    def _hand_over(self, slot: int) -> None:
+        """rank 0, GPU path: give the gathered digests of `slot` to the consumer, read in place."""
+        self.copied[slot].synchronize()
+        self._fold_gathered(self.host_all[slot].view(self.world, self.B + 1, self.ndbl), borrowed=True)
+        self.borrowed[slot] = True
 
     def exchange(self, final: bool = False) -> int:
         """Close the current super-batch.  Unless `final`, only the super-batch BEFORE it is gathered now
@@ -118,7 +142,12 @@ class ShardedDiff:
         while len(self.sb_pushed) - self.sb_done > keep:
             self._exchange_one(final)
         if final and self.consumer is not None:
+            if self.on_gpu and self.world > 1 and self.pending is not None:
+                self._hand_over(self.pending)
+                self.pending = None
             self.consumer.flush()
+            if self.on_gpu and self.world > 1:
+                self.borrowed = [False, False]
         return self.folded
 
     def finish(self):

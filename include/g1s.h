@@ -188,10 +188,10 @@ int g1s_diff_consume_records(g1s_diff *d, const void *records, size_t count, siz
 /* ---- per-frame digests (what scales across GPUs) ------------------------------------
  * The host model splits into a per-frame half (a pure function of one record: AR solve, strength
  * measurements, strength solve) and a sequential merge.  A PRODUCER handle with a digest sink runs
- * the per-frame half itself and writes one fixed-size digest (g1s_digest_bytes(), ~27 KB, independent
+ * the per-frame half itself and writes one fixed-size digest (g1s_digest_bytes(), ~11 KB, independent
  * of the frame size) per retired frame into the caller's buffer, in frame order; the rank that owns
  * the model folds them with g1s_diff_consume_digests.  Same results as exchanging the full records,
- * 10x less traffic and no per-frame work left on the sequential rank but the merge itself. */
+ * 27x less traffic and no per-frame work left on the sequential rank but the merge itself. */
 size_t g1s_digest_bytes(void);
 /* buffer must hold capacity_frames digests and stay valid while it is the sink; resets the count.
  * The sink is a ring: digest k (counted from the reset) lands in slot k % capacity_frames, so a reader
@@ -204,6 +204,9 @@ int64_t g1s_diff_digest_count(const g1s_diff *d);
  * Returns early if fewer frames are in flight. */
 int g1s_diff_wait_retired(g1s_diff *d, int64_t frames);
 int g1s_diff_consume_digests(g1s_diff *d, const void *digests, size_t count);
+/* Same without the copy: the digests are read in place by the fold thread, so the memory must stay
+ * valid and unchanged until g1s_diff_flush on this (CONSUMER) handle has returned. */
+int g1s_diff_consume_digests_borrowed(g1s_diff *d, const void *digests, size_t count);
 /* Evaluates the per-frame half for one record without touching the model (any handle of the stream's
  * geometry; no device work) and writes its digest. */
 int g1s_diff_digest_from_record(g1s_diff *d, const void *record, size_t bytes, void *digest_out);
