@@ -203,16 +203,7 @@ struct g1s_diff {
   cudaStream_t d2h_stream = nullptr;   // record read-back, overlapping the kernels of the next batch
   Slot slots[kSlots];
   int cur = 0;            // slot being filled
-  // Submitted batches are retired (wait for the device, per-frame host model, taps / digests, queue the fold)
-  // by a dedicated thread in submission order, so the caller only ever blocks for back-pressure: when the
-  // slot it wants to fill next is still in flight.
-  std::thread retirer;
-  std::mutex rmu;                       // guards rq, Slot::in_flight, rstop, rerr*, and publishes `retired`
-  std::condition_variable rcv_work, rcv_free;
-  std::deque<int> rq;                   // slot indices, submission order
-  bool rstop = false;
-  int rerr = 0;                         // first error met by the retire thread (reported by the next call)
-  std::string rerr_text;
+  int oldest = 0;         // oldest slot possibly in flight
   std::unique_ptr<DiffSequencer> seq;
   std::unique_ptr<HostPool> pool;
   std::unique_ptr<FoldQueue> folder;
@@ -364,20 +355,16 @@ int submit(g1s_diff *d, Slot &s) {
   CU_TRY(d, cudaStreamWaitEvent(d->d2h_stream, s.computed, 0));
   CU_TRY(d, cudaMemcpyAsync(s.h_records, s.d_records, d->rl.bytes * s.count, cudaMemcpyDeviceToHost, d->d2h_stream));
   CU_TRY(d, cudaEventRecord(s.done, d->d2h_stream));
-  {
-    std::lock_guard<std::mutex> lk(d->rmu);
-    s.in_flight = true;
-    d->rq.push_back((int)(&s - d->slots));
-  }
-  d->rcv_work.notify_one();
+  s.in_flight = true;
   d->kernels_launched += 2 + gram_launches;
   d->k0_launches += 1;
   d->k1_launches += 1;
   return G1S_OK;
 }
 
-// Retire thread: waits for a slot's device work and hands its records to the host model (frame order).
-int retire_slot(g1s_diff *d, Slot &s) {
+// Waits for a slot's device work and folds its records into the model (frame order).
+int retire(g1s_diff *d, Slot &s) {
+  if (!s.in_flight) return G1S_OK;
   CU_TRY(d, cudaEventSynchronize(s.done));
   float ms = 0;
   if (cudaEventElapsedTime(&ms, s.k0_beg, s.k0_end) == cudaSuccess) d->k0_ms += ms;
@@ -386,64 +373,37 @@ int retire_slot(g1s_diff *d, Slot &s) {
   d->folder->wait(s.fold_ticket);  // the slot's previous batch must have left the fold thread
   s.fold_ticket = fold_records(d, s.h_records, s.count, d->rl.bytes, s.latest);
   d->frames_done += s.count;
+  s.in_flight = false;
   s.count = 0;
   s.host_frames = 0;
   return G1S_OK;
-}
-
-void retire_loop(g1s_diff *d) {
-  cudaSetDevice(d->cfg.device);
-  for (;;) {
-    int i;
-    {
-      std::unique_lock<std::mutex> lk(d->rmu);
-      d->rcv_work.wait(lk, [&] { return d->rstop || !d->rq.empty(); });
-      if (d->rq.empty()) return;
-      i = d->rq.front();
-      d->rq.pop_front();
-    }
-    const int rc = retire_slot(d, d->slots[i]);
-    {
-      std::lock_guard<std::mutex> lk(d->rmu);
-      d->slots[i].in_flight = false;
-      if (rc != G1S_OK && d->rerr == G1S_OK) d->rerr = rc, d->rerr_text = d->err;
-    }
-    d->rcv_free.notify_all();
-  }
-}
-
-// an error met by the retire thread surfaces on the caller's next call (the reference aborts the run too)
-int retire_error(g1s_diff *d) {
-  std::lock_guard<std::mutex> lk(d->rmu);
-  if (d->rerr != G1S_OK) d->err = d->rerr_text;
-  return d->rerr;
 }
 
 int rotate(g1s_diff *d) {
   int rc = submit(d, d->slots[d->cur]);
   if (rc != G1S_OK) return rc;
   d->cur = (d->cur + 1) % kSlots;
-  {  // back-pressure: the slot we are about to fill must have been retired
-    std::unique_lock<std::mutex> lk(d->rmu);
-    d->rcv_free.wait(lk, [&] { return !d->slots[d->cur].in_flight; });
+  // the slot we are about to fill must be free; retire in submission order
+  while (d->slots[d->cur].in_flight) {
+    rc = retire(d, d->slots[d->oldest]);
+    if (rc != G1S_OK) return rc;
+    d->oldest = (d->oldest + 1) % kSlots;
   }
-  return retire_error(d);
+  return G1S_OK;
 }
 
 int drain(g1s_diff *d) {
   int rc = submit(d, d->slots[d->cur]);
   if (rc != G1S_OK) return rc;
-  {
-    std::unique_lock<std::mutex> lk(d->rmu);
-    if (d->slots[d->cur].in_flight) d->cur = (d->cur + 1) % kSlots;
-    d->rcv_free.wait(lk, [&] {
-      for (const Slot &s : d->slots)
-        if (s.in_flight) return false;
-      return true;
-    });
+  if (d->slots[d->cur].in_flight) d->cur = (d->cur + 1) % kSlots;
+  for (int k = 0; k < kSlots; ++k) {
+    rc = retire(d, d->slots[d->oldest]);
+    if (rc != G1S_OK) return rc;
+    d->oldest = (d->oldest + 1) % kSlots;
   }
+  d->oldest = d->cur;
   d->folder->wait_all();
-  return retire_error(d);
+  return G1S_OK;
 }
 
 int check_frames(g1s_diff *d, const g1s_frame *s, const g1s_frame *n) {
@@ -625,7 +585,6 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     CU_NEW(cudaEventCreate(&s.k1_end));
   }
 #undef CU_NEW
-  d->retirer = std::thread(retire_loop, d.get());
   *out = d.release();
   return G1S_OK;
 }
@@ -849,14 +808,6 @@ int g1s_diff_finish(g1s_diff *d, g1s_segment *out, size_t cap, size_t *n) {
 
 void g1s_diff_destroy(g1s_diff *d) {
   if (!d) return;
-  if (d->retirer.joinable()) {  // retires what is still queued, then exits
-    {
-      std::lock_guard<std::mutex> lk(d->rmu);
-      d->rstop = true;
-    }
-    d->rcv_work.notify_all();
-    d->retirer.join();
-  }
   d->folder.reset();  // runs the queued folds to completion, then joins
   if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
   if (d->d2h_stream) cudaStreamSynchronize(d->d2h_stream);
@@ -923,16 +874,12 @@ int64_t g1s_diff_digest_count(const g1s_diff *d) { return d ? (int64_t)d->sink_c
 int g1s_diff_wait_retired(g1s_diff *d, int64_t frames) {
   if (!d) return G1S_E_ARG;
   if (d->cfg.mode == G1S_MODE_CONSUMER) return G1S_OK;
-  {
-    std::unique_lock<std::mutex> lk(d->rmu);
-    d->rcv_free.wait(lk, [&] {
-      if (d->retired >= frames) return true;
-      for (const Slot &s : d->slots)
-        if (s.in_flight) return false;
-      return true;
-    });
+  while (d->retired < frames && d->slots[d->oldest].in_flight) {
+    const int rc = retire(d, d->slots[d->oldest]);
+    if (rc != G1S_OK) return rc;
+    d->oldest = (d->oldest + 1) % kSlots;
   }
-  return retire_error(d);
+  return G1S_OK;
 }
 
 int g1s_diff_consume_digests(g1s_diff *d, const void *digests, size_t count) {
