@@ -184,8 +184,9 @@ std::vector<std::pair<double, double>> StrengthSolver::fit_piecewise(int max_poi
     const double dx = pts[min_index + 1].first - pts[min_index - 1].first;
     const double avg = residual[min_index] / dx;
     if ((int)pts.size() <= max_points && avg > tol) break;
+    // Only the points move up; residual[] keeps its slots, as in libaom's noise_model.c (memmove of
+    // lut->points only) which the crate ports -- verified against the libaom 3.13.1 binary (oracle/aom_pin.py).
     pts.erase(pts.begin() + min_index);
-    residual.erase(residual.begin() + min_index);
     update_residual(pts, residual, min_index - 1, min_index + 1);
   }
   return pts;

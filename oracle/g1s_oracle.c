@@ -5,13 +5,23 @@
  * C-ABI library) links, loads or calls this file; only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
  *
- * PARITY UNPINNED.  The arithmetic of this path lives in the third-party crate
- * `av1-grain 0.4.2` (/root/reference/Cargo.toml:15, Cargo.lock:92-104), whose
- * source is not vendored in /root/reference and is not on this box; the reference
- * holds no golden vector or test for `diff` (tests/sanity_tests.rs never runs it).
- * What follows restates the crate's published algorithm (module `diff`, itself a
- * port of libaom aom_dsp/noise_model.c + mathutils.h::linsolve) from its public
- * description, anchored on the reference's own call sites:
+ * PARITY: PINNED TO THE UPSTREAM BINARY, NOT TO THE REFERENCE BINARY.  The arithmetic of this path
+ * lives in the third-party crate `av1-grain 0.4.2` (/root/reference/Cargo.toml:15, Cargo.lock:92-104),
+ * whose source is not vendored in /root/reference and is not on this box; the reference holds no golden
+ * vector or test for `diff` (tests/sanity_tests.rs never runs it) and cannot be built here (no Rust).
+ * That crate module is a port of libaom aom_dsp/noise_model.c + mathutils.h::linsolve, and a compiled
+ * libaom 3.13.1 ships in this image: oracle/aom_pin.py calls its aom_flat_block_finder_* /
+ * aom_noise_model_* entry points directly.  In G1SO_GRAM_REF_ORDER + G1SO_EXP_LIBM mode this file is
+ * BIT-IDENTICAL to that binary on every case of tests/aom_cases.py plus a 60-case random sweep: flat-block
+ * maps, statuses, observation counts, the f64 bit patterns of the AR solution / AR gain / strength solution
+ * of the latest and combined state after every frame, and every integer of every emitted segment
+ * (tests/test_aom_pin.py, goldens under tests/golden/aom/).  One restated detail turned out wrong and was
+ * corrected by this pin: fit_piecewise moves only the points, residual[] keeps its slots.
+ * Still "parity unpinned" (crate-only behaviour that libaom cannot witness): the truncating `>> (bd-8)`
+ * reduction of high-bit-depth input, timestamps, the fixed seed, swallowing of NoiseStatus::Error, and NaN
+ * handling in get_grain_parameters when a chroma strength is exactly zero (Rust's f64::max / `as` casts are
+ * followed, C's macros differ: tests/test_aom_pin.py::test_nan_correlation_follows_rust_semantics_not_c).
+ * What follows restates the algorithm anchored on the reference's own call sites:
  *   DiffGenerator::new        src/main.rs:420-427
  *   DiffGenerator::diff_frame src/main.rs:442, 462, 482, 502
  *   DiffGenerator::finish     src/main.rs:524
@@ -24,7 +34,9 @@
  *                        reference's loop order (what the crate does);
  *   G1SO_GRAM_EXACT_INT  exact int64 sums, one division at the end (what the CUDA
  *                        engine computes).  Tests assert both modes give identical
- *                        grain tables on the whole corpus.
+ *                        grain tables on the whole corpus; the modes differ by ~1e-14
+ *                        in the solutions, which can only show where fit_piecewise
+ *                        meets a structural tie.
  * Two exp() flavours for the flat-block sigmoid score:
  *   G1SO_EXP_LIBM        libm exp (what Rust's f64::exp calls);
  *   G1SO_EXP_FIXED       a fixed +,*,fma sequence that CPU and GPU evaluate
@@ -288,7 +300,8 @@ static void ss_fit_piecewise(const strength_solver *s, int max_output_points, st
     if (lut->n <= max_output_points && avg_residual > kTolerance) break;
     const int num_remaining = lut->n - min_index - 1;
     memmove(lut->pts + min_index, lut->pts + min_index + 1, sizeof(lut->pts[0]) * num_remaining);
-    memmove(residual + min_index, residual + min_index + 1, sizeof(residual[0]) * num_remaining);
+    /* libaom (and its port) shift only the points: residual[] keeps its old slots (checked against the
+     * libaom 3.13.1 binary, oracle/aom_pin.py) */
     lut->n--;
     update_piecewise_linear_residual(s, lut, residual, min_index - 1, min_index + 1);
   }
