@@ -114,6 +114,34 @@ def run_cpu_sample(wl, nframes, cores=1):
     return nframes / dt, dt
 
 
+def run_libaom_sample(wl, nframes=1):
+    """Corroboration of the CPU baseline: the same frames (reduced to 8 bits, outside the timed region) through
+    libaom 3.13.1's own compiled noise_model.c (oracle/aom_pin.py), the code av1-grain's `diff` ports.  Returns
+    None where the bundled libaom is absent."""
+    try:
+        from grav1synth_b200.synth import make_pair_numpy
+        from oracle import aom_pin as P
+        ok, where = P.available()
+        if not ok:
+            return None
+        spec = synth_spec(wl)
+        frames = [make_pair_numpy(spec, k) for k in range(nframes)]
+        frames = [([P.to_u8(p, spec.bit_depth) for p in s], [P.to_u8(p, spec.bit_depth) for p in d])
+                  for s, d in frames]
+        a = P.AomNoiseModel()
+        t0 = time.perf_counter()
+        for s, d in frames:
+            a.update(s, d)
+        a.finish()
+        dt = time.perf_counter() - t0
+        a.close()
+        return {"value": nframes / dt, "unit": "frames/s", "cores": 1,
+                "sample": f"{nframes} frame pair(s), {dt:.1f} s, {os.path.basename(where)}: aom_flat_block_finder_run + "
+                          "aom_noise_model_update + get_grain_parameters on the 8-bit-reduced planes"}
+    except Exception as e:  # the corroboration must never break the bench line
+        return {"unavailable": repr(e)[:200]}
+
+
 def reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference binary cannot be
     built here (Rust; hot path in the un-vendored crate av1-grain 0.4.2), so this times the C oracle in
@@ -148,6 +176,9 @@ def reference_arm(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    up = run_libaom_sample(wl, 1)
+    if up is not None:
+        line["cpu_baseline"]["upstream_libaom"] = up
     print(json.dumps(line), flush=True)
 
 
@@ -346,6 +377,9 @@ def main():
                                 "sample": f"{args.cpu_frames} frame pairs of the same workload, {dt:.1f} s; "
                                           "C restatement of av1-grain 0.4.2 diff (reference op order), host has "
                                           f"{os.cpu_count()} cores, reference diff loop is single-threaded"}
+        up = run_libaom_sample(wl, 1)
+        if up is not None:
+            line["cpu_baseline"]["upstream_libaom"] = up
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
