@@ -2,8 +2,11 @@
 (/root/reference/src/main.rs:347-533, arguments :846-871) over the B200 engine, reading .y4m clips
 instead of going through FFmpeg.  Same checks and messages as the reference's Diff arm; the per-pixel
 work goes through the C ABI (g1s_diff_create / push_frame / finish) and the table through
-g1s_write_grain_table.  Only `diff` exists: the other sub-commands never touch pixels and are out of
-scope.
+g1s_write_grain_table.
+
+`python -m grav1synth_b200 inspect INPUT -o OUT [-y] [--fps N/D]` -- the reference's `inspect` (src/main.rs:145-196):
+AV1 OBU headers of an .ivf / .obu file -> grain table, CPU only (C++ parser behind g1s_inspect_*).
+`apply` / `generate` / `remove` rewrite bitstreams and are not built.
 """
 from __future__ import annotations
 
@@ -28,7 +31,15 @@ def main(argv=None) -> int:
                    help='A semicolon-separated list of filters to apply to the source before running the diff, e.g. '
                         '"crop:top=42,left=64" (resize is parsed but not available in this build).')
     d.add_argument("--device", type=int, default=0)
+    i = sub.add_parser("inspect", help="Outputs a film grain table corresponding to a given AV1 video, or reports "
+                                       "if there is no film grain information.")
+    i.add_argument("input", help="The AV1 file to inspect (.ivf or low-overhead .obu).")
+    i.add_argument("-o", "--output", required=True, help="The path to the output film grain table.")
+    i.add_argument("-y", "--overwrite", action="store_true", help="Overwrite the output file without prompting.")
+    i.add_argument("--fps", default=None, help="Frame rate N/D (default: the IVF header's rate/scale).")
     args = ap.parse_args(argv)
+    if args.command == "inspect":
+        return inspect_main(args)
 
     # src/main.rs:354-368
     if os.path.abspath(args.source) == os.path.abspath(args.output) or \
@@ -77,6 +88,35 @@ def main(argv=None) -> int:
     write_grain_table(differ.finish(), args.output)
     log.info("Computed diff for %d frames", frames)
     log.info("Done, wrote output file to %s", args.output)
+    return 0
+
+
+def inspect_main(args) -> int:
+    """src/main.rs:145-196."""
+    if os.path.abspath(args.input) == os.path.abspath(args.output):
+        log.error("Input and output paths are the same. This is probably a typo, because this would overwrite "
+                  "your input. Exiting.")
+        return 0
+    if os.path.exists(args.output) and not args.overwrite:
+        if not sys.stdin.isatty() or input(f"File {args.output} exists. Overwrite? [y/n] ").strip().lower() != "y":
+            log.warning("Not overwriting existing file. Exiting.")
+            return 0
+    from .diff import write_grain_table
+    from .inspect import UPDATE_GRAIN, BitstreamParser
+    fps = (0, 0)
+    if args.fps:
+        n, _, d = args.fps.partition("/")
+        fps = (int(n), int(d or 1))
+    parser = BitstreamParser()
+    fps = parser.push_file(args.input, fps)
+    if fps[0] <= 0 or fps[1] <= 0:
+        raise SystemExit("the container carries no frame rate: pass --fps N/D")
+    headers = parser.get_grain_headers()
+    if not any(h.kind == UPDATE_GRAIN for h in headers):
+        log.info("No film grain headers found--this video does not use grain synthesis")
+        return 0
+    write_grain_table(parser.aggregate_grain_headers(*fps), args.output)
+    log.info("Done, wrote grain table to %s", args.output)
     return 0
 
 

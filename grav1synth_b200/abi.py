@@ -26,6 +26,7 @@ G1S_E_NCCL = -4
 G1S_E_NOMEM = -5
 G1S_E_STATE = -6
 G1S_E_IO = -7
+G1S_E_STREAM = -8
 
 MODE_FULL = 0
 MODE_PRODUCER = 1
@@ -49,11 +50,11 @@ class CSegment(C.Structure):
         ("cb_luma_mult", C.c_uint8),
         ("cr_mult", C.c_uint8),
         ("cr_luma_mult", C.c_uint8),
-        ("reserved_", C.c_uint8 * 3),
+        ("num_ar_coeffs_plus1", C.c_uint8 * 3),
         ("cb_offset", C.c_uint16),
         ("cr_offset", C.c_uint16),
         ("random_seed", C.c_uint16),
-        ("reserved2_", C.c_uint16),
+        ("clip_to_restricted_range", C.c_uint16),
         ("scaling_points_y", (C.c_uint8 * 2) * NUM_Y_POINTS),
         ("scaling_points_cb", (C.c_uint8 * 2) * NUM_UV_POINTS),
         ("scaling_points_cr", (C.c_uint8 * 2) * NUM_UV_POINTS),
@@ -126,9 +127,9 @@ class GrainTableSegment:
             scaling_points_cr=[(int(p[0]), int(p[1])) for p in list(s.scaling_points_cr)[: s.num_cr_points]],
             scaling_shift=int(s.scaling_shift),
             ar_coeff_lag=int(s.ar_coeff_lag),
-            ar_coeffs_y=[int(v) for v in s.ar_coeffs_y],
-            ar_coeffs_cb=[int(v) for v in s.ar_coeffs_cb],
-            ar_coeffs_cr=[int(v) for v in s.ar_coeffs_cr],
+            ar_coeffs_y=_coeffs(s.ar_coeffs_y, s.num_ar_coeffs_plus1[0]),
+            ar_coeffs_cb=_coeffs(s.ar_coeffs_cb, s.num_ar_coeffs_plus1[1]),
+            ar_coeffs_cr=_coeffs(s.ar_coeffs_cr, s.num_ar_coeffs_plus1[2]),
             ar_coeff_shift=int(s.ar_coeff_shift),
             cb_mult=int(s.cb_mult),
             cb_luma_mult=int(s.cb_luma_mult),
@@ -142,6 +143,12 @@ class GrainTableSegment:
             random_seed=int(s.random_seed),
             raw=copy,
         )
+
+
+def _coeffs(arr, count_plus1: int) -> List[int]:
+    """All coefficients (diff path, count byte 0) or the explicit count the inspect path recorded."""
+    vals = [int(v) for v in arr]
+    return vals if count_plus1 == 0 else vals[: count_plus1 - 1]
 
 
 def segments_to_c(segs: Sequence[GrainTableSegment]):

@@ -764,9 +764,11 @@ std::string format_grain_table(const g1s_segment *segs, size_t n) {
     // coefficient counts follow the lag (AV1 5.9.30): 2*lag*(lag+1) luma, one more for chroma
     const int lag = std::min<int>(p.ar_coeff_lag, 3);
     const int ny = 2 * lag * (lag + 1);
-    coeffs("\tcY", p.ar_coeffs_y, ny);
-    coeffs("\tcCb", p.ar_coeffs_cb, ny + 1);
-    coeffs("\tcCr", p.ar_coeffs_cr, ny + 1);
+    // ... unless the segment carries explicit counts (inspect path: the reference prints the parsed ArrayVecs as they are)
+    auto count = [&](int k, int dflt, int cap) { return p.num_ar_coeffs_plus1[k] ? std::min<int>(p.num_ar_coeffs_plus1[k] - 1, cap) : dflt; };
+    coeffs("\tcY", p.ar_coeffs_y, count(0, ny, G1S_NUM_Y_COEFFS));
+    coeffs("\tcCb", p.ar_coeffs_cb, count(1, ny + 1, G1S_NUM_UV_COEFFS));
+    coeffs("\tcCr", p.ar_coeffs_cr, count(2, ny + 1, G1S_NUM_UV_COEFFS));
   }
   return s;
 }

@@ -54,7 +54,8 @@ enum g1s_status {
   G1S_E_NCCL = -4,        /* reserved for the multi-process merge                 */
   G1S_E_NOMEM = -5,
   G1S_E_STATE = -6,       /* call after finish, or capacity too small             */
-  G1S_E_IO = -7
+  G1S_E_IO = -7,
+  G1S_E_STREAM = -8       /* malformed AV1 / IVF data (inspect path)               */
 };
 
 /* One grain-table segment: field-for-field the data carried by
@@ -71,10 +72,13 @@ typedef struct g1s_segment {
   uint8_t overlap_flag;
   uint8_t chroma_scaling_from_luma;
   uint8_t cb_mult, cb_luma_mult, cr_mult, cr_luma_mult;
-  uint8_t reserved_[3];
+  /* Explicit AR coefficient counts + 1 for Y, Cb, Cr; 0 = "follow the lag" (24/25/25 at lag 3), which is what the
+   * diff path emits.  The inspect path needs them: a parsed header carries no luma coefficients when it has no luma
+   * points and a single 0 for a chroma plane without coefficients (src/parser/grain.rs:221-243). */
+  uint8_t num_ar_coeffs_plus1[3];
   uint16_t cb_offset, cr_offset;
   uint16_t random_seed;
-  uint16_t reserved2_;
+  uint16_t clip_to_restricted_range; /* inspect path only (src/parser/grain.rs:65); the table text does not carry it */
   uint8_t scaling_points_y[G1S_NUM_Y_POINTS][2];
   uint8_t scaling_points_cb[G1S_NUM_UV_POINTS][2];
   uint8_t scaling_points_cr[G1S_NUM_UV_POINTS][2];
@@ -218,6 +222,43 @@ int g1s_write_grain_table(const g1s_segment *segs, size_t n, const char *path);
 int64_t g1s_format_grain_table(const g1s_segment *segs, size_t n, char *buf, size_t cap);
 
 int g1s_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * `inspect` (BASELINE configs[0]): AV1 OBU headers -> film grain headers -> grain table.
+ * CPU only, exactly like the reference: replaces BitstreamParser::<false>::get_grain_headers
+ * (src/parser.rs:120-173, fed by FFmpeg packets there) and aggregate_grain_headers (src/main.rs:713-772) as driven
+ * by the `Inspect` arm (src/main.rs:172-196).  A packet is one demuxed sample: whole OBUs of one temporal unit. */
+typedef struct g1s_inspect g1s_inspect;
+
+enum g1s_grain_kind { G1S_GRAIN_DISABLE = 0, G1S_GRAIN_COPY_REF_FRAME = 1, G1S_GRAIN_UPDATE = 2 }; /* FilmGrainHeader */
+
+typedef struct g1s_stream_info {
+  int32_t have_sequence_header, seq_profile, bit_depth, monochrome, ss_x, ss_y;
+  int32_t max_frame_width, max_frame_height, film_grain_params_present;
+  int32_t color_primaries, transfer_characteristics, matrix_coefficients, color_range;
+  int32_t order_hint_bits, reduced_still_picture_header, reserved_;
+  uint64_t packets, obus;
+} g1s_stream_info;
+
+int g1s_inspect_create(g1s_inspect **out);
+void g1s_inspect_destroy(g1s_inspect *h);
+const char *g1s_inspect_last_error(const g1s_inspect *h);
+/* src/parser.rs:136-165: parse every OBU of the packet; one header is recorded per SHOWN frame header. */
+int g1s_inspect_push_packet(g1s_inspect *h, const uint8_t *data, size_t size);
+/* Demux an IVF file or a Section-5 low-overhead .obu stream and push its packets.  *fps_num / *fps_den <= 0 on entry
+ * are replaced by the IVF header's rate / scale (the reference asks FFmpeg: src/main.rs:173). */
+int g1s_inspect_push_file(g1s_inspect *h, const char *path, int64_t *fps_num, int64_t *fps_den);
+size_t g1s_inspect_num_headers(const g1s_inspect *h);
+/* kind: enum g1s_grain_kind; params (may be NULL) is meaningful for G1S_GRAIN_UPDATE, random_seed = grain_seed. */
+int g1s_inspect_header(const g1s_inspect *h, size_t i, int32_t *kind, g1s_segment *params);
+/* aggregate_grain_headers: one packet per header, time_per_packet = den / num * 1e7 accumulated in f64 and ceiled.
+ * *n == 0 with G1S_OK means "no film grain headers found" (src/main.rs:177-183). G1S_E_STATE: cap too small. */
+int g1s_inspect_finish(g1s_inspect *h, int64_t fps_num, int64_t fps_den, g1s_segment *out, size_t cap, size_t *n);
+int g1s_inspect_stream_info(const g1s_inspect *h, g1s_stream_info *info);
+/* Test hook: parse ONE syntax group (named as in the AV1 spec / the reference's functions) from a raw bit buffer;
+ * returns bits consumed or a negative status.  Lets tests replay the reference's own unit-test vectors. */
+int64_t g1s_obu_probe(const char *what, const uint8_t *data, size_t size, const int64_t *args, size_t nargs,
+                      int64_t *out, size_t nout, g1s_segment *seg);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,34 @@ def _elf_symtab(path: str, wanted: Sequence[str]) -> Dict[str, int]:
     return out
 
 
+def _elf_symtab_objects(path: str, wanted: Sequence[str]) -> Dict[str, int]:
+    """Like _elf_symtab, for data objects (STT_OBJECT)."""
+    out: Dict[str, int] = {}
+    with open(path, "rb") as f:
+        eh = f.read(64)
+        e_shoff, = struct.unpack_from("<Q", eh, 0x28)
+        e_shentsize, e_shnum, _ = struct.unpack_from("<HHH", eh, 0x3A)
+        f.seek(e_shoff)
+        sh = f.read(e_shentsize * e_shnum)
+        secs = [struct.unpack_from("<IIQQQQIIQQ", sh, i * e_shentsize) for i in range(e_shnum)]
+        for (_, sh_type, _, _, sh_offset, sh_size, sh_link, _, _, sh_entsize) in secs:
+            if sh_type != 2:
+                continue
+            f.seek(secs[sh_link][4])
+            strtab = f.read(secs[sh_link][5])
+            f.seek(sh_offset)
+            sym = f.read(sh_size)
+            want = {w.encode(): w for w in wanted}
+            for i in range(sh_size // sh_entsize):
+                st_name, st_info, _, st_shndx, st_value, _ = struct.unpack_from("<IBBHQQ", sym, i * sh_entsize)
+                if (st_info & 0xF) != 1 or st_shndx == 0:  # STT_OBJECT, defined
+                    continue
+                nm = strtab[st_name:strtab.index(b"\0", st_name)]
+                if nm in want:
+                    out[want[nm]] = st_value
+    return out
+
+
 def _load_base(path: str) -> int:
     real = os.path.realpath(path)
     with open("/proc/self/maps") as m:

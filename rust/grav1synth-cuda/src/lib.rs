@@ -31,11 +31,11 @@ pub struct g1s_segment {
     pub cb_luma_mult: u8,
     pub cr_mult: u8,
     pub cr_luma_mult: u8,
-    pub reserved_: [u8; 3],
+    pub num_ar_coeffs_plus1: [u8; 3],
     pub cb_offset: u16,
     pub cr_offset: u16,
     pub random_seed: u16,
-    pub reserved2_: u16,
+    pub clip_to_restricted_range: u16,
     pub scaling_points_y: [[u8; 2]; 14],
     pub scaling_points_cb: [[u8; 2]; 10],
     pub scaling_points_cr: [[u8; 2]; 10],
