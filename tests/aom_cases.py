@@ -75,6 +75,12 @@ def _hd_frame():
     return [make_pair_numpy(spec, 0)]
 
 
+def _uhd_frame():
+    # BASELINE configs[2] geometry: one 3840x2160 10-bit 4:2:0 pair (the frame of test_full_size_4k_10bit_frame_against_oracle)
+    spec = SynthSpec(3840, 2160, 10, textured=0.1, sigma0=1.0, sigma1=1.5, seed=2026)
+    return [make_pair_numpy(spec, 0)]
+
+
 CASES = {}
 for _name, (_spec, _n, _fps) in CORPUS.items():
     CASES[_name] = (lambda n=_name: corpus_frames(n)[2], _spec.bit_depth, (_spec.ss_x, _spec.ss_y), _fps)
@@ -88,6 +94,7 @@ for _s in range(8):
     CASES[f"random_{_s}"] = (lambda s=_s: _random(s)[0], _random(_s)[1], (1, 1), (24, 1))
 CASES["long_12_frames"] = (_long, 8, (1, 1), (24, 1))
 CASES["hd_1080p_frame"] = (_hd_frame, 8, (1, 1), (24, 1))
+CASES["uhd_4k_10bit_frame"] = (_uhd_frame, 10, (1, 1), (24, 1))
 
 # Cases where the exact-integer Gram (what the CUDA engine accumulates) lands on the other side of a structural
 # tie inside fit_piecewise than the reference's per-term f64 accumulation does: the

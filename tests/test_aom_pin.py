@@ -28,7 +28,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "aom")
 # aom_noise_status_t -> the oracle's NoiseStatus (Ok, DifferentType, Error)
 STATUS = {P.STATUS_OK: 0, P.STATUS_DIFFERENT_NOISE_TYPE: 1, P.STATUS_INSUFFICIENT_FLAT_BLOCKS: 2,
           P.STATUS_INTERNAL_ERROR: 2, P.STATUS_INVALID_ARGUMENT: 2}
-SLOW = {"hd_1080p_frame", "long_12_frames"}
+SLOW = {"hd_1080p_frame", "long_12_frames", "uhd_4k_10bit_frame"}
 
 
 def golden(name):

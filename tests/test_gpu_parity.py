@@ -321,7 +321,7 @@ def test_full_size_properties_1080p_batch():
 @pytest.mark.parametrize("name", ["c2_small_8bit", "c3_small_10bit", "odd_size_8bit", "yuv444_8bit", "yuv422_10bit",
                                   "heavy_grain_12bit", "saturated_residual", "sparse_int8_overflow",
                                   "zero_frame_mid_stream", "random_4", "random_5", "long_12_frames",
-                                  "hd_1080p_frame"])
+                                  "hd_1080p_frame", "uhd_4k_10bit_frame"])
 def test_engine_gives_libaom_tables(name):
     """The CUDA engine against the UPSTREAM BINARY: tests/golden/aom/*.json is what libaom 3.13.1's own
     noise_model.c (the code av1-grain's `diff` ports; oracle/aom_pin.py, tests/golden/make_aom_golden.py)
