@@ -6,7 +6,8 @@ g1s_write_grain_table.
 
 `python -m grav1synth_b200 inspect INPUT -o OUT [-y] [--fps N/D]` -- the reference's `inspect` (src/main.rs:145-196):
 AV1 OBU headers of an .ivf / .obu file -> grain table, CPU only (C++ parser behind g1s_inspect_*).
-`apply` / `generate` / `remove` rewrite bitstreams and are not built.
+`apply IN.ivf -g TABLE -o OUT.ivf` / `remove IN.ivf -o OUT.ivf` -- src/main.rs:197-246, 309-346: film grain headers
+rewritten by the C++ parser (g1s_rewrite_*), IVF in and out.  `generate` (photon-noise tables) is not built.
 """
 from __future__ import annotations
 
@@ -37,9 +38,22 @@ def main(argv=None) -> int:
     i.add_argument("-o", "--output", required=True, help="The path to the output film grain table.")
     i.add_argument("-y", "--overwrite", action="store_true", help="Overwrite the output file without prompting.")
     i.add_argument("--fps", default=None, help="Frame rate N/D (default: the IVF header's rate/scale).")
+    a = sub.add_parser("apply", help="Applies film grain from a table file to a given AV1 video, and outputs it at a "
+                                     "given `output` path. Overwrites any existing grain.")
+    a.add_argument("input", help="The AV1 file to apply grain to (.ivf).")
+    a.add_argument("-o", "--output", required=True, help="The path to write the grain-synthed AV1 file.")
+    a.add_argument("-y", "--overwrite", action="store_true", help="Overwrite the output file without prompting.")
+    a.add_argument("-g", "--grain", required=True, help="The path to the input film grain table.")
+    r = sub.add_parser("remove", help="Removes all film grain from a given AV1 video, and outputs it at a given "
+                                      "`output` path.")
+    r.add_argument("input", help="The AV1 file to remove grain from (.ivf).")
+    r.add_argument("-o", "--output", required=True, help="The path to write the non-grain-synthed AV1 file.")
+    r.add_argument("-y", "--overwrite", action="store_true", help="Overwrite the output file without prompting.")
     args = ap.parse_args(argv)
     if args.command == "inspect":
         return inspect_main(args)
+    if args.command in ("apply", "remove"):
+        return rewrite_main(args)
 
     # src/main.rs:354-368
     if os.path.abspath(args.source) == os.path.abspath(args.output) or \
@@ -117,6 +131,31 @@ def inspect_main(args) -> int:
         return 0
     write_grain_table(parser.aggregate_grain_headers(*fps), args.output)
     log.info("Done, wrote grain table to %s", args.output)
+    return 0
+
+
+def rewrite_main(args) -> int:
+    """`apply` (src/main.rs:197-246) and `remove` (:309-346): IVF in, IVF out."""
+    if os.path.abspath(args.input) == os.path.abspath(args.output):
+        log.error("Input and output paths are the same. This is probably a typo, because this would overwrite "
+                  "your input. Exiting.")
+        return 0
+    if os.path.exists(args.output) and not args.overwrite:
+        if not sys.stdin.isatty() or input(f"File {args.output} exists. Overwrite? [y/n] ").strip().lower() != "y":
+            log.warning("Not overwriting existing file. Exiting.")
+            return 0
+    from .grain_table import parse_grain_table
+    from .inspect import GrainRewriter, rewrite_ivf
+    table = None
+    if args.command == "apply":
+        with open(args.grain) as f:
+            table = parse_grain_table(f.read())
+    with open(args.input, "rb") as f:
+        data = f.read()
+    out = rewrite_ivf(data, GrainRewriter(table))
+    with open(args.output, "wb") as f:
+        f.write(out)
+    log.info("Done, wrote output file to %s", args.output)
     return 0
 
 

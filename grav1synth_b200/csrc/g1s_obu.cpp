@@ -133,7 +133,67 @@ struct FrameHeader {
   bool show_frame = false, show_existing_frame = false;
   GrainHeader grain;
   TileInfo tile_info;
+  // for the rewriter (apply / remove): where film_grain_params() starts, whether it may be present, the frame type
+  size_t grain_pos = 0;
+  bool film_grain_allowed = false;
+  int frame_type = 0;
 };
+
+// MSB-first bit sink for rewritten headers
+struct BitWriter {
+  std::vector<uint8_t> bytes;
+  size_t nbits = 0;
+  void put(uint64_t v, unsigned n) {
+    for (unsigned i = n; i-- > 0;) {
+      if ((nbits & 7) == 0) bytes.push_back(0);
+      if ((v >> i) & 1) bytes.back() |= (uint8_t)(0x80u >> (nbits & 7));
+      ++nbits;
+    }
+  }
+  void copy_bits(const uint8_t *src, size_t count) {
+    for (size_t i = 0; i < count; ++i) put((src[i >> 3] >> (7 - (i & 7))) & 1u, 1);
+  }
+};
+
+constexpr uint16_t DEFAULT_GRAIN_SEED = 10956;  // av1_grain::DEFAULT_GRAIN_SEED (frame.rs:3, :637-640)
+
+// write_film_grain_bits (frame.rs:700-826): apply_grain = 1 and every parameter of `p`, update_grain = 1 on inter frames
+void write_film_grain_bits(BitWriter &bw, const g1s_segment &p, int frame_type, bool monochrome, int ss_x, int ss_y) {
+  bw.put(1, 1);
+  bw.put(p.random_seed, 16);
+  if (frame_type == INTER_FRAME) bw.put(1, 1);
+  bw.put(p.num_y_points, 4);
+  for (int i = 0; i < p.num_y_points; ++i) bw.put(p.scaling_points_y[i][0], 8), bw.put(p.scaling_points_y[i][1], 8);
+  const bool csfl = monochrome ? false : p.chroma_scaling_from_luma != 0;
+  if (!monochrome) bw.put(csfl, 1);
+  int ncb = 0, ncr = 0;
+  if (!(monochrome || csfl || (ss_x == 1 && ss_y == 1 && p.num_y_points == 0))) {
+    ncb = p.num_cb_points, ncr = p.num_cr_points;
+    bw.put((unsigned)ncb, 4);
+    for (int i = 0; i < ncb; ++i) bw.put(p.scaling_points_cb[i][0], 8), bw.put(p.scaling_points_cb[i][1], 8);
+    bw.put((unsigned)ncr, 4);
+    for (int i = 0; i < ncr; ++i) bw.put(p.scaling_points_cr[i][0], 8), bw.put(p.scaling_points_cr[i][1], 8);
+  }
+  bw.put((unsigned)(p.scaling_shift - 8) & 3, 2);
+  bw.put(p.ar_coeff_lag & 3u, 2);
+  const int lag = p.ar_coeff_lag & 3;
+  const int num_pos_luma = 2 * lag * (lag + 1);
+  int num_pos_chroma = num_pos_luma;
+  if (p.num_y_points > 0) {
+    for (int i = 0; i < num_pos_luma; ++i) bw.put((uint8_t)(p.ar_coeffs_y[i] + 128), 8);
+    num_pos_chroma = num_pos_luma + 1;
+  }
+  if (csfl || ncb > 0)
+    for (int i = 0; i < num_pos_chroma; ++i) bw.put((uint8_t)(p.ar_coeffs_cb[i] + 128), 8);
+  if (csfl || ncr > 0)
+    for (int i = 0; i < num_pos_chroma; ++i) bw.put((uint8_t)(p.ar_coeffs_cr[i] + 128), 8);
+  bw.put((unsigned)(p.ar_coeff_shift - 6) & 3, 2);
+  bw.put(p.grain_scale_shift & 3u, 2);
+  if (ncb > 0) bw.put(p.cb_mult, 8), bw.put(p.cb_luma_mult, 8), bw.put(p.cb_offset & 0x1FFu, 9);
+  if (ncr > 0) bw.put(p.cr_mult, 8), bw.put(p.cr_luma_mult, 8), bw.put(p.cr_offset & 0x1FFu, 9);
+  bw.put(p.overlap_flag ? 1 : 0, 1);
+  bw.put(p.clip_to_restricted_range ? 1 : 0, 1);
+}
 
 // FilmGrainParams equality as the reference defines it (grain.rs:83-105): everything but the seed.
 bool same_grain(const g1s_segment &a, const g1s_segment &b) {
@@ -721,6 +781,15 @@ struct g1s_inspect {
   bool big_ref_valid[NUM_REF_FRAMES] = {false};
   std::vector<GrainHeader> headers;  // one per shown frame header, in stream order (parser.rs:155-158)
   uint64_t packets = 0, obus = 0;
+  // rewriter (BitstreamParser::<true>, parser.rs:74-101): `write` mirrors every OBU into packet_out; `have_table`
+  // is incoming_grain_header.is_some() (apply) vs None (remove)
+  bool write = false, have_table = false;
+  std::vector<g1s_segment> table;
+  std::vector<uint8_t> packet_out;
+  uint64_t packet_ts = 0;
+  uint64_t frames_with_grain = 0, frames_grain_disabled = 0;
+  std::vector<uint8_t> rewrite_frame_payload(const uint8_t *payload, size_t obu_size, const FrameHeader &fh,
+                                             size_t header_end_bits, bool is_frame_obu);
 
   FrameHeader uncompressed_header(BitReader &br, bool has_ext, int temporal_id, int spatial_id, bool verify_alignment);
   // returns true and fills `out` when the header belongs to a shown frame
@@ -866,6 +935,9 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
   br.flag();                                                                           // reduced_tx_set
   global_motion_params(br, frame_is_intra, allow_high_precision_mv);
   const bool film_grain_allowed = show_frame || showable_frame;
+  fh.grain_pos = br.pos;
+  fh.film_grain_allowed = film_grain_allowed;
+  fh.frame_type = frame_type;
   fh.grain = film_grain_params(br, s.film_grain_params_present && film_grain_allowed, frame_type, s.num_planes == 1,
                                s.ss_x, s.ss_y);
   for (int i = 0; i < NUM_REF_FRAMES; ++i) {
@@ -903,8 +975,43 @@ void g1s_inspect::tile_group_header(BitReader &br, const TileInfo &ti) {
   if (tg_end == num_tiles - 1) seen_frame_header = false;
 }
 
+// New payload of an OBU_FRAME / OBU_FRAME_HEADER whose header was just parsed (frame.rs:608-676): the bits before
+// film_grain_params() are kept, the grain syntax is replaced (or dropped), the rest is re-aligned.
+std::vector<uint8_t> g1s_inspect::rewrite_frame_payload(const uint8_t *payload, size_t obu_size, const FrameHeader &fh,
+                                                        size_t header_end_bits, bool is_frame_obu) {
+  BitWriter bw;
+  bw.copy_bits(payload, fh.grain_pos);
+  if (have_table && fh.film_grain_allowed) {  // sequence_header.new_film_grain_state && film_grain_allowed
+    g1s_segment *seg = nullptr;
+    for (g1s_segment &t : table)
+      if (t.start_time <= packet_ts && packet_ts < t.end_time) {
+        seg = &t;
+        break;
+      }
+    if (seg) {
+      seg->random_seed = (uint16_t)(seg->random_seed + DEFAULT_GRAIN_SEED);  // wrapping_add, kept for the next frame
+      write_film_grain_bits(bw, *seg, fh.frame_type, seq.num_planes == 1, seq.ss_x, seq.ss_y);
+      ++frames_with_grain;
+    } else {
+      bw.put(0, 1);  // apply_grain = 0
+      ++frames_grain_disabled;
+    }
+  }
+  std::vector<uint8_t> out;
+  if (is_frame_obu) {
+    out = bw.bytes;  // byte_alignment(): the partial byte is already zero-padded
+    const size_t tile_off = (header_end_bits + 7) >> 3;
+    out.insert(out.end(), payload + tile_off, payload + obu_size);
+  } else {
+    bw.put(1, 1);  // trailing_bits()
+    out = bw.bytes;
+  }
+  return out;
+}
+
 void g1s_inspect::parse_packet(const uint8_t *data, size_t size) {
   ++packets;
+  packet_out.clear();
   size_t off = 0;
   while (off < size) {
     ++obus;
@@ -933,7 +1040,36 @@ void g1s_inspect::parse_packet(const uint8_t *data, size_t size) {
     }
     if (off + hdr + obu_size > size) throw ParseError("OBU larger than its packet");
     const uint8_t *payload = data + off + hdr;
+    const size_t obu_hdr_bytes = has_ext ? 2 : 1;
+    const uint8_t *obu_start = data + off;
     off += hdr + obu_size;
+    std::vector<uint8_t> new_payload;
+    bool replaced = false;
+    // write mode: the OBU goes out again when this scope ends, with `new_payload` instead of its payload if replaced
+    struct Emit {
+      g1s_inspect *self;
+      const uint8_t *obu_start, *payload;
+      size_t obu_hdr_bytes, obu_size;
+      bool has_size;
+      std::vector<uint8_t> *np;
+      bool *replaced;
+      ~Emit() {
+        if (!self->write) return;
+        std::vector<uint8_t> &o = self->packet_out;
+        o.insert(o.end(), obu_start, obu_start + obu_hdr_bytes);
+        const uint8_t *body = *replaced ? np->data() : payload;
+        const size_t n = *replaced ? np->size() : obu_size;
+        if (has_size) {
+          size_t v = n;
+          do {
+            uint8_t b = v & 0x7f;
+            v >>= 7;
+            o.push_back((uint8_t)(b | (v ? 0x80 : 0)));
+          } while (v);
+        }
+        o.insert(o.end(), body, body + n);
+      }
+    } emit{this, obu_start, payload, obu_hdr_bytes, obu_size, has_size, &new_payload, &replaced};
 
     // operating point 0 only (obu.rs:92-116)
     if (type != OBU_SEQUENCE_HEADER && type != OBU_TEMPORAL_DELIMITER && has_ext && seq.valid) {
@@ -944,6 +1080,15 @@ void g1s_inspect::parse_packet(const uint8_t *data, size_t size) {
       case OBU_SEQUENCE_HEADER: {
         BitReader br(payload, obu_size);
         seq = parse_sequence_header(br);
+        if (write) {  // film_grain_params_present follows what is being written (sequence.rs:404-423)
+          new_payload.assign(payload, payload + obu_size);
+          const size_t bit = br.pos - 1;
+          if (have_table)
+            new_payload[bit >> 3] |= (uint8_t)(0x80u >> (bit & 7));
+          else
+            new_payload[bit >> 3] &= (uint8_t)~(0x80u >> (bit & 7));
+          replaced = true;
+        }
         break;
       }
       case OBU_TEMPORAL_DELIMITER:
@@ -961,6 +1106,10 @@ void g1s_inspect::parse_packet(const uint8_t *data, size_t size) {
           // between a hidden frame and the shown frame before it.)
           if (!fh.show_existing_frame) cur_tile_info = fh.tile_info;
           have_frame_header = true;
+          if (write && !fh.show_existing_frame) {
+            new_payload = rewrite_frame_payload(payload, obu_size, fh, br.pos, true);
+            replaced = true;
+          }
         } else if (!have_frame_header) {
           throw ParseError("tile data before any frame header");
         }
@@ -976,6 +1125,10 @@ void g1s_inspect::parse_packet(const uint8_t *data, size_t size) {
           if (shown) headers.push_back(fh.grain);
           if (!fh.show_existing_frame) cur_tile_info = fh.tile_info;
           have_frame_header = true;
+          if (write && !fh.show_existing_frame) {
+            new_payload = rewrite_frame_payload(payload, obu_size, fh, br.pos, false);
+            replaced = true;
+          }
         }
         break;
       }
@@ -1067,6 +1220,40 @@ int g1s_inspect_finish(g1s_inspect *h, int64_t fps_num, int64_t fps_den, g1s_seg
   *n = segs.size();
   if (segs.size() > cap || (!out && !segs.empty())) return G1S_E_STATE;
   if (!segs.empty()) std::memcpy(out, segs.data(), segs.size() * sizeof(g1s_segment));
+  return G1S_OK;
+}
+
+// ---- apply / remove: BitstreamParser::<true>::modify_grain_headers (parser.rs:175-348) without the FFmpeg muxer
+int g1s_rewrite_create(const g1s_segment *table, size_t n, int apply, g1s_inspect **out) {
+  if (!out || (apply && (!table || n == 0))) return G1S_E_ARG;
+  g1s_inspect *h = new (std::nothrow) g1s_inspect();
+  if (!h) return G1S_E_NOMEM;
+  h->write = true;
+  h->have_table = apply != 0;
+  if (apply) h->table.assign(table, table + n);
+  *out = h;
+  return G1S_OK;
+}
+
+int g1s_rewrite_packet(g1s_inspect *h, const uint8_t *data, size_t size, uint64_t packet_ts, size_t *out_size) {
+  if (!h || !h->write || (!data && size) || !out_size) return G1S_E_ARG;
+  h->packet_ts = packet_ts;
+  const int rc = g1s_inspect_push_packet(h, data, size);
+  *out_size = rc == G1S_OK ? h->packet_out.size() : 0;
+  return rc;
+}
+
+int g1s_rewrite_take(g1s_inspect *h, uint8_t *out, size_t cap) {
+  if (!h || !h->write || (!out && !h->packet_out.empty())) return G1S_E_ARG;
+  if (cap < h->packet_out.size()) return G1S_E_STATE;
+  if (!h->packet_out.empty()) std::memcpy(out, h->packet_out.data(), h->packet_out.size());
+  return G1S_OK;
+}
+
+int g1s_rewrite_counters(const g1s_inspect *h, uint64_t *with_grain, uint64_t *disabled) {
+  if (!h) return G1S_E_ARG;
+  if (with_grain) *with_grain = h->frames_with_grain;
+  if (disabled) *disabled = h->frames_grain_disabled;
   return G1S_OK;
 }
 

@@ -140,3 +140,72 @@ def probe(what: str, data: bytes, args: Sequence[int] = (), nout: int = 16):
     seg = CSegment()
     rc = L.g1s_obu_probe(what.encode(), data, len(data), a, len(args), o, nout, C.byref(seg))
     return int(rc), [int(v) for v in o], seg
+
+
+# ---------------------------------------------------------------- apply / remove
+EXPORTS += ["g1s_rewrite_create", "g1s_rewrite_packet", "g1s_rewrite_take", "g1s_rewrite_counters"]
+
+
+class GrainRewriter(BitstreamParser):
+    """`BitstreamParser::<true>` (src/parser.rs:74-101, :175-348): packets in, packets with rewritten film grain
+    headers out.  `table` = segments to apply (None removes film grain).  All rewriting is in csrc/g1s_obu.cpp."""
+
+    def __init__(self, table: Optional[Sequence[GrainTableSegment]] = None):
+        self._L = _L()
+        L = self._L
+        L.g1s_rewrite_create.argtypes = [C.POINTER(CSegment), C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+        L.g1s_rewrite_packet.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_size_t)]
+        L.g1s_rewrite_take.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.g1s_rewrite_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        self._h = C.c_void_p()
+        self.frame_rate = (0, 0)
+        if table is not None:
+            arr = abi.segments_to_c(table)
+            for i, s in enumerate(table):
+                # tables read from text carry no clip flag: the reference sets it (src/parser/grain.rs:130)
+                arr[i].clip_to_restricted_range = 1
+            rc = L.g1s_rewrite_create(arr, len(table), 1, C.byref(self._h))
+        else:
+            rc = L.g1s_rewrite_create(None, 0, 0, C.byref(self._h))
+        if rc != 0:
+            raise G1SError(rc, "g1s_rewrite_create failed")
+
+    def rewrite_packet(self, data: bytes, packet_ts: int) -> bytes:
+        n = C.c_size_t(0)
+        self._check(self._L.g1s_rewrite_packet(self._h, data, len(data), packet_ts, C.byref(n)))
+        buf = C.create_string_buffer(max(1, n.value))
+        self._check(self._L.g1s_rewrite_take(self._h, buf, n.value))
+        return buf.raw[: n.value]
+
+    def counters(self) -> Tuple[int, int]:
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._L.g1s_rewrite_counters(self._h, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+
+def pts_to_av1_ts(pts: int, time_base: Tuple[int, int]) -> int:
+    """ffmpeg_pts_to_av1_ts (src/parser.rs:103-118): ceil(pts * num * 1e7 / den), 0 for negative pts."""
+    num, den = time_base
+    if pts < 0 or den == 0:
+        return 0
+    return -(-(pts * num * 10_000_000) // den)
+
+
+def rewrite_ivf(data: bytes, rewriter: GrainRewriter) -> bytes:
+    """IVF in, IVF out (the reference remuxes through FFmpeg; IVF is the container this build reads and writes)."""
+    import struct
+    if data[:4] != b"DKIF" or data[8:12] != b"AV01":
+        raise ValueError("not an AV01 IVF file")
+    hdr_len = struct.unpack_from("<H", data, 6)[0]
+    rate, scale = struct.unpack_from("<II", data, 16)
+    out = bytearray(data[:max(32, hdr_len)])
+    off = max(32, hdr_len)
+    while off + 12 <= len(data):
+        size, pts = struct.unpack_from("<IQ", data, off)
+        pkt = data[off + 12: off + 12 + size]
+        if len(pkt) != size:
+            raise ValueError("truncated IVF frame")
+        new = rewriter.rewrite_packet(pkt, pts_to_av1_ts(pts, (scale, rate)))
+        out += struct.pack("<IQ", len(new), pts) + new
+        off += 12 + size
+    return bytes(out)

@@ -255,6 +255,18 @@ int g1s_inspect_header(const g1s_inspect *h, size_t i, int32_t *kind, g1s_segmen
  * *n == 0 with G1S_OK means "no film grain headers found" (src/main.rs:177-183). G1S_E_STATE: cap too small. */
 int g1s_inspect_finish(g1s_inspect *h, int64_t fps_num, int64_t fps_den, g1s_segment *out, size_t cap, size_t *n);
 int g1s_inspect_stream_info(const g1s_inspect *h, g1s_stream_info *info);
+/* `apply` / `remove`: BitstreamParser::<true>::modify_grain_headers (src/parser.rs:175-348) and the
+ * header rewriting of src/parser/frame.rs:608-826 / sequence.rs:404-423, without the FFmpeg muxer: one packet in, one
+ * packet out.  apply != 0: every frame header that may carry film grain gets the parameters of the table segment with
+ * start_time <= packet_ts < end_time (apply_grain = 1, update_grain = 1 on inter frames, seed advanced by
+ * DEFAULT_GRAIN_SEED per frame), or apply_grain = 0 when no segment covers it; apply == 0 (table ignored): film grain
+ * is removed (film_grain_params_present = 0, grain syntax dropped).  OBU sizes are re-encoded.  packet_ts is in 1e-7 s
+ * (src/parser.rs:103-118).  The handle also collects the ORIGINAL grain headers like an inspect handle. */
+int g1s_rewrite_create(const g1s_segment *table, size_t n, int apply, g1s_inspect **out);
+int g1s_rewrite_packet(g1s_inspect *h, const uint8_t *data, size_t size, uint64_t packet_ts, size_t *out_size);
+/* copies the packet produced by the last g1s_rewrite_packet call (G1S_E_STATE: cap < *out_size) */
+int g1s_rewrite_take(g1s_inspect *h, uint8_t *out, size_t cap);
+int g1s_rewrite_counters(const g1s_inspect *h, uint64_t *frames_with_grain, uint64_t *frames_grain_disabled);
 /* Test hook: parse ONE syntax group (named as in the AV1 spec / the reference's functions) from a raw bit buffer;
  * returns bits consumed or a negative status.  Lets tests replay the reference's own unit-test vectors. */
 int64_t g1s_obu_probe(const char *what, const uint8_t *data, size_t size, const int64_t *args, size_t nargs,

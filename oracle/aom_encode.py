@@ -160,3 +160,45 @@ def encode(frames, w: int, h: int, options: Optional[Dict[str, str]] = None, fps
         return packets
     finally:
         L.aom_codec_destroy(ctx)
+
+
+def decode(packets: Sequence[bytes]):
+    """libaom's decoder over the temporal units: list of (y, u, v) numpy planes per output frame (film grain applied,
+    as every AV1 decoder does by default).  Raises EncodeError when libaom rejects the stream."""
+    L = _lib()
+    L.aom_codec_av1_dx.restype = C.c_void_p
+    L.aom_codec_dec_init_ver.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int]
+    L.aom_codec_decode.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p]
+    L.aom_codec_get_frame.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.aom_codec_get_frame.restype = C.c_void_p
+    ctx = C.create_string_buffer(512)
+    rc = 3
+    for ver in range(10, 50):
+        rc = L.aom_codec_dec_init_ver(ctx, L.aom_codec_av1_dx(), None, 0, ver)
+        if rc != 3:
+            break
+    if rc != 0:
+        raise EncodeError(f"aom_codec_dec_init_ver failed: {rc}")
+    frames = []
+    try:
+        for k, pk in enumerate(packets):
+            if L.aom_codec_decode(ctx, pk, len(pk), None) != 0:
+                raise EncodeError(f"libaom cannot decode packet {k}: {L.aom_codec_error_detail(ctx)}")
+            it = C.c_void_p(None)
+            while True:
+                img = L.aom_codec_get_frame(ctx, C.byref(it))
+                if not img:
+                    break
+                hdr = (C.c_uint32 * 16).from_address(img)
+                w, h = hdr[10], hdr[11]  # d_w, d_h
+                planes = (C.c_void_p * 3).from_address(img + 64)
+                strides = (C.c_int * 3).from_address(img + 88)
+                out = []
+                for i in range(3):
+                    pw, ph = (w, h) if i == 0 else ((w + 1) // 2, (h + 1) // 2)
+                    a = np.ctypeslib.as_array((C.c_uint8 * (strides[i] * ph)).from_address(planes[i]))
+                    out.append(a.reshape(ph, strides[i])[:, :pw].copy())
+                frames.append(tuple(out))
+        return frames
+    finally:
+        L.aom_codec_destroy(ctx)

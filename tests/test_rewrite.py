@@ -1,0 +1,165 @@
+"""`apply` / `remove`: the header rewriter of csrc/g1s_obu.cpp -- CPU tests.
+
+Witnesses: libaom's own encoder and decoder (oracle/aom_encode.py).
+ * remove: stripping the film grain from a stream libaom encoded WITH `film-grain-test` must give, byte for byte, the
+   stream libaom produces for the same frames WITHOUT film grain;
+ * apply: the rewritten stream must still decode with libaom, `inspect` must read the applied table back on every
+   frame (seed advancing by DEFAULT_GRAIN_SEED, update_grain on inter frames, apply_grain = 0 outside the table's
+   segments), and applying then removing must restore the input.
+Plus writer-level checks on hand-built streams that need no libaom.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import av1_writer as W
+from av1_writer import Frame, Grain, Seq
+from helpers import ROOT
+from grav1synth_b200 import inspect as I
+from grav1synth_b200.grain_table import parse_grain_table
+from oracle import aom_pin
+from test_inspect import GA, GB, expected_view, header_view
+
+ok, why = aom_pin.available()
+needs_libaom = pytest.mark.skipif(not ok, reason="libaom pin unavailable: " + str(why))
+T24 = 10_000_000 / 24
+
+
+def golden_table(name):
+    return parse_grain_table(open(os.path.join(ROOT, "tests", "golden", name + ".tbl")).read())
+
+
+def ts(k):
+    return int(np.ceil(k * T24))
+
+
+@needs_libaom
+@pytest.mark.parametrize("vector,lag", [(5, None), (1, 0), (12, 19), (3, 19), (16, None), (9, 0)])
+def test_remove_gives_libaoms_own_grainless_stream(vector, lag):
+    from oracle import aom_encode as E
+    fr = E.synthetic_frames(10, 176, 144, seed=vector)
+    # constant quality (rc_end_usage = AOM_Q): with rate control the bytes spent on grain headers feed back into the
+    # quantiser choice and the two encodes legitimately diverge
+    q = dict(options={"cq-level": "32"}, cfg_words={24: 3}, lag_in_frames=lag)
+    plain = E.encode(fr, 176, 144, **q)
+    q["options"] = {"cq-level": "32", "film-grain-test": str(vector)}
+    grainy = E.encode(fr, 176, 144, **q)
+    assert grainy != plain
+    rw = I.GrainRewriter(None)
+    assert [rw.rewrite_packet(p, ts(k)) for k, p in enumerate(grainy)] == plain
+    # the handle still reports what the INPUT carried
+    assert any(h.kind == I.UPDATE_GRAIN for h in rw.get_grain_headers())
+
+
+@needs_libaom
+@pytest.mark.parametrize("table", ["c2_small_8bit", "heavy_grain_12bit"])
+def test_apply_diff_table_to_a_libaom_stream(table):
+    from oracle import aom_encode as E
+    segs = golden_table(table)
+    fr = E.synthetic_frames(8, 176, 144, seed=4)
+    plain = E.encode(fr, 176, 144, {}, lag_in_frames=19)
+    rw = I.GrainRewriter(segs)
+    out = [rw.rewrite_packet(p, ts(k)) for k, p in enumerate(plain)]
+    assert rw.counters()[0] >= 8 and rw.counters()[1] == 0
+    # libaom decodes the result, and film grain now changes the pictures
+    dec_plain, dec_out = E.decode(plain), E.decode(out)
+    assert len(dec_out) == len(dec_plain) == 8
+    assert all(not np.array_equal(a[0], b[0]) for a, b in zip(dec_plain, dec_out))
+    # inspect reads the table back
+    p = I.BitstreamParser()
+    for pk in out:
+        p.push_packet(pk)
+    hs = p.get_grain_headers()
+    assert len(hs) == 8
+    shown_ts = iter(ts(k) for k in range(8))
+    seeds = {}
+    for h in hs:
+        if h.kind == I.COPY_REF_FRAME:   # show_existing_frame of an already rewritten hidden frame
+            next(shown_ts)
+            continue
+        assert h.kind == I.UPDATE_GRAIN and h.clip_to_restricted_range
+        g = h.params
+        seg = next(s for s in segs if all(getattr(g, f) == getattr(s, f) for f in (
+            "scaling_points_y", "scaling_points_cb", "scaling_points_cr", "ar_coeffs_y", "ar_coeffs_cb", "ar_coeffs_cr",
+            "scaling_shift", "ar_coeff_shift", "ar_coeff_lag", "cb_mult", "cb_luma_mult", "cb_offset", "overlap_flag")))
+        seeds.setdefault(id(seg), []).append(g.random_seed)
+    for seg in segs:
+        # frame.rs:637-640: the segment's seed advances by DEFAULT_GRAIN_SEED for every frame it is written to
+        # (hidden frames included, so the shown frames may skip steps); strictly increasing step counts
+        steps = {(seg.random_seed + n * 10956) % 65536: n for n in range(1, 40)}
+        got = [steps[s] for s in seeds.get(id(seg), [])]
+        assert got == sorted(got) and len(set(got)) == len(got)
+    # apply then remove restores the input exactly
+    rm = I.GrainRewriter(None)
+    assert [rm.rewrite_packet(pk, ts(k)) for k, pk in enumerate(out)] == plain
+
+
+@needs_libaom
+def test_apply_outside_the_table_disables_grain():
+    from oracle import aom_encode as E
+    seg = golden_table("c2_small_8bit")[0]
+    seg.raw.start_time, seg.raw.end_time = ts(2), ts(5)        # covers packets 2, 3, 4 only
+    fr = E.synthetic_frames(7, 176, 144, seed=6)
+    plain = E.encode(fr, 176, 144, {}, lag_in_frames=0)
+    rw = I.GrainRewriter([seg])
+    out = [rw.rewrite_packet(p, ts(k)) for k, p in enumerate(plain)]
+    assert len(E.decode(out)) == 7
+    p = I.BitstreamParser()
+    for pk in out:
+        p.push_packet(pk)
+    assert [h.kind for h in p.get_grain_headers()] == [I.DISABLE] * 2 + [I.UPDATE_GRAIN] * 3 + [I.DISABLE] * 2
+    assert rw.counters() == (3, 4)
+    segs = p.aggregate_grain_headers(24, 1)
+    assert len(segs) == 1 and (segs[0].start_time, segs[0].end_time) == (ts(2), ts(5))
+
+
+def test_rewrite_hand_built_stream_roundtrip(tmp_path):
+    """No libaom needed: apply on the writer's stream (OBU_FRAME with two tiles, standalone frame header + tile group,
+    hidden frame, show_existing_frame, padding, an OBU without size field), read back with inspect, IVF in/out, CLI."""
+    seq = Seq()
+    split = Frame(frame_type=1, order_hint=3, grain=GB, tile_cols_log2=1)
+    packets = [
+        W.temporal_delimiter() + seq.obu() + Frame(frame_type=0, grain=GA).frame_obu(seq),
+        W.temporal_delimiter() + Frame(frame_type=1, order_hint=8, show_frame=False, refresh_frame_flags=0x40,
+                                       grain=GB).frame_obu(seq) +
+        Frame(frame_type=1, order_hint=1, grain=Grain(kind="copy"), tile_cols_log2=1).frame_obu(seq),
+        W.temporal_delimiter() + split.frame_header_obu(seq) + split.tile_group_obu(seq) + W.obu(W.OBU_PADDING, b"\0\0"),
+        W.temporal_delimiter() + Frame(show_existing_frame=6).frame_header_obu(seq),
+        W.temporal_delimiter() + Frame(frame_type=1, order_hint=9, grain=Grain(kind="disable")).frame_obu(seq, has_size=False),
+    ]
+    table = golden_table("c3_small_10bit")
+    rw = I.GrainRewriter(table)
+    out = [rw.rewrite_packet(p, ts(k)) for k, p in enumerate(packets)]
+    assert rw.counters() == (5, 0)                               # 4 shown frames with a header + the hidden one
+    p = I.BitstreamParser()
+    for pk in out:
+        p.push_packet(pk)
+    hs = p.get_grain_headers()
+    assert [h.kind for h in hs] == [I.UPDATE_GRAIN, I.UPDATE_GRAIN, I.UPDATE_GRAIN, I.COPY_REF_FRAME, I.UPDATE_GRAIN]
+    want = table[0]
+    for h in hs:
+        if h.kind == I.UPDATE_GRAIN:
+            assert h.params.scaling_points_y == want.scaling_points_y and h.params.ar_coeffs_cr == want.ar_coeffs_cr
+    seeds = [h.params.random_seed for h in hs if h.kind == I.UPDATE_GRAIN]
+    step = lambda n: (want.random_seed + n * 10956) % 65536
+    assert seeds == [step(1), step(3), step(4), step(5)]          # step(2) went to the hidden frame
+    # tile data and the other OBUs are untouched: removing again restores the input, except that the input's own
+    # grain syntax is gone, which is exactly `remove` applied to the input
+    rm1, rm2 = I.GrainRewriter(None), I.GrainRewriter(None)
+    assert [rm1.rewrite_packet(pk, ts(k)) for k, pk in enumerate(out)] == \
+           [rm2.rewrite_packet(pk, ts(k)) for k, pk in enumerate(packets)]
+    # CLI: apply and remove on IVF files
+    from grav1synth_b200.__main__ import main
+    src, tbl, applied, removed = (tmp_path / n for n in ("in.ivf", "t.tbl", "applied.ivf", "removed.ivf"))
+    src.write_bytes(W.ivf(packets, seq.width, seq.height, 24, 1))
+    tbl.write_text(open(os.path.join(ROOT, "tests", "golden", "c3_small_10bit.tbl")).read())
+    assert main(["apply", str(src), "-o", str(applied), "-g", str(tbl)]) == 0
+    assert main(["remove", str(applied), "-o", str(removed)]) == 0
+    q = I.BitstreamParser()
+    q.push_file(str(applied))
+    assert [h.kind for h in q.get_grain_headers()] == [h.kind for h in hs]
+    r = I.BitstreamParser()
+    r.push_file(str(removed))
+    assert all(h.kind == I.DISABLE or h.kind == I.COPY_REF_FRAME for h in r.get_grain_headers())
+    assert r.stream_info()["film_grain_params_present"] == 0
