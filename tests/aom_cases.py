@@ -81,6 +81,40 @@ def _uhd_frame():
     return [make_pair_numpy(spec, 0)]
 
 
+def codec_source(n=3, w=352, h=288, seed=3):
+    """Textured, noisy 8-bit 4:2:0 source frames for the codec pair (deterministic)."""
+    rng = np.random.default_rng(seed)
+    xs = np.linspace(0, 1, w)[None, :]
+    ys = np.linspace(0, 1, h)[:, None]
+    out = []
+    for k in range(n):
+        base = 30 + 190 * (0.5 + 0.5 * np.sin(3 * xs + 2 * ys + 0.05 * k))
+        tex = 25 * (np.sin(40 * xs) * np.sin(37 * ys) > 0.8)
+        y = base + tex + rng.normal(0, 3.0 + 3 * base / 255, (h, w))
+        u = 128 + 25 * np.sin(5 * xs[:, ::2] + 0 * ys[::2]) + rng.normal(0, 1.5, (h // 2, w // 2))
+        v = 128 + 25 * np.cos(4 * ys[::2] + 0 * xs[:, ::2]) + rng.normal(0, 1.5, (h // 2, w // 2))
+        out.append([np.clip(np.rint(p), 0, 255).astype(np.uint8) for p in (y, u, v)])
+    return out
+
+
+def _codec_pair():
+    """Source frames against what a real codec made of them: the 'denoised' side is libaom's DECODE of the committed
+    stream tests/golden/aom/codec_pair_cq28.ivf (libaom's own encode of the source at constant quality, no film grain;
+    tests/golden/make_aom_golden.py writes it).  Needs the bundled libaom at test time to decode."""
+    import os
+    import struct
+    from oracle import aom_encode as E
+    d = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "aom", "codec_pair_cq28.ivf"), "rb").read()
+    off, packets = 32, []
+    while off + 12 <= len(d):
+        sz = struct.unpack_from("<I", d, off)[0]
+        packets.append(d[off + 12: off + 12 + sz])
+        off += 12 + sz
+    den = E.decode(packets)
+    return [(s, list(dd)) for s, dd in zip(codec_source(), den)]
+
+
+NEEDS_LIBAOM = {"codec_pair_cq28"}
 CASES = {}
 for _name, (_spec, _n, _fps) in CORPUS.items():
     CASES[_name] = (lambda n=_name: corpus_frames(n)[2], _spec.bit_depth, (_spec.ss_x, _spec.ss_y), _fps)
@@ -95,6 +129,7 @@ for _s in range(8):
 CASES["long_12_frames"] = (_long, 8, (1, 1), (24, 1))
 CASES["hd_1080p_frame"] = (_hd_frame, 8, (1, 1), (24, 1))
 CASES["uhd_4k_10bit_frame"] = (_uhd_frame, 10, (1, 1), (24, 1))
+CASES["codec_pair_cq28"] = (_codec_pair, 8, (1, 1), (24, 1))
 
 # Cases where the exact-integer Gram (what the CUDA engine accumulates) lands on the other side of a structural
 # tie inside fit_piecewise than the reference's per-term f64 accumulation does: the

@@ -24,7 +24,17 @@ ok, where = P.available()
 if not ok:
     sys.exit("libaom pin unavailable: " + where)
 os.makedirs(os.path.join(HERE, "aom"), exist_ok=True)
-for name in CASES:
+# the codec pair's stream: libaom's encode of aom_cases.codec_source() at constant quality 28, no film grain
+_ivf = os.path.join(HERE, "aom", "codec_pair_cq28.ivf")
+if not os.path.exists(_ivf):
+    import av1_writer as W
+    from aom_cases import codec_source
+    from oracle import aom_encode as E
+    _pk = E.encode([tuple(f) for f in codec_source()], 352, 288, {"cq-level": "28", "cpu-used": "6"}, lag_in_frames=0,
+                   cfg_words={24: 3})
+    with open(_ivf, "wb") as f:
+        f.write(W.ivf(_pk, 352, 288, 24, 1))
+for name in (sys.argv[1:] or CASES):
     frames, bd, ss, fps = load(name)
     a = P.AomNoiseModel(ss[0], ss[1])
     per_frame = []

@@ -17,7 +17,7 @@ import os
 import numpy as np
 import pytest
 
-from aom_cases import CASES, EXACT_INT_TIE_FLIPS, load
+from aom_cases import CASES, EXACT_INT_TIE_FLIPS, NEEDS_LIBAOM, load
 from helpers import ROOT, gram_to_pairs, numpy_record
 from grav1synth_b200 import abi
 from grav1synth_b200 import diff as D
@@ -29,6 +29,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "aom")
 STATUS = {P.STATUS_OK: 0, P.STATUS_DIFFERENT_NOISE_TYPE: 1, P.STATUS_INSUFFICIENT_FLAT_BLOCKS: 2,
           P.STATUS_INTERNAL_ERROR: 2, P.STATUS_INVALID_ARGUMENT: 2}
 SLOW = {"hd_1080p_frame", "long_12_frames", "uhd_4k_10bit_frame"}
+
+
+def load_or_skip(name):
+    if name in NEEDS_LIBAOM and not P.available()[0]:
+        pytest.skip("this case decodes a committed stream with the bundled libaom, which is absent here")
+    return load(name)
 
 
 def golden(name):
@@ -52,7 +58,7 @@ def digest(x, sx):
 @pytest.mark.parametrize("name", list(CASES))
 def test_reference_order_oracle_is_bit_identical_to_libaom(name):
     want = golden(name)
-    frames, bd, ss, fps = load(name)
+    frames, bd, ss, fps = load_or_skip(name)
     g = O.OracleDiffGenerator(fps[0], fps[1], bd, bd, O.GRAM_REF_ORDER, O.EXP_LIBM, ss[0], ss[1])
     assert len(frames) == len(want["frames"])
     for k, ((s, d), w) in enumerate(zip(frames, want["frames"])):
@@ -79,7 +85,7 @@ def test_reference_order_oracle_is_bit_identical_to_libaom(name):
 @pytest.mark.parametrize("name", [n for n in CASES if n not in SLOW])
 def test_exact_integer_oracle_gives_libaom_tables(name):
     want = golden(name)
-    frames, bd, ss, fps = load(name)
+    frames, bd, ss, fps = load_or_skip(name)
     g = O.OracleDiffGenerator(fps[0], fps[1], bd, bd, O.GRAM_EXACT_INT, O.EXP_FIXED, ss[0], ss[1])
     for (s, d), w in zip(frames, want["frames"]):
         g.diff_frame(s, d)
@@ -100,11 +106,11 @@ def test_exact_integer_oracle_gives_libaom_tables(name):
 
 @pytest.mark.parametrize("name", ["c2_small_8bit", "c3_small_10bit", "yuv444_8bit", "heavy_grain_12bit",
                                   "saturated_residual", "sparse_int8_overflow", "zero_frame_mid_stream",
-                                  "random_4", "random_5"])
+                                  "random_4", "random_5", "codec_pair_cq28"])
 def test_host_model_gives_libaom_tables(name):
     """The product's C++ host model (consumer handle of libg1s.so fed exact integer records) against libaom."""
     want = golden(name)
-    frames, bd, ss, fps = load(name)
+    frames, bd, ss, fps = load_or_skip(name)
     h, w = frames[0][0][0].shape
     o = O.OracleDiffGenerator(fps[0], fps[1], bd, bd, O.GRAM_EXACT_INT, O.EXP_FIXED, ss[0], ss[1])
     c = D.DiffGenerator(fps[0], fps[1], bd, bd, w, h, ss[0], ss[1], mode=abi.MODE_CONSUMER)
