@@ -7,7 +7,8 @@ g1s_write_grain_table.
 `python -m grav1synth_b200 inspect INPUT -o OUT [-y] [--fps N/D]` -- the reference's `inspect` (src/main.rs:145-196):
 AV1 OBU headers of an .ivf / .obu file -> grain table, CPU only (C++ parser behind g1s_inspect_*).
 `apply IN.ivf -g TABLE -o OUT.ivf` / `remove IN.ivf -o OUT.ivf` -- src/main.rs:197-246, 309-346: film grain headers
-rewritten by the C++ parser (g1s_rewrite_*), IVF in and out.  `generate` (photon-noise tables) is not built.
+rewritten by the C++ parser (g1s_rewrite_*), IVF in and out.  `generate IN.ivf --iso N [--chroma] -o OUT.ivf`
+(src/main.rs:247-308) applies a photon-noise segment (g1s_generate_photon_noise).
 """
 from __future__ import annotations
 
@@ -49,10 +50,17 @@ def main(argv=None) -> int:
     r.add_argument("input", help="The AV1 file to remove grain from (.ivf).")
     r.add_argument("-o", "--output", required=True, help="The path to write the non-grain-synthed AV1 file.")
     r.add_argument("-y", "--overwrite", action="store_true", help="Overwrite the output file without prompting.")
+    g = sub.add_parser("generate", help="Generates photon-noise-based film grain for a given AV1 video at a given ISO "
+                                        "strength, and outputs it at a given `output` path. Overwrites any existing grain.")
+    g.add_argument("input", help="The AV1 file to apply grain to (.ivf).")
+    g.add_argument("-o", "--output", required=True, help="The path to write the grain-synthed AV1 file.")
+    g.add_argument("-y", "--overwrite", action="store_true", help="Overwrite the output file without prompting.")
+    g.add_argument("--iso", type=int, required=True, help="The ISO strength of the generated grain (>= 1).")
+    g.add_argument("--chroma", action="store_true", help="Whether to apply grain to the chroma planes as well.")
     args = ap.parse_args(argv)
     if args.command == "inspect":
         return inspect_main(args)
-    if args.command in ("apply", "remove"):
+    if args.command in ("apply", "remove", "generate"):
         return rewrite_main(args)
 
     # src/main.rs:354-368
@@ -152,6 +160,16 @@ def rewrite_main(args) -> int:
             table = parse_grain_table(f.read())
     with open(args.input, "rb") as f:
         data = f.read()
+    if args.command == "generate":  # src/main.rs:247-308: one segment over the whole stream from the stream's parameters
+        if args.iso < 1:
+            raise SystemExit("--iso must be at least 1")
+        from .inspect import TRANSFER_BT1886, TRANSFER_SMPTE2084, BitstreamParser, generate_photon_noise_params
+        probe = BitstreamParser()
+        probe.push_file(args.input)
+        info = probe.stream_info()
+        trc = TRANSFER_SMPTE2084 if info["transfer_characteristics"] == 16 else TRANSFER_BT1886
+        table = [generate_photon_noise_params(0, 2 ** 64 - 1, args.iso, info["max_frame_width"],
+                                              info["max_frame_height"], trc, args.chroma)]
     out = rewrite_ivf(data, GrainRewriter(table))
     with open(args.output, "wb") as f:
         f.write(out)

@@ -1257,6 +1257,83 @@ int g1s_rewrite_counters(const g1s_inspect *h, uint64_t *with_grain, uint64_t *d
   return G1S_OK;
 }
 
+// ---- generate: av1_grain::generate_photon_noise_params as called at src/main.rs:288-303 (crate source absent; this is
+// the algorithm of libaom examples/photon_noise_table.c, which the crate ports, in f32 like both).  The BT.470BG branch
+// exists because the reference's only fixture, tests/example-table.tbl, is an output of that generator with gamma 2.8
+// (e.g. 1920x1080 at ISO 750): tests reproduce it byte for byte.  The BT.1886 and PQ curves are the crate's two
+// transfer functions, restated from its published formulae (unpinned); its `full_range` argument is not modelled.
+namespace {
+struct Transfer {
+  int id;
+  float to_linear(float x) const {
+    if (id == G1S_TRANSFER_SMPTE2084) {
+      const float m1 = 2610.f / 16384.f, m2 = 128.f * 2523.f / 4096.f, c1 = 3424.f / 4096.f, c2 = 32.f * 2413.f / 4096.f,
+                  c3 = 32.f * 2392.f / 4096.f;
+      const float p = std::pow(x, 1.f / m2);
+      return std::pow(std::fmax(0.f, p - c1) / (c2 - c3 * p), 1.f / m1);
+    }
+    if (id == G1S_TRANSFER_BT470BG) return std::pow(x, 2.8f);
+    return bt1886_alpha() * std::pow(std::fmax(0.f, x + bt1886_beta()), 2.4f) / 203.f;
+  }
+  float from_linear(float x) const {
+    if (id == G1S_TRANSFER_SMPTE2084) {
+      const float m1 = 2610.f / 16384.f, m2 = 128.f * 2523.f / 4096.f, c1 = 3424.f / 4096.f, c2 = 32.f * 2413.f / 4096.f,
+                  c3 = 32.f * 2392.f / 4096.f;
+      if (x < 1.1920929e-7f) return 0.f;
+      const float p = std::pow(x, m1);
+      return std::pow((c1 + c2 * p) / (1.f + c3 * p), m2);
+    }
+    if (id == G1S_TRANSFER_BT470BG) return std::pow(x, 1.f / 2.8f);
+    return std::pow(x * 203.f / bt1886_alpha(), 1.f / 2.4f) - bt1886_beta();
+  }
+  // ITU-R BT.1886 with Lw = 203 cd/m2, Lb = 0.1 cd/m2: L = alpha * max(x + beta, 0)^2.4
+  static float inv_white() { return std::pow(203.f, 1.f / 2.4f); }
+  static float inv_black() { return std::pow(0.1f, 1.f / 2.4f); }
+  static float bt1886_alpha() { return std::pow(inv_white() - inv_black(), 2.4f); }
+  static float bt1886_beta() { return inv_black() / (inv_white() - inv_black()); }
+};
+}  // namespace
+
+int g1s_generate_photon_noise(uint32_t iso, uint32_t width, uint32_t height, int transfer, int chroma_grain,
+                              int32_t random_seed, uint64_t start_time, uint64_t end_time, g1s_segment *out) {
+  if (!out || iso == 0 || width == 0 || height == 0 || transfer < 0 || transfer > G1S_TRANSFER_BT470BG) return G1S_E_ARG;
+  const Transfer tf{transfer};
+  std::memset(out, 0, sizeof *out);
+  const float kPhotonsPerLxSPerUm2 = 11260.f, kEffectiveQuantumEfficiency = 0.20f, kPhotoResponseNonUniformity = 0.005f,
+              kInputReferredReadNoise = 1.5f;
+  const float mid_tone_exposure = 10.f / (float)iso;                                  // lx.s on an 18 % card
+  const float pixel_area_um2 = (36000 * 24000.f) / ((float)width * (float)height);   // 35 mm sensor
+  const float mid_tone_electrons = kEffectiveQuantumEfficiency * kPhotonsPerLxSPerUm2 * mid_tone_exposure * pixel_area_um2;
+  const float max_electrons = mid_tone_electrons / tf.to_linear(0.5f);
+  out->num_y_points = G1S_NUM_Y_POINTS;
+  for (int i = 0; i < G1S_NUM_Y_POINTS; ++i) {
+    const float x = (float)i / (G1S_NUM_Y_POINTS - 1.f);
+    const float linear = tf.to_linear(x);
+    const float electrons = max_electrons * linear;
+    // read noise, photon shot noise and photo-response non-uniformity added in quadrature (electrons rms)
+    const float noise = std::sqrt(kInputReferredReadNoise * kInputReferredReadNoise + electrons +
+                                  kPhotoResponseNonUniformity * kPhotoResponseNonUniformity * electrons * electrons);
+    const float linear_noise = noise / max_electrons;
+    const float lo = std::fmax(0.f, linear - 2 * linear_noise), hi = std::fmin(1.f, linear + 2 * linear_noise);
+    const float slope = (tf.from_linear(hi) - tf.from_linear(lo)) / (hi - lo);
+    const float encoded_noise = linear_noise * slope;
+    out->scaling_points_y[i][0] = (uint8_t)std::round(255.f * x);
+    out->scaling_points_y[i][1] = (uint8_t)std::fmin(255.f, std::round(255.f * 7.88f * encoded_noise));
+  }
+  out->start_time = start_time;
+  out->end_time = end_time;
+  out->scaling_shift = 8;
+  out->ar_coeff_lag = 0;
+  out->ar_coeff_shift = 6;
+  out->num_ar_coeffs_plus1[0] = 1;  // no luma coefficients, a single 0 per chroma plane (as a parsed lag-0 header)
+  out->num_ar_coeffs_plus1[1] = out->num_ar_coeffs_plus1[2] = 2;
+  out->overlap_flag = 1;
+  out->chroma_scaling_from_luma = chroma_grain ? 1 : 0;
+  out->random_seed = random_seed < 0 ? DEFAULT_GRAIN_SEED : (uint16_t)random_seed;
+  out->clip_to_restricted_range = 1;
+  return G1S_OK;
+}
+
 int g1s_inspect_stream_info(const g1s_inspect *h, g1s_stream_info *info) {
   if (!h || !info) return G1S_E_ARG;
   std::memset(info, 0, sizeof *info);

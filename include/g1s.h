@@ -267,6 +267,13 @@ int g1s_rewrite_packet(g1s_inspect *h, const uint8_t *data, size_t size, uint64_
 /* copies the packet produced by the last g1s_rewrite_packet call (G1S_E_STATE: cap < *out_size) */
 int g1s_rewrite_take(g1s_inspect *h, uint8_t *out, size_t cap);
 int g1s_rewrite_counters(const g1s_inspect *h, uint64_t *frames_with_grain, uint64_t *frames_grain_disabled);
+/* `generate` (src/main.rs:247-308): av1_grain::generate_photon_noise_params -- a photon-noise grain segment for a
+ * camera ISO setting, frame size and transfer function (luma scaling points only, lag 0); apply it with g1s_rewrite_*.
+ * random_seed < 0 takes DEFAULT_GRAIN_SEED.  G1S_TRANSFER_BT470BG is not reachable from the reference's CLI: it is the
+ * curve behind the reference's fixture tests/example-table.tbl and is kept to reproduce it. */
+enum g1s_transfer { G1S_TRANSFER_BT1886 = 0, G1S_TRANSFER_SMPTE2084 = 1, G1S_TRANSFER_BT470BG = 2 };
+int g1s_generate_photon_noise(uint32_t iso, uint32_t width, uint32_t height, int transfer, int chroma_grain,
+                              int32_t random_seed, uint64_t start_time, uint64_t end_time, g1s_segment *out);
 /* Test hook: parse ONE syntax group (named as in the AV1 spec / the reference's functions) from a raw bit buffer;
  * returns bits consumed or a negative status.  Lets tests replay the reference's own unit-test vectors. */
 int64_t g1s_obu_probe(const char *what, const uint8_t *data, size_t size, const int64_t *args, size_t nargs,
