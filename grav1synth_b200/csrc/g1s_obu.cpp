@@ -15,8 +15,9 @@
 // Where the reference simplifies the spec the same simplification is kept, so that both read the same bits:
 // found_ref keeps the sequence maximum frame size (no per-reference sizes), segmentation data is not inherited
 // from the primary reference, show_existing_frame of a key frame does not refresh reference slots, and
-// OBU_REDUNDANT_FRAME_HEADER is skipped.  One deliberate difference: a standalone OBU_TILE_GROUP is an
-// `unreachable!()` in the reference (obu.rs:215-219); here its header is read to find the end of the frame.
+// OBU_REDUNDANT_FRAME_HEADER is skipped.  Two deliberate differences, both where the reference cannot continue: a
+// standalone OBU_TILE_GROUP is an `unreachable!()` there (obu.rs:215-219), here its header is read to find the end of
+// the frame; and frame_refs_short_signaling runs the spec's set_frame_refs process, which the reference stubs out.
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -795,8 +796,58 @@ struct g1s_inspect {
   // returns true and fills `out` when the header belongs to a shown frame
   bool parse_frame_header(BitReader &br, bool has_ext, int tid, int sid, bool verify_alignment, FrameHeader *out);
   void tile_group_header(BitReader &br, const TileInfo &ti);
+  void set_frame_refs(int last_frame_idx, int gold_frame_idx, uint64_t order_hint, int order_hint_bits);
   void parse_packet(const uint8_t *data, size_t size);
 };
+
+// AV1 spec 7.8, "set frame refs process": with frame_refs_short_signaling only LAST and GOLDEN are coded, the other
+// five references follow from the order hints of the eight slots.
+void g1s_inspect::set_frame_refs(int last_frame_idx, int gold_frame_idx, uint64_t order_hint, int order_hint_bits) {
+  enum { LAST = 0, LAST2 = 1, LAST3 = 2, GOLDEN = 3, BWDREF = 4, ALTREF2 = 5, ALTREF = 6 };
+  bool used[NUM_REF_FRAMES] = {false};
+  int64_t shifted[NUM_REF_FRAMES];
+  for (int i = 0; i < REFS_PER_FRAME; ++i) ref_frame_idx[i] = -1;
+  ref_frame_idx[LAST] = last_frame_idx;
+  ref_frame_idx[GOLDEN] = gold_frame_idx;
+  used[last_frame_idx] = used[gold_frame_idx] = true;
+  const int64_t cur = (int64_t)1 << (order_hint_bits - 1);
+  for (int i = 0; i < NUM_REF_FRAMES; ++i)
+    shifted[i] = cur + get_relative_dist((int64_t)big_ref_order_hint[i], (int64_t)order_hint, order_hint_bits);
+  auto find = [&](bool backward, bool latest) {
+    int ref = -1;
+    int64_t best = 0;
+    for (int i = 0; i < NUM_REF_FRAMES; ++i) {
+      const int64_t hint = shifted[i];
+      if (used[i] || (backward ? hint < cur : hint >= cur)) continue;
+      if (ref < 0 || (latest ? hint >= best : hint < best)) {
+        ref = i;
+        best = hint;
+      }
+    }
+    return ref;
+  };
+  auto take = [&](int slot, int ref) {
+    if (ref >= 0) {
+      ref_frame_idx[slot] = ref;
+      used[ref] = true;
+    }
+  };
+  take(ALTREF, find(true, true));     // the backward reference furthest in the future
+  take(BWDREF, find(true, false));    // the closest backward reference
+  take(ALTREF2, find(true, false));   // the next closest
+  static const int kOrder[REFS_PER_FRAME - 2] = {LAST2, LAST3, BWDREF, ALTREF2, ALTREF};
+  for (int slot : kOrder)
+    if (ref_frame_idx[slot] < 0) take(slot, find(false, true));  // remaining: forward references, latest first
+  int ref = -1;
+  int64_t earliest = 0;
+  for (int i = 0; i < NUM_REF_FRAMES; ++i)
+    if (ref < 0 || shifted[i] < earliest) {
+      ref = i;
+      earliest = shifted[i];
+    }
+  for (int i = 0; i < REFS_PER_FRAME; ++i)
+    if (ref_frame_idx[i] < 0) ref_frame_idx[i] = ref;
+}
 
 FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int temporal_id, int spatial_id,
                                              bool verify_alignment) {
@@ -875,13 +926,16 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
     if (s.order_hint_bits > 0) {
       frame_refs_short_signaling = br.flag();
       if (frame_refs_short_signaling) {
-        br.f(3);  // last_frame_idx
-        br.f(3);  // gold_frame_idx
+        const int last_frame_idx = (int)br.f(3);
+        const int gold_frame_idx = (int)br.f(3);
+        // The reference stubs set_frame_refs() out and leaves every index at 0 (frame.rs:415-437, :941); the indices
+        // decide whether skip_mode_present is coded, so the spec's process (7.8) is run here instead.
+        set_frame_refs(last_frame_idx, gold_frame_idx, order_hint, s.order_hint_bits);
       }
     }
     for (int i = 0; i < REFS_PER_FRAME; ++i) {
       if (frame_refs_short_signaling) {
-        ref_frame_idx[i] = 0;
+        // ref_frame_idx[i] was derived above
       } else {
         ref_frame_idx[i] = (int)br.f(3);
         if (s.frame_id_numbers_present) br.f((unsigned)s.delta_frame_id_len_minus_2 + 2);  // delta_frame_id_minus_1

@@ -319,6 +319,7 @@ class Frame:
     gm_translation_on_last: bool = False
     grain: Grain = field(default_factory=Grain)
     show_existing_frame: Optional[int] = None  # frame_to_show_map_idx: the header is only that
+    short_signaling: Optional[Tuple[int, int]] = None  # (last_frame_idx, gold_frame_idx): frame_refs_short_signaling
 
     def header_bits(self, s: Seq) -> BitBuilder:
         b = BitBuilder()
@@ -372,8 +373,10 @@ class Frame:
                 b.push_bool(False)  # allow_intrabc
         else:
             if s.order_hint_bits > 0:
-                b.push_bool(False)  # frame_refs_short_signaling
-            for idx in self.ref_frame_idx:
+                b.push_bool(self.short_signaling is not None)  # frame_refs_short_signaling
+                if self.short_signaling is not None:
+                    b.push_bits(self.short_signaling[0], 3).push_bits(self.short_signaling[1], 3)
+            for idx in (self.ref_frame_idx if self.short_signaling is None else ()):
                 b.push_bits(idx, 3)
                 if s.frame_id_numbers:
                     b.push_bits(0, 2 + 2)  # delta_frame_id_minus_1, delta_frame_id_length_minus_2 = 2

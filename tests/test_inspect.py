@@ -555,6 +555,38 @@ def test_skip_mode_bit_is_tracked_across_frames():
     assert [h.params.random_seed for h in p.get_grain_headers()] == [111, 222, 999]
 
 
+def test_frame_refs_short_signaling_derives_the_references():
+    """With short signalling only LAST and GOLDEN are coded; AV1 7.8 derives the rest from the slots' order hints, and
+    those decide whether skip_mode_present exists.  (The reference stubs the process out: frame.rs:941.)"""
+    seq = Seq()
+    def stream(short, skip_bit):
+        return [
+            W.temporal_delimiter() + seq.obu() + Frame(frame_type=0, order_hint=0, grain=GA).frame_obu(seq),
+            # slot 7 <- a hidden future frame (order hint 8); slot 1 <- frame 2
+            W.temporal_delimiter() + Frame(frame_type=1, order_hint=8, show_frame=False, refresh_frame_flags=0x80,
+                                           grain=Grain(kind="disable")).frame_obu(seq) +
+            Frame(frame_type=1, order_hint=2, refresh_frame_flags=0x02, grain=GA2).frame_obu(seq),
+            # frame 4: LAST = slot 1 (hint 2), GOLDEN = slot 0 (hint 0); the derivation must find slot 7 (hint 8) as the
+            # backward reference, which allows skip mode
+            W.temporal_delimiter() + Frame(frame_type=1, order_hint=4, refresh_frame_flags=0x04, short_signaling=short,
+                                           reference_select=True, skip_mode_bit=skip_bit, grain=GB).frame_obu(seq),
+        ]
+    p = I.BitstreamParser()
+    for pk in stream((1, 0), True):
+        p.push_packet(pk)
+    assert [h.params.random_seed for h in p.get_grain_headers()] == [111, 999, 222]
+    assert header_view(p.get_grain_headers()[2]) == expected_view(I.UPDATE_GRAIN, GB, seq)
+    # without the skip_mode_present bit the same header no longer parses to GB
+    q = I.BitstreamParser()
+    try:
+        for pk in stream((1, 0), None):
+            q.push_packet(pk)
+        hs = q.get_grain_headers()
+        assert len(hs) < 3 or header_view(hs[2]) != expected_view(I.UPDATE_GRAIN, GB, seq)
+    except G1SError:
+        pass
+
+
 def test_malformed_streams_are_reported():
     seq = Seq()
     good = W.temporal_delimiter() + seq.obu() + Frame(frame_type=0, grain=GA).frame_obu(seq)
