@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--frames", type=int, default=60, help="frame pairs per step per GPU (3 engine batches at 4K)")
     ap.add_argument("--batch", type=int, default=0, help="frame pairs per kernel launch (engine batch)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-narrow", action="store_true",
+                    help="e2e leg: reduce >8-bit host samples to 8 bits while staging (cfg.host_narrow), half the H2D bytes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the CPU-baseline sample")
     return ap.parse_args()
@@ -329,7 +331,8 @@ def main():
         np_frames = [([t.numpy().view(np.uint16) if bd > 8 else t.numpy() for t in hs],
                       [t.numpy().view(np.uint16) if bd > 8 else t.numpy() for t in hd]) for hs, hd in host]
         if world == 1:
-            g = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=args.batch)
+            g = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=args.batch,
+                                host_narrow=args.host_narrow)
             sd2 = None
 
             def e2e_step():
@@ -366,7 +369,9 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         line["e2e"] = {"value": world * F * n_e2e / float(dt.item()), "unit": "frames/s",
-                       "h2d_bytes_per_step": F * pair_bytes, "d2h_bytes_per_step": F * g.record_bytes, "records_bytes_per_frame": g.record_bytes,
+                       "h2d_bytes_per_step": F * (pair_bytes // 2 if (args.host_narrow and bd > 8 and world == 1) else pair_bytes),
+                       "d2h_bytes_per_step": F * g.record_bytes, "records_bytes_per_frame": g.record_bytes,
+                       "host_narrow": bool(args.host_narrow and bd > 8 and world == 1),
                        "steps": n_e2e, "api": "g1s_diff_push_frame (C ABI) with host planes + g1s_diff_flush"}
         g.close()
 

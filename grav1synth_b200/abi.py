@@ -85,7 +85,8 @@ class CDiffConfig(C.Structure):
         ("mode", C.c_int32),
         ("gram_kernel", C.c_int32),
         ("host_threads", C.c_int32),
-        ("reserved_", C.c_int32 * 4),
+        ("host_narrow", C.c_int32),
+        ("reserved_", C.c_int32 * 3),
     ]
 
 

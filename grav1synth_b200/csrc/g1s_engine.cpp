@@ -197,6 +197,10 @@ struct g1s_diff {
   PlaneGeom pg[3]{};
   size_t pair_bytes = 0;
   int batch = 1;
+  // cfg.host_narrow: samples wider than 8 bits are reduced (truncating >>, frame_into_u8) while they are staged, so
+  // the device, and the PCIe link, only ever see 8-bit planes; host_* keep what the caller's planes look like
+  bool narrow = false;
+  int host_bytes[2] = {1, 1}, host_shift[2] = {0, 0};
   cudaStream_t stream = nullptr;       // kernels + record read-back
   cudaEvent_t marks[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;  // per-frame host->device copies, overlapping the staging of the next frame
@@ -487,6 +491,13 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   g.den_shift = cfg->den_bit_depth - 8;
   g.src_bytes = cfg->src_bit_depth > 8 ? 2 : 1;
   g.den_bytes = cfg->den_bit_depth > 8 ? 2 : 1;
+  d->host_bytes[0] = g.src_bytes, d->host_bytes[1] = g.den_bytes;
+  d->host_shift[0] = g.src_shift, d->host_shift[1] = g.den_shift;
+  d->narrow = cfg->host_narrow != 0 && !consumer && (g.src_bytes == 2 || g.den_bytes == 2);
+  if (d->narrow) {  // from here on this is an 8-bit stream for the frame store and the kernels
+    g.src_shift = g.den_shift = 0;
+    g.src_bytes = g.den_bytes = 1;
+  }
   g.nbw = (g.width + kBlock - 1) / kBlock;
   g.nbh = (g.height + kBlock - 1) / kBlock;
   g.nb = g.nbw * g.nbh;
@@ -589,6 +600,13 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   return G1S_OK;
 }
 
+// util.rs::frame_into_u8 on one row: `(v >> (bit_depth - 8)) as u8`, vectorised by the compiler for the host's ISA.
+extern "C" __attribute__((target_clones("arch=skylake-avx512", "avx2", "default"))) void g1s_narrow_row(uint8_t *dst,
+                                                                                              const uint16_t *src, int n,
+                                                                                              int shift) {
+  for (int i = 0; i < n; ++i) dst[i] = (uint8_t)(src[i] >> shift);
+}
+
 int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *denoised) {
   if (!d) return G1S_E_ARG;
   if (d->finished || d->cfg.mode == G1S_MODE_CONSUMER) {
@@ -603,12 +621,12 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
   FrameDesc &fd = s.h_descs[s.count];
   std::memset(&fd, 0, sizeof fd);
   const g1s_frame *fr[2] = {source, denoised};
-  const int bytes[2] = {d->geom.src_bytes, d->geom.den_bytes};
+  const int bytes[2] = {d->host_bytes[0], d->host_bytes[1]};  // of the caller's samples
 
   // Planes that already live in page-locked host memory go to the device directly (one 2-D DMA per plane at
   // PCIe rate, no staging copy, no host cores); the call still returns only when the borrowed memory is no
   // longer needed.  Pageable planes take the staged path below.
-  bool pinned = std::getenv("G1S_NO_DIRECT_H2D") == nullptr;
+  bool pinned = !d->narrow && std::getenv("G1S_NO_DIRECT_H2D") == nullptr;  // narrowing always stages
   for (int c = 0; c < d->geom.planes && pinned; ++c)
     for (int k = 0; k < 2 && pinned; ++k) {
       cudaPointerAttributes at;
@@ -653,6 +671,8 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
     const uint8_t *src;
     size_t dst_pitch, src_pitch, row_bytes;
     int rows;
+    int narrow_shift;  // >= 0: the source rows are uint16 and are reduced to uint8 with this shift while copied
+    int width;
   };
   CopyTask tasks[96];
   int ntasks = 0;
@@ -670,7 +690,8 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
       const int rows_per = (p.h + chunks - 1) / chunks;
       for (int r0 = 0; r0 < p.h; r0 += rows_per)
         tasks[ntasks++] = {dst + (size_t)r0 * p.pitch[k], src + (size_t)r0 * fr[k]->stride_bytes[c], p.pitch[k],
-                           fr[k]->stride_bytes[c], row_bytes, std::min(rows_per, p.h - r0)};
+                           fr[k]->stride_bytes[c], row_bytes, std::min(rows_per, p.h - r0),
+                           (d->narrow && bytes[k] == 2) ? d->host_shift[k] : -1, p.w};
       const void *dev = s.d_frames + base + p.off[k];
       if (k == 0) {
         fd.src[c] = dev;
@@ -683,7 +704,11 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
   }
   d->pool->parallel_for(ntasks, [&](int i) {
     const CopyTask &t = tasks[i];
-    if (t.dst_pitch == t.src_pitch) {
+    if (t.narrow_shift >= 0) {
+      for (int y = 0; y < t.rows; ++y)
+        g1s_narrow_row(t.dst + (size_t)y * t.dst_pitch, reinterpret_cast<const uint16_t *>(t.src + (size_t)y * t.src_pitch),
+                       t.width, t.narrow_shift);
+    } else if (t.dst_pitch == t.src_pitch) {
       std::memcpy(t.dst, t.src, t.dst_pitch * (size_t)(t.rows - 1) + t.row_bytes);
     } else {
       for (int y = 0; y < t.rows; ++y) std::memcpy(t.dst + (size_t)y * t.dst_pitch, t.src + (size_t)y * t.src_pitch, t.row_bytes);
@@ -702,6 +727,10 @@ int g1s_diff_push_frame_device(g1s_diff *d, const g1s_frame *source, const g1s_f
   if (!d) return G1S_E_ARG;
   if (d->finished || d->cfg.mode == G1S_MODE_CONSUMER) {
     d->err = d->finished ? "push after finish" : "consumer handles take records, not frames";
+    return G1S_E_STATE;
+  }
+  if (d->narrow) {
+    d->err = "host_narrow handles reduce samples while staging host frames; device frames would bypass that";
     return G1S_E_STATE;
   }
   int rc = check_frames(d, source, denoised);

@@ -30,6 +30,7 @@ EXPORTS = [
     "g1s_diff_get_counters", "g1s_diff_mark", "g1s_diff_marks_elapsed_ms", "g1s_record_layout", "g1s_diff_record_bytes", "g1s_diff_set_record_tap",
     "g1s_diff_consume_record", "g1s_diff_consume_records", "g1s_digest_bytes", "g1s_diff_set_digest_sink",
     "g1s_diff_digest_count", "g1s_diff_wait_retired", "g1s_diff_consume_digests", "g1s_diff_consume_digests_borrowed", "g1s_diff_digest_from_record", "g1s_write_grain_table", "g1s_format_grain_table",
+    "g1s_narrow_row",
 ]
 
 
@@ -142,7 +143,8 @@ class DiffGenerator:
 
     def __init__(self, fps_num: int, fps_den: int, source_bit_depth: int, denoised_bit_depth: int, width: int,
                  height: int, ss_x: int = 1, ss_y: int = 1, monochrome: bool = False, device: int = 0,
-                 batch_frames: int = 0, mode: int = abi.MODE_FULL, gram_kernel: int = 0, host_threads: int = 0):
+                 batch_frames: int = 0, mode: int = abi.MODE_FULL, gram_kernel: int = 0, host_threads: int = 0,
+                 host_narrow: bool = False):
         self._L = lib()
         cfg = CDiffConfig()
         cfg.fps_num, cfg.fps_den = fps_num, fps_den
@@ -151,6 +153,7 @@ class DiffGenerator:
         cfg.monochrome, cfg.device, cfg.batch_frames, cfg.mode = int(monochrome), device, batch_frames, mode
         cfg.gram_kernel = gram_kernel
         cfg.host_threads = host_threads
+        cfg.host_narrow = int(host_narrow)
         self.cfg = cfg
         h = C.c_void_p()
         rc = self._L.g1s_diff_create(C.byref(cfg), C.byref(h))

@@ -120,7 +120,11 @@ typedef struct g1s_diff_config {
                                    allows it), 1 = force the generic int32 kernel    */
   int32_t host_threads;         /* threads evaluating the per-frame half of the host model;
                                    0 = auto (half the cores, at most 8)              */
-  int32_t reserved_[4];
+  int32_t host_narrow;          /* non-zero: host frames wider than 8 bits are reduced to 8 bits (the truncating
+                                   `>> (bit_depth - 8)` of frame_into_u8, which is all the path ever reads) by the
+                                   staging threads, halving the bytes that cross PCIe; results are identical.
+                                   Such a handle does not take device frames.  Default 0.   */
+  int32_t reserved_[3];
 } g1s_diff_config;
 
 typedef struct g1s_diff g1s_diff;
@@ -274,6 +278,8 @@ int g1s_rewrite_counters(const g1s_inspect *h, uint64_t *frames_with_grain, uint
 enum g1s_transfer { G1S_TRANSFER_BT1886 = 0, G1S_TRANSFER_SMPTE2084 = 1, G1S_TRANSFER_BT470BG = 2 };
 int g1s_generate_photon_noise(uint32_t iso, uint32_t width, uint32_t height, int transfer, int chroma_grain,
                               int32_t random_seed, uint64_t start_time, uint64_t end_time, g1s_segment *out);
+/* Host-side reduction used by host_narrow (exported for tests): dst[i] = (uint8_t)(src[i] >> shift). */
+void g1s_narrow_row(uint8_t *dst, const uint16_t *src, int n, int shift);
 /* Test hook: parse ONE syntax group (named as in the AV1 spec / the reference's functions) from a raw bit buffer;
  * returns bits consumed or a negative status.  Lets tests replay the reference's own unit-test vectors. */
 int64_t g1s_obu_probe(const char *what, const uint8_t *data, size_t size, const int64_t *args, size_t nargs,

@@ -68,7 +68,8 @@ pub struct g1s_diff_config {
     pub mode: i32,
     pub gram_kernel: i32,
     pub host_threads: i32,
-    pub reserved_: [i32; 4],
+    pub host_narrow: i32,
+    pub reserved_: [i32; 3],
 }
 
 pub enum g1s_diff {}
@@ -135,7 +136,8 @@ impl DiffGenerator {
                 mode: 0,
                 gram_kernel: 0,
                 host_threads: 0,
-                reserved_: [0; 4],
+                host_narrow: 0,
+                reserved_: [0; 3],
             };
             let rc = unsafe { g1s_diff_create(&cfg, &mut self.h) };
             ensure!(rc == 0, "g1s_diff_create failed: {}", last_error(std::ptr::null()));
