@@ -32,15 +32,23 @@ def test_host_narrow_gives_identical_records_and_tables(name):
 
     def run(**kw):
         g = D.DiffGenerator(fps[0], fps[1], spec.bit_depth, spec.bit_depth, spec.width, spec.height, spec.ss_x, spec.ss_y, **kw)
+        rl = D.RecordLayout(g.num_blocks)
         recs = []
-        g.set_record_tap(lambda i, r: recs.append(bytes(r)))
+        g.set_record_tap(lambda i, r: recs.append({k: np.array(v) for k, v in rl.unpack(np.array(r)).items()}))
         for s, d in frames:
             g.diff_frame(s, d)
         return g.finish(), recs
 
     plain, narrow = run(), run(host_narrow=True)
     assert narrow[0] == plain[0]
-    assert narrow[1] == plain[1]
+    assert len(narrow[1]) == len(plain[1]) == len(frames)
+    for a, b in zip(plain[1], narrow[1]):
+        m = a["flat"] != 0
+        assert np.array_equal(a["flat"], b["flat"]) and a["num_flat"] == b["num_flat"]
+        assert np.array_equal(a["score"].view(np.uint32), b["score"].view(np.uint32))
+        assert np.array_equal(a["gram"], b["gram"]) and np.array_equal(a["nobs"], b["nobs"])
+        assert np.array_equal(a["luma_sum"][m], b["luma_sum"][m])
+        assert np.array_equal(a["rsum"][:, m], b["rsum"][:, m]) and np.array_equal(a["rsq"][:, m], b["rsq"][:, m])
 
 
 @pytest.mark.gpu
