@@ -83,6 +83,26 @@ extern "C" {
     fn g1s_diff_last_error(d: *const g1s_diff) -> *const c_char;
 }
 
+/// The CPU-only bitstream side (`inspect`, `apply`, `remove`, `generate`): see INTEGRATION.md sections 6 and 7 for where
+/// these replace `BitstreamParser::get_grain_headers` / `modify_grain_headers` and `aggregate_grain_headers`.
+pub enum g1s_inspect {}
+extern "C" {
+    pub fn g1s_inspect_create(out: *mut *mut g1s_inspect) -> c_int;
+    pub fn g1s_inspect_push_packet(h: *mut g1s_inspect, data: *const u8, size: usize) -> c_int;
+    pub fn g1s_inspect_num_headers(h: *const g1s_inspect) -> usize;
+    pub fn g1s_inspect_header(h: *const g1s_inspect, i: usize, kind: *mut i32, params: *mut g1s_segment) -> c_int;
+    pub fn g1s_inspect_finish(h: *mut g1s_inspect, fps_num: i64, fps_den: i64, out: *mut g1s_segment, cap: usize,
+                              n: *mut usize) -> c_int;
+    pub fn g1s_inspect_last_error(h: *const g1s_inspect) -> *const c_char;
+    pub fn g1s_inspect_destroy(h: *mut g1s_inspect);
+    pub fn g1s_rewrite_create(table: *const g1s_segment, n: usize, apply: c_int, out: *mut *mut g1s_inspect) -> c_int;
+    pub fn g1s_rewrite_packet(h: *mut g1s_inspect, data: *const u8, size: usize, packet_ts: u64,
+                              out_size: *mut usize) -> c_int;
+    pub fn g1s_rewrite_take(h: *mut g1s_inspect, out: *mut u8, cap: usize) -> c_int;
+    pub fn g1s_generate_photon_noise(iso: u32, width: u32, height: u32, transfer: c_int, chroma_grain: c_int,
+                                     random_seed: i32, start_time: u64, end_time: u64, out: *mut g1s_segment) -> c_int;
+}
+
 fn last_error(d: *const g1s_diff) -> String {
     unsafe { CStr::from_ptr(g1s_diff_last_error(d)) }.to_string_lossy().into_owned()
 }
