@@ -13,11 +13,14 @@
 // and g1s_inspect_file demuxes IVF and Section-5 ("low overhead") .obu files itself.
 //
 // Where the reference simplifies the spec the same simplification is kept, so that both read the same bits:
-// found_ref keeps the sequence maximum frame size (no per-reference sizes), segmentation data is not inherited
+// segmentation data is not inherited
 // from the primary reference, show_existing_frame of a key frame does not refresh reference slots, and
-// OBU_REDUNDANT_FRAME_HEADER is skipped.  Two deliberate differences, both where the reference cannot continue: a
+// OBU_REDUNDANT_FRAME_HEADER is skipped.  Deliberate differences, all where the reference cannot continue or would
+// read bits the stream does not have (each is exercised on libaom-encoded streams in tests/test_inspect_libaom.py): a
 // standalone OBU_TILE_GROUP is an `unreachable!()` there (obu.rs:215-219), here its header is read to find the end of
-// the frame; and frame_refs_short_signaling runs the spec's set_frame_refs process, which the reference stubs out.
+// the frame; frame_refs_short_signaling runs the spec's set_frame_refs process, which the reference stubs out;
+// found_ref takes the frame size of the referenced slot; and UpscaledWidth is tracked, so that allow_intrabc and the
+// loop-restoration parameters of a super-resolved frame follow the spec.
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -433,7 +436,7 @@ void superres_params(BitReader &br, bool enable_superres, Dimensions &frame, Dim
   frame.width = (upscaled.width * 8 + denom / 2) / denom;
 }
 
-Dimensions frame_size(BitReader &br, bool override_flag, const SequenceHeader &s) {
+Dimensions frame_size(BitReader &br, bool override_flag, const SequenceHeader &s, uint32_t *upscaled_width) {
   Dimensions d;
   if (override_flag) {
     d.width = (uint32_t)br.f((unsigned)s.frame_width_bits_minus_1 + 1) + 1;
@@ -444,6 +447,7 @@ Dimensions frame_size(BitReader &br, bool override_flag, const SequenceHeader &s
   }
   Dimensions up = d;
   superres_params(br, s.enable_superres, d, up);
+  *upscaled_width = up.width;
   return d;
 }
 
@@ -780,6 +784,8 @@ struct g1s_inspect {
   uint64_t ref_order_hint[NUM_REF_FRAMES] = {0};
   uint64_t big_ref_order_hint[NUM_REF_FRAMES] = {0};
   bool big_ref_valid[NUM_REF_FRAMES] = {false};
+  // sizes saved with every reference slot (spec 7.20): found_ref takes the frame size from the referenced slot
+  uint32_t ref_upscaled_width[NUM_REF_FRAMES] = {0}, ref_frame_height[NUM_REF_FRAMES] = {0};
   std::vector<GrainHeader> headers;  // one per shown frame header, in stream order (parser.rs:155-158)
   uint64_t packets = 0, obus = 0;
   // rewriter (BitstreamParser::<true>, parser.rs:74-101): `write` mirrors every OBU into packet_out; `have_table`
@@ -916,11 +922,14 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
   }
   bool allow_high_precision_mv = false, use_ref_frame_mvs = false;
   Dimensions fsize, upscaled;
+  uint32_t true_upscaled_width = 0;  // UpscaledWidth of the spec, saved with the reference slots
   if (frame_is_intra) {
-    fsize = frame_size(br, frame_size_override_flag, s);
-    upscaled = fsize;  // as the reference: the post-superres size stands for both (frame.rs:389-399)
+    fsize = frame_size(br, frame_size_override_flag, s, &true_upscaled_width);
+    upscaled = fsize;
     render_size(br);
-    if (allow_screen_content_tools && upscaled.width == fsize.width) allow_intrabc = br.flag();
+    // spec 5.9.2: allow_intrabc is coded only when UpscaledWidth == FrameWidth.  (The reference compares the
+    // post-superres width with itself, frame.rs:389-399, and would read a bit that a super-resolved frame lacks.)
+    if (allow_screen_content_tools && true_upscaled_width == fsize.width) allow_intrabc = br.flag();
   } else {
     bool frame_refs_short_signaling = false;
     if (s.order_hint_bits > 0) {
@@ -942,19 +951,26 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
       }
     }
     if (frame_size_override_flag && !error_resilient_mode) {
-      bool found_ref = false;
-      for (int i = 0; i < REFS_PER_FRAME && !found_ref; ++i) found_ref = br.flag();
-      if (found_ref) {
-        fsize = Dimensions{s.max_frame_width_minus_1 + 1, s.max_frame_height_minus_1 + 1};
+      int found_ref = -1;
+      for (int i = 0; i < REFS_PER_FRAME && found_ref < 0; ++i)
+        if (br.flag()) found_ref = i;
+      if (found_ref >= 0) {
+        // The reference keeps the sequence maximum here (frame.rs:456-470 with :949-975), which reads the same bits
+        // unless the tile-column / tile-row limits differ between the two sizes; the slot's own size is used instead.
+        const int slot = ref_frame_idx[found_ref];
+        fsize = Dimensions{ref_upscaled_width[slot], ref_frame_height[slot]};
+        if (fsize.width == 0 || fsize.height == 0)
+          fsize = Dimensions{s.max_frame_width_minus_1 + 1, s.max_frame_height_minus_1 + 1};
         upscaled = fsize;
         superres_params(br, s.enable_superres, fsize, upscaled);
+        true_upscaled_width = upscaled.width;
       } else {
-        fsize = frame_size(br, frame_size_override_flag, s);
+        fsize = frame_size(br, frame_size_override_flag, s, &true_upscaled_width);
         upscaled = Dimensions{s.max_frame_width_minus_1 + 1, s.max_frame_height_minus_1 + 1};
         render_size(br);
       }
     } else {
-      fsize = frame_size(br, frame_size_override_flag, s);
+      fsize = frame_size(br, frame_size_override_flag, s, &true_upscaled_width);
       upscaled = fsize;
       render_size(br);
     }
@@ -964,6 +980,7 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
     use_ref_frame_mvs = (error_resilient_mode || !s.enable_ref_frame_mvs) ? false : br.flag();
   }
   (void)use_ref_frame_mvs;
+  const uint32_t upscaled_width_for_refs = true_upscaled_width;
   const uint32_t mi_cols = 2 * ((fsize.width + 7) >> 3), mi_rows = 2 * ((fsize.height + 7) >> 3);
   if (!(s.reduced_still_picture_header || disable_cdf_update)) br.flag();  // disable_frame_end_update_cdf
   fh.tile_info = tile_info(br, s.use_128x128_superblock, mi_cols, mi_rows);
@@ -976,7 +993,8 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
     const int qindex = get_qindex_ignoring_delta(seg, q.base_q_idx, sg);
     coded_lossless = qindex == 0 && q.y_dc == 0 && q.u_ac == 0 && q.u_dc == 0 && q.v_ac == 0 && q.v_dc == 0;
   }
-  const bool all_lossless = coded_lossless && fsize.width == upscaled.width;
+  (void)upscaled;
+  const bool all_lossless = coded_lossless && fsize.width == true_upscaled_width;  // spec: FrameWidth == UpscaledWidth
   loop_filter_params(br, coded_lossless, allow_intrabc, s.num_planes);
   cdef_params(br, coded_lossless, allow_intrabc, s.enable_cdef, s.num_planes);
   lr_params(br, all_lossless, allow_intrabc, s);
@@ -998,6 +1016,8 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
     if ((refresh_frame_flags >> i) & 1) {
       big_ref_valid[i] = true;
       big_ref_order_hint[i] = order_hint;
+      ref_upscaled_width[i] = upscaled_width_for_refs;
+      ref_frame_height[i] = fsize.height;
     }
   }
   if (verify_alignment) br.byte_alignment(true);
