@@ -84,9 +84,16 @@ CFG_ERROR_RESILIENT, CFG_LAG_IN_FRAMES = 12, 14
 CFG_SUPERRES_MODE, CFG_SUPERRES_DENOMINATOR, CFG_SUPERRES_KF_DENOMINATOR = 19, 20, 21
 
 
+AOM_IMG_FMT_I444 = 0x106
+AOM_IMG_FMT_HIGHBITDEPTH = 0x800
+AOM_CODEC_USE_HIGHBITDEPTH = 0x40000
+
+
 def encode(frames, w: int, h: int, options: Optional[Dict[str, str]] = None, fps: int = 24,
-           lag_in_frames: Optional[int] = None, cfg_words: Optional[Dict[int, int]] = None) -> List[bytes]:
-    """Encodes I420 frames with libaom; returns one bytes object per emitted temporal unit, in output order."""
+           lag_in_frames: Optional[int] = None, cfg_words: Optional[Dict[int, int]] = None, bit_depth: int = 8,
+           chroma444: bool = False) -> List[bytes]:
+    """Encodes planar frames with libaom (4:2:0, or 4:4:4 = profile 1; 8-bit planes, scaled up to `bit_depth` for a
+    high-bit-depth encode); returns one bytes object per emitted temporal unit, in output order."""
     L = _lib()
     iface = L.aom_codec_av1_cx()
     cfg = C.create_string_buffer(4096)
@@ -102,6 +109,10 @@ def encode(frames, w: int, h: int, options: Optional[Dict[str, str]] = None, fps
     # ... g_lag_in_frames, rc_dropframe_thresh, rc_resize_{mode, denominator, kf_denominator},
     # rc_superres_{mode, denominator, kf_denominator, qthresh, kf_qthresh}
     assert (u32[17], u32[18], u32[20], u32[21]) == (8, 8, 8, 8), "unexpected aom_codec_enc_cfg_t layout (scaling)"
+    if bit_depth > 8:
+        u32[8] = u32[9] = bit_depth  # g_bit_depth, g_input_bit_depth
+    if chroma444:
+        u32[2] = 1                   # g_profile
     if lag_in_frames is not None:
         u32[CFG_LAG_IN_FRAMES] = lag_in_frames
     for idx, val in (cfg_words or {}).items():
@@ -109,7 +120,7 @@ def encode(frames, w: int, h: int, options: Optional[Dict[str, str]] = None, fps
     ctx = C.create_string_buffer(512)
     rc = 3
     for ver in range(20, 60):  # AOM_ENCODER_ABI_VERSION of this build (ABI_MISMATCH = 3 until it fits)
-        rc = L.aom_codec_enc_init_ver(ctx, iface, cfg, 0, ver)
+        rc = L.aom_codec_enc_init_ver(ctx, iface, cfg, AOM_CODEC_USE_HIGHBITDEPTH if bit_depth > 8 else 0, ver)
         if rc != 3:
             break
     if rc != 0:
@@ -120,11 +131,12 @@ def encode(frames, w: int, h: int, options: Optional[Dict[str, str]] = None, fps
         for k, v in opts.items():
             if L.aom_codec_set_option(ctx, k.encode(), str(v).encode()) != 0:
                 raise EncodeError(f"option {k}={v} rejected: {L.aom_codec_error_detail(ctx)}")
-        img = L.aom_img_alloc(None, AOM_IMG_FMT_I420, w, h, 32)
+        fmt = (AOM_IMG_FMT_I444 if chroma444 else AOM_IMG_FMT_I420) | (AOM_IMG_FMT_HIGHBITDEPTH if bit_depth > 8 else 0)
+        img = L.aom_img_alloc(None, fmt, w, h, 32)
         if not img:
             raise EncodeError("aom_img_alloc failed")
         hdr = (C.c_uint32 * 16).from_address(img)
-        assert hdr[0] == AOM_IMG_FMT_I420 and hdr[7] == w and hdr[8] == h, "unexpected aom_image_t layout"
+        assert hdr[0] == fmt and hdr[7] == w and hdr[8] == h, "unexpected aom_image_t layout"
         planes = (C.c_void_p * 3).from_address(img + 64)
         strides = (C.c_int * 3).from_address(img + 88)
         packets: List[bytes] = []
@@ -143,9 +155,15 @@ def encode(frames, w: int, h: int, options: Optional[Dict[str, str]] = None, fps
 
         for k, (y, u, v) in enumerate(frames):
             for i, p in enumerate((y, u, v)):
+                if chroma444 and i > 0 and p.shape != y.shape:
+                    p = np.repeat(np.repeat(p, 2, axis=0), 2, axis=1)[: y.shape[0], : y.shape[1]]
                 ph, pw = p.shape
-                dst = np.ctypeslib.as_array((C.c_uint8 * (strides[i] * ph)).from_address(planes[i])).reshape(ph, strides[i])
-                dst[:, :pw] = p
+                if bit_depth > 8:
+                    dst = np.ctypeslib.as_array((C.c_uint16 * (strides[i] // 2 * ph)).from_address(planes[i]))
+                    dst.reshape(ph, strides[i] // 2)[:, :pw] = p.astype(np.uint16) << (bit_depth - 8)
+                else:
+                    dst = np.ctypeslib.as_array((C.c_uint8 * (strides[i] * ph)).from_address(planes[i]))
+                    dst.reshape(ph, strides[i])[:, :pw] = p
             if L.aom_codec_encode(ctx, img, k, 1, 0) != 0:
                 raise EncodeError(f"aom_codec_encode failed: {L.aom_codec_error_detail(ctx)}")
             drain()

@@ -111,6 +111,9 @@ ENCODER_VARIANTS = {
     "lossless": dict(lag=None, opts={"lossless": "1"}),
     "cdf_update_off_reduced_tx": dict(lag=None, opts={"cdf-update-mode": "0", "reduced-tx-type-set": "1"}),
     "uhd_8k_one_frame": dict(lag=None, opts={}, size=(7680, 4320), frames=1),
+    "main_profile_10bit": dict(lag=None, opts={}, enc=dict(bit_depth=10), frames=6),
+    "high_profile_444": dict(lag=None, opts={}, enc=dict(chroma444=True), frames=6),
+    "high_profile_444_10bit": dict(lag=0, opts={}, enc=dict(chroma444=True, bit_depth=10), frames=6),
 }
 
 
@@ -123,15 +126,18 @@ def test_encoder_variants_change_the_header_syntax_not_the_grain(name):
     n = v.get("frames", 10)
     opts = {"film-grain-test": "1"}   # vector 1 updates its parameters on every frame
     opts.update(v["opts"])
-    packets = E.encode(E.synthetic_frames(n, w, h, seed=3), w, h, opts, lag_in_frames=v["lag"], cfg_words=v.get("cfg"))
+    enc = v.get("enc", {})
+    packets = E.encode(E.synthetic_frames(n, w, h, seed=3), w, h, opts, lag_in_frames=v["lag"], cfg_words=v.get("cfg"),
+                       **enc)
     p, hs = inspect_packets(packets)
     assert len(hs) == n
-    want = vector_view(E.test_vector(1))
+    want = vector_view(E.test_vector(1))   # has luma points, so 4:4:4 codes the same syntax as 4:2:0
     assert all(header_view(h) == want for h in hs if h.kind == I.UPDATE_GRAIN)
     assert hs[0].kind == I.UPDATE_GRAIN and all(h.kind != I.DISABLE for h in hs)
     assert sum(h.kind == I.UPDATE_GRAIN for h in hs) >= (n + 1) // 2
     info = p.stream_info()
-    assert (info["max_frame_width"], info["max_frame_height"], info["bit_depth"]) == (w, h, 8)
+    assert (info["max_frame_width"], info["max_frame_height"], info["bit_depth"]) == (w, h, enc.get("bit_depth", 8))
+    assert (info["ss_x"], info["ss_y"]) == ((0, 0) if enc.get("chroma444") else (1, 1))
     segs = p.aggregate_grain_headers(24, 1)
     assert len(segs) == 1 and segs[0].start_time == 0 and segs[0].end_time == -(-n * 10_000_000 // 24)
 
