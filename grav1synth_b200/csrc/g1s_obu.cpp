@@ -795,6 +795,9 @@ struct g1s_inspect {
   std::vector<uint8_t> packet_out;
   uint64_t packet_ts = 0;
   uint64_t frames_with_grain = 0, frames_grain_disabled = 0;
+  // the rewritten header of the current frame as a standalone frame_header_obu() payload: repeats of the header inside
+  // the frame (OBU_FRAME_HEADER again, OBU_REDUNDANT_FRAME_HEADER) must stay bit-identical to it (spec 7.5)
+  std::vector<uint8_t> current_header_payload;
   std::vector<uint8_t> rewrite_frame_payload(const uint8_t *payload, size_t obu_size, const FrameHeader &fh,
                                              size_t header_end_bits, bool is_frame_obu);
 
@@ -1076,10 +1079,10 @@ std::vector<uint8_t> g1s_inspect::rewrite_frame_payload(const uint8_t *payload, 
     out = bw.bytes;  // byte_alignment(): the partial byte is already zero-padded
     const size_t tile_off = (header_end_bits + 7) >> 3;
     out.insert(out.end(), payload + tile_off, payload + obu_size);
-  } else {
-    bw.put(1, 1);  // trailing_bits()
-    out = bw.bytes;
   }
+  bw.put(1, 1);  // trailing_bits()
+  current_header_payload = bw.bytes;
+  if (!is_frame_obu) out = current_header_payload;
   return out;
 }
 
@@ -1203,6 +1206,17 @@ void g1s_inspect::parse_packet(const uint8_t *data, size_t size) {
             new_payload = rewrite_frame_payload(payload, obu_size, fh, br.pos, false);
             replaced = true;
           }
+          if (fh.show_existing_frame) current_header_payload.clear();
+        } else if (write && !current_header_payload.empty()) {
+          new_payload = current_header_payload;  // a repeat of the current frame's header
+          replaced = true;
+        }
+        break;
+      }
+      case 7: {  // OBU_REDUNDANT_FRAME_HEADER: parsed by nobody (obu.rs:236-249), kept equal to the rewritten header
+        if (write && seen_frame_header && !current_header_payload.empty()) {
+          new_payload = current_header_payload;
+          replaced = true;
         }
         break;
       }

@@ -124,7 +124,10 @@ def test_rewrite_hand_built_stream_roundtrip(tmp_path):
         W.temporal_delimiter() + Frame(frame_type=1, order_hint=8, show_frame=False, refresh_frame_flags=0x40,
                                        grain=GB).frame_obu(seq) +
         Frame(frame_type=1, order_hint=1, grain=Grain(kind="copy"), tile_cols_log2=1).frame_obu(seq),
-        W.temporal_delimiter() + split.frame_header_obu(seq) + split.tile_group_obu(seq) + W.obu(W.OBU_PADDING, b"\0\0"),
+        # frame header, the header repeated (as OBU_FRAME_HEADER and as a redundant copy), the tile group, padding
+        W.temporal_delimiter() + split.frame_header_obu(seq) + split.frame_header_obu(seq) +
+        W.obu(W.OBU_REDUNDANT_FRAME_HEADER, split.header_bits(seq).push_bool(True).to_bytes()) +
+        split.tile_group_obu(seq) + W.obu(W.OBU_PADDING, b"\0\0"),
         W.temporal_delimiter() + Frame(show_existing_frame=6).frame_header_obu(seq),
         W.temporal_delimiter() + Frame(frame_type=1, order_hint=9, grain=Grain(kind="disable")).frame_obu(seq, has_size=False),
     ]
@@ -141,6 +144,24 @@ def test_rewrite_hand_built_stream_roundtrip(tmp_path):
     for h in hs:
         if h.kind == I.UPDATE_GRAIN:
             assert h.params.scaling_points_y == want.scaling_points_y and h.params.ar_coeffs_cr == want.ar_coeffs_cr
+    # the repeated headers inside packet 2 were rewritten to the same bytes as the first copy
+    def obus(pk):
+        out, off = [], 0
+        while off < len(pk):
+            t, has_size = (pk[off] >> 3) & 15, (pk[off] >> 1) & 1
+            n, k, shift = 0, off + 1, 0
+            while True:
+                n |= (pk[k] & 0x7F) << shift
+                shift += 7
+                k += 1
+                if not pk[k - 1] & 0x80:
+                    break
+            out.append((t, pk[k:k + n]))
+            off = k + n
+        return out
+    copies = [body for t, body in obus(out[2]) if t in (W.OBU_FRAME_HEADER, W.OBU_REDUNDANT_FRAME_HEADER)]
+    assert len(copies) == 3 and copies[0] == copies[1] == copies[2]
+    assert copies[0] != [body for t, body in obus(packets[2]) if t == W.OBU_FRAME_HEADER][0]
     seeds = [h.params.random_seed for h in hs if h.kind == I.UPDATE_GRAIN]
     step = lambda n: (want.random_seed + n * 10956) % 65536
     assert seeds == [step(1), step(3), step(4), step(5)]          # step(2) went to the hidden frame
