@@ -53,6 +53,40 @@ def test_remove_gives_libaoms_own_grainless_stream(vector, lag):
 
 
 @needs_libaom
+@pytest.mark.parametrize("name,opts,kw", [
+    ("two_tile_groups", {"tile-columns": "1", "num-tile-groups": "2"}, {}),            # OBU_FRAME_HEADER + OBU_TILE_GROUPs
+    ("high_profile_444_10bit", {}, dict(chroma444=True, bit_depth=10)),
+    ("superres", {}, dict(cfg_words={19: 1, 20: 12, 21: 12})),
+    ("error_resilient_low_delay", {}, dict(cfg_words={12: 1}, lag_in_frames=0)),
+])
+def test_remove_and_apply_on_other_stream_structures(name, opts, kw):
+    from oracle import aom_encode as E
+    fr = E.synthetic_frames(8, 704, 576, seed=5)
+    kw = dict(kw)
+    cfg = dict(kw.pop("cfg_words", {}))
+    cfg[24] = 3   # constant quality, see above
+    base = dict({"cq-level": "32"}, **opts)
+    plain = E.encode(fr, 704, 576, dict(base), cfg_words=cfg, **kw)
+    grainy = E.encode(fr, 704, 576, dict(base, **{"film-grain-test": "3"}), cfg_words=cfg, **kw)
+    rm = I.GrainRewriter(None)
+    assert [rm.rewrite_packet(p, ts(k)) for k, p in enumerate(grainy)] == plain
+    ap = I.GrainRewriter(golden_table("c2_small_8bit"))
+    applied = [ap.rewrite_packet(p, ts(k)) for k, p in enumerate(plain)]
+    if kw.get("bit_depth", 8) == 8:
+        assert len(E.decode(applied)) == 8
+    p = I.BitstreamParser()
+    for pk in applied:
+        p.push_packet(pk)
+    hs = p.get_grain_headers()
+    assert len(hs) == 8 and all(h.kind in (I.UPDATE_GRAIN, I.COPY_REF_FRAME) for h in hs)
+    want = golden_table("c2_small_8bit")[0]
+    assert all(h.params.scaling_points_y == want.scaling_points_y and h.params.ar_coeffs_cb == want.ar_coeffs_cb
+               for h in hs if h.kind == I.UPDATE_GRAIN)
+    rm2 = I.GrainRewriter(None)
+    assert [rm2.rewrite_packet(pk, ts(k)) for k, pk in enumerate(applied)] == plain
+
+
+@needs_libaom
 @pytest.mark.parametrize("table", ["c2_small_8bit", "heavy_grain_12bit"])
 def test_apply_diff_table_to_a_libaom_stream(table):
     from oracle import aom_encode as E
