@@ -99,7 +99,7 @@ def encode(frames, w: int, h: int, options: Optional[Dict[str, str]] = None, fps
     cfg = C.create_string_buffer(4096)
     if L.aom_codec_enc_config_default(iface, cfg, 0) != 0:
         raise EncodeError("aom_codec_enc_config_default failed")
-    u32 = (C.c_uint32 * 32).from_buffer(cfg)
+    u32 = (C.c_uint32 * 64).from_buffer(cfg)
     # aom_codec_enc_cfg_t starts: g_usage, g_threads, g_profile, g_w, g_h, g_limit, g_forced_max_frame_width,
     # g_forced_max_frame_height, g_bit_depth, g_input_bit_depth, g_timebase{num, den}, g_error_resilient, g_pass,
     # g_lag_in_frames

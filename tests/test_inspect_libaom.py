@@ -111,6 +111,12 @@ ENCODER_VARIANTS = {
     "lossless": dict(lag=None, opts={"lossless": "1"}),
     "cdf_update_off_reduced_tx": dict(lag=None, opts={"cdf-update-mode": "0", "reduced-tx-type-set": "1"}),
     "uhd_8k_one_frame": dict(lag=None, opts={}, size=(7680, 4320), frames=1),
+    "forward_keyframes": dict(lag=19, opts={}, cfg={45: 1, 47: 8, 48: 8}, frames=24),      # fwd_kf_enabled, kf_min/max_dist
+    "keyframe_every_5": dict(lag=19, opts={}, cfg={47: 5, 48: 5}, frames=24),
+    "s_frames": dict(lag=0, opts={}, cfg={49: 4, 50: 1, 12: 1}, frames=24),                 # sframe_dist / mode, error resilient
+    "monochrome": dict(lag=None, opts={}, cfg={52: 1}, frames=6, mono=True),
+    "reduced_still_picture": dict(lag=None, opts={}, cfg={5: 1, 53: 0}, frames=1),          # g_limit = 1
+    "full_header_still_picture": dict(lag=None, opts={}, cfg={5: 1, 53: 1}, frames=1),
     "main_profile_10bit": dict(lag=None, opts={}, enc=dict(bit_depth=10), frames=6),
     "high_profile_444": dict(lag=None, opts={}, enc=dict(chroma444=True), frames=6),
     "high_profile_444_10bit": dict(lag=0, opts={}, enc=dict(chroma444=True, bit_depth=10), frames=6),
@@ -132,6 +138,10 @@ def test_encoder_variants_change_the_header_syntax_not_the_grain(name):
     p, hs = inspect_packets(packets)
     assert len(hs) == n
     want = vector_view(E.test_vector(1))   # has luma points, so 4:4:4 codes the same syntax as 4:2:0
+    if v.get("mono"):                       # no chroma syntax at all
+        want.update(scaling_points_cb=[], scaling_points_cr=[], ar_coeffs_cb=[0], ar_coeffs_cr=[0], cb_mult=0,
+                    cb_luma_mult=0, cb_offset=0, cr_mult=0, cr_luma_mult=0, cr_offset=0)
+        assert p.stream_info()["monochrome"] == 1
     assert all(header_view(h) == want for h in hs if h.kind == I.UPDATE_GRAIN)
     assert hs[0].kind == I.UPDATE_GRAIN and all(h.kind != I.DISABLE for h in hs)
     assert sum(h.kind == I.UPDATE_GRAIN for h in hs) >= (n + 1) // 2
