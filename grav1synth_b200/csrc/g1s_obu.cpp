@@ -12,15 +12,17 @@
 // The reference gets packets from FFmpeg; here a packet is whatever the caller pushes (g1s_inspect_push_packet),
 // and g1s_inspect_file demuxes IVF and Section-5 ("low overhead") .obu files itself.
 //
-// Where the reference simplifies the spec the same simplification is kept, so that both read the same bits:
-// segmentation data is not inherited
-// from the primary reference, show_existing_frame of a key frame does not refresh reference slots, and
-// OBU_REDUNDANT_FRAME_HEADER is skipped.  Deliberate differences, all where the reference cannot continue or would
-// read bits the stream does not have (each is exercised on libaom-encoded streams in tests/test_inspect_libaom.py): a
-// standalone OBU_TILE_GROUP is an `unreachable!()` there (obu.rs:215-219), here its header is read to find the end of
-// the frame; frame_refs_short_signaling runs the spec's set_frame_refs process, which the reference stubs out;
-// found_ref takes the frame size of the referenced slot; and UpscaledWidth is tracked, so that allow_intrabc and the
-// loop-restoration parameters of a super-resolved frame follow the spec.
+// Where the reference simplifies the spec harmlessly the same simplification is kept, so that both read the same
+// bits: segmentation data is not inherited from the primary reference, and OBU_REDUNDANT_FRAME_HEADER is not parsed.
+// Deliberate differences, all where the reference cannot continue or would read bits the stream does not have (each
+// is exercised on libaom-encoded streams in tests/test_inspect_libaom.py or on hand-built ones in test_inspect.py):
+//  * a standalone OBU_TILE_GROUP is an `unreachable!()` there (obu.rs:215-219); here its header is read to find the
+//    end of the frame;
+//  * frame_refs_short_signaling runs the spec's set_frame_refs process (7.8), which the reference stubs out;
+//  * found_ref takes the frame size of the referenced slot (the reference keeps the sequence maximum);
+//  * UpscaledWidth is tracked, so that allow_intrabc and the loop-restoration parameters of a super-resolved frame
+//    follow the spec (5.9.2, 5.9.20);
+//  * show_existing_frame of a key frame refreshes the reference slots (7.21), which forward key frames rely on.
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -786,6 +788,7 @@ struct g1s_inspect {
   bool big_ref_valid[NUM_REF_FRAMES] = {false};
   // sizes saved with every reference slot (spec 7.20): found_ref takes the frame size from the referenced slot
   uint32_t ref_upscaled_width[NUM_REF_FRAMES] = {0}, ref_frame_height[NUM_REF_FRAMES] = {0};
+  int ref_frame_type[NUM_REF_FRAMES] = {0};
   std::vector<GrainHeader> headers;  // one per shown frame header, in stream order (parser.rs:155-158)
   uint64_t packets = 0, obus = 0;
   // rewriter (BitstreamParser::<true>, parser.rs:74-101): `write` mirrors every OBU into packet_out; `have_table`
@@ -868,8 +871,19 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
   bool show_frame = true, showable_frame = true, error_resilient_mode = false;
   if (!s.reduced_still_picture_header) {
     if (br.flag()) {  // show_existing_frame
-      br.f(3);        // frame_to_show_map_idx
+      const int shown_slot = (int)br.f(3);  // frame_to_show_map_idx
       if (id_len) br.f((unsigned)id_len);
+      if (have_frame_header && ref_frame_type[shown_slot] == KEY_FRAME && big_ref_valid[shown_slot]) {
+        // spec 7.21: showing a key frame refreshes every slot with it (the reference skips this; later frames' skip-mode
+        // decision reads these order hints)
+        for (int i = 0; i < NUM_REF_FRAMES; ++i) {
+          big_ref_order_hint[i] = big_ref_order_hint[shown_slot];
+          ref_upscaled_width[i] = ref_upscaled_width[shown_slot];
+          ref_frame_height[i] = ref_frame_height[shown_slot];
+          ref_frame_type[i] = KEY_FRAME;
+          big_ref_valid[i] = true;
+        }
+      }
       if (!have_frame_header) throw ParseError("show_existing_frame before any frame header");
       if (verify_alignment) br.byte_alignment(true);
       fh.show_frame = true;
@@ -1021,6 +1035,7 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
       big_ref_order_hint[i] = order_hint;
       ref_upscaled_width[i] = upscaled_width_for_refs;
       ref_frame_height[i] = fsize.height;
+      ref_frame_type[i] = frame_type;
     }
   }
   if (verify_alignment) br.byte_alignment(true);
