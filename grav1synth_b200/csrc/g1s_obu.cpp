@@ -13,7 +13,7 @@
 // and g1s_inspect_file demuxes IVF and Section-5 ("low overhead") .obu files itself.
 //
 // Where the reference simplifies the spec harmlessly the same simplification is kept, so that both read the same
-// bits: segmentation data is not inherited from the primary reference, and OBU_REDUNDANT_FRAME_HEADER is not parsed.
+// bits (OBU_REDUNDANT_FRAME_HEADER is not parsed).
 // Deliberate differences, all where the reference cannot continue or would read bits the stream does not have (each
 // is exercised on libaom-encoded streams in tests/test_inspect_libaom.py or on hand-built ones in test_inspect.py):
 //  * a standalone OBU_TILE_GROUP is an `unreachable!()` there (obu.rs:215-219); here its header is read to find the
@@ -22,7 +22,8 @@
 //  * found_ref takes the frame size of the referenced slot (the reference keeps the sequence maximum);
 //  * UpscaledWidth is tracked, so that allow_intrabc and the loop-restoration parameters of a super-resolved frame
 //    follow the spec (5.9.2, 5.9.20);
-//  * show_existing_frame of a key frame refreshes the reference slots (7.21), which forward key frames rely on.
+//  * show_existing_frame of a key frame refreshes the reference slots (7.21), which forward key frames rely on;
+//  * segmentation features are inherited from the primary reference frame when they are not re-sent (7.20).
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -552,7 +553,11 @@ struct Segmentation {
   int16_t value[MAX_SEGMENTS][SEG_LVL_MAX] = {{0}};
 };
 
-Segmentation segmentation_params(BitReader &br, int primary_ref_frame) {
+// `previous` = the segmentation parameters saved with the primary reference frame (load_previous(), spec 7.20): they
+// stay in force when segmentation is enabled without segmentation_update_data.  (The reference starts from an empty
+// set there, frame.rs:1326-1395; the only use of the values is the lossless test, so the bits read are the same
+// unless a lossless stream relies on inherited ALT_Q features.)
+Segmentation segmentation_params(BitReader &br, int primary_ref_frame, const Segmentation *previous = nullptr) {
   static const int kBits[SEG_LVL_MAX] = {8, 6, 6, 6, 6, 3, 0, 0};
   static const bool kSigned[SEG_LVL_MAX] = {true, true, true, true, true, false, false, false};
   static const int kMax[SEG_LVL_MAX] = {255, 63, 63, 63, 63, 7, 0, 0};
@@ -563,6 +568,10 @@ Segmentation segmentation_params(BitReader &br, int primary_ref_frame) {
   if (primary_ref_frame != PRIMARY_REF_NONE) {
     if (br.flag()) br.flag();  // segmentation_update_map, segmentation_temporal_update
     update_data = br.flag();
+  }
+  if (!update_data && previous) {
+    std::memcpy(sg.has, previous->has, sizeof sg.has);
+    std::memcpy(sg.value, previous->value, sizeof sg.value);
   }
   if (update_data) {
     for (int i = 0; i < MAX_SEGMENTS; ++i)
@@ -789,6 +798,7 @@ struct g1s_inspect {
   // sizes saved with every reference slot (spec 7.20): found_ref takes the frame size from the referenced slot
   uint32_t ref_upscaled_width[NUM_REF_FRAMES] = {0}, ref_frame_height[NUM_REF_FRAMES] = {0};
   int ref_frame_type[NUM_REF_FRAMES] = {0};
+  Segmentation ref_segmentation[NUM_REF_FRAMES];
   std::vector<GrainHeader> headers;  // one per shown frame header, in stream order (parser.rs:155-158)
   uint64_t packets = 0, obus = 0;
   // rewriter (BitstreamParser::<true>, parser.rs:74-101): `write` mirrors every OBU into packet_out; `have_table`
@@ -881,6 +891,7 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
           ref_upscaled_width[i] = ref_upscaled_width[shown_slot];
           ref_frame_height[i] = ref_frame_height[shown_slot];
           ref_frame_type[i] = KEY_FRAME;
+          ref_segmentation[i] = ref_segmentation[shown_slot];
           big_ref_valid[i] = true;
         }
       }
@@ -1002,7 +1013,8 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
   if (!(s.reduced_still_picture_header || disable_cdf_update)) br.flag();  // disable_frame_end_update_cdf
   fh.tile_info = tile_info(br, s.use_128x128_superblock, mi_cols, mi_rows);
   const QuantParams q = quantization_params(br, s.num_planes, s.separate_uv_delta_q);
-  const Segmentation sg = segmentation_params(br, primary_ref_frame);
+  const Segmentation sg = segmentation_params(
+      br, primary_ref_frame, primary_ref_frame == PRIMARY_REF_NONE ? nullptr : &ref_segmentation[ref_frame_idx[primary_ref_frame]]);
   const bool delta_q_present = delta_q_params(br, q.base_q_idx);
   delta_lf_params(br, delta_q_present, allow_intrabc);
   bool coded_lossless = true;
@@ -1036,6 +1048,7 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
       ref_upscaled_width[i] = upscaled_width_for_refs;
       ref_frame_height[i] = fsize.height;
       ref_frame_type[i] = frame_type;
+      ref_segmentation[i] = sg;
     }
   }
   if (verify_alignment) br.byte_alignment(true);

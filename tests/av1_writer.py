@@ -316,6 +316,9 @@ class Frame:
     skip_mode_bit: Optional[bool] = None   # written after reference_select when the test knows skip mode is allowed
     allow_screen_content_tools: bool = False
     segmentation: bool = False
+    seg_value: int = -7               # ALT_Q feature of segment 1 when the data is sent
+    seg_inherit: bool = False         # segmentation enabled, update_map = update_data = 0: keep the reference's data
+    lossless: Optional[bool] = None   # what the decoder will conclude (None: derived for the default cases)
     gm_translation_on_last: bool = False
     grain: Grain = field(default_factory=Grain)
     show_existing_frame: Optional[int] = None  # frame_to_show_map_idx: the header is only that
@@ -421,7 +424,10 @@ class Frame:
         b.push_bool(False)  # using_qmatrix
         # segmentation_params
         b.push_bool(self.segmentation)
-        if self.segmentation:
+        if self.segmentation and self.seg_inherit:
+            assert primary != 7
+            b.push_bool(False).push_bool(False)  # segmentation_update_map, segmentation_update_data
+        elif self.segmentation:
             if primary != 7:
                 b.push_bool(True).push_bool(False).push_bool(True)  # update_map, temporal_update, update_data
             for seg in range(8):
@@ -429,12 +435,14 @@ class Frame:
                     on = seg == 1 and feat == 0
                     b.push_bool(on)
                     if on:
-                        b.push_su(-7, 9)
+                        b.push_su(self.seg_value, 9)
         if self.base_q_idx > 0:
             b.push_bool(False)  # delta_q_present
         lossless = False  # delta_q_u_dc != 0 with chroma; monochrome: lossless iff base_q_idx == 0
         if num_planes == 1:
             lossless = self.base_q_idx == 0  # the test segment feature (-7 on ALT_Q) clamps back to qindex 0
+        if self.lossless is not None:
+            lossless = self.lossless
         if not lossless:
             b.push_bits(12, 6).push_bits(0, 6)  # loop_filter_level[0..1]
             if num_planes > 1:

@@ -587,6 +587,28 @@ def test_frame_refs_short_signaling_derives_the_references():
         pass
 
 
+def test_inherited_segmentation_decides_losslessness():
+    """base_q_idx = 0 everywhere, but segment 1 carries ALT_Q = +20: the key frame is not lossless, and neither is the
+    inter frame that keeps the data of its primary reference (segmentation enabled, nothing re-sent) -- so its
+    loop-filter / CDEF / restoration / tx-mode syntax is present (spec 7.20 load_previous)."""
+    seq = Seq(monochrome=True)
+    packets = [
+        W.temporal_delimiter() + seq.obu() +
+        Frame(frame_type=0, base_q_idx=0, segmentation=True, seg_value=20, lossless=False, grain=GA).frame_obu(seq),
+        W.temporal_delimiter() +
+        Frame(frame_type=1, order_hint=1, base_q_idx=0, primary_ref_frame=0, segmentation=True, seg_inherit=True,
+              lossless=False, grain=GB).frame_obu(seq),
+        # and a frame that switches segmentation off is lossless again
+        W.temporal_delimiter() +
+        Frame(frame_type=1, order_hint=2, base_q_idx=0, primary_ref_frame=0, lossless=True, grain=GA2).frame_obu(seq),
+    ]
+    p = I.BitstreamParser()
+    for pk in packets:
+        p.push_packet(pk)
+    assert [header_view(h) for h in p.get_grain_headers()] == [
+        expected_view(I.UPDATE_GRAIN, GA, seq), expected_view(I.UPDATE_GRAIN, GB, seq), expected_view(I.UPDATE_GRAIN, GA2, seq)]
+
+
 def test_malformed_streams_are_reported():
     seq = Seq()
     good = W.temporal_delimiter() + seq.obu() + Frame(frame_type=0, grain=GA).frame_obu(seq)
