@@ -218,3 +218,63 @@ def test_rewrite_hand_built_stream_roundtrip(tmp_path):
     r.push_file(str(removed))
     assert all(h.kind == I.DISABLE or h.kind == I.COPY_REF_FRAME for h in r.get_grain_headers())
     assert r.stream_info()["film_grain_params_present"] == 0
+
+
+@needs_libaom
+def test_random_tables_survive_apply_libaom_decode_and_inspect():
+    """30 random (valid) film grain parameter sets: every branch of the grain syntax writer (no luma points, chroma
+    scaling from luma, 0..3 lags, with / without chroma points and multipliers) must give a stream libaom decodes and
+    `inspect` reads back exactly."""
+    from oracle import aom_encode as E
+    from grav1synth_b200.abi import CSegment, GrainTableSegment
+    rng = np.random.default_rng(77)
+    fr = E.synthetic_frames(3, 176, 144, seed=8)
+    plain = E.encode(fr, 176, 144, {}, lag_in_frames=0)
+
+    def points(n):
+        xs = np.sort(rng.choice(256, n, replace=False))
+        return [(int(x), int(rng.integers(0, 256))) for x in xs]
+
+    for trial in range(30):
+        s = CSegment()
+        s.start_time, s.end_time, s.random_seed = 0, 2 ** 63, int(rng.integers(0, 65536))
+        ny = int(rng.choice([0, 1, 2, 7, 14]))
+        csfl = bool(rng.integers(0, 2)) and ny > 0
+        # 4:2:0: grain goes to both chroma planes or to neither (libaom enforces the spec's constraint)
+        ncb, ncr = (0, 0) if (csfl or ny == 0 or rng.integers(0, 3) == 0) else (int(rng.integers(1, 11)), int(rng.integers(1, 11)))
+        for dst, n, cnt in ((s.scaling_points_y, ny, "num_y_points"), (s.scaling_points_cb, ncb, "num_cb_points"),
+                            (s.scaling_points_cr, ncr, "num_cr_points")):
+            setattr(s, cnt, n)
+            for k, (x, y) in enumerate(points(n)):
+                dst[k][0], dst[k][1] = x, y
+        s.chroma_scaling_from_luma = int(csfl)
+        s.scaling_shift, s.ar_coeff_lag = int(rng.integers(8, 12)), int(rng.integers(0, 4))
+        s.ar_coeff_shift, s.grain_scale_shift = int(rng.integers(6, 10)), int(rng.integers(0, 4))
+        for arr in (s.ar_coeffs_y, s.ar_coeffs_cb, s.ar_coeffs_cr):
+            for k in range(len(arr)):
+                arr[k] = int(rng.integers(-128, 128))
+        s.cb_mult, s.cb_luma_mult, s.cb_offset = int(rng.integers(0, 256)), int(rng.integers(0, 256)), int(rng.integers(0, 512))
+        s.cr_mult, s.cr_luma_mult, s.cr_offset = int(rng.integers(0, 256)), int(rng.integers(0, 256)), int(rng.integers(0, 512))
+        s.overlap_flag = int(rng.integers(0, 2))
+        seg = GrainTableSegment.from_c(s)
+        rw = I.GrainRewriter([seg])
+        out = [rw.rewrite_packet(p, ts(k)) for k, p in enumerate(plain)]
+        assert len(E.decode(out)) == 3, trial
+        p = I.BitstreamParser()
+        for pk in out:
+            p.push_packet(pk)
+        hs = p.get_grain_headers()
+        assert [h.kind for h in hs] == [I.UPDATE_GRAIN] * 3
+        npl = 2 * s.ar_coeff_lag * (s.ar_coeff_lag + 1)
+        npc = npl + 1 if ny else npl
+        for h in hs:
+            g = h.params
+            assert g.scaling_points_y == seg.scaling_points_y and g.chroma_scaling_from_luma == csfl
+            assert g.scaling_points_cb == seg.scaling_points_cb[:ncb] and g.scaling_points_cr == seg.scaling_points_cr[:ncr]
+            assert (g.scaling_shift, g.ar_coeff_lag, g.ar_coeff_shift, g.grain_scale_shift, g.overlap_flag) == \
+                   (seg.scaling_shift, seg.ar_coeff_lag, seg.ar_coeff_shift, seg.grain_scale_shift, seg.overlap_flag)
+            assert g.ar_coeffs_y == (seg.ar_coeffs_y[:npl] if ny else [])
+            assert g.ar_coeffs_cb == (seg.ar_coeffs_cb[:npc] if (csfl or ncb) else [0])
+            assert g.ar_coeffs_cr == (seg.ar_coeffs_cr[:npc] if (csfl or ncr) else [0])
+            assert (g.cb_mult, g.cb_luma_mult, g.cb_offset) == ((seg.cb_mult, seg.cb_luma_mult, seg.cb_offset) if ncb else (0, 0, 0))
+            assert (g.cr_mult, g.cr_luma_mult, g.cr_offset) == ((seg.cr_mult, seg.cr_luma_mult, seg.cr_offset) if ncr else (0, 0, 0))
