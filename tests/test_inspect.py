@@ -9,7 +9,6 @@ Two kinds of evidence:
    (/root/reference/src/main.rs:713-772).
 """
 import math
-import os
 
 import pytest
 

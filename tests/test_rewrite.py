@@ -19,7 +19,7 @@ from helpers import ROOT
 from grav1synth_b200 import inspect as I
 from grav1synth_b200.grain_table import parse_grain_table
 from oracle import aom_pin
-from test_inspect import GA, GB, expected_view, header_view
+from test_inspect import GA, GB
 
 ok, why = aom_pin.available()
 needs_libaom = pytest.mark.skipif(not ok, reason="libaom pin unavailable: " + str(why))

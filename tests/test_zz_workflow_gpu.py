@@ -8,7 +8,6 @@ import json
 import os
 import struct
 
-import numpy as np
 import pytest
 
 from helpers import ROOT
