@@ -181,6 +181,28 @@ def reference_arm(args):
     up = run_libaom_sample(wl, 1)
     if up is not None:
         line["cpu_baseline"]["upstream_libaom"] = up
+    # Courtesy number, NOT what the reference does: its diff loop is single-threaded and its model update is sequential
+    # across frames.  One independent frame per host thread (ctypes releases the GIL) bounds what a frame-parallel
+    # rewrite of the reference could reach on this box.
+    try:
+        from concurrent.futures import ThreadPoolExecutor
+        workers = max(1, min(os.cpu_count() or 1, 256))
+
+        def one(i):
+            h = O.OracleDiffGenerator(24, 1, spec.bit_depth, spec.bit_depth, O.GRAM_REF_ORDER, O.EXP_LIBM)
+            h.diff_frame(*frames[i % 2])
+            h.close()
+
+        t1 = time.perf_counter()
+        with ThreadPoolExecutor(workers) as ex:
+            list(ex.map(one, range(workers)))
+        dtp = time.perf_counter() - t1
+        line["cpu_baseline"]["frame_parallel_courtesy"] = {
+            "value": workers / dtp, "unit": "frames/s", "cores": workers,
+            "sample": f"{workers} independent frame pairs, one per host thread, {dtp:.1f} s; per-frame work only "
+                      "(no sequential model combine) -- an upper bound for a hypothetical multi-threaded reference"}
+    except Exception as e:
+        line["cpu_baseline"]["frame_parallel_courtesy"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line), flush=True)
 
 
