@@ -23,7 +23,8 @@
 //  * UpscaledWidth is tracked, so that allow_intrabc and the loop-restoration parameters of a super-resolved frame
 //    follow the spec (5.9.2, 5.9.20);
 //  * show_existing_frame of a key frame refreshes the reference slots (7.21), which forward key frames rely on;
-//  * segmentation features are inherited from the primary reference frame when they are not re-sent (7.20).
+//  * segmentation features are inherited from the primary reference frame when they are not re-sent (7.20);
+//  * ref_order_hint[i] of an error-resilient frame replaces the slot's saved order hint (5.9.2).
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -942,10 +943,13 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
       (frame_type == SWITCH_FRAME || (frame_type == KEY_FRAME && show_frame)) ? 0xFFu : (unsigned)br.f(8);
   if ((!frame_is_intra || refresh_frame_flags != 0xFFu) && error_resilient_mode && s.order_hint_bits > 0) {
     for (int i = 0; i < NUM_REF_FRAMES; ++i) {
+      // spec 5.9.2: the signalled hint REPLACES the slot's saved hint (and invalidates the slot when it differs).  The
+      // reference saves the previous signalled value instead (frame.rs:355-362), which zeroes the saved hints the
+      // first time an error-resilient inter frame arrives and then mis-decides skip_mode_present.
       const uint64_t cur = br.f((unsigned)s.order_hint_bits);  // ref_order_hint[i]
-      big_ref_order_hint[i] = ref_order_hint[i];
+      if (cur != big_ref_order_hint[i]) big_ref_valid[i] = false;
+      big_ref_order_hint[i] = cur;
       ref_order_hint[i] = cur;
-      if (ref_order_hint[i] != big_ref_order_hint[i]) big_ref_valid[i] = false;
     }
   }
   bool allow_high_precision_mv = false, use_ref_frame_mvs = false;

