@@ -24,7 +24,8 @@
 //    follow the spec (5.9.2, 5.9.20);
 //  * show_existing_frame of a key frame refreshes the reference slots (7.21), which forward key frames rely on;
 //  * segmentation features are inherited from the primary reference frame when they are not re-sent (7.20);
-//  * ref_order_hint[i] of an error-resilient frame replaces the slot's saved order hint (5.9.2).
+//  * ref_order_hint[i] of an error-resilient frame replaces the slot's saved order hint (5.9.2);
+//  * with uniform tile spacing the tile counts are ceil(sb / tile size) as in 5.9.15 (the reference floors).
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -483,12 +484,15 @@ TileInfo tile_info(BitReader &br, bool use_128, uint32_t mi_cols, uint32_t mi_ro
     t.tile_cols_log2 = min_log2_tile_cols;
     while (t.tile_cols_log2 < max_log2_tile_cols && br.flag()) ++t.tile_cols_log2;
     const uint32_t tile_width_sb = (sb_cols + (1u << t.tile_cols_log2) - 1) >> t.tile_cols_log2;
-    t.tile_cols = sb_cols / tile_width_sb;  // the reference floors here (frame.rs:1106)
+    // spec 5.9.15 counts the tile starts, i.e. ceil(sbCols / tileWidthSb).  The reference floors (frame.rs:1106, :1121),
+    // which loses the last, narrower tile (7 superblock columns at log2 = 1 are 2 tiles, not 1) and with it the
+    // end-of-frame detection in tile_group_obu(); found by fuzzing resized libaom streams.
+    t.tile_cols = (sb_cols + tile_width_sb - 1) / tile_width_sb;
     const uint32_t min_log2_tile_rows = min_log2_tiles > t.tile_cols_log2 ? min_log2_tiles - t.tile_cols_log2 : 0;
     t.tile_rows_log2 = min_log2_tile_rows;
     while (t.tile_rows_log2 < max_log2_tile_rows && br.flag()) ++t.tile_rows_log2;
     const uint32_t tile_height_sb = (sb_rows + (1u << t.tile_rows_log2) - 1) >> t.tile_rows_log2;
-    t.tile_rows = sb_rows / tile_height_sb;
+    t.tile_rows = (sb_rows + tile_height_sb - 1) / tile_height_sb;
   } else {
     uint32_t widest = 0, start = 0, n = 0;
     while (start < sb_cols) {
@@ -802,6 +806,7 @@ struct g1s_inspect {
   Segmentation ref_segmentation[NUM_REF_FRAMES];
   std::vector<GrainHeader> headers;  // one per shown frame header, in stream order (parser.rs:155-158)
   uint64_t packets = 0, obus = 0;
+  uint32_t last_frame_width = 0, last_frame_height = 0;
   // rewriter (BitstreamParser::<true>, parser.rs:74-101): `write` mirrors every OBU into packet_out; `have_table`
   // is incoming_grain_header.is_some() (apply) vs None (remove)
   bool write = false, have_table = false;
@@ -1013,6 +1018,8 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
   }
   (void)use_ref_frame_mvs;
   const uint32_t upscaled_width_for_refs = true_upscaled_width;
+  last_frame_width = fsize.width;
+  last_frame_height = fsize.height;
   const uint32_t mi_cols = 2 * ((fsize.width + 7) >> 3), mi_rows = 2 * ((fsize.height + 7) >> 3);
   if (!(s.reduced_still_picture_header || disable_cdf_update)) br.flag();  // disable_frame_end_update_cdf
   fh.tile_info = tile_info(br, s.use_128x128_superblock, mi_cols, mi_rows);
@@ -1475,6 +1482,10 @@ int g1s_inspect_stream_info(const g1s_inspect *h, g1s_stream_info *info) {
   info->reduced_still_picture_header = s.reduced_still_picture_header;
   info->packets = h->packets;
   info->obus = h->obus;
+  info->last_frame_width = (int32_t)h->last_frame_width;
+  info->last_frame_height = (int32_t)h->last_frame_height;
+  info->last_tile_cols = (int32_t)h->cur_tile_info.tile_cols;
+  info->last_tile_rows = (int32_t)h->cur_tile_info.tile_rows;
   return G1S_OK;
 }
 

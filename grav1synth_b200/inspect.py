@@ -30,7 +30,8 @@ class CStreamInfo(C.Structure):
         "have_sequence_header", "seq_profile", "bit_depth", "monochrome", "ss_x", "ss_y", "max_frame_width",
         "max_frame_height", "film_grain_params_present", "color_primaries", "transfer_characteristics",
         "matrix_coefficients", "color_range", "order_hint_bits", "reduced_still_picture_header", "reserved_")] + \
-        [("packets", C.c_uint64), ("obus", C.c_uint64)]
+        [("packets", C.c_uint64), ("obus", C.c_uint64)] + \
+        [(n, C.c_int32) for n in ("last_frame_width", "last_frame_height", "last_tile_cols", "last_tile_rows")]
 
 
 _bound = False

@@ -242,6 +242,8 @@ typedef struct g1s_stream_info {
   int32_t color_primaries, transfer_characteristics, matrix_coefficients, color_range;
   int32_t order_hint_bits, reduced_still_picture_header, reserved_;
   uint64_t packets, obus;
+  /* the most recent frame header: coded size (after super-resolution down-scaling) and tile grid */
+  int32_t last_frame_width, last_frame_height, last_tile_cols, last_tile_rows;
 } g1s_stream_info;
 
 int g1s_inspect_create(g1s_inspect **out);

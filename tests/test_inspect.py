@@ -142,6 +142,11 @@ def test_tile_info_vectors():
     assert out[:4] == [1, 1, 0, 0]
     out, _ = probe("tile_info", B().push_bool(True).push_bool(False).push_bool(False), [1, 480, 272])  # 128x128 SB
     assert out[:4] == [1, 1, 0, 0]
+    # not from the reference: 7 superblock columns split at log2 = 1 are tiles of 4 + 3, i.e. TWO tiles (spec 5.9.15
+    # counts tile starts; the reference's floor division, frame.rs:1106, would say one)
+    b = B().push_bool(True).push_bool(True).push_bool(False).push_bool(False).push_bits(0, 1).push_bits(0, 2)
+    out, _ = probe("tile_info", b, [0, 100, 56])
+    assert out[:4] == [2, 1, 1, 0]
 
 
 def test_quantization_params_vectors():

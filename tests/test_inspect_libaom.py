@@ -94,6 +94,10 @@ ENCODER_VARIANTS = {
     # hidden alt-refs under error resilience: every inter frame re-signals ref_order_hint[], which must REPLACE the saved
     # hints (the reference keeps stale ones, frame.rs:355-362, and then mis-reads skip_mode_present) -- found by fuzzing
     "error_resilient_altref": dict(lag=19, opts={}, cfg={12: 1}, frames=12),
+    # 640 wide resized to 427: 7 superblock columns in 2 tiles (4 + 3), two tile groups with libaom's redundant frame
+    # header between them -- the tile count must be the spec's ceil, not the reference's floor (found by fuzzing)
+    "resized_uneven_tiles_redundant_headers": dict(lag=0, opts={"tile-columns": "1", "num-tile-groups": "2"},
+                                                   cfg={12: 1, 16: 1, 17: 12, 18: 12}, size=(640, 360), frames=6),
     "sb128_no_global_motion": dict(lag=None, opts={"sb-size": "128", "enable-global-motion": "0"}),
     "screen_content_palette": dict(lag=None, opts={"tune-content": "screen"}),
     "full_hd": dict(lag=None, opts={}, size=(1920, 1080), frames=3),

@@ -58,6 +58,9 @@ def test_remove_gives_libaoms_own_grainless_stream(vector, lag):
     ("high_profile_444_10bit", {}, dict(chroma444=True, bit_depth=10)),
     ("superres", {}, dict(cfg_words={19: 1, 20: 12, 21: 12})),
     ("error_resilient_low_delay", {}, dict(cfg_words={12: 1}, lag_in_frames=0)),
+    # uneven tiles + redundant frame headers between the tile groups: every copy of the header must be rewritten
+    ("resized_uneven_tiles_redundant_headers", {"tile-columns": "1", "num-tile-groups": "2"},
+     dict(cfg_words={12: 1, 16: 1, 17: 12, 18: 12}, lag_in_frames=0)),
 ])
 def test_remove_and_apply_on_other_stream_structures(name, opts, kw):
     from oracle import aom_encode as E
