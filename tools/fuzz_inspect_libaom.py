@@ -22,7 +22,8 @@ OPTS = [("tile-columns", ["0", "1", "2"]), ("tile-rows", ["0", "1"]), ("num-tile
         ("lossless", ["0", "0", "0", "1"]), ("cdf-update-mode", ["0", "1", "2"]), ("reduced-tx-type-set", ["0", "1"]), ("auto-alt-ref", ["0", "1"]),
         ("enable-intrabc", ["0", "1"]), ("enable-palette", ["0", "1"]), ("frame-parallel", ["0", "1"]), ("aq-mode", ["0", "1", "2", "3"]),
         ("enable-warped-motion", ["0", "1"]), ("enable-ref-frame-mvs", ["0", "1"]), ("error-resilient-mode", None)]
-CFG = [(12, [0, 1]), (16, [0, 0, 1, 2, 3]), (19, [0, 0, 1, 2]), (45, [0, 1]), (49, [0, 3]), (52, [0, 0, 0, 1]), (24, [0, 1, 3])]
+# rc_resize_mode 2 (random, a libaom test mode) is left out: libaom 3.13.1 itself corrupts its heap with it on small frames
+CFG = [(12, [0, 1]), (16, [0, 0, 1, 3]), (19, [0, 0, 1, 2]), (45, [0, 1]), (49, [0, 3]), (52, [0, 0, 0, 1]), (24, [0, 1, 3])]
 t0 = time.time(); n = bad = 0
 while time.time() - t0 < float(sys.argv[1]):
     opts = {}
