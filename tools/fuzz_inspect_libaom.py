@@ -4,8 +4,9 @@ stream must parse to the signalled parameters, lose its grain under `remove`, an
 
     python tools/fuzz_inspect_libaom.py SECONDS [SEED]
 
-Round 1: found the stale ref_order_hint[] handling under error resilience + alt-refs (inherited from the reference's
-parser, fixed to follow the spec); 0 failures afterwards.
+Round 1 (about 1 200 configurations over four runs): found the stale ref_order_hint[] handling under error resilience +
+alt-refs and the floored uniform tile count (both inherited from the reference's parser, both fixed to follow the
+spec); the last run, 290 configurations, had no failure.
 """
 import sys, time, random
 import os
