@@ -55,14 +55,18 @@ def _zero_frame_mid_stream():
     return list(frames[:2]) + [(frames[2][1], frames[2][1])] + list(frames[2:])
 
 
-def _random(seed):
+def _random_spec(seed):
     r = np.random.default_rng(1000 + seed)
     w = int(r.integers(40, 420))
     h = int(r.integers(40, 260))
     bd = int(r.choice([8, 10, 12]))
-    spec = SynthSpec(w, h, bd, textured=float(r.choice([0.0, 0.3, 0.6, 0.9])), sigma0=float(r.uniform(0.8, 2.5)),
+    return SynthSpec(w, h, bd, textured=float(r.choice([0.0, 0.3, 0.6, 0.9])), sigma0=float(r.uniform(0.8, 2.5)),
                      sigma1=float(r.uniform(0.0, 2.0)), ar_strength=float(r.uniform(0, 0.5)), seed=seed)
-    return [make_pair_numpy(spec, k) for k in range(2)], bd
+
+
+def _random(seed):
+    spec = _random_spec(seed)
+    return [make_pair_numpy(spec, k) for k in range(2)], spec.bit_depth
 
 
 def _long():
@@ -125,7 +129,7 @@ CASES["flat_everything"] = (_flat_everything, 8, (1, 1), (24, 1))
 CASES["single_block"] = (_single_block, 8, (1, 1), (24, 1))
 CASES["zero_frame_mid_stream"] = (_zero_frame_mid_stream, 8, (1, 1), (24, 1))
 for _s in range(8):
-    CASES[f"random_{_s}"] = (lambda s=_s: _random(s)[0], _random(_s)[1], (1, 1), (24, 1))
+    CASES[f"random_{_s}"] = (lambda s=_s: _random(s)[0], _random_spec(_s).bit_depth, (1, 1), (24, 1))
 CASES["long_12_frames"] = (_long, 8, (1, 1), (24, 1))
 CASES["hd_1080p_frame"] = (_hd_frame, 8, (1, 1), (24, 1))
 CASES["uhd_4k_10bit_frame"] = (_uhd_frame, 10, (1, 1), (24, 1))
