@@ -126,3 +126,15 @@ def test_segment_cut_matches_oracle():
         h.consume_record(rl.pack(pairs, r["nobs"], r["num_flat"], r["luma_sum"], r["rsum"], r["rsq"], scores, flat))
     want, got = g.finish(), h.finish()
     assert len(want) >= 2 and got == want
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under grav1synth_b200/ may import, load or link it (and libg1s.so must not
+    carry its symbols)."""
+    import glob
+    import subprocess
+    for path in glob.glob(os.path.join(ROOT, "grav1synth_b200", "*.py")):
+        src = open(path).read()
+        assert "import oracle" not in src and "from oracle" not in src and "libg1s_oracle" not in src, path
+    syms = subprocess.run(["nm", "-D", "--defined-only", D.LIB_PATH], capture_output=True, text=True).stdout
+    assert "g1s_oracle" not in syms and "aom_noise_model" not in syms
