@@ -32,6 +32,8 @@ def test_struct_sizes_match_header():
     assert C.sizeof(abi.CSegment) == 8 + 8 + 16 + 8 + 28 + 20 + 20 + 24 + 25 + 25 + 2  # = 184, 8-byte aligned
     assert C.sizeof(abi.CFrame) == 3 * 8 + 3 * 8 + 8
     assert C.sizeof(abi.CDiffConfig) == 16 + 4 * 16
+    from grav1synth_b200.inspect import CStreamInfo
+    assert C.sizeof(CStreamInfo) == 16 * 4 + 2 * 8 + 4 * 4   # g1s_stream_info
 
 
 def test_writer_matches_reference_fixture(tmp_path):
