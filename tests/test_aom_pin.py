@@ -167,3 +167,32 @@ def test_nan_correlation_follows_rust_semantics_not_c():
     assert want["ar_coeff_shift"] == 6 and got["ar_coeff_shift"] > 6
     scale = 1 << (got["ar_coeff_shift"] - 6)
     assert all(abs(g - w * scale) <= scale for g, w in zip(got["ar_coeffs_y"], want["ar_coeffs_y"]))
+
+
+def test_grain_tables_round_trip_through_libaoms_reader_and_writer(tmp_path):
+    """aom_film_grain_table_read + aom_film_grain_table_write (libaom's own, reached through the symbol table) on the
+    tables g1s_write_grain_table produced: byte-identical, so the text format is exactly libaom's -- including the
+    reference fixture tests/example-table.tbl (short coefficient lists at lag 0)."""
+    import ctypes as C
+    import glob
+    ok, path = P.available()
+    if not ok:
+        pytest.skip("libaom pin unavailable: " + path)
+    syms = P._elf_symtab(path, ("aom_film_grain_table_read", "aom_film_grain_table_write", "aom_film_grain_table_free"))
+    assert len(syms) == 3
+    base = P._load_base(path)
+    rd = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_void_p)(base + syms["aom_film_grain_table_read"])
+    wr = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_void_p)(base + syms["aom_film_grain_table_write"])
+    fr = C.CFUNCTYPE(None, C.c_void_p)(base + syms["aom_film_grain_table_free"])
+    from test_oracle import EXAMPLE_TABLE
+    example = tmp_path / "example-table.tbl"
+    example.write_text(EXAMPLE_TABLE)
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.tbl"))) + [str(example)]
+    assert len(files) >= 8
+    for f in files:
+        table, err = C.create_string_buffer(64), C.create_string_buffer(8192)   # aom_film_grain_table_t, error info
+        assert rd(table, f.encode(), err) == 0, f
+        out = tmp_path / "roundtrip.tbl"
+        assert wr(table, str(out).encode(), err) == 0, f
+        fr(table)
+        assert out.read_bytes() == open(f, "rb").read(), f
