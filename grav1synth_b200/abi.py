@@ -28,6 +28,7 @@ G1S_E_STATE = -6
 G1S_E_IO = -7
 G1S_E_STREAM = -8
 
+GRAM_EXACT_INT, GRAM_REF_ORDER = 0, 1
 MODE_FULL = 0
 MODE_PRODUCER = 1
 MODE_CONSUMER = 2
@@ -86,7 +87,10 @@ class CDiffConfig(C.Structure):
         ("gram_kernel", C.c_int32),
         ("host_threads", C.c_int32),
         ("host_narrow", C.c_int32),
-        ("reserved_", C.c_int32 * 3),
+        ("gram_order", C.c_int32),
+        ("n_devices", C.c_int32),
+        ("device_ids", C.c_int32 * 8),
+        ("reserved_", C.c_int32 * 4),
     ]
 
 

@@ -178,7 +178,7 @@ struct Slot {
   uint8_t *d_records = nullptr;
   uint8_t *h_records = nullptr;  // pinned
   cudaEvent_t done = nullptr, k0_beg = nullptr, k0_end = nullptr, kr_beg = nullptr, k1_beg = nullptr, k1_end = nullptr,
-              copied = nullptr, computed = nullptr;
+              ks_beg = nullptr, ks_end = nullptr, copied = nullptr, computed = nullptr;
   int count = 0;                 // frames staged
   int host_frames = 0;           // of which need the H2D copy (contiguous prefix is not required)
   bool in_flight = false;
@@ -231,7 +231,8 @@ struct g1s_diff {
   ResidualStore rstore{};
   bool tensor_path = false;  // residual_kernel + gram_imma_kernel available for this stream
   // counters
-  double kernels_launched = 0, k1_ms = 0, k1_launches = 0, k0_ms = 0, k0_launches = 0, frames_done = 0, kr_ms = 0;
+  double kernels_launched = 0, k1_ms = 0, k1_launches = 0, k0_ms = 0, k0_launches = 0, frames_done = 0, kr_ms = 0,
+         ks_ms = 0;
 };
 
 namespace {
@@ -256,6 +257,7 @@ FrameRecordView view_of(const g1s_diff *d, const uint8_t *rec) {
   v.rsum = reinterpret_cast<const int32_t *>(rec + d->rl.off_rsum);
   v.rsq = reinterpret_cast<const uint32_t *>(rec + d->rl.off_rsq);
   v.flat = rec + d->rl.off_flat;
+  v.gramf = d->cfg.gram_order == G1S_GRAM_REF_ORDER ? reinterpret_cast<const double *>(rec + d->rl.off_gramf) : nullptr;
   return v;
 }
 
@@ -353,6 +355,13 @@ int submit(g1s_diff *d, Slot &s) {
     launch_gram_generic(s.d_descs, s.count, d->geom, s.d_records, d->rl, /*only_overflow=*/false, st);
     CU_TRY(d, cudaEventRecord(s.k1_end, st));
   }
+  if (d->cfg.gram_order == G1S_GRAM_REF_ORDER) {
+    // strict mode: the same sums once more, term by term in the reference's order and rounding (f64 chains)
+    CU_TRY(d, cudaEventRecord(s.ks_beg, st));
+    launch_gram_strict(s.d_descs, s.count, d->geom, s.d_records, d->rl, st);
+    CU_TRY(d, cudaEventRecord(s.ks_end, st));
+    gram_launches += 1;
+  }
   CU_TRY(d, cudaGetLastError());
   // the read-back rides its own stream so the next batch's kernels start right behind this batch's
   CU_TRY(d, cudaEventRecord(s.computed, st));
@@ -374,6 +383,8 @@ int retire(g1s_diff *d, Slot &s) {
   if (cudaEventElapsedTime(&ms, s.k0_beg, s.k0_end) == cudaSuccess) d->k0_ms += ms;
   if (cudaEventElapsedTime(&ms, s.k1_beg, s.k1_end) == cudaSuccess) d->k1_ms += ms;
   if (cudaEventElapsedTime(&ms, s.kr_beg, s.k1_beg) == cudaSuccess) d->kr_ms += ms;
+  if (d->cfg.gram_order == G1S_GRAM_REF_ORDER && cudaEventElapsedTime(&ms, s.ks_beg, s.ks_end) == cudaSuccess)
+    d->ks_ms += ms;
   d->folder->wait(s.fold_ticket);  // the slot's previous batch must have left the fold thread
   s.fold_ticket = fold_records(d, s.h_records, s.count, d->rl.bytes, s.latest);
   d->frames_done += s.count;
@@ -454,6 +465,10 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   }
   if (cfg->mode < G1S_MODE_FULL || cfg->mode > G1S_MODE_CONSUMER) {
     g_create_error = "unknown mode";
+    return G1S_E_ARG;
+  }
+  if (cfg->gram_order != G1S_GRAM_EXACT_INT && cfg->gram_order != G1S_GRAM_REF_ORDER) {
+    g_create_error = "unknown gram_order";
     return G1S_E_ARG;
   }
   const bool consumer = cfg->mode == G1S_MODE_CONSUMER;
@@ -594,6 +609,8 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     CU_NEW(cudaEventCreate(&s.kr_beg));
     CU_NEW(cudaEventCreate(&s.k1_beg));
     CU_NEW(cudaEventCreate(&s.k1_end));
+    CU_NEW(cudaEventCreate(&s.ks_beg));
+    CU_NEW(cudaEventCreate(&s.ks_end));
   }
 #undef CU_NEW
   *out = d.release();
@@ -769,6 +786,8 @@ size_t g1s_record_layout(int32_t num_blocks, size_t off[8]) {
   return rl.bytes;
 }
 
+size_t g1s_record_gramf_offset(int32_t num_blocks) { return RecordLayout::make(num_blocks).off_gramf; }
+
 size_t g1s_diff_record_bytes(const g1s_diff *d) { return d ? d->rl.bytes : 0; }
 
 int g1s_diff_set_record_tap(g1s_diff *d, g1s_record_fn fn, void *user) {
@@ -850,7 +869,7 @@ void g1s_diff_destroy(g1s_diff *d) {
     if (s.h_descs) cudaFreeHost(s.h_descs);
     if (s.d_records) cudaFree(s.d_records);
     if (s.h_records) cudaFreeHost(s.h_records);
-    for (cudaEvent_t e : {s.done, s.k0_beg, s.k0_end, s.kr_beg, s.k1_beg, s.k1_end, s.copied, s.computed})
+    for (cudaEvent_t e : {s.done, s.k0_beg, s.k0_end, s.kr_beg, s.k1_beg, s.k1_end, s.ks_beg, s.ks_end, s.copied, s.computed})
       if (e) cudaEventDestroy(e);
   }
   for (cudaEvent_t e : d->marks)
@@ -867,9 +886,9 @@ int64_t g1s_diff_frames_pushed(const g1s_diff *d) { return d ? d->pushed : 0; }
 
 int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n) {
   if (!d || !out) return G1S_E_ARG;
-  const double v[9] = {d->kernels_launched, d->k1_ms,       d->k1_launches, d->k0_ms,          d->k0_launches,
-                       d->frames_done,      d->tma_batches, d->kr_ms,       d->vector_batches};
-  for (size_t i = 0; i < n && i < 9; ++i) out[i] = v[i];
+  const double v[10] = {d->kernels_launched, d->k1_ms,       d->k1_launches, d->k0_ms,          d->k0_launches,
+                        d->frames_done,      d->tma_batches, d->kr_ms,       d->vector_batches, d->ks_ms};
+  for (size_t i = 0; i < n && i < 10; ++i) out[i] = v[i];
   return G1S_OK;
 }
 

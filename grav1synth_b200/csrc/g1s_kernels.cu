@@ -37,6 +37,7 @@ RecordLayout RecordLayout::make(int nb) {
   r.off_flat = take(nb);
   r.off_ovf_count = take(sizeof(int64_t));
   r.off_ovf = take(3 * (size_t)nb);
+  r.off_gramf = take(sizeof(double) * 3 * kPairs);
   r.bytes = (o + 15) & ~size_t(15);
   return r;
 }

@@ -47,9 +47,11 @@ struct FlatConsts {
 //   uint8  flat[nb]            0 / 1 / 255 flat flags (padded to 8 bytes)
 //   int64  ovf_count           blocks whose residual tile left the int8 range (device bookkeeping)
 //   uint8  ovf[3][nb]          per plane: block must be accumulated by the generic (int32) kernel
+//   double gramf[3][kPairs]    strict mode only (gram_order = reference order): the same tap pairs accumulated
+//                              term by term as RN(acc + RN(product / 255^2)) in the reference's pixel order
 struct RecordLayout {
   size_t off_gram, off_nobs, off_num_flat, off_luma_sum, off_rsum, off_rsq, off_score, off_flat, off_ovf_count,
-      off_ovf, bytes;
+      off_ovf, off_gramf, bytes;
   static RecordLayout make(int nb);
 };
 
@@ -61,6 +63,10 @@ void launch_flat_select(int nframes, const Geometry &g, uint8_t *records, const 
 // only_overflow = true: just the blocks the tensor-core kernel flagged (Gram sums and statistics).
 void launch_gram_generic(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
                          const RecordLayout &rl, bool only_overflow, cudaStream_t st);
+// Strict mode (g1s_diff_config.gram_order = G1S_GRAM_REF_ORDER): fills RecordLayout::off_gramf with the f64 sums in
+// the reference's accumulation order; needs the final flat flags.  Any subsampling, any residual magnitude.
+void launch_gram_strict(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
+                        const RecordLayout &rl, cudaStream_t st);
 // Engine-owned s8 planes of a batch, written by residual_kernel and read (through TMA boxes) by
 // gram_imma_kernel: per frame the residual of Y, Cb, Cr and, for chroma's luma tap, the sum of the
 // co-sited 2x2 luma residuals split as 8*hi + lo.  Pitches are multiples of 16 bytes, plane offsets of 256.

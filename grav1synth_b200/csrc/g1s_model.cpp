@@ -333,6 +333,19 @@ void NoiseModel::load_equations(int c, const FrameRecordView &rec, ChannelState 
   const int n = st.eqns.n;
   const int64_t *G = rec.gram + (size_t)c * kPairs;
   const double nss = c ? (double)(1 << (g_.ss_x + g_.ss_y)) : 1.0;
+  if (rec.gramf) {
+    // strict mode: the device accumulated every entry term by term in the reference's order (gram_reforder_kernel);
+    // chains through the luma tap were summed on the unscaled integers, and RN commutes with the power-of-two scale
+    const double *F = rec.gramf + (size_t)c * kPairs;
+    auto at = [&](int i, int j) { return i <= j ? F[pair_index(i, j)] : F[pair_index(j, i)]; };
+    for (int i = 0; i < n; ++i) {
+      const double si = i == 24 ? nss : 1.0;
+      for (int j = 0; j < n; ++j) st.eqns.A[i * n + j] += at(i, j) / (si * (j == 24 ? nss : 1.0));
+      st.eqns.b[i] += at(i, 25) / si;
+    }
+    st.num_observations += rec.nobs[c];
+    return;
+  }
   for (int i = 0; i < n; ++i) {
     const double si = i == 24 ? nss : 1.0;
     for (int j = 0; j < n; ++j) {

@@ -25,6 +25,7 @@ struct FrameRecordView {
   const int32_t *rsum;       // [3][nb]
   const uint32_t *rsq;       // [3][nb]
   const uint8_t *flat;       // [nb]
+  const double *gramf = nullptr;  // [3][351] strict mode: reference-order f64 sums of product / 255^2 (else null)
 };
 
 enum class NoiseStatus { Ok, DifferentType, Error };

@@ -27,7 +27,7 @@ RECORD_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t)
 EXPORTS = [
     "g1s_abi_version", "g1s_diff_create", "g1s_diff_push_frame", "g1s_diff_push_frame_device", "g1s_diff_flush",
     "g1s_diff_finish", "g1s_diff_destroy", "g1s_diff_last_error", "g1s_diff_frames_pushed",
-    "g1s_diff_get_counters", "g1s_diff_mark", "g1s_diff_marks_elapsed_ms", "g1s_record_layout", "g1s_diff_record_bytes", "g1s_diff_set_record_tap",
+    "g1s_diff_get_counters", "g1s_diff_mark", "g1s_diff_marks_elapsed_ms", "g1s_record_layout", "g1s_record_gramf_offset", "g1s_diff_record_bytes", "g1s_diff_set_record_tap",
     "g1s_diff_consume_record", "g1s_diff_consume_records", "g1s_digest_bytes", "g1s_diff_set_digest_sink",
     "g1s_diff_digest_count", "g1s_diff_wait_retired", "g1s_diff_consume_digests", "g1s_diff_consume_digests_borrowed", "g1s_diff_digest_from_record", "g1s_write_grain_table", "g1s_format_grain_table",
     "g1s_narrow_row",
@@ -66,6 +66,8 @@ def lib() -> C.CDLL:
         L.g1s_diff_marks_elapsed_ms.restype = C.c_double
         L.g1s_record_layout.argtypes = [C.c_int32, C.POINTER(C.c_size_t)]
         L.g1s_record_layout.restype = C.c_size_t
+        L.g1s_record_gramf_offset.argtypes = [C.c_int32]
+        L.g1s_record_gramf_offset.restype = C.c_size_t
         L.g1s_diff_record_bytes.argtypes = [C.c_void_p]
         L.g1s_diff_record_bytes.restype = C.c_size_t
         L.g1s_diff_set_record_tap.argtypes = [C.c_void_p, RECORD_FN, C.c_void_p]
@@ -96,6 +98,7 @@ class RecordLayout:
         self.bytes = int(lib().g1s_record_layout(num_blocks, off))
         self.nb = num_blocks
         self.off = dict(zip(self.NAMES, [int(o) for o in off]))
+        self.off["gramf"] = int(lib().g1s_record_gramf_offset(num_blocks))
 
     def unpack(self, rec: np.ndarray) -> dict:
         nb, o = self.nb, self.off
@@ -109,9 +112,11 @@ class RecordLayout:
             "rsq": b[o["rsq"]:o["rsq"] + 12 * nb].view(np.uint32).reshape(3, nb),
             "score": b[o["score"]:o["score"] + 4 * nb].view(np.float32),
             "flat": b[o["flat"]:o["flat"] + nb],
+            # strict mode only (zeros otherwise): reference-order f64 sums of product / 255^2 over the same tap pairs
+            "gramf": b[o["gramf"]:o["gramf"] + 8 * 3 * 351].view(np.float64).reshape(3, 351),
         }
 
-    def pack(self, gram, nobs, num_flat, luma_sum, rsum, rsq, score, flat) -> np.ndarray:
+    def pack(self, gram, nobs, num_flat, luma_sum, rsum, rsq, score, flat, gramf=None) -> np.ndarray:
         rec = np.zeros(self.bytes, np.uint8)
         u = self.unpack(rec)
         u["gram"][:] = gram
@@ -122,6 +127,8 @@ class RecordLayout:
         u["rsq"][:] = rsq
         u["score"][:] = score
         u["flat"][:] = flat
+        if gramf is not None:
+            u["gramf"][:] = gramf
         return rec
 
 
@@ -144,7 +151,7 @@ class DiffGenerator:
     def __init__(self, fps_num: int, fps_den: int, source_bit_depth: int, denoised_bit_depth: int, width: int,
                  height: int, ss_x: int = 1, ss_y: int = 1, monochrome: bool = False, device: int = 0,
                  batch_frames: int = 0, mode: int = abi.MODE_FULL, gram_kernel: int = 0, host_threads: int = 0,
-                 host_narrow: bool = False):
+                 host_narrow: bool = False, gram_order: int = 0, devices: Optional[Sequence[int]] = None):
         self._L = lib()
         cfg = CDiffConfig()
         cfg.fps_num, cfg.fps_den = fps_num, fps_den
@@ -154,6 +161,11 @@ class DiffGenerator:
         cfg.gram_kernel = gram_kernel
         cfg.host_threads = host_threads
         cfg.host_narrow = int(host_narrow)
+        cfg.gram_order = int(gram_order)  # abi.GRAM_EXACT_INT (fast) / abi.GRAM_REF_ORDER (strict: the reference's integers)
+        if devices is not None and len(devices) > 1:
+            cfg.n_devices = len(devices)
+            for i, dv in enumerate(devices):
+                cfg.device_ids[i] = int(dv)
         self.cfg = cfg
         h = C.c_void_p()
         rc = self._L.g1s_diff_create(C.byref(cfg), C.byref(h))
@@ -279,10 +291,10 @@ class DiffGenerator:
         return float(self._L.g1s_diff_marks_elapsed_ms(self._h))
 
     def counters(self) -> dict:
-        out = (C.c_double * 9)()
-        self._check(self._L.g1s_diff_get_counters(self._h, out, 9))
+        out = (C.c_double * 10)()
+        self._check(self._L.g1s_diff_get_counters(self._h, out, 10))
         k = ("kernels_launched", "gram_ms", "gram_launches", "flat_ms", "flat_launches", "frames_done", "tma_batches",
-             "residual_ms", "vector_batches")
+             "residual_ms", "vector_batches", "strict_ms")
         return dict(zip(k, [float(v) for v in out]))
 
 

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define G1S_ABI_VERSION 1
+#define G1S_ABI_VERSION 2
 
 /* Capacities fixed by the AV1 film-grain syntax; av1_grain::NUM_Y_POINTS etc. as
  * imported at /root/reference/src/parser/grain.rs:2 and used at :26-49. */
@@ -51,7 +51,7 @@ enum g1s_status {
   G1S_E_ARG = -1,         /* bad argument / unsupported configuration            */
   G1S_E_DIMS = -2,        /* source and denoised frame dimensions differ          */
   G1S_E_CUDA = -3,        /* CUDA runtime failure or no device (no CPU fallback)  */
-  G1S_E_NCCL = -4,        /* reserved for the multi-process merge                 */
+  G1S_E_NCCL = -4,        /* multi-device handle: a peer device failed / is unusable */
   G1S_E_NOMEM = -5,
   G1S_E_STATE = -6,       /* call after finish, or capacity too small             */
   G1S_E_IO = -7,
@@ -106,6 +106,16 @@ typedef struct g1s_frame {
  * device work) with g1s_diff_consume_record. */
 enum g1s_mode { G1S_MODE_FULL = 0, G1S_MODE_PRODUCER = 1, G1S_MODE_CONSUMER = 2 };
 
+/* How the AR normal equations (A[i][j] += buf[i]*buf[j] / 255^2, the inner loop behind diff_frame,
+ * src/main.rs:442) are accumulated.
+ *   EXACT_INT  exact integer sums on the int8 tensor cores, one division per entry at the end.  More accurate
+ *              than the reference and ~1e-13 away from it; the grain table can differ from the reference's in
+ *              the choice of scaling points where fit_piecewise meets a tie (about 5 % of streams).
+ *   REF_ORDER  strict mode: every entry is accumulated term by term in f64, in the reference's pixel order and
+ *              with its roundings (gram_reforder_kernel), so every integer of every table equals the
+ *              reference's.  FP64-bound, roughly 20x slower than EXACT_INT, still >1000x the CPU. */
+enum g1s_gram_order { G1S_GRAM_EXACT_INT = 0, G1S_GRAM_REF_ORDER = 1 };
+
 typedef struct g1s_diff_config {
   int64_t fps_num, fps_den;     /* Rational64 passed to DiffGenerator::new           */
   int32_t src_bit_depth;        /* 8..16, bit depth of the source stream             */
@@ -124,8 +134,16 @@ typedef struct g1s_diff_config {
                                    `>> (bit_depth - 8)` of frame_into_u8, which is all the path ever reads) by the
                                    staging threads, halving the bytes that cross PCIe; results are identical.
                                    Such a handle does not take device frames.  Default 0.   */
-  int32_t reserved_[3];
+  int32_t gram_order;           /* enum g1s_gram_order; default 0 = EXACT_INT (fast)                  */
+  int32_t n_devices;            /* 0 or 1: one GPU (`device`).  2..G1S_MAX_DEVICES: ONE handle drives that many GPUs
+                                   of this process: batches of frames are dealt round-robin to
+                                   device_ids[0..n_devices), every device runs the kernels and the per-frame half of
+                                   the model, the per-frame digests are folded in frame order on the caller's
+                                   process.  Same table as one GPU.  mode must be G1S_MODE_FULL.          */
+  int32_t device_ids[8];        /* CUDA ordinals, used when n_devices >= 2                              */
+  int32_t reserved_[4];
 } g1s_diff_config;
+#define G1S_MAX_DEVICES 8
 
 typedef struct g1s_diff g1s_diff;
 
@@ -166,7 +184,8 @@ int64_t g1s_diff_frames_pushed(const g1s_diff *d);
  * out[2] = its launch count, out[3] = device ms of the flat-block kernel,
  * out[4] = its launch count, out[5] = frames fully processed, out[6] = batches that took
  * the int8 tensor-core path (residual kernel + TMA-fed Gram kernel), out[7] = device ms of the
- * residual kernel, out[8] = batches whose planes were 16-byte aligned (128-bit loads). */
+ * residual kernel, out[8] = batches whose planes were 16-byte aligned (128-bit loads), out[9] = device ms of the
+ * strict-mode (reference-order) Gram kernel. */
 int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n);
 
 /* Records CUDA event `which` (0 or 1) on the engine's kernel stream; g1s_diff_marks_elapsed_ms returns the
@@ -182,6 +201,10 @@ double g1s_diff_marks_elapsed_ms(g1s_diff *d);
  * flat[nb] u8.  g1s_record_layout fills off[0..7] with the byte offsets of those eight
  * arrays in that order and returns the record size. */
 size_t g1s_record_layout(int32_t num_blocks, size_t off[8]);
+/* Strict mode (gram_order = G1S_GRAM_REF_ORDER) adds gramf[3][351] f64 to the record: the same tap pairs as gram,
+ * accumulated term by term as RN(acc + RN(product / 255^2)) in the reference's pixel order, products through the
+ * luma tap unscaled.  Byte offset of that array (zeros in EXACT_INT mode). */
+size_t g1s_record_gramf_offset(int32_t num_blocks);
 size_t g1s_diff_record_bytes(const g1s_diff *d);
 typedef void (*g1s_record_fn)(void *user, int64_t frame_index, const void *record, size_t bytes);
 /* Called on the caller's thread (inside push/flush/finish) once per frame, in frame

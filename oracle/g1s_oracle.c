@@ -1064,6 +1064,16 @@ int64_t g1s_oracle_last_gram(const g1s_oracle *o, int c, int64_t *G) {
   memcpy(G, o->last_gram[c], sizeof(int64_t) * 26 * 26);
   return o->last_gram_nobs[c];
 }
+/* The normal equations add_block_observations left for the most recent frame: A [n][n] row-major and b [n]
+ * (n = 24 luma, 25 chroma), in whatever accumulation mode the handle runs.  In G1SO_GRAM_REF_ORDER these are the
+ * reference's own per-term f64 sums: what the engine's strict mode (gram_reforder_kernel) must reproduce bit for bit. */
+int g1s_oracle_last_eqns(const g1s_oracle *o, int c, double *A, double *b) {
+  const noise_state *s = &o->latest[c];
+  const int n = s->eqns.n;
+  memcpy(A, s->eqns.A, sizeof(double) * n * n);
+  memcpy(b, s->eqns.b, sizeof(double) * n);
+  return n;
+}
 /* state dump for debugging/tests: which = 0 latest, 1 combined */
 void g1s_oracle_get_state(const g1s_oracle *o, int which, int c, double *ar_x, double *ar_gain, double *str_x,
                           int64_t *nobs) {

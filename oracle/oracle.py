@@ -60,6 +60,7 @@ def lib() -> C.CDLL:
         L.g1s_oracle_get_state.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]
         L.g1s_oracle_exp_fixed.restype = C.c_double
+        L.g1s_oracle_last_eqns.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.g1s_oracle_exp_fixed.argtypes = [C.c_double]
         L.g1s_oracle_write_table.argtypes = [C.POINTER(CSegment), C.c_size_t, C.c_char_p]
         _lib = L
@@ -130,6 +131,14 @@ class OracleDiffGenerator:
         G = np.zeros((26, 26), np.int64)
         nobs = self._L.g1s_oracle_last_gram(self._h, c, G.ctypes.data)
         return G, int(nobs)
+
+    def last_eqns(self, c: int):
+        """(A [n][n], b [n]) of the latest frame's AR normal equations, in this handle's accumulation mode."""
+        n = 24 if c == 0 else 25
+        A = np.zeros((n, n))
+        b = np.zeros(n)
+        self._L.g1s_oracle_last_eqns(self._h, c, A.ctypes.data, b.ctypes.data)
+        return A, b
 
     def state(self, which: int, c: int):
         n = 24 if c == 0 else 25
