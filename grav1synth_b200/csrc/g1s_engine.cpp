@@ -303,7 +303,7 @@ bool build_residual_maps(g1s_diff *d, Slot &s, std::vector<CUtensorMap> &host) {
       const cuuint64_t strides[1] = {(cuuint64_t)(luma ? rs.pitch_l : rs.pitch_c)};
       const cuuint32_t bx[2] = {(cuuint32_t)box[k][0], (cuuint32_t)box[k][1]};
       const cuuint32_t estr[2] = {1, 1};
-      void *base = fb + (k < 3 ? rs.off_res[k] : (k == 3 ? rs.off_hi : rs.off_lo));
+      void *base = fb + (k < 3 ? rs.off_res[k] : rs.off_tap);
       const CUresult r = d->encode_tiled(&host[(size_t)i * kResidualMaps + k], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims,
                                          strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

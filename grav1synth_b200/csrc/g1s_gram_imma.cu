@@ -3,33 +3,31 @@
 //
 // Replaces NoiseModel::add_block_observations (extract_ar_row + the n x n outer-product accumulation) of
 // av1-grain's diff module (reached from /root/reference/src/main.rs:442) for every flat block whose
-// residuals fit in int8; the rare block that does not was flagged by residual_kernel and is redone
-// exactly by gram_generic_kernel.  All sums are integers, so the result is bit-identical to the oracle
-// whatever the summation order.
+// residuals (and, for chroma, luma tap) fit in int8; the rare block that does not was flagged by
+// residual_kernel and is redone exactly by gram_generic_kernel.  All sums are integers, so the result is
+// bit-identical to the oracle whatever the summation order.
 //
-// The kernel never touches the frames: residual_kernel left the s8 residual of Y / Cb / Cr and the two
-// halves of chroma's luma tap in engine-owned planes, and every warp pulls the tiles of its own work items
-// into its own slice of shared memory with the TMA engine (cp.async.bulk.tensor.2d, SASS UTMALDG; frame
-// edges are zero-filled by the hardware, so there is no edge path), one or two items ahead of its k-loop.
+// The kernel never touches the frames: residual_kernel left the s8 residual of Y / Cb / Cr and chroma's
+// luma tap (sum of the co-sited 2x2 luma residuals) in engine-owned planes, and every warp pulls the tiles
+// of its own work items into its own slice of shared memory with the TMA engine (cp.async.bulk.tensor.2d,
+// SASS UTMALDG; frame edges are zero-filled by the hardware, so there is no edge path), one or two items
+// ahead of its k-loop.
 //
 // Why warps are autonomous.  Measured on the B200 (tools/imma_probe.cu, profiles/): the legacy IMMA path
 // holds a sub-partition's issue port for its whole 8.4 cycles, so a sub-partition's time is
 // 8.4 * IMMAs + (every other warp instruction it issues) -- nothing overlaps, polls and barrier spins are
 // paid in full.  So: no CTA barriers, no shared rings, no inter-warp waits.  A warp has a plane for life
-// (7 luma + 5 chroma warps per CTA, the measured 3:1:1 cost ratio of Y:Cb:Cr), an equal contiguous share
-// of that plane's blocks over the whole batch, its own mbarriers, and it adds its int32 accumulators to
-// the frame's int64 record directly when its share leaves a frame (about 330 atomics, once or twice per
-// warp per launch).
-//   work item   luma: one 32x32 block (32 k-steps); chroma: two adjacent 16x16 blocks (16 k-steps)
-//   One k-step = 32 pixels of one row.  X[k][a] = residual at pixel k shifted by tap a;
-//   D += X^T X over the upper block-triangle (6 m16n8k32 MMAs).  Tap a = 8q+g with g = cx+3 (lane
-//   group), q = cy+3: a thread's four taps are the SAME column offset on four consecutive rows, so its
-//   operands slide down one row per k-step: one new 32-bit window (two LDS + funnel shift) per half is
-//   fetched, the B operand of a row is a register pair and the A operand of two consecutive rows a
-//   register quad that serves as the lower m-tile now and as the upper m-tile two steps later.
-//   The observation mask (block margins, frame clipping) is a byte mask on k applied to the operand
-//   words (mask^2 = mask, so masking both A and B is exact).  Chroma's luma tap rides in lane group 7.
-//   int32 accumulators are bounded by the share: <= 96 blocks * 32 k-steps * 32 * 2^14 < 2^31.
+// (5 luma + 3 chroma warps per CTA), an equal contiguous share of that plane's blocks over the whole batch,
+// its own mbarriers, and it adds its int32 accumulators to the frame's int64 record directly when its share
+// leaves a frame (about 330 atomics, once or twice per warp per launch).
+//   work item   luma: one 32x32 block; chroma: two adjacent 16x16 blocks (32 columns either way)
+//   Tap a = 8q+g with g = cx+3 (the mma lane group), q = cy+3.  A lane's operand of a residual row is ONE
+//   32-bit window per half (two LDS + funnel shift), and the same window is the row's B pair and its half of
+//   an A quad.  The arithmetic is the row-pair deduplicated form described above the k-loops: 2.5 MMAs per
+//   residual row instead of 6 per observed row (round 1), every row fetched once.
+//   The observation mask (block margins, frame clipping) is a byte mask on k applied to the A operand.
+//   Chroma's luma tap rides in lane group g = 7 (those lanes walk the luma-tap tile), so it costs no MMA.
+//   int32 item accumulators are bounded by the share: <= 96 blocks * 1024 * 127^2 < 2^31.
 #include "g1s_kernels.h"
 
 #include <algorithm>
@@ -40,37 +38,35 @@ namespace g1s {
 namespace {
 
 #ifndef G1S_GRAM_WARPS
-#define G1S_GRAM_WARPS 12
-#define G1S_LUMA_WARPS 7
+#define G1S_GRAM_WARPS 8
+#define G1S_LUMA_WARPS 5
 #endif
 constexpr int kGramWarps = G1S_GRAM_WARPS;
 constexpr int kGramThreads = 32 * kGramWarps;
-constexpr int kLumaWarps = G1S_LUMA_WARPS;  // per CTA; the others are chroma warps (measured cost ratio Y : Cb : Cr about 3 : 1 : 1)
-constexpr int kMaxShare = 96;     // luma blocks per warp and launch: bounds the int32 accumulators
+constexpr int kLumaWarps = G1S_LUMA_WARPS;  // per CTA; the others are chroma warps (pair steps per frame: Y 147 k, Cb + Cr 82 k)
+constexpr int kMaxShare = 96;     // luma blocks per warp and launch: bounds the int32 item accumulators
 constexpr int kWin = 30;          // blocks per flag window: one ballot holds blocks bx0-1 .. bx0+30
-constexpr int kPL = 16;           // tile pitch in 32-bit words (64-byte box rows), luma
-constexpr int kPC = 16;           // the same for chroma and the luma-tap tiles
 constexpr int kLumaRows = 35;     // 3 halo rows + 32
-constexpr int kChromaRows = 19;   // 3 halo rows + 16
-constexpr int kLoRows = 20;       // the lo tile starts one row higher (row -1 of the first step is read, never used)
+constexpr int kChromaRows = 19;   // 3 halo rows + 16 (residual and luma-tap tiles alike)
 constexpr int kBoxW = 64;         // 16 + 32 + 16 samples: one luma block, or two chroma blocks
 // Boxes start 16 samples left of the item (the innermost TMA coordinate must be a multiple of 16 bytes,
 // tools/tma_probe.cu).  The k-loops address tiles whose column 0 is the item's origin - 4 samples:
 constexpr int kResCol0 = 3;       // word of that column inside a residual box row
-constexpr int kTapCol0 = 4;       // word of the item's first sample inside a hi / lo box row
+constexpr int kTapCol0 = 4;       // word of the item's first sample inside a luma-tap box row
 constexpr int kLumaBytes = kLumaRows * kBoxW;      // 2240
 constexpr int kChromaBytes = kChromaRows * kBoxW;  // 1216
-constexpr int kLoBytes = kLoRows * kBoxW;          // 1280
-constexpr int kLumaSlot = 2304, kLumaStages = 3;   // per luma warp: 3 x 2304 = 6912 bytes
-constexpr int kOffHi = 1280, kOffLo = 2560, kChromaSlot = 3840, kChromaStages = 2;  // per chroma warp: 2 x 3840
+// A pair step may read one row past the box (the unused upper half of an item's last pair): slots hold one row more.
+constexpr int kLumaSlot = 2304;                    // 36 rows
+constexpr int kOffTap = 1280, kChromaSlot = 2560;  // residual tile (20 rows) | luma-tap tile (20 rows)
+constexpr int kStages = 3;
 constexpr int kWarpSmem = 7680;
-constexpr int kMaxStages = 3;
-static_assert(kLumaBytes <= kLumaSlot && kChromaBytes <= kOffHi && kLumaSlot * kLumaStages <= kWarpSmem &&
-                  kChromaSlot * kChromaStages <= kWarpSmem && kLumaSlot % 128 == 0 && kOffHi % 128 == 0,
+static_assert(kLumaBytes + kBoxW <= kLumaSlot && kChromaBytes + kBoxW <= kOffTap && kOffTap + kChromaBytes + kBoxW <= kChromaSlot &&
+                  kLumaSlot * kStages <= kWarpSmem && kChromaSlot * kStages <= kWarpSmem && kLumaSlot % 128 == 0 &&
+                  kOffTap % 128 == 0 && kChromaSlot % 128 == 0,
               "per-warp tile layout");
 
 struct __align__(16) GramSmem {
-  uint64_t full[kGramWarps][kMaxStages];  // one mbarrier per warp and stage: the warp's own TMA completions
+  uint64_t full[kGramWarps][kStages];  // one mbarrier per warp and stage: the warp's own TMA completions
   int4 fifo[kGramWarps][4];               // per warp: items requested from the TMA engine, not yet consumed
 };
 
@@ -92,150 +88,135 @@ __device__ __forceinline__ uint32_t byte_mask(int first, int lo, int hi) {
 
 // ------------------------------------------------------------------------------ k-loops
 //
-//   tile/pitch : s8 residual tile, row r <-> plane row (unit origin - 3 + r), col 0 <-> origin - 4
-//   colw       : word column of this lane's window for half 0 ( = unit word base + t + ((g+1)>>2) )
+// Row-pair deduplication.  With tap a = 8q+g (q = cy+3 the tap ROW, g = cx+3 the tap column) the Gram entry of two
+// taps only involves the two residual rows s = y+q-3 and s' = y+q'-3 of each observed row y:
+//     G[(q,g)][(q',g')] = sum over observed rows y of  D_{s'}[dy][g'][g],     dy = q'-q = s'-s in 0..3,
+//     D_{s'}[dy][g'][g] = sum_k mask(k) r(s', k+g'-3) r(s'-dy, k+g-3)          (k = the 32 columns of the item)
+// and the x mask (block margins, frame clip, flatness) is the same for every row of a block.  D_{s'}[dy] is
+// therefore shared by every q' >= dy: the ten (q, q') row-pair blocks of the Gram need only FOUR products per
+// residual row, not ten per observed row.  One k-step takes two consecutive rows a, a+1 as the A operand
+// (16 = 2 rows x 8 columns g') and the rows a-3 .. a+1 as five B operands: five m16n8k32 per two rows (2.5 per row
+// against 6 per row for the direct form), and every row is fetched from shared memory exactly once.
+// The five accumulators RUN over the whole share; what an item contributes to G[(q,.)][(q',.)] is the difference of
+// the running sum between the end and the start of the row window [y0+q', y1+q') of q' ("snapshots", a few integer
+// adds at the two ends of an item), separately for the rows that sit in the lower (even) and upper (odd) half of
+// their pair.  Differences cancel whatever the accumulators held before, so nothing is ever reset, rows above the
+// item may be stale registers and rows below it stale shared memory.
+//
+//   base       : the lane's window word in tile row 0 (g = 7 lanes, chroma: in the luma-tap tile; funnel shift 0)
 //   sh         : funnel shift in bits ( = 8 * ((g+1) & 3) )
-//   mx[h]      : byte mask of the observed pixels of half h (x margins, frame clip, block not flat)
-// Row slots are indexed by (row - ys) & 3; P[s] is the operand pair of a row, Q[s] the operand
-// quad of rows (s, s+1).
+//   mx[h]      : byte mask of the observed pixels of half h (x margins, frame clip, block not flat), applied to A only
+// Tile rows: row r <-> plane row (item origin - 3 + r); observed rows y in [y0, y1) are tile rows [y0+3, y1+3), the
+// rows entering the products are tile rows [y0, y1+3).
 
-struct Window {
-  uint32_t Q[4][4];
-  uint32_t P[4][2];
+struct Ring {
+  uint32_t B[6][2];  // B operand pairs (unmasked windows) of the six most recent rows, slot = row position mod 6
 };
 
-// x & m, emitted as a distinct instruction per TAG.  A window word is consumed from three different
-// operand tuples (the row's B pair, the upper half of one A quad, the lower half of the next) and
-// mma.sync needs each tuple in consecutive aligned registers; without distinct values ptxas keeps one
-// copy and rebuilds the quads with ~12 moves per k-step.  Three ANDs per word is the minimum.
-template <int TAG>
-__device__ __forceinline__ uint32_t and_tag(uint32_t x, uint32_t m) {
-  uint32_t r;
-  if (TAG == 0) asm("lop3.b32 %0, %1, %2, 0, 0xC0;" : "=r"(r) : "r"(x), "r"(m));
-  if (TAG == 1) asm("lop3.b32 %0, %1, %2, 1, 0xC0;" : "=r"(r) : "r"(x), "r"(m));
-  if (TAG == 2) asm("lop3.b32 %0, %1, %2, 2, 0xC0;" : "=r"(r) : "r"(x), "r"(m));
-  return r;
+constexpr int kRowWords = 16;  // 64-byte box rows
+
+// Pair step S (mod 3): rows a, a+1 -> ring slots 2S, 2S+1; products with rows a-3 .. a+1.
+template <int S>
+__device__ __forceinline__ void pair_step(Ring &w, const uint32_t *__restrict__ p, int sh, const uint32_t (&mx)[2],
+                                          int (&acc)[5][4]) {
+  const uint32_t r00 = __funnelshift_r(p[0], p[1], sh), r01 = __funnelshift_r(p[4], p[5], sh);
+  const uint32_t r10 = __funnelshift_r(p[kRowWords], p[kRowWords + 1], sh);
+  const uint32_t r11 = __funnelshift_r(p[kRowWords + 4], p[kRowWords + 5], sh);
+  w.B[(2 * S) % 6][0] = r00, w.B[(2 * S) % 6][1] = r01;
+  w.B[(2 * S + 1) % 6][0] = r10, w.B[(2 * S + 1) % 6][1] = r11;
+  const uint32_t q[4] = {r00 & mx[0], r10 & mx[0], r01 & mx[1], r11 & mx[1]};
+  imma_16832(acc[0], q, w.B[(2 * S + 3) % 6]);  // row a-3: dy 3 (lower row) | 4 (upper row, unused)
+  imma_16832(acc[1], q, w.B[(2 * S + 4) % 6]);  // row a-2: dy 2 | 3
+  imma_16832(acc[2], q, w.B[(2 * S + 5) % 6]);  // row a-1: dy 1 | 2
+  imma_16832(acc[3], q, w.B[(2 * S) % 6]);      // row a  : dy 0 | 1
+  imma_16832(acc[4], q, w.B[(2 * S + 1) % 6]);  // row a+1: (unused) | dy 0
 }
 
-// Fetches the lane's window of one tile row (p: word of half 0; half 1 is 4 words = 16 pixels further)
-// and files it as: B pair of the row, upper row of quad `qprev`, lower row of quad `qthis`.
-__device__ __forceinline__ void fetch_row(const uint32_t *__restrict__ p, int sh, const uint32_t (&mx)[2],
-                                          uint32_t (&pair)[2], uint32_t (&qprev)[4], uint32_t (&qthis)[4]) {
-  const uint32_t r0 = __funnelshift_r(p[0], p[1], sh);
-  const uint32_t r1 = __funnelshift_r(p[4], p[5], sh);
-  pair[0] = and_tag<0>(r0, mx[0]);
-  pair[1] = and_tag<0>(r1, mx[1]);
-  qprev[1] = and_tag<1>(r0, mx[0]);
-  qprev[3] = and_tag<1>(r1, mx[1]);
-  qthis[0] = and_tag<2>(r0, mx[0]);
-  qthis[2] = and_tag<2>(r1, mx[1]);
-}
+// Gacc index of (q', dy), dy <= q'.
+__host__ __device__ constexpr int gidx(int q, int dy) { return q * (q + 1) / 2 + dy; }
 
-// Rows ys, ys+1, ys+2 -> slots 0, 1, 2 (quad 3's upper row is scratch here).
-template <int PITCH>
-__device__ __forceinline__ void window_init(Window &w, const uint32_t *__restrict__ p, int sh,
-                                            const uint32_t (&mx)[2]) {
-  fetch_row(p, sh, mx, w.P[0], w.Q[3], w.Q[0]);
-  fetch_row(p + PITCH, sh, mx, w.P[1], w.Q[0], w.Q[1]);
-  fetch_row(p + 2 * PITCH, sh, mx, w.P[2], w.Q[1], w.Q[2]);
-}
-
-// One k-step of the six common tiles; K is the (compile-time) slot of the step's first row,
-// pnew the lane's window word in the tile row three below it.
-template <int K>
-__device__ __forceinline__ void step6(Window &w, const uint32_t *__restrict__ pnew, int sh, const uint32_t (&mx)[2],
-                                      int (&acc)[6][4]) {
-  fetch_row(pnew, sh, mx, w.P[(K + 3) & 3], w.Q[(K + 2) & 3], w.Q[(K + 3) & 3]);
-  imma_16832(acc[0], w.Q[K & 3], w.P[K & 3]);
-  imma_16832(acc[1], w.Q[K & 3], w.P[(K + 1) & 3]);
-  imma_16832(acc[2], w.Q[K & 3], w.P[(K + 2) & 3]);
-  imma_16832(acc[3], w.Q[K & 3], w.P[(K + 3) & 3]);
-  imma_16832(acc[4], w.Q[(K + 2) & 3], w.P[(K + 2) & 3]);
-  imma_16832(acc[5], w.Q[(K + 2) & 3], w.P[(K + 3) & 3]);
-}
-
-// p0: the lane's window word in tile row ys (the first observed row's cy = -3 tap row).
-__device__ __forceinline__ void luma_rows(const uint32_t *__restrict__ p0, int sh, int nrows,
-                                          const uint32_t (&mx)[2], int (&acc)[6][4]) {
-  Window w;
-  window_init<kPL>(w, p0, sh, mx);
-  const uint32_t *p = p0 + 3 * kPL;
-  int n = nrows;
-#pragma unroll 1
-  for (; n >= 4; n -= 4, p += 4 * kPL) {
-    step6<0>(w, p, sh, mx, acc);
-    step6<1>(w, p + kPL, sh, mx, acc);
-    step6<2>(w, p + 2 * kPL, sh, mx, acc);
-    step6<3>(w, p + 3 * kPL, sh, mx, acc);
+// Adds (sign = +1) or subtracts the running sums to / from the item accumulators of the tap rows q' named by `ev`
+// (bit q': rows in the lower half of their pair, bit 4+q': upper half).  Unsigned arithmetic: the running sums wrap.
+__device__ __forceinline__ void snapshot(uint32_t (&G)[10][2], const int (&acc)[5][4], uint32_t ev, bool add) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (ev & (1u << q)) {
+#pragma unroll
+      for (int dy = 0; dy <= q; ++dy) {
+        const uint32_t v0 = (uint32_t)acc[3 - dy][0], v1 = (uint32_t)acc[3 - dy][1];
+        G[gidx(q, dy)][0] += add ? v0 : 0u - v0;
+        G[gidx(q, dy)][1] += add ? v1 : 0u - v1;
+      }
+    }
+    if (ev & (16u << q)) {
+#pragma unroll
+      for (int dy = 0; dy <= q; ++dy) {
+        const uint32_t v0 = (uint32_t)acc[4 - dy][2], v1 = (uint32_t)acc[4 - dy][3];
+        G[gidx(q, dy)][0] += add ? v0 : 0u - v0;
+        G[gidx(q, dy)][1] += add ? v1 : 0u - v1;
+      }
+    }
   }
-  if (n > 0) step6<0>(w, p, sh, mx, acc);
-  if (n > 1) step6<1>(w, p + kPL, sh, mx, acc);
-  if (n > 2) step6<2>(w, p + 2 * kPL, sh, mx, acc);
 }
 
-// Chroma.  The luma tap (split as 8*hi + lo so both parts fit int8) rides in the otherwise unused lane
-// group g = 7: those lanes step through the hi tile instead of the residual tile (same pitch, funnel shift 0), so
-// their A rows 7 / 15 of the lower m-tile are hi(y) / lo(y) and the four existing tiles (m0 x n0..n3)
-// deliver every (tap, luma tap) product for free.  The quad's upper row is a separate register from the
-// next quad's lower row, which is what lets it carry lo(y) instead of hi(y+1).
-//   p  : window word of the fetched tile row (g = 7: hs row of the same index)
-//   lp : ls word of the row above the fetched one (only g = 7 lanes use the value)
-__device__ __forceinline__ void fetch_row_c(const uint32_t *__restrict__ p, const uint32_t *__restrict__ lp, int sh,
-                                            bool is7, const uint32_t (&mx)[2], uint32_t (&pair)[2],
-                                            uint32_t (&qprev)[4], uint32_t (&qthis)[4]) {
-  const uint32_t r0 = __funnelshift_r(p[0], p[1], sh);
-  const uint32_t r1 = __funnelshift_r(p[4], p[5], sh);
-  const uint32_t x0 = is7 ? lp[0] : r0;
-  const uint32_t x1 = is7 ? lp[4] : r1;
-  pair[0] = and_tag<0>(r0, mx[0]);
-  pair[1] = and_tag<0>(r1, mx[1]);
-  qprev[1] = and_tag<1>(x0, mx[0]);
-  qprev[3] = and_tag<1>(x1, mx[1]);
-  qthis[0] = and_tag<2>(r0, mx[0]);
-  qthis[2] = and_tag<2>(r1, mx[1]);
-}
-
-template <int K>
-__device__ __forceinline__ void step6c(Window &w, const uint32_t *__restrict__ pnew, const uint32_t *__restrict__ lp,
-                                       int sh, bool is7, const uint32_t (&mx)[2], int (&acc)[6][4], int &ll) {
-  fetch_row_c(pnew, lp, sh, is7, mx, w.P[(K + 3) & 3], w.Q[(K + 2) & 3], w.Q[(K + 3) & 3]);
-  // g = 7 lanes: the upper row of this step's quad is the masked lo part of the luma tap of the observed
-  // row; lo * lo is the one self product the tiles do not deliver (other lanes: ignored)
-  ll = __dp4a((int)w.Q[K & 3][1], (int)w.Q[K & 3][1], ll);
-  ll = __dp4a((int)w.Q[K & 3][3], (int)w.Q[K & 3][3], ll);
-  imma_16832(acc[0], w.Q[K & 3], w.P[K & 3]);
-  imma_16832(acc[1], w.Q[K & 3], w.P[(K + 1) & 3]);
-  imma_16832(acc[2], w.Q[K & 3], w.P[(K + 2) & 3]);
-  imma_16832(acc[3], w.Q[K & 3], w.P[(K + 3) & 3]);
-  imma_16832(acc[4], w.Q[(K + 2) & 3], w.P[(K + 2) & 3]);
-  imma_16832(acc[5], w.Q[(K + 2) & 3], w.P[(K + 3) & 3]);
-}
-
-// p0 / lp0: the lane's words for tile row ys (lp0 already points one ls row above it).
-__device__ __forceinline__ void chroma_rows(const uint32_t *__restrict__ p0, const uint32_t *__restrict__ lp0, int sh,
-                                            bool is7, int nrows, const uint32_t (&mx)[2], int (&acc)[6][4], int &ll) {
-  Window w;
-  fetch_row_c(p0, lp0, sh, is7, mx, w.P[0], w.Q[3], w.Q[0]);
-  fetch_row_c(p0 + kPC, lp0 + kPC, sh, is7, mx, w.P[1], w.Q[0], w.Q[1]);
-  fetch_row_c(p0 + 2 * kPC, lp0 + 2 * kPC, sh, is7, mx, w.P[2], w.Q[1], w.Q[2]);
-  const uint32_t *p = p0 + 3 * kPC, *lp = lp0 + 3 * kPC;
-  int n = nrows;
-#pragma unroll 1
-  for (; n >= 4; n -= 4, p += 4 * kPC, lp += 4 * kPC) {
-    step6c<0>(w, p, lp, sh, is7, mx, acc, ll);
-    step6c<1>(w, p + kPC, lp + kPC, sh, is7, mx, acc, ll);
-    step6c<2>(w, p + 2 * kPC, lp + 2 * kPC, sh, is7, mx, acc, ll);
-    step6c<3>(w, p + 3 * kPC, lp + 3 * kPC, sh, is7, mx, acc, ll);
+// Window bookkeeping of one item with n = y1 - y0 observed rows, pairs i = 0 .. P-1 (pair i = tile rows y0+2i, +1):
+// tap row q' sums the lower-half rows of pairs [ceil(q'/2), ceil((n+q')/2)) and the upper-half rows of pairs
+// [ceil((q'-1)/2), ceil((n+q'-1)/2)).  Start events are fixed (after pair -1: E0 O0 O1; 0: E1 E2 O2 O3; 1: E3).
+__device__ __forceinline__ uint32_t start_events(int i) { return i == -1 ? 0x31u : (i == 0 ? 0xC6u : (i == 1 ? 0x08u : 0u)); }
+__device__ __forceinline__ uint32_t end_events(int i, int n) {
+  uint32_t ev = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (i == ((n + q + 1) >> 1) - 1) ev |= 1u << q;
+    if (i == ((n + q) >> 1) - 1) ev |= 16u << q;
   }
-  if (n > 0) step6c<0>(w, p, lp, sh, is7, mx, acc, ll);
-  if (n > 1) step6c<1>(w, p + kPC, lp + kPC, sh, is7, mx, acc, ll);
-  if (n > 2) step6c<2>(w, p + 2 * kPC, lp + 2 * kPC, sh, is7, mx, acc, ll);
+  return ev;
 }
 
-// MMA tap index a = 8q+g  ->  record tap index (0..23 AR taps, 25 centre sample), -1 unused.
-__device__ __forceinline__ int record_tap(int a) {
+// All rows of one item (or of one block of a chroma pair): base points at tile row 0.
+__device__ __forceinline__ void item_rows(const uint32_t *__restrict__ base, int sh, int y0, int y1, const uint32_t (&mx)[2],
+                                          Ring &w, int (&acc)[5][4], uint32_t (&G)[10][2]) {
+  const int n = y1 - y0, P = (n + 4) >> 1;
+  uint32_t hm = 3u;  // pairs followed by events
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int e = ((n + q + 1) >> 1) - 1, o = ((n + q) >> 1) - 1;
+    if (e >= 0) hm |= 1u << e;
+    if (o >= 0) hm |= 1u << o;
+  }
+  asm volatile("" : "+r"(hm));  // keep it in a register: ptxas otherwise rebuilds the mask in front of every test
+  snapshot(G, acc, start_events(-1), false);
+  if (const uint32_t ev = end_events(-1, n)) snapshot(G, acc, ev, true);
+  auto hook = [&](int i) {
+    if (const uint32_t ev = start_events(i)) snapshot(G, acc, ev, false);
+    if (const uint32_t ev = end_events(i, n)) snapshot(G, acc, ev, true);
+  };
+  const uint32_t *p = base + y0 * kRowWords;
+  int i = 0;
+#pragma unroll 1
+  for (; i + 3 <= P; i += 3, p += 6 * kRowWords) {
+    pair_step<0>(w, p, sh, mx, acc);
+    if ((hm >> i) & 1u) hook(i);
+    pair_step<1>(w, p + 2 * kRowWords, sh, mx, acc);
+    if ((hm >> i) & 2u) hook(i + 1);
+    pair_step<2>(w, p + 4 * kRowWords, sh, mx, acc);
+    if ((hm >> i) & 4u) hook(i + 2);
+  }
+  if (i < P) {
+    pair_step<0>(w, p, sh, mx, acc);
+    if ((hm >> i) & 1u) hook(i);
+    if (i + 1 < P) {
+      pair_step<1>(w, p + 2 * kRowWords, sh, mx, acc);
+      if ((hm >> i) & 2u) hook(i + 1);
+    }
+  }
+}
+
+// MMA tap index a = 8q+g  ->  record tap index (0..23 AR taps, 24 chroma's luma tap, 25 centre sample), -1 unused.
+// Column g = 7 is the luma-tap tile (chroma; a junk window for luma): only its row q = 3 (cy = 0) is a tap.
+__device__ __forceinline__ int record_tap(int a, bool chroma) {
   const int q = a >> 3, g = a & 7;
-  if (g == 7) return -1;
+  if (g == 7) return (chroma && q == 3) ? 24 : -1;
   if (q < 3) return 7 * q + g;
   if (g < 3) return 21 + g;
   if (g == 3) return 25;
@@ -244,18 +225,13 @@ __device__ __forceinline__ int record_tap(int a) {
 
 __device__ __forceinline__ int pair_index(int i, int j) { return i * kTaps - i * (i - 1) / 2 + (j - i); }
 
-// Adds accumulator element D[a][b] (a <= b: the mirrored element is covered by another tile).
-__device__ __forceinline__ void emit(unsigned long long *gram, int a, int b, int v) {
+// Adds element (a, b) of the tap-by-tap Gram in MMA indices, a <= b (the mirrored element of a dy = 0 block is
+// covered by the transposed position of the same block).
+__device__ __forceinline__ void emit(unsigned long long *gram, int a, int b, int v, bool chroma) {
   if (a > b || v == 0) return;
-  const int ia = record_tap(a), ib = record_tap(b);
+  const int ia = record_tap(a, chroma), ib = record_tap(b, chroma);
   if (ia < 0 || ib < 0) return;
   atomicAdd(&gram[pair_index(min(ia, ib), max(ia, ib))], (unsigned long long)(long long)v);
-}
-// D[luma tap part][b]: weight 8 for the high part, 1 for the low part.
-__device__ __forceinline__ void emit_luma_tap(unsigned long long *gram, int b, int v, int weight) {
-  const int ib = record_tap(b);
-  if (ib < 0 || v == 0) return;
-  atomicAdd(&gram[pair_index(min(ib, 24), max(ib, 24))], (unsigned long long)((long long)v * weight));
 }
 
 // ------------------------------------------------------------------------------ TMA + mbarrier
@@ -302,13 +278,6 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, 
 }
 
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// MODE 0: the product.  MODE 1 / 2 are measurement aids (G1S_GRAM_MODE, wrong results by design):
-// 1 = TMA traffic and waits only, no k-loops; 2 = k-loops on whatever is in shared memory, no TMA traffic.
-template <int MODE>
 __global__ void __launch_bounds__(kGramThreads, 2)
 gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int nframes,
                  const uint8_t *__restrict__ tmaps) {
@@ -342,58 +311,46 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
   if (i_lo >= i_hi) return;  // whole warp; nothing below synchronises across warps
 
   uint8_t *const my_tiles = tiles + warp * kWarpSmem;
-  const int nstages = luma ? kLumaStages : kChromaStages;
   const int slot = luma ? kLumaSlot : kChromaSlot;
   if (lane == 0) {
-    for (int s = 0; s < kMaxStages; ++s) mbar_init(&sm.full[warp][s], 1);
+    for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[warp][s], 1);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncwarp();
 
-  int acc[6][4];
+  int acc[5][4];        // running sums of the five row products (never reset, see the k-loop notes)
+  uint32_t G[10][2];    // this share's Gram blocks (q', dy) since the last flush
+  Ring ring;
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < 5; ++i)
 #pragma unroll
     for (int r = 0; r < 4; ++r) acc[i][r] = 0;
-  int ll = 0;    // chroma, g = 7 lanes: sum lo*lo of the luma tap over observed pixels
+#pragma unroll
+  for (int i = 0; i < 10; ++i) G[i][0] = G[i][1] = 0u;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) ring.B[i][0] = ring.B[i][1] = 0u;
   int nobs = 0;  // observations of the items accumulated since the last flush
 
-  const int sh = 8 * ((gq + 1) & 3);
+  int sh = 8 * ((gq + 1) & 3);
+  asm volatile("" : "+r"(sh));  // same: one register instead of four instructions per funnel shift group
   const int dxw = (gq + 1) >> 2;
   const bool is7 = gq == 7;
 
-  // Accumulators -> the frame's int64 record, straight from registers (every (lane, tile, element) owns one tap pair).
+  // Gram blocks -> the frame's int64 record, straight from registers: element r of block (q', dy) in lane (gq, t)
+  // is the product of the later tap (q', g' = gq) with the earlier tap (q' - dy, g = 2t + r).
   auto flush = [&](int f) {
     uint8_t *rec = records + (size_t)f * rl.bytes;
     unsigned long long *gram = reinterpret_cast<unsigned long long *>(rec + rl.off_gram) + (size_t)plane * kPairs;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int mrow = i >= 4 ? 16 : 0;
-      const int ncol = i >= 4 ? 8 * (i - 2) : 8 * i;
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int v = acc[i][r];
-        acc[i][r] = 0;
-        if (v == 0) continue;
-        const int b = ncol + 2 * t + (r & 1);
-        if (plane > 0 && is7 && i < 4) {
-          // rows 7 / 15 of the lower m-tile: luma tap hi / lo
-          if (b == 7)  // column 7 of the first n-tile is hi again: (8h + l)^2 = 64 hh + 16 hl + ll
-            atomicAdd(&gram[pair_index(24, 24)], (unsigned long long)((long long)v * ((r >> 1) ? 16 : 64)));
-          else
-            emit_luma_tap(gram, b, v, (r >> 1) ? 1 : 8);
-        } else {
-          emit(gram, mrow + gq + 8 * (r >> 1), b, v);
+      for (int dy = 0; dy <= q; ++dy)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int v = (int)G[gidx(q, dy)][r];
+          G[gidx(q, dy)][r] = 0u;
+          emit(gram, 8 * (q - dy) + 2 * t + r, 8 * q + gq, v, !luma);
         }
-      }
-    }
-    if (plane > 0) {
-      int v = is7 ? ll : 0;
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (lane == 28 && v) atomicAdd(&gram[pair_index(24, 24)], (unsigned long long)(long long)v);
-      ll = 0;
-    }
     if (lane == 0 && nobs)
       atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + plane, (unsigned long long)(long long)nobs);
     nobs = 0;
@@ -446,7 +403,7 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
   load_window();
 
   int head = 0, tail = 0;       // fifo positions (items requested / consumed)
-  int hstage = 0, tstage = 0;   // their stages ( = position % nstages, kept incrementally)
+  int hstage = 0, tstage = 0;   // their stages ( = position % kStages, kept incrementally)
   uint32_t phases = 0;          // bit s: parity to wait for on stage s
   auto produce = [&]() {        // request the next item with work; false if there is none left
     while (m_todo == 0) {
@@ -470,24 +427,21 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
              | (((m_ovf >> l) & 3u) << 6);           // overflow A, B
     }
     const int stage = hstage;
-    if (++hstage == nstages) hstage = 0;
+    if (++hstage == kStages) hstage = 0;
     if (lane == 0) {
       sm.fifo[warp][head & 3] = make_int4(pf, pby, pwx + k, (int)bits);
-      if (MODE != 2) {
-        const uint8_t *fmaps = tmaps + (size_t)pf * kResidualMaps * 128;
-        uint8_t *st = my_tiles + stage * slot;
-        uint64_t *bar = &sm.full[warp][stage];
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this warp's reads of the stage precede the refill
-        if (luma) {
-          mbar_expect_tx(bar, kLumaBytes);
-          tma_load_2d(st, fmaps, 32 * (pwx + k) - 16, 32 * pby - 3, bar);
-        } else {
-          const int cx = 32 * (pwx + k) - 16, cy = 16 * pby;
-          mbar_expect_tx(bar, 2 * kChromaBytes + kLoBytes);
-          tma_load_2d(st, fmaps + plane * 128, cx, cy - 3, bar);
-          tma_load_2d(st + kOffHi, fmaps + 3 * 128, cx, cy, bar);
-          tma_load_2d(st + kOffLo, fmaps + 4 * 128, cx, cy - 1, bar);
-        }
+      const uint8_t *fmaps = tmaps + (size_t)pf * kResidualMaps * 128;
+      uint8_t *st = my_tiles + stage * slot;
+      uint64_t *bar = &sm.full[warp][stage];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this warp's reads of the stage precede the refill
+      if (luma) {
+        mbar_expect_tx(bar, kLumaBytes);
+        tma_load_2d(st, fmaps, 32 * (pwx + k) - 16, 32 * pby - 3, bar);
+      } else {
+        const int cx = 32 * (pwx + k) - 16, cy = 16 * pby - 3;
+        mbar_expect_tx(bar, 2 * kChromaBytes);
+        tma_load_2d(st, fmaps + plane * 128, cx, cy, bar);
+        tma_load_2d(st + kOffTap, fmaps + 3 * 128, cx, cy, bar);
       }
     }
     ++head;
@@ -497,13 +451,13 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
   int cf = -1;  // frame the accumulators belong to
   for (;;) {
     __syncwarp();  // every lane is done with the stage about to be refilled
-    while (head - tail < nstages && produce()) {
+    while (head - tail < kStages && produce()) {
     }
     if (head == tail) break;
     __syncwarp();
     const int4 item = sm.fifo[warp][tail & 3];
     const int stage = tstage;
-    if (++tstage == nstages) tstage = 0;
+    if (++tstage == kStages) tstage = 0;
     ++tail;
     const int f = item.x, by = item.y, ix = item.z;
     const uint32_t bits = (uint32_t)item.w;
@@ -511,26 +465,30 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
       if (cf >= 0) flush(cf);
       cf = f;
     }
-    if (MODE != 2) {
-      mbar_wait(&sm.full[warp][stage], (phases >> stage) & 1u);
-      phases ^= 1u << stage;
-    }
-    if (MODE == 1) continue;
+    mbar_wait(&sm.full[warp][stage], (phases >> stage) & 1u);
+    phases ^= 1u << stage;
     const uint8_t *st = my_tiles + stage * slot;
+    // up to two passes over the item's rows: (first observed row, masks of the two halves)
+    int npass = 0, y1, ya = 0, yb = 0;
+    uint32_t ma[2] = {0u, 0u}, mb[2] = {0u, 0u};
+    const uint32_t *base;
     if (luma) {
       const int xs = (bits & 1u) ? 0 : kLag, y0 = (bits & 4u) ? 0 : kLag;
       const int x1 = min(W - 32 * ix - kLag, (bits & 2u) ? 32 : 32 - kLag);
-      const int y1 = min(H - 32 * by, 32);
+      y1 = min(H - 32 * by, 32);
       if (x1 > xs && y1 > y0) {
-        uint32_t mx[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-        if (xs != 0 || x1 != 32) mx[0] = byte_mask(4 * t, xs, x1), mx[1] = byte_mask(16 + 4 * t, xs, x1);
-        luma_rows(reinterpret_cast<const uint32_t *>(st) + y0 * kPL + kResCol0 + t + dxw, sh, y1 - y0, mx, acc);
+        const bool full = xs == 0 && x1 == 32;
+        ma[0] = full ? 0xFFFFFFFFu : byte_mask(4 * t, xs, x1);
+        ma[1] = full ? 0xFFFFFFFFu : byte_mask(16 + 4 * t, xs, x1);
+        ya = y0;
+        npass = 1;
         nobs += (x1 - xs) * (y1 - y0);
       }
+      base = reinterpret_cast<const uint32_t *>(st) + kResCol0 + t + dxw;
     } else {
       // blocks 2 ix (half 0) and 2 ix + 1 (half 1); bits: flat left, A, B, right | flat above A, B | overflow A, B
       const int bxa = 2 * ix;
-      const int y1 = min(ph - 16 * by, 16);
+      y1 = min(ph - 16 * by, 16);
       const bool fla = (bits & 2u) && !(bits & 64u), flb = (bits & 4u) && !(bits & 128u);
       const int xsa = (bits & 1u) ? 0 : kLag, xsb = (bits & 2u) ? 0 : kLag;
       const int y0a = (bits & 16u) ? 0 : kLag, y0b = (bits & 32u) ? 0 : kLag;
@@ -540,24 +498,27 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
       const bool on1 = flb && x1b > xsb && y1 > y0b;
       const uint32_t m0 = !on0 ? 0u : (xsa == 0 && x1a == 16) ? 0xFFFFFFFFu : byte_mask(4 * t, xsa, x1a);
       const uint32_t m1 = !on1 ? 0u : (xsb == 0 && x1b == 16) ? 0xFFFFFFFFu : byte_mask(4 * t, xsb, x1b);
-      const int ya = on0 ? y0a : 99, yb = on1 ? y0b : 99;
-      const int ylo = min(ya, yb), yhi = min(max(ya, yb), y1);
-      // g = 7 lanes walk the hi tile (and the lo tile one row up) instead of the residual tile
-      const uint32_t *base = is7 ? reinterpret_cast<const uint32_t *>(st + kOffHi) + kTapCol0 + t
-                                 : reinterpret_cast<const uint32_t *>(st) + kResCol0 + t + dxw;
-      const uint32_t *lbase = reinterpret_cast<const uint32_t *>(st + kOffLo) + kTapCol0 + t;  // storage row r = lo row r - 1
-      if (ylo < y1) {
-        // rows where only one block of the pair is observed (its top margin is 0, the other's is 3)
-        if (yhi > ylo) {
-          const uint32_t mx[2] = {ya <= ylo ? m0 : 0u, yb <= ylo ? m1 : 0u};
-          chroma_rows(base + ylo * kPC, lbase + ylo * kPC, sh, is7, yhi - ylo, mx, acc, ll);
-        }
-        if (y1 > yhi) {
-          const uint32_t mx[2] = {m0, m1};
-          chroma_rows(base + yhi * kPC, lbase + yhi * kPC, sh, is7, y1 - yhi, mx, acc, ll);
+      if (on0 && on1 && y0a == y0b) {
+        ma[0] = m0, ma[1] = m1, ya = y0a, npass = 1;
+      } else {
+        // the two blocks start on different rows (one has a flat block above it, the other not) or only one is
+        // observed: their row windows differ, so they are accumulated one after the other
+        if (on0) ma[0] = m0, ya = y0a, npass = 1;
+        if (on1) {
+          if (npass == 0) ma[1] = m1, ya = y0b;
+          else mb[1] = m1, yb = y0b;
+          ++npass;
         }
       }
+      // g = 7 lanes walk the luma-tap tile (same rows, no shift) instead of the residual tile
+      base = is7 ? reinterpret_cast<const uint32_t *>(st + kOffTap) + kTapCol0 + t
+                 : reinterpret_cast<const uint32_t *>(st) + kResCol0 + t + dxw;
       nobs += (on0 ? (x1a - xsa) * (y1 - y0a) : 0) + (on1 ? (x1b - xsb) * (y1 - y0b) : 0);
+    }
+#pragma unroll 1
+    for (int pass = 0; pass < npass; ++pass) {
+      if (pass == 1) ma[0] = mb[0], ma[1] = mb[1], ya = yb;
+      item_rows(base, sh, ya, y1, ma, ring, acc, G);
     }
   }
   if (cf >= 0) flush(cf);
@@ -573,35 +534,29 @@ bool gram_imma_supported(const Geometry &g) {
 void gram_imma_tma_boxes(int box[kResidualMaps][2]) {
   box[0][0] = kBoxW, box[0][1] = kLumaRows;
   for (int k = 1; k < kResidualMaps; ++k) box[k][0] = kBoxW, box[k][1] = kChromaRows;
-  box[4][1] = kLoRows;
 }
 
 void launch_gram_imma(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, const void *tmaps,
                       cudaStream_t st) {
   const int smem = kGramWarps * kWarpSmem;
-  static int slots = 0, mode = 0;  // resident CTAs on the device: the persistent grid is one wave
+  // resident CTAs of the current device (the persistent grid is one wave); cached per device, and the
+  // dynamic-shared-memory attribute is a per-device property of the function as well
+  static int slots_of[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int &slots = slots_of[dev & 63];
   if (slots == 0) {
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
+    int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(gram_imma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(gram_imma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(gram_imma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gram_imma_kernel<0>, kGramThreads, smem);
-    if (const char *e = std::getenv("G1S_GRAM_MODE")) mode = std::atoi(e);
+    cudaFuncSetAttribute(gram_imma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gram_imma_kernel, kGramThreads, smem);
     slots = sms * std::max(per_sm, 1);
   }
   // A warp's share must stay below kMaxShare items (int32 accumulators): more CTAs than one wave if the batch is huge.
   const long long blocks = (long long)nframes * g.nb;
   const long long need = (blocks + (long long)kMaxShare * kLumaWarps - 1) / ((long long)kMaxShare * kLumaWarps);
   const int grid = (int)std::max<long long>(std::min<long long>(slots, std::max<long long>(1, blocks / 8)), need);
-  const uint8_t *tm = static_cast<const uint8_t *>(tmaps);
-  if (mode == 1)
-    gram_imma_kernel<1><<<grid, kGramThreads, smem, st>>>(g, records, rl, nframes, tm);
-  else if (mode == 2)
-    gram_imma_kernel<2><<<grid, kGramThreads, smem, st>>>(g, records, rl, nframes, tm);
-  else
-    gram_imma_kernel<0><<<grid, kGramThreads, smem, st>>>(g, records, rl, nframes, tm);
+  gram_imma_kernel<<<grid, kGramThreads, smem, st>>>(g, records, rl, nframes, static_cast<const uint8_t *>(tmaps));
 }
 
 }  // namespace g1s

@@ -68,17 +68,18 @@ void launch_gram_generic(const FrameDesc *frames, int nframes, const Geometry &g
 void launch_gram_strict(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
                         const RecordLayout &rl, cudaStream_t st);
 // Engine-owned s8 planes of a batch, written by residual_kernel and read (through TMA boxes) by
-// gram_imma_kernel: per frame the residual of Y, Cb, Cr and, for chroma's luma tap, the sum of the
-// co-sited 2x2 luma residuals split as 8*hi + lo.  Pitches are multiples of 16 bytes, plane offsets of 256.
+// gram_imma_kernel: per frame the residual of Y, Cb, Cr and chroma's luma tap, the sum of the co-sited 2x2 luma
+// residuals (blocks where it leaves int8 are flagged for the exact kernel, like residuals that do).  Pitches are
+// multiples of 16 bytes, plane offsets of 256.
 struct ResidualStore {
   int8_t *base;            // frame f of the batch starts at base + f * frame_bytes
   size_t frame_bytes;
   size_t off_res[3];
-  size_t off_hi, off_lo;
+  size_t off_tap;
   uint32_t pitch_l, pitch_c;
   static ResidualStore make(const Geometry &g);  // offsets / pitches only; base stays null
 };
-constexpr int kResidualMaps = 5;  // TMA descriptors per frame: res Y, Cb, Cr, tap hi, tap lo
+constexpr int kResidualMaps = 4;  // TMA descriptors per frame: residual Y, Cb, Cr, chroma's luma tap
 
 // int8 tensor-core (mma.sync m16n8k32) path for 4:2:0 / monochrome streams: residual_kernel then
 // gram_imma_kernel.

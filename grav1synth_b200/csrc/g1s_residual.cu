@@ -7,13 +7,13 @@
 //   source - denoised                 the residual every tap of extract_ar_row reads, written once as
 //                                     an s8 plane per channel (engine-owned, pitch a multiple of 16 so
 //                                     the Gram kernel's TMA boxes can fetch tiles with hardware zero fill)
-//   chroma's luma tap                 sum of the co-sited 2x2 luma residuals, split as 8*hi + lo so both
-//                                     parts are int8 tensor-core operands (two s8 planes, chroma size)
+//   chroma's luma tap                 sum of the co-sited 2x2 luma residuals as one s8 plane of chroma size (a
+//                                     tensor-core operand); where it leaves int8 the chroma blocks are flagged
 //   get_block_mean / get_noise_var    per 32x32 block: sum of source luma, sum r, sum r^2 per plane
 //   int8 range check                  blocks whose Gram reach contains |r| > 127 are flagged for the exact
 //                                     int32 kernel (gram_generic_kernel)
 //
-// Bound: HBM.  Per frame pair at 3840x2160 10-bit it reads 49.8 MB and writes 16.6 MB; a warp owns a
+// Bound: HBM.  Per frame pair at 3840x2160 10-bit it reads 49.8 MB and writes 14.5 MB; a warp owns a
 // 256-sample wide strip of one block row (8 luma blocks, or 16 chroma blocks of one plane) and walks
 // it two rows at a time with 128-bit loads (four in flight per lane), so each warp instruction moves a
 // contiguous 512-byte segment; block statistics stay in registers until the strip is done (two
@@ -118,11 +118,10 @@ residual_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, R
     const uint8_t *dp = static_cast<const uint8_t *>(fd.den[0]) + (size_t)Y0 * dstr;
     int8_t *out = store + rs.off_res[0] + (size_t)Y0 * rs.pitch_l + x8;
     const bool taps = has_chroma && (x8 >> 1) < pw;
-    int8_t *hi = store + rs.off_hi + (size_t)(Y0 >> 1) * rs.pitch_c + (x8 >> 1);
-    int8_t *lo = store + rs.off_lo + (size_t)(Y0 >> 1) * rs.pitch_c + (x8 >> 1);
+    int8_t *tap = store + rs.off_tap + (size_t)(Y0 >> 1) * rs.pitch_c + (x8 >> 1);
     int sum_r = 0;
     unsigned sum_q = 0, sum_l = 0;
-    uint32_t ov = 0;
+    uint32_t ov = 0, ovt = 0;
 #pragma unroll 2
     for (int y = 0; y < rows; y += 2) {
       const bool two = y + 1 < rows;
@@ -149,21 +148,21 @@ residual_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, R
 #pragma unroll
       for (int i = 0; i < 4; ++i) sum_l = __dp2a_lo(s0[i] + s1[i], 0x0101u, sum_l);  // lanes <= 510, no carry
       if (taps && two) {
-        // l + 1024 per chroma sample (l = sum of the 2x2 luma residuals, |l| <= 1020):
-        // hi = (l >> 3) = ((l + 1024) >> 3) - 128 -> byte ^ 0x80; lo = (l + 1024) & 7
+        // u = l + 1024 per chroma sample (l = sum of the 2x2 luma residuals, |l| <= 1020); 1024 = 0 mod 256, so the
+        // s8 value is the low byte of u, and l fits int8 <=> 896 <= u < 1152 <=> (u - 896) >> 8 == 0
         uint32_t u[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) u[i] = __dp2a_lo(b0[i] + b1[i], 0x0101u, 0u);
-        const uint32_t v01 = __byte_perm(u[0], u[1], 0x5410), v23 = __byte_perm(u[2], u[3], 0x5410);
-        const uint32_t h01 = (v01 >> 3) & 0x00FF00FFu, h23 = (v23 >> 3) & 0x00FF00FFu;
-        *reinterpret_cast<uint32_t *>(hi) = __byte_perm(h01, h23, 0x6420) ^ 0x80808080u;
-        *reinterpret_cast<uint32_t *>(lo) = __byte_perm(v01 & 0x00070007u, v23 & 0x00070007u, 0x6420);
+        for (int i = 0; i < 4; ++i) {
+          u[i] = __dp2a_lo(b0[i] + b1[i], 0x0101u, 0u);
+          ovt |= (u[i] - 896u) >> 8;
+        }
+        *reinterpret_cast<uint32_t *>(tap) =
+            __byte_perm(__byte_perm(u[0], u[1], 0x5410), __byte_perm(u[2], u[3], 0x5410), 0x6420);
       }
       sp += 2 * (size_t)sstr;
       dp += 2 * (size_t)dstr;
       out += 2 * (size_t)rs.pitch_l;
-      hi += rs.pitch_c;
-      lo += rs.pitch_c;
+      tap += rs.pitch_c;
     }
     // block statistics: four lanes per 32-sample block
 #pragma unroll
@@ -181,6 +180,9 @@ residual_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, R
     if (ov & 0xFF00FF00u)
       flag_overflow(rec + rl.off_ovf, reinterpret_cast<unsigned long long *>(rec + rl.off_ovf_count), g.nbw, g.nbh, 0,
                     has_chroma ? 2 : 0, x8, 5, by);  // the luma tap needs exact luma
+    else if (ovt)  // only chroma's luma tap left int8: the chroma blocks over these four chroma samples
+      flag_overflow(rec + rl.off_ovf, reinterpret_cast<unsigned long long *>(rec + rl.off_ovf_count), g.nbw, g.nbh, 1, 2,
+                    x8 >> 1, 4, by);
   } else {
     // ------------------------------------------------------------------ chroma strip (16 blocks of one plane)
     rem -= nl;
@@ -245,13 +247,12 @@ ResidualStore ResidualStore::make(const Geometry &g) {
   r.pitch_c = (uint32_t)up(pw ? pw : 1, 16);
   size_t o = 0;
   r.off_res[0] = o, o += up((size_t)r.pitch_l * g.height, 256);
-  r.off_res[1] = r.off_res[2] = r.off_hi = r.off_lo = 0;
+  r.off_res[1] = r.off_res[2] = r.off_tap = 0;
   if (g.planes == 3) {
     const size_t cb = up((size_t)r.pitch_c * (ph ? ph : 1), 256);
     r.off_res[1] = o, o += cb;
     r.off_res[2] = o, o += cb;
-    r.off_hi = o, o += cb;
-    r.off_lo = o, o += cb;
+    r.off_tap = o, o += cb;
   }
   r.frame_bytes = o;
   return r;
