@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--host-narrow", action="store_true",
                     help="e2e leg: reduce >8-bit host samples to 8 bits while staging (cfg.host_narrow), half the H2D bytes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strict", action="store_true", help="skip the strict-mode (reference-order Gram) pass")
+    ap.add_argument("--strict-steps", type=int, default=2)
+    ap.add_argument("--strict-batch", type=int, default=0, help="frames per launch in the strict pass (0: min(frames, 60))")
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames of the CPU-baseline sample")
     return ap.parse_args()
 
@@ -341,6 +344,34 @@ def main():
     table = eng.finish() if world == 1 else sd.finish()
     if rank == 0:
         line["config"]["segments"] = len(table)
+
+    # ---- strict mode (gram_order = REF_ORDER): the reference's per-term f64 accumulation reproduced bit for bit on
+    # the device, so every table integer equals the reference's; same device-resident frames, its own timed pass
+    if world == 1 and not args.no_strict:
+        sb = args.strict_batch or min(F, 60)
+        gs = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=sb, gram_order=abi.GRAM_REF_ORDER)
+
+        def strict_step():
+            for (sp, ss), (dp, ds) in dev_args:
+                gs.diff_frame_device(sp, ss, dp, ds)
+
+        strict_step()
+        gs.flush()
+        cs0 = gs.counters()
+        gs.mark(0)
+        ts0 = time.perf_counter()
+        for _ in range(args.strict_steps):
+            strict_step()
+        gs.flush()
+        gs.mark(1)
+        s_ms = max(gs.marks_elapsed_ms(), (time.perf_counter() - ts0) * 1e3)
+        cs1 = gs.counters()
+        strict_table = gs.finish()
+        line["value_strict"] = F * args.strict_steps / (s_ms * 1e-3)
+        line["strict"] = {"unit": "frames/s", "gram_order": "REF_ORDER (per-term f64 chains, reference pixel order)",
+                          "frames": F * args.strict_steps, "frames_per_launch": sb,
+                          "device_ms_strict_kernel_per_frame": (cs1["strict_ms"] - cs0["strict_ms"]) / (F * args.strict_steps),
+                          "segments": len(strict_table), "bound": "fp64 pipe / chain latency (5 f64 ops per term)"}
 
     # ---- e2e: host buffers through the C ABI (push_frame), copies inside the timed region
     if not args.no_e2e:

@@ -44,7 +44,7 @@ namespace {
 constexpr int kGramWarps = G1S_GRAM_WARPS;
 constexpr int kGramThreads = 32 * kGramWarps;
 constexpr int kLumaWarps = G1S_LUMA_WARPS;  // per CTA; the others are chroma warps (pair steps per frame: Y 147 k, Cb + Cr 82 k)
-constexpr int kMaxShare = 96;     // luma blocks per warp and launch: bounds the int32 item accumulators
+constexpr int kMaxShare = 96;     // items between two flushes of a warp: bounds the int32 item accumulators (96 * 1024 * 127^2 < 2^31)
 constexpr int kWin = 30;          // blocks per flag window: one ballot holds blocks bx0-1 .. bx0+30
 constexpr int kLumaRows = 35;     // 3 halo rows + 32
 constexpr int kChromaRows = 19;   // 3 halo rows + 16 (residual and luma-tap tiles alike)
@@ -448,7 +448,8 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
     return true;
   };
 
-  int cf = -1;  // frame the accumulators belong to
+  int cf = -1;     // frame the accumulators belong to
+  int since = 0;   // items accumulated since the last flush: the int32 item accumulators hold kMaxShare of them
   for (;;) {
     __syncwarp();  // every lane is done with the stage about to be refilled
     while (head - tail < kStages && produce()) {
@@ -461,10 +462,12 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
     ++tail;
     const int f = item.x, by = item.y, ix = item.z;
     const uint32_t bits = (uint32_t)item.w;
-    if (f != cf) {
+    if (f != cf || since == kMaxShare) {
       if (cf >= 0) flush(cf);
       cf = f;
+      since = 0;
     }
+    ++since;
     mbar_wait(&sm.full[warp][stage], (phases >> stage) & 1u);
     phases ^= 1u << stage;
     const uint8_t *st = my_tiles + stage * slot;
@@ -552,10 +555,9 @@ void launch_gram_imma(int nframes, const Geometry &g, uint8_t *records, const Re
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gram_imma_kernel, kGramThreads, smem);
     slots = sms * std::max(per_sm, 1);
   }
-  // A warp's share must stay below kMaxShare items (int32 accumulators): more CTAs than one wave if the batch is huge.
+  // one wave of persistent CTAs whatever the batch size: a warp flushes its int32 item accumulators every kMaxShare items
   const long long blocks = (long long)nframes * g.nb;
-  const long long need = (blocks + (long long)kMaxShare * kLumaWarps - 1) / ((long long)kMaxShare * kLumaWarps);
-  const int grid = (int)std::max<long long>(std::min<long long>(slots, std::max<long long>(1, blocks / 8)), need);
+  const int grid = (int)std::min<long long>(slots, std::max<long long>(1, blocks / 8));
   gram_imma_kernel<<<grid, kGramThreads, smem, st>>>(g, records, rl, nframes, static_cast<const uint8_t *>(tmaps));
 }
 

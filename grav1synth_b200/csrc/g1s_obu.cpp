@@ -209,17 +209,21 @@ bool same_grain(const g1s_segment &a, const g1s_segment &b) {
   auto pts = [](const uint8_t(*x)[2], int nx, const uint8_t(*y)[2], int ny) {
     return nx == ny && std::memcmp(x, y, (size_t)nx * 2) == 0;
   };
-  auto co = [](const int8_t *x, int nx, const int8_t *y, int ny) {
-    return nx == ny && std::memcmp(x, y, (size_t)nx) == 0;
+  // num_ar_coeffs_plus1 is the count + 1, or 0 for "follow the lag" (2 * lag * (lag + 1), +1 for chroma)
+  const int lag_n = 2 * a.ar_coeff_lag * (a.ar_coeff_lag + 1);
+  auto co = [&](const int8_t *x, int px, const int8_t *y, int py, int follow, int cap) {
+    if (px != py) return false;
+    const int n = std::min(px ? px - 1 : follow, cap);
+    return std::memcmp(x, y, (size_t)n) == 0;
   };
   return pts(a.scaling_points_y, a.num_y_points, b.scaling_points_y, b.num_y_points) &&
          pts(a.scaling_points_cb, a.num_cb_points, b.scaling_points_cb, b.num_cb_points) &&
          pts(a.scaling_points_cr, a.num_cr_points, b.scaling_points_cr, b.num_cr_points) &&
          a.scaling_shift == b.scaling_shift && a.ar_coeff_lag == b.ar_coeff_lag &&
-         co(a.ar_coeffs_y, a.num_ar_coeffs_plus1[0], b.ar_coeffs_y, b.num_ar_coeffs_plus1[0]) &&
-         co(a.ar_coeffs_cb, a.num_ar_coeffs_plus1[1], b.ar_coeffs_cb, b.num_ar_coeffs_plus1[1]) &&
-         co(a.ar_coeffs_cr, a.num_ar_coeffs_plus1[2], b.ar_coeffs_cr, b.num_ar_coeffs_plus1[2]) &&
-         a.num_ar_coeffs_plus1[0] == b.num_ar_coeffs_plus1[0] && a.ar_coeff_shift == b.ar_coeff_shift &&
+         co(a.ar_coeffs_y, a.num_ar_coeffs_plus1[0], b.ar_coeffs_y, b.num_ar_coeffs_plus1[0], lag_n, G1S_NUM_Y_COEFFS) &&
+         co(a.ar_coeffs_cb, a.num_ar_coeffs_plus1[1], b.ar_coeffs_cb, b.num_ar_coeffs_plus1[1], lag_n + 1, G1S_NUM_UV_COEFFS) &&
+         co(a.ar_coeffs_cr, a.num_ar_coeffs_plus1[2], b.ar_coeffs_cr, b.num_ar_coeffs_plus1[2], lag_n + 1, G1S_NUM_UV_COEFFS) &&
+         a.ar_coeff_shift == b.ar_coeff_shift &&
          a.cb_mult == b.cb_mult && a.cb_luma_mult == b.cb_luma_mult && a.cb_offset == b.cb_offset &&
          a.cr_mult == b.cr_mult && a.cr_luma_mult == b.cr_luma_mult && a.cr_offset == b.cr_offset &&
          a.chroma_scaling_from_luma == b.chroma_scaling_from_luma && a.grain_scale_shift == b.grain_scale_shift &&
@@ -888,8 +892,13 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
   if (!s.reduced_still_picture_header) {
     if (br.flag()) {  // show_existing_frame
       const int shown_slot = (int)br.f(3);  // frame_to_show_map_idx
+      // spec 5.9.2: temporal_point_info() precedes display_frame_id here too (the reference skips it, and then fails
+      // its alignment check on such streams)
+      if (s.has_decoder_model && !(s.has_timing_info && s.equal_picture_interval))
+        br.f((unsigned)s.frame_presentation_time_length_minus_1 + 1);
       if (id_len) br.f((unsigned)id_len);
-      if (have_frame_header && ref_frame_type[shown_slot] == KEY_FRAME && big_ref_valid[shown_slot]) {
+      if (!have_frame_header) throw ParseError("show_existing_frame before any frame header");
+      if (ref_frame_type[shown_slot] == KEY_FRAME && big_ref_valid[shown_slot]) {
         // spec 7.21: showing a key frame refreshes every slot with it (the reference skips this; later frames' skip-mode
         // decision reads these order hints)
         for (int i = 0; i < NUM_REF_FRAMES; ++i) {
@@ -901,7 +910,6 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
           big_ref_valid[i] = true;
         }
       }
-      if (!have_frame_header) throw ParseError("show_existing_frame before any frame header");
       if (verify_alignment) br.byte_alignment(true);
       fh.show_frame = true;
       fh.show_existing_frame = true;
@@ -926,7 +934,13 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
   const bool disable_cdf_update = br.flag();
   const bool allow_screen_content_tools =
       s.force_screen_content_tools == SELECT_SCREEN_CONTENT_TOOLS ? br.flag() : s.force_screen_content_tools == 1;
-  if (allow_screen_content_tools && s.force_integer_mv == SELECT_INTEGER_MV) br.flag();  // force_integer_mv
+  // spec 5.9.2: the FRAME-level force_integer_mv (coded only under SELECT_INTEGER_MV) gates allow_high_precision_mv
+  // below; the reference reads the bit and then tests the sequence-level value (frame.rs:469), which shifts every
+  // later field of such an inter frame by one bit
+  int force_integer_mv = 0;
+  if (allow_screen_content_tools)
+    force_integer_mv = s.force_integer_mv == SELECT_INTEGER_MV ? (int)br.flag() : s.force_integer_mv;
+  if (frame_is_intra) force_integer_mv = 1;
   if (s.frame_id_numbers_present) br.f((unsigned)id_len);                               // current_frame_id
   const bool frame_size_override_flag =
       frame_type == SWITCH_FRAME ? true : (s.reduced_still_picture_header ? false : br.flag());
@@ -980,12 +994,10 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
       }
     }
     for (int i = 0; i < REFS_PER_FRAME; ++i) {
-      if (frame_refs_short_signaling) {
-        // ref_frame_idx[i] was derived above
-      } else {
-        ref_frame_idx[i] = (int)br.f(3);
-        if (s.frame_id_numbers_present) br.f((unsigned)s.delta_frame_id_len_minus_2 + 2);  // delta_frame_id_minus_1
-      }
+      if (!frame_refs_short_signaling) ref_frame_idx[i] = (int)br.f(3);  // else derived above
+      // spec 5.9.2: delta_frame_id_minus_1 is coded for every reference whenever frame ids are present, short
+      // signaling or not
+      if (s.frame_id_numbers_present) br.f((unsigned)s.delta_frame_id_len_minus_2 + 2);
     }
     if (frame_size_override_flag && !error_resilient_mode) {
       int found_ref = -1;
@@ -1011,7 +1023,7 @@ FrameHeader g1s_inspect::uncompressed_header(BitReader &br, bool has_ext, int te
       upscaled = fsize;
       render_size(br);
     }
-    allow_high_precision_mv = s.force_integer_mv == 1 ? false : br.flag();
+    allow_high_precision_mv = force_integer_mv ? false : br.flag();
     if (!br.flag()) br.f(2);  // is_filter_switchable, interpolation_filter
     br.flag();                // is_motion_mode_switchable
     use_ref_frame_mvs = (error_resilient_mode || !s.enable_ref_frame_mvs) ? false : br.flag();

@@ -102,6 +102,7 @@ class Seq:
     enable_ref_frame_mvs: bool = False
     choose_screen_content_tools: bool = True   # SELECT_SCREEN_CONTENT_TOOLS
     timing_info: bool = False
+    equal_picture_interval: bool = True
     decoder_model: bool = False
     frame_id_numbers: bool = False
     operating_point_idc: Sequence[int] = (0,)
@@ -119,7 +120,9 @@ class Seq:
         else:
             b.push_bool(self.timing_info)
             if self.timing_info:
-                b.push_bits(1001, 32).push_bits(24000, 32).push_bool(True).push_uvlc(0)  # equal_picture_interval
+                b.push_bits(1001, 32).push_bits(24000, 32).push_bool(self.equal_picture_interval)
+                if self.equal_picture_interval:
+                    b.push_uvlc(0)  # num_ticks_per_picture_minus_1
                 b.push_bool(self.decoder_model)
                 if self.decoder_model:
                     b.push_bits(9, 5).push_bits(1, 32).push_bits(9, 5).push_bits(9, 5)
@@ -323,6 +326,7 @@ class Frame:
     grain: Grain = field(default_factory=Grain)
     show_existing_frame: Optional[int] = None  # frame_to_show_map_idx: the header is only that
     short_signaling: Optional[Tuple[int, int]] = None  # (last_frame_idx, gold_frame_idx): frame_refs_short_signaling
+    force_integer_mv: bool = False    # frame-level bit, coded when allow_screen_content_tools (sequence value is SELECT)
 
     def header_bits(self, s: Seq) -> BitBuilder:
         b = BitBuilder()
@@ -330,6 +334,8 @@ class Frame:
         num_planes = 1 if mono else 3
         if self.show_existing_frame is not None:
             b.push_bool(True).push_bits(self.show_existing_frame, 3)
+            if s.timing_info and s.decoder_model and not s.equal_picture_interval:
+                b.push_bits(5, 10)  # temporal_point_info: frame_presentation_time (length_minus_1 = 9)
             if s.frame_id_numbers:
                 b.push_bits(0, s.id_len())
             return b
@@ -337,6 +343,8 @@ class Frame:
         err_res = self.error_resilient
         if not s.reduced_still_picture_header:
             b.push_bool(False).push_bits(ft, 2).push_bool(self.show_frame)
+            if self.show_frame and s.timing_info and s.decoder_model and not s.equal_picture_interval:
+                b.push_bits(5, 10)  # temporal_point_info
             if not self.show_frame:
                 b.push_bool(self.showable_frame)
             if ft == 3 or (ft == 0 and self.show_frame):
@@ -348,7 +356,7 @@ class Frame:
         if s.reduced_still_picture_header or s.choose_screen_content_tools:
             b.push_bool(sct)
             if sct:
-                b.push_bool(False)  # force_integer_mv (seq_choose_integer_mv = 1 / reduced -> SELECT)
+                b.push_bool(self.force_integer_mv)  # coded: seq_choose_integer_mv = 1 / reduced -> SELECT
         else:
             sct = False
         if s.frame_id_numbers:
@@ -379,14 +387,16 @@ class Frame:
                 b.push_bool(self.short_signaling is not None)  # frame_refs_short_signaling
                 if self.short_signaling is not None:
                     b.push_bits(self.short_signaling[0], 3).push_bits(self.short_signaling[1], 3)
-            for idx in (self.ref_frame_idx if self.short_signaling is None else ()):
-                b.push_bits(idx, 3)
-                if s.frame_id_numbers:
+            for idx in self.ref_frame_idx:
+                if self.short_signaling is None:
+                    b.push_bits(idx, 3)
+                if s.frame_id_numbers:  # for every reference, short signaling or not (spec 5.9.2)
                     b.push_bits(0, 2 + 2)  # delta_frame_id_minus_1, delta_frame_id_length_minus_2 = 2
             if s.enable_superres:
                 b.push_bool(False)
             b.push_bool(False)  # render_and_frame_size_different
-            b.push_bool(True)   # allow_high_precision_mv (sequence force_integer_mv is SELECT)
+            if not (sct and self.force_integer_mv):
+                b.push_bool(True)   # allow_high_precision_mv: absent when the FRAME's force_integer_mv is 1
             b.push_bool(True)   # is_filter_switchable
             b.push_bool(False)  # is_motion_mode_switchable
             if not err_res and s.enable_ref_frame_mvs:

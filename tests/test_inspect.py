@@ -632,3 +632,73 @@ def test_inspect_symbols_exported():
     L = ctypes.CDLL(LIB_PATH)
     for name in I.EXPORTS:
         assert hasattr(L, name), name
+
+
+def test_frame_level_force_integer_mv_gates_allow_high_precision_mv():
+    """spec 5.9.2: under SELECT_INTEGER_MV the frame codes its own force_integer_mv, and allow_high_precision_mv is
+    absent when that bit is 1.  (The reference reads the bit and then tests the sequence-level value, frame.rs:469, so
+    every later field of such an inter frame is off by one bit.)"""
+    seq = Seq()
+    for fim in (False, True):
+        packets = [
+            W.temporal_delimiter() + seq.obu() + Frame(frame_type=0, order_hint=0, grain=GA).frame_obu(seq),
+            W.temporal_delimiter() + Frame(frame_type=1, order_hint=1, allow_screen_content_tools=True,
+                                           force_integer_mv=fim, grain=GB).frame_obu(seq),
+        ]
+        p = I.BitstreamParser()
+        for pk in packets:
+            p.push_packet(pk)
+        hs = p.get_grain_headers()
+        assert len(hs) == 2 and header_view(hs[1]) == expected_view(I.UPDATE_GRAIN, GB, seq), fim
+
+
+def test_delta_frame_ids_are_coded_with_short_signaling_too():
+    """spec 5.9.2: delta_frame_id_minus_1 follows every reference when frame ids are present, whether ref_frame_idx[i]
+    itself was coded or derived by frame_refs_short_signaling."""
+    seq = Seq(frame_id_numbers=True)
+    for short in (None, (0, 0)):
+        packets = [
+            W.temporal_delimiter() + seq.obu() + Frame(frame_type=0, order_hint=0, grain=GA).frame_obu(seq),
+            W.temporal_delimiter() + Frame(frame_type=1, order_hint=1, short_signaling=short, grain=GB).frame_obu(seq),
+        ]
+        p = I.BitstreamParser()
+        for pk in packets:
+            p.push_packet(pk)
+        hs = p.get_grain_headers()
+        assert len(hs) == 2 and header_view(hs[1]) == expected_view(I.UPDATE_GRAIN, GB, seq), short
+
+
+def test_temporal_point_info_in_shown_and_show_existing_headers():
+    """Decoder model without equal_picture_interval: frame_presentation_time is coded in every shown frame header AND
+    in show_existing_frame headers (the reference skips the latter and then fails its alignment check)."""
+    seq = Seq(timing_info=True, decoder_model=True, equal_picture_interval=False)
+    hidden = Frame(frame_type=1, order_hint=2, show_frame=False, showable_frame=True, refresh_frame_flags=0x02, grain=GB)
+    packets = [
+        W.temporal_delimiter() + seq.obu() + Frame(frame_type=0, order_hint=0, grain=GA).frame_obu(seq),
+        W.temporal_delimiter() + hidden.frame_obu(seq) + Frame(frame_type=1, order_hint=1, grain=GA2).frame_obu(seq),
+        W.temporal_delimiter() + Frame(show_existing_frame=1).frame_header_obu(seq),
+    ]
+    p = I.BitstreamParser()
+    for pk in packets:
+        p.push_packet(pk)
+    hs = p.get_grain_headers()
+    assert [h.kind for h in hs] == [I.UPDATE_GRAIN, I.UPDATE_GRAIN, I.COPY_REF_FRAME]
+
+
+def test_aggregation_compares_every_coefficient_the_count_names():
+    """same_grain (grain.rs:83-105 equality) looks at exactly the coefficients the count byte names (count + 1 is
+    stored): headers that differ only in the LAST chroma coefficient (the luma-correlation tap, 25th at lag 3) are two
+    segments, headers that differ only in the seed are one."""
+    seq = Seq()
+    base = dict(points_y=((0, 30), (255, 90)), ar_coeff_lag=3, scaling_shift=11, ar_coeff_shift=9)
+    cr_a = [((i * 3) % 23) - 11 for i in range(25)]
+    cr_b = cr_a[:24] + [cr_a[24] + 1]
+
+    def table(g1, g2):
+        p = I.BitstreamParser()
+        p.push_packet(W.temporal_delimiter() + seq.obu() + Frame(frame_type=0, order_hint=0, grain=g1).frame_obu(seq))
+        p.push_packet(W.temporal_delimiter() + Frame(frame_type=1, order_hint=1, grain=g2).frame_obu(seq))
+        return p.aggregate_grain_headers(24, 1)
+
+    assert len(table(Grain(seed=5, ar_coeffs_cr=cr_a, **base), Grain(seed=6, ar_coeffs_cr=cr_a, **base))) == 1
+    assert len(table(Grain(seed=5, ar_coeffs_cr=cr_a, **base), Grain(seed=6, ar_coeffs_cr=cr_b, **base))) == 2
