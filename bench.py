@@ -241,6 +241,14 @@ def main():
     F = args.frames
     pair_bytes = frame_pair_bytes(W, H, 1, 1, bd, bd)
 
+    # ---- multi-GPU parity, before anything is timed: a two-scene stream through the NCCL-sharded path must give the
+    # single-GPU table (segment cut and short tail super-batch included); a mismatch fails the run
+    parity = None
+    if world > 1:
+        from grav1synth_b200.sharded import parity_check
+        pframes, pseg = parity_check(local_rank)
+        parity = {"parity_checked": True, "parity_frames": pframes, "parity_segments": pseg}
+
     # ---- synthetic frames, generated directly in HBM (distinct per rank), outside the timed region
     dev = f"cuda:{local_rank}"
     frames = [make_pair(spec, rank * F + k, dev) for k in range(F)]
@@ -341,6 +349,8 @@ def main():
     }
     if clk is not None:
         line["clocks"] = clk
+    if parity is not None:
+        line.update(parity)
     table = eng.finish() if world == 1 else sd.finish()
     if rank == 0:
         line["config"]["segments"] = len(table)

@@ -201,8 +201,12 @@ struct g1s_diff {
   // the device, and the PCIe link, only ever see 8-bit planes; host_* keep what the caller's planes look like
   bool narrow = false;
   int host_bytes[2] = {1, 1}, host_shift[2] = {0, 0};
-  cudaStream_t stream = nullptr;       // kernels + record read-back
-  cudaEvent_t marks[2] = {nullptr, nullptr};
+  cudaStream_t stream = nullptr;       // kernels of even batches (and the benchmark marks)
+  cudaStream_t stream2 = nullptr;      // kernels of odd batches: consecutive batches overlap on the device, so the
+                                       // FP64-bound flat-block finder of one runs beside the HBM- / tensor-bound
+                                       // residual and Gram kernels of the other (null: one stream, G1S_STREAMS=1)
+  cudaEvent_t marks[2] = {nullptr, nullptr}, join = nullptr;
+  uint64_t submitted = 0;
   cudaStream_t copy_stream = nullptr;  // per-frame host->device copies, overlapping the staging of the next frame
   cudaStream_t d2h_stream = nullptr;   // record read-back, overlapping the kernels of the next batch
   Slot slots[kSlots];
@@ -315,7 +319,7 @@ bool build_residual_maps(g1s_diff *d, Slot &s, std::vector<CUtensorMap> &host) {
 
 int submit(g1s_diff *d, Slot &s) {
   if (s.count == 0) return G1S_OK;
-  cudaStream_t st = d->stream;
+  cudaStream_t st = (d->stream2 && (d->submitted++ & 1)) ? d->stream2 : d->stream;
   if (s.host_frames > 0) {  // frames were sent one by one on the copy stream as they were pushed
     CU_TRY(d, cudaEventRecord(s.copied, d->copy_stream));
     CU_TRY(d, cudaStreamWaitEvent(st, s.copied, 0));
@@ -579,6 +583,11 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
       (void)cudaGetLastError();
   }
   CU_NEW(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  {
+    const char *e = std::getenv("G1S_STREAMS");
+    if (!e || std::atoi(e) >= 2) CU_NEW(cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
+    CU_NEW(cudaEventCreateWithFlags(&d->join, cudaEventDisableTiming));
+  }
   CU_NEW(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
   CU_NEW(cudaStreamCreateWithFlags(&d->d2h_stream, cudaStreamNonBlocking));
   // int8 tensor-core path (residual_kernel + gram_imma_kernel): 4:2:0 / monochrome, TMA descriptors available
@@ -860,6 +869,7 @@ void g1s_diff_destroy(g1s_diff *d) {
   if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
   if (d->d2h_stream) cudaStreamSynchronize(d->d2h_stream);
   if (d->stream) cudaStreamSynchronize(d->stream);
+  if (d->stream2) cudaStreamSynchronize(d->stream2);
   for (Slot &s : d->slots) {
     if (s.d_frames) cudaFree(s.d_frames);
     if (s.h_frames) cudaFreeHost(s.h_frames);
@@ -874,7 +884,9 @@ void g1s_diff_destroy(g1s_diff *d) {
   }
   for (cudaEvent_t e : d->marks)
     if (e) cudaEventDestroy(e);
+  if (d->join) cudaEventDestroy(d->join);
   if (d->stream) cudaStreamDestroy(d->stream);
+  if (d->stream2) cudaStreamDestroy(d->stream2);
   if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
   if (d->d2h_stream) cudaStreamDestroy(d->d2h_stream);
   delete d;
@@ -895,6 +907,10 @@ int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n) {
 int g1s_diff_mark(g1s_diff *d, int which) {
   if (!d || which < 0 || which > 1 || !d->stream) return G1S_E_ARG;
   if (!d->marks[which]) CU_TRY(d, cudaEventCreate(&d->marks[which]));
+  if (d->stream2) {  // the mark covers both kernel streams
+    CU_TRY(d, cudaEventRecord(d->join, d->stream2));
+    CU_TRY(d, cudaStreamWaitEvent(d->stream, d->join, 0));
+  }
   CU_TRY(d, cudaEventRecord(d->marks[which], d->stream));
   return G1S_OK;
 }

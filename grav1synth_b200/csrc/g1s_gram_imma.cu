@@ -159,57 +159,60 @@ __device__ __forceinline__ void snapshot(uint32_t (&G)[10][2], const int (&acc)[
   }
 }
 
-// Window bookkeeping of one item with n = y1 - y0 observed rows, pairs i = 0 .. P-1 (pair i = tile rows y0+2i, +1):
-// tap row q' sums the lower-half rows of pairs [ceil(q'/2), ceil((n+q')/2)) and the upper-half rows of pairs
-// [ceil((q'-1)/2), ceil((n+q'-1)/2)).  Start events are fixed (after pair -1: E0 O0 O1; 0: E1 E2 O2 O3; 1: E3).
-__device__ __forceinline__ uint32_t start_events(int i) { return i == -1 ? 0x31u : (i == 0 ? 0xC6u : (i == 1 ? 0x08u : 0u)); }
-__device__ __forceinline__ uint32_t end_events(int i, int n) {
-  uint32_t ev = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    if (i == ((n + q + 1) >> 1) - 1) ev |= 1u << q;
-    if (i == ((n + q) >> 1) - 1) ev |= 16u << q;
-  }
-  return ev;
+// Window bookkeeping of one item with n = y1 - y0 observed rows, pairs i = 0 .. P-1 (pair i = tile rows y0+2i, +1),
+// P = (n + 4) / 2 = m + 2 with m = n / 2: tap row q' sums the lower-half rows of pairs [ceil(q'/2), ceil((n+q')/2)) and
+// the upper-half rows of pairs [ceil((q'-1)/2), ceil((n+q'-1)/2)).  Written out (E = lower half, O = upper half):
+//   windows open   before pair 0: E0 O0 O1     after pair 0: E1 E2 O2 O3     after pair 1: E3
+//   windows close  n even   after pair m-1: E0 O0 O1    m: E1 E2 O2 O3    m+1: E3
+//                  n odd    after pair m-1: O0          m: E0 E1 O1 O2    m+1: E2 E3 O3
+// so an item is: two pair steps with fixed snapshots, a hook-free core of m - 3 steps, three steps with the closing
+// snapshots.  That needs m >= 3; the rare shorter items (a sliver of rows at the bottom of the frame) are handed to
+// the exact generic kernel by the caller.
+constexpr int kMinRows = 6;
+constexpr uint32_t kEvA = 0x31u, kEvB = 0xC6u, kEvC = 0x08u;          // {E0 O0 O1}, {E1 E2 O2 O3}, {E3}
+constexpr uint32_t kOddA = 0x10u, kOddB = 0x63u, kOddC = 0x8Cu;       // {O0}, {E0 E1 O1 O2}, {E2 E3 O3}
+
+// A pair step whose ring phase is only known at run time (the steps outside the unrolled core).
+__device__ __forceinline__ void pair_step_rt(int &ph, Ring &w, const uint32_t *__restrict__ p, int sh,
+                                             const uint32_t (&mx)[2], int (&acc)[5][4]) {
+  if (ph == 0) pair_step<0>(w, p, sh, mx, acc);
+  else if (ph == 1) pair_step<1>(w, p, sh, mx, acc);
+  else pair_step<2>(w, p, sh, mx, acc);
+  ph = ph == 2 ? 0 : ph + 1;
 }
 
-// All rows of one item (or of one block of a chroma pair): base points at tile row 0.
+// All rows of one item (or of one block of a chroma pair): base points at tile row 0; n = y1 - y0 >= kMinRows.
 __device__ __forceinline__ void item_rows(const uint32_t *__restrict__ base, int sh, int y0, int y1, const uint32_t (&mx)[2],
                                           Ring &w, int (&acc)[5][4], uint32_t (&G)[10][2]) {
-  const int n = y1 - y0, P = (n + 4) >> 1;
-  uint32_t hm = 3u;  // pairs followed by events
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int e = ((n + q + 1) >> 1) - 1, o = ((n + q) >> 1) - 1;
-    if (e >= 0) hm |= 1u << e;
-    if (o >= 0) hm |= 1u << o;
-  }
-  asm volatile("" : "+r"(hm));  // keep it in a register: ptxas otherwise rebuilds the mask in front of every test
-  snapshot(G, acc, start_events(-1), false);
-  if (const uint32_t ev = end_events(-1, n)) snapshot(G, acc, ev, true);
-  auto hook = [&](int i) {
-    if (const uint32_t ev = start_events(i)) snapshot(G, acc, ev, false);
-    if (const uint32_t ev = end_events(i, n)) snapshot(G, acc, ev, true);
-  };
+  const int n = y1 - y0, m = n >> 1;
+  const bool odd = n & 1;
   const uint32_t *p = base + y0 * kRowWords;
-  int i = 0;
+  int ph = 0;
+  snapshot(G, acc, kEvA, false);
+  pair_step<0>(w, p, sh, mx, acc);
+  snapshot(G, acc, kEvB, false);
+  pair_step<1>(w, p + 2 * kRowWords, sh, mx, acc);
+  snapshot(G, acc, kEvC, false);
+  p += 4 * kRowWords;
+  int core = m - 3;  // pairs 2 .. m-2
 #pragma unroll 1
-  for (; i + 3 <= P; i += 3, p += 6 * kRowWords) {
-    pair_step<0>(w, p, sh, mx, acc);
-    if ((hm >> i) & 1u) hook(i);
-    pair_step<1>(w, p + 2 * kRowWords, sh, mx, acc);
-    if ((hm >> i) & 2u) hook(i + 1);
-    pair_step<2>(w, p + 4 * kRowWords, sh, mx, acc);
-    if ((hm >> i) & 4u) hook(i + 2);
+  for (; core >= 3; core -= 3, p += 6 * kRowWords) {
+    pair_step<2>(w, p, sh, mx, acc);
+    pair_step<0>(w, p + 2 * kRowWords, sh, mx, acc);
+    pair_step<1>(w, p + 4 * kRowWords, sh, mx, acc);
   }
-  if (i < P) {
-    pair_step<0>(w, p, sh, mx, acc);
-    if ((hm >> i) & 1u) hook(i);
-    if (i + 1 < P) {
-      pair_step<1>(w, p + 2 * kRowWords, sh, mx, acc);
-      if ((hm >> i) & 2u) hook(i + 1);
-    }
-  }
+  ph = 2;
+#pragma unroll 1
+  for (; core > 0; --core, p += 2 * kRowWords) pair_step_rt(ph, w, p, sh, mx, acc);
+  pair_step_rt(ph, w, p, sh, mx, acc);  // pair m-1
+  if (odd) snapshot(G, acc, kOddA, true);
+  else snapshot(G, acc, kEvA, true);
+  pair_step_rt(ph, w, p + 2 * kRowWords, sh, mx, acc);  // pair m
+  if (odd) snapshot(G, acc, kOddB, true);
+  else snapshot(G, acc, kEvB, true);
+  pair_step_rt(ph, w, p + 4 * kRowWords, sh, mx, acc);  // pair m+1
+  if (odd) snapshot(G, acc, kOddC, true);
+  else snapshot(G, acc, kEvC, true);
 }
 
 // MMA tap index a = 8q+g  ->  record tap index (0..23 AR taps, 24 chroma's luma tap, 25 centre sample), -1 unused.
@@ -473,13 +476,16 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
     const uint8_t *st = my_tiles + stage * slot;
     // up to two passes over the item's rows: (first observed row, masks of the two halves)
     int npass = 0, y1, ya = 0, yb = 0;
+    bool short_a = false, short_b = false;  // blocks of the item left to the generic kernel (too few rows)
     uint32_t ma[2] = {0u, 0u}, mb[2] = {0u, 0u};
     const uint32_t *base;
     if (luma) {
       const int xs = (bits & 1u) ? 0 : kLag, y0 = (bits & 4u) ? 0 : kLag;
       const int x1 = min(W - 32 * ix - kLag, (bits & 2u) ? 32 : 32 - kLag);
       y1 = min(H - 32 * by, 32);
-      if (x1 > xs && y1 > y0) {
+      if (x1 > xs && y1 > y0 && y1 - y0 < kMinRows) {
+        short_a = true;
+      } else if (x1 > xs && y1 > y0) {
         const bool full = xs == 0 && x1 == 32;
         ma[0] = full ? 0xFFFFFFFFu : byte_mask(4 * t, xs, x1);
         ma[1] = full ? 0xFFFFFFFFu : byte_mask(16 + 4 * t, xs, x1);
@@ -497,8 +503,10 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
       const int y0a = (bits & 16u) ? 0 : kLag, y0b = (bits & 32u) ? 0 : kLag;
       const int x1a = min(pw - 16 * bxa - kLag, (bits & 4u) ? 16 : 16 - kLag);
       const int x1b = min(pw - 16 * (bxa + 1) - kLag, (bits & 8u) ? 16 : 16 - kLag);
-      const bool on0 = fla && x1a > xsa && y1 > y0a;
-      const bool on1 = flb && x1b > xsb && y1 > y0b;
+      bool on0 = fla && x1a > xsa && y1 > y0a;
+      bool on1 = flb && x1b > xsb && y1 > y0b;
+      if (on0 && y1 - y0a < kMinRows) short_a = true, on0 = false;
+      if (on1 && y1 - y0b < kMinRows) short_b = true, on1 = false;
       const uint32_t m0 = !on0 ? 0u : (xsa == 0 && x1a == 16) ? 0xFFFFFFFFu : byte_mask(4 * t, xsa, x1a);
       const uint32_t m1 = !on1 ? 0u : (xsb == 0 && x1b == 16) ? 0xFFFFFFFFu : byte_mask(4 * t, xsb, x1b);
       if (on0 && on1 && y0a == y0b) {
@@ -522,6 +530,17 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
     for (int pass = 0; pass < npass; ++pass) {
       if (pass == 1) ma[0] = mb[0], ma[1] = mb[1], ya = yb;
       item_rows(base, sh, ya, y1, ma, ring, acc, G);
+    }
+    if (short_a | short_b) {
+      // a sliver of fewer than kMinRows observed rows (bottom of the frame): the exact generic kernel, launched right
+      // after this one, accumulates the block; only this warp ever reads or writes the flags of its own items
+      uint8_t *rec = records + (size_t)f * rl.bytes;
+      if (lane == 0) {
+        const int b0 = by * g.nbw + (luma ? ix : 2 * ix);
+        if (short_a) (rec + rl.off_ovf)[(size_t)plane * g.nb + b0] = 1;
+        if (short_b) (rec + rl.off_ovf)[(size_t)plane * g.nb + b0 + 1] = 1;
+        atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_ovf_count), 1ull);
+      }
     }
   }
   if (cf >= 0) flush(cf);

@@ -160,3 +160,44 @@ class ShardedDiff:
 def owner_of(frame_index: int, world: int, frames_per_rank: int) -> int:
     """Rank that owns a global frame index under the round-robin batch dealing."""
     return (frame_index // frames_per_rank) % world
+
+
+def parity_check(device: int, frames_per_rank: int = 3, super_batches: int = 5, gram_order: int = 0):
+    """Multi-rank parity, on an initialised process group: a small two-scene stream (segment cut, short tail
+    super-batch) goes through ShardedDiff -- every rank pushes only the frames it owns -- and through ONE single-GPU
+    handle on rank 0; the two grain tables must be identical.  Returns (frames, segments) on rank 0, (frames, None)
+    elsewhere; raises on a mismatch.  Used by bench.py before its timed region at N > 1 and by tools/sharded_check.py."""
+    from .synth import SynthSpec, make_pair_numpy
+    rank, world = dist.get_rank(), dist.get_world_size()
+    B, nsb = frames_per_rank, super_batches
+    a = SynthSpec(320, 208, 10, textured=0.2, sigma0=1.0, sigma1=1.5, seed=5)
+    b = SynthSpec(320, 208, 10, textured=0.2, sigma0=2.5, sigma1=0.5, ar_strength=0.6, seed=6)
+    total = world * B * (nsb - 1) + (world - 1) * B + 1  # the tail super-batch: full ranks, then one frame
+    frames = {k: make_pair_numpy(a if k < total // 2 else b, k) for k in range(total)
+              if rank == 0 or owner_of(k, world, B) == rank}
+    sd = ShardedDiff(30000, 1001, 10, 10, a.width, a.height, 1, 1, frames_per_rank=B, device=device, batch_frames=2)
+    k = 0
+    while k < total:
+        base = k
+        for j in range(world * B):
+            g = base + j
+            if g < total and owner_of(g, world, B) == rank:
+                sd.push_local(*frames[g])
+        k = min(total, base + world * B)
+        sd.exchange(final=k >= total)
+    table = sd.finish()
+    sd.producer.close()
+    nseg = None
+    if rank == 0:
+        ref = DiffGenerator(30000, 1001, 10, 10, a.width, a.height, device=device)
+        for g in range(total):
+            ref.diff_frame(*frames[g])
+        want = ref.finish()
+        ref.close()
+        if table != want:
+            raise AssertionError("sharded grain table differs from the single-handle table")
+        if len(want) < 2:
+            raise AssertionError("the parity stream is meant to cut a segment")
+        nseg = len(want)
+    dist.barrier()
+    return total, nseg
