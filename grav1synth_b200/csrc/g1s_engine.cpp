@@ -36,7 +36,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 
 // Minimal fork-join pool for the per-frame (order independent) half of the host model.
 class HostPool {
@@ -175,6 +175,8 @@ struct Slot {
   FrameDesc *h_descs = nullptr;  // pinned
   int8_t *d_res = nullptr;           // B * ResidualStore::frame_bytes: s8 residual + luma-tap planes (tensor-core path)
   CUtensorMap *d_rmaps = nullptr;    // [B][kResidualMaps] TMA descriptors of d_res, built once
+  void *d_plan = nullptr;            // gram_plan_kernel's unit descriptors of the batch
+  int *d_plan_counts = nullptr;      // [B][3] units per frame and plane
   uint8_t *d_records = nullptr;
   uint8_t *h_records = nullptr;  // pinned
   cudaEvent_t done = nullptr, k0_beg = nullptr, k0_end = nullptr, kr_beg = nullptr, k1_beg = nullptr, k1_end = nullptr,
@@ -202,9 +204,10 @@ struct g1s_diff {
   bool narrow = false;
   int host_bytes[2] = {1, 1}, host_shift[2] = {0, 0};
   cudaStream_t stream = nullptr;       // kernels of even batches (and the benchmark marks)
-  cudaStream_t stream2 = nullptr;      // kernels of odd batches: consecutive batches overlap on the device, so the
-                                       // FP64-bound flat-block finder of one runs beside the HBM- / tensor-bound
-                                       // residual and Gram kernels of the other (null: one stream, G1S_STREAMS=1)
+  cudaStream_t more[3] = {nullptr, nullptr, nullptr};  // kernel streams of the other batches in flight: consecutive
+                                       // batches overlap on the device, so the FP64-bound flat-block finder of one
+                                       // runs beside the HBM- / tensor-bound residual and Gram kernels of another
+  int nstreams = 1;                    // G1S_STREAMS, default 3
   cudaEvent_t marks[2] = {nullptr, nullptr}, join = nullptr;
   uint64_t submitted = 0;
   cudaStream_t copy_stream = nullptr;  // per-frame host->device copies, overlapping the staging of the next frame
@@ -319,7 +322,8 @@ bool build_residual_maps(g1s_diff *d, Slot &s, std::vector<CUtensorMap> &host) {
 
 int submit(g1s_diff *d, Slot &s) {
   if (s.count == 0) return G1S_OK;
-  cudaStream_t st = (d->stream2 && (d->submitted++ & 1)) ? d->stream2 : d->stream;
+  const int which = (int)(d->submitted++ % (uint64_t)d->nstreams);
+  cudaStream_t st = which ? d->more[which - 1] : d->stream;
   if (s.host_frames > 0) {  // frames were sent one by one on the copy stream as they were pushed
     CU_TRY(d, cudaEventRecord(s.copied, d->copy_stream));
     CU_TRY(d, cudaStreamWaitEvent(st, s.copied, 0));
@@ -347,10 +351,11 @@ int submit(g1s_diff *d, Slot &s) {
     CU_TRY(d, cudaEventRecord(s.kr_beg, st));
     launch_residual(s.d_descs, s.count, d->geom, rs, s.d_records, d->rl, aligned, st);
     CU_TRY(d, cudaEventRecord(s.k1_beg, st));
-    launch_gram_imma(s.count, d->geom, s.d_records, d->rl, s.d_rmaps, st);
+    launch_gram_plan(s.count, d->geom, s.d_records, d->rl, s.d_plan, s.d_plan_counts, st);
+    launch_gram_imma(s.count, d->geom, s.d_records, d->rl, s.d_rmaps, s.d_plan, s.d_plan_counts, st);
     CU_TRY(d, cudaEventRecord(s.k1_end, st));
     launch_gram_generic(s.d_descs, s.count, d->geom, s.d_records, d->rl, /*only_overflow=*/true, st);
-    gram_launches = 3;
+    gram_launches = 4;
     d->tma_batches += 1;
     if (aligned) d->vector_batches += 1;
   } else {
@@ -567,7 +572,7 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
       if (eff >= best) best = eff, batch = b;
     }
   }
-  d->batch = batch;
+  d->batch = batch = std::min(batch, 64);  // the Gram kernel's warps keep a batch's unit counts in two registers per lane
 
   if (consumer) {
     *out = d.release();
@@ -585,7 +590,8 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   CU_NEW(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   {
     const char *e = std::getenv("G1S_STREAMS");
-    if (!e || std::atoi(e) >= 2) CU_NEW(cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
+    d->nstreams = e ? std::min(std::max(std::atoi(e), 1), 4) : 3;  // measured: 16.1 / 17.6 / 18.5 k frames/s with 1 / 2 / 3
+    for (int i = 1; i < d->nstreams; ++i) CU_NEW(cudaStreamCreateWithFlags(&d->more[i - 1], cudaStreamNonBlocking));
     CU_NEW(cudaEventCreateWithFlags(&d->join, cudaEventDisableTiming));
   }
   CU_NEW(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
@@ -599,6 +605,8 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     if (d->tensor_path) {
       CU_NEW(cudaMalloc(&s.d_res, d->rstore.frame_bytes * batch));
       CU_NEW(cudaMalloc(&s.d_rmaps, sizeof(CUtensorMap) * kResidualMaps * batch));
+      CU_NEW(cudaMalloc(&s.d_plan, gram_plan_bytes(batch, g)));
+      CU_NEW(cudaMalloc(&s.d_plan_counts, sizeof(int) * 3 * batch));
       std::vector<CUtensorMap> host;
       if (!build_residual_maps(d.get(), s, host)) {
         d->err = "cuTensorMapEncodeTiled failed for the residual planes";
@@ -869,12 +877,15 @@ void g1s_diff_destroy(g1s_diff *d) {
   if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
   if (d->d2h_stream) cudaStreamSynchronize(d->d2h_stream);
   if (d->stream) cudaStreamSynchronize(d->stream);
-  if (d->stream2) cudaStreamSynchronize(d->stream2);
+  for (cudaStream_t m : d->more)
+    if (m) cudaStreamSynchronize(m);
   for (Slot &s : d->slots) {
     if (s.d_frames) cudaFree(s.d_frames);
     if (s.h_frames) cudaFreeHost(s.h_frames);
     if (s.d_res) cudaFree(s.d_res);
     if (s.d_rmaps) cudaFree(s.d_rmaps);
+    if (s.d_plan) cudaFree(s.d_plan);
+    if (s.d_plan_counts) cudaFree(s.d_plan_counts);
     if (s.d_descs) cudaFree(s.d_descs);
     if (s.h_descs) cudaFreeHost(s.h_descs);
     if (s.d_records) cudaFree(s.d_records);
@@ -886,7 +897,8 @@ void g1s_diff_destroy(g1s_diff *d) {
     if (e) cudaEventDestroy(e);
   if (d->join) cudaEventDestroy(d->join);
   if (d->stream) cudaStreamDestroy(d->stream);
-  if (d->stream2) cudaStreamDestroy(d->stream2);
+  for (cudaStream_t m : d->more)
+    if (m) cudaStreamDestroy(m);
   if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
   if (d->d2h_stream) cudaStreamDestroy(d->d2h_stream);
   delete d;
@@ -907,10 +919,11 @@ int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n) {
 int g1s_diff_mark(g1s_diff *d, int which) {
   if (!d || which < 0 || which > 1 || !d->stream) return G1S_E_ARG;
   if (!d->marks[which]) CU_TRY(d, cudaEventCreate(&d->marks[which]));
-  if (d->stream2) {  // the mark covers both kernel streams
-    CU_TRY(d, cudaEventRecord(d->join, d->stream2));
-    CU_TRY(d, cudaStreamWaitEvent(d->stream, d->join, 0));
-  }
+  for (cudaStream_t m : d->more)  // the mark covers every kernel stream
+    if (m) {
+      CU_TRY(d, cudaEventRecord(d->join, m));
+      CU_TRY(d, cudaStreamWaitEvent(d->stream, d->join, 0));
+    }
   CU_TRY(d, cudaEventRecord(d->marks[which], d->stream));
   return G1S_OK;
 }

@@ -1,4 +1,4 @@
-// gram_imma_kernel — the AR normal-equation (Gram) accumulation on the int8 tensor-core path
+// gram_plan_kernel + gram_imma_kernel — the AR normal-equation (Gram) accumulation on the int8 tensor-core path
 // (mma.sync.m16n8k32.s8, SASS IMMA.16832.S8.S8), 4:2:0 and monochrome.
 //
 // Replaces NoiseModel::add_block_observations (extract_ar_row + the n x n outer-product accumulation) of
@@ -7,27 +7,32 @@
 // residual_kernel and is redone exactly by gram_generic_kernel.  All sums are integers, so the result is
 // bit-identical to the oracle whatever the summation order.
 //
-// The kernel never touches the frames: residual_kernel left the s8 residual of Y / Cb / Cr and chroma's
-// luma tap (sum of the co-sited 2x2 luma residuals) in engine-owned planes, and every warp pulls the tiles
-// of its own work items into its own slice of shared memory with the TMA engine (cp.async.bulk.tensor.2d,
-// SASS UTMALDG; frame edges are zero-filled by the hardware, so there is no edge path), one or two items
-// ahead of its k-loop.
+// Two kernels.
+//  * gram_plan_kernel (one CTA per frame and plane, one thread per block column) turns the flat-block map into
+//    the work list of the plane: it applies add_block_observations' rectangle rules (3-sample margins unless the
+//    neighbour block is flat, frame clipping), joins vertically adjacent blocks whose column ranges agree into
+//    STRIPS (one row window, so the window bookkeeping below is paid once per strip instead of once per block and
+//    the 3 halo rows between joined blocks are not read twice), and writes one 16-byte descriptor per strip and
+//    tile ("unit").  It also counts the observations and hands slivers of fewer than kMinRows rows to the generic
+//    kernel.  All the irregular, scalar work of the path lives here, massively parallel and off the hot loop.
+//  * gram_imma_kernel never touches the frames or the flags: residual_kernel left the s8 residual of Y / Cb / Cr
+//    and chroma's luma tap in engine-owned planes, and every warp walks a contiguous share of its plane's units,
+//    pulling each unit's tile into its own slice of shared memory with the TMA engine (cp.async.bulk.tensor.2d,
+//    SASS UTMALDG; frame edges are zero-filled by the hardware, so there is no edge path), two units ahead.
 //
 // Why warps are autonomous.  Measured on the B200 (tools/imma_probe.cu, profiles/): the legacy IMMA path
 // holds a sub-partition's issue port for its whole 8.4 cycles, so a sub-partition's time is
 // 8.4 * IMMAs + (every other warp instruction it issues) -- nothing overlaps, polls and barrier spins are
 // paid in full.  So: no CTA barriers, no shared rings, no inter-warp waits.  A warp has a plane for life
-// (5 luma + 3 chroma warps per CTA), an equal contiguous share of that plane's blocks over the whole batch,
-// its own mbarriers, and it adds its int32 accumulators to the frame's int64 record directly when its share
-// leaves a frame (about 330 atomics, once or twice per warp per launch).
-//   work item   luma: one 32x32 block; chroma: two adjacent 16x16 blocks (32 columns either way)
+// (5 luma + 3 chroma warps per CTA), its own mbarriers, and it adds its int32 accumulators to the frame's
+// int64 record directly when its share leaves a frame.
+//   unit        one tile of a strip: luma one 32x32 block, chroma two adjacent 16x16 blocks (32 columns either way)
 //   Tap a = 8q+g with g = cx+3 (the mma lane group), q = cy+3.  A lane's operand of a residual row is ONE
 //   32-bit window per half (two LDS + funnel shift), and the same window is the row's B pair and its half of
 //   an A quad.  The arithmetic is the row-pair deduplicated form described above the k-loops: 2.5 MMAs per
 //   residual row instead of 6 per observed row (round 1), every row fetched once.
 //   The observation mask (block margins, frame clipping) is a byte mask on k applied to the A operand.
 //   Chroma's luma tap rides in lane group g = 7 (those lanes walk the luma-tap tile), so it costs no MMA.
-//   int32 item accumulators are bounded by the share: <= 96 blocks * 1024 * 127^2 < 2^31.
 #include "g1s_kernels.h"
 
 #include <algorithm>
@@ -43,19 +48,20 @@ namespace {
 #endif
 constexpr int kGramWarps = G1S_GRAM_WARPS;
 constexpr int kGramThreads = 32 * kGramWarps;
-constexpr int kLumaWarps = G1S_LUMA_WARPS;  // per CTA; the others are chroma warps (pair steps per frame: Y 147 k, Cb + Cr 82 k)
-constexpr int kMaxShare = 96;     // items between two flushes of a warp: bounds the int32 item accumulators (96 * 1024 * 127^2 < 2^31)
-constexpr int kWin = 30;          // blocks per flag window: one ballot holds blocks bx0-1 .. bx0+30
+constexpr int kLumaWarps = G1S_LUMA_WARPS;  // per CTA; the others are chroma warps (pair steps per frame: Y about 135 k, Cb + Cr about 70 k)
+constexpr int kMaxObs = 130000;   // observations between two flushes of a warp: bounds the int32 strip accumulators (x 127^2 < 2^31)
+constexpr int kMinRows = 6;       // shortest row window the strip code handles (two opening + three closing pair steps)
+constexpr int kMaxStrip = 64;     // block rows per strip: 64 * 1024 observations * 127^2 < 2^31
 constexpr int kLumaRows = 35;     // 3 halo rows + 32
 constexpr int kChromaRows = 19;   // 3 halo rows + 16 (residual and luma-tap tiles alike)
 constexpr int kBoxW = 64;         // 16 + 32 + 16 samples: one luma block, or two chroma blocks
-// Boxes start 16 samples left of the item (the innermost TMA coordinate must be a multiple of 16 bytes,
-// tools/tma_probe.cu).  The k-loops address tiles whose column 0 is the item's origin - 4 samples:
+// Boxes start 16 samples left of the unit (the innermost TMA coordinate must be a multiple of 16 bytes,
+// tools/tma_probe.cu).  The k-loops address tiles whose column 0 is the unit's origin - 4 samples:
 constexpr int kResCol0 = 3;       // word of that column inside a residual box row
-constexpr int kTapCol0 = 4;       // word of the item's first sample inside a luma-tap box row
+constexpr int kTapCol0 = 4;       // word of the unit's first sample inside a luma-tap box row
 constexpr int kLumaBytes = kLumaRows * kBoxW;      // 2240
 constexpr int kChromaBytes = kChromaRows * kBoxW;  // 1216
-// A pair step may read one row past the box (the unused upper half of an item's last pair): slots hold one row more.
+// A pair step may read one row past the box (the unused upper half of a strip's last pair): slots hold one row more.
 constexpr int kLumaSlot = 2304;                    // 36 rows
 constexpr int kOffTap = 1280, kChromaSlot = 2560;  // residual tile (20 rows) | luma-tap tile (20 rows)
 constexpr int kStages = 3;
@@ -67,8 +73,17 @@ static_assert(kLumaBytes + kBoxW <= kLumaSlot && kChromaBytes + kBoxW <= kOffTap
 
 struct __align__(16) GramSmem {
   uint64_t full[kGramWarps][kStages];  // one mbarrier per warp and stage: the warp's own TMA completions
-  int4 fifo[kGramWarps][4];               // per warp: items requested from the TMA engine, not yet consumed
+  uint4 fifo[kGramWarps][4];           // per warp: descriptors of the units requested from the TMA engine, not yet consumed
 };
+
+// ------------------------------------------------------------------------------ unit descriptors
+//
+//   w0  frame (8 bits) | unit column (12: luma block column, chroma pair column) | block row (12)
+//   w1  r0: first tile row of the unit's pair steps (6) | pair steps (6) | first unit of its strip (1) | last (1) |
+//       the strip's row count n is odd (1) | k range of half 0 lo (6), hi (6)
+//   w2  k range of half 1 lo (6), hi (6)            (k = 0..32: observed columns of the unit; luma: both halves the same)
+//   w3  observations of the strip (first unit only)
+constexpr uint32_t kFirst = 1u << 12, kLast = 1u << 13, kOdd = 1u << 14;
 
 __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
@@ -76,7 +91,6 @@ __device__ __forceinline__ void imma_16832(int (&c)[4], const uint32_t (&a)[4], 
       : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-
 
 // Byte i of the result is 0xFF iff lo <= first + i < hi (i = 0..3).
 __device__ __forceinline__ uint32_t byte_mask(int first, int lo, int hi) {
@@ -159,16 +173,15 @@ __device__ __forceinline__ void snapshot(uint32_t (&G)[10][2], const int (&acc)[
   }
 }
 
-// Window bookkeeping of one item with n = y1 - y0 observed rows, pairs i = 0 .. P-1 (pair i = tile rows y0+2i, +1),
-// P = (n + 4) / 2 = m + 2 with m = n / 2: tap row q' sums the lower-half rows of pairs [ceil(q'/2), ceil((n+q')/2)) and
-// the upper-half rows of pairs [ceil((q'-1)/2), ceil((n+q'-1)/2)).  Written out (E = lower half, O = upper half):
+// Window bookkeeping of one strip with n observed rows [y0, y0 + n), pair steps i = 0 .. P-1 (pair i = strip rows
+// y0+2i, +1 counted from the first tile's row 0), P = (n + 4) / 2 = m + 2 with m = n / 2: tap row q' sums the
+// lower-half rows of pairs [ceil(q'/2), ceil((n+q')/2)) and the upper-half rows of pairs
+// [ceil((q'-1)/2), ceil((n+q'-1)/2)).  Written out (E = lower half, O = upper half):
 //   windows open   before pair 0: E0 O0 O1     after pair 0: E1 E2 O2 O3     after pair 1: E3
 //   windows close  n even   after pair m-1: E0 O0 O1    m: E1 E2 O2 O3    m+1: E3
 //                  n odd    after pair m-1: O0          m: E0 E1 O1 O2    m+1: E2 E3 O3
-// so an item is: two pair steps with fixed snapshots, a hook-free core of m - 3 steps, three steps with the closing
-// snapshots.  That needs m >= 3; the rare shorter items (a sliver of rows at the bottom of the frame) are handed to
-// the exact generic kernel by the caller.
-constexpr int kMinRows = 6;
+// so a strip is: two pair steps with fixed snapshots (in its first unit), hook-free steps, three steps with the closing
+// snapshots (in its last unit).  That needs m >= 3: gram_plan_kernel hands shorter windows to the generic kernel.
 constexpr uint32_t kEvA = 0x31u, kEvB = 0xC6u, kEvC = 0x08u;          // {E0 O0 O1}, {E1 E2 O2 O3}, {E3}
 constexpr uint32_t kOddA = 0x10u, kOddB = 0x63u, kOddC = 0x8Cu;       // {O0}, {E0 E1 O1 O2}, {E2 E3 O3}
 
@@ -181,38 +194,43 @@ __device__ __forceinline__ void pair_step_rt(int &ph, Ring &w, const uint32_t *_
   ph = ph == 2 ? 0 : ph + 1;
 }
 
-// All rows of one item (or of one block of a chroma pair): base points at tile row 0; n = y1 - y0 >= kMinRows.
-__device__ __forceinline__ void item_rows(const uint32_t *__restrict__ base, int sh, int y0, int y1, const uint32_t (&mx)[2],
-                                          Ring &w, int (&acc)[5][4], uint32_t (&G)[10][2]) {
-  const int n = y1 - y0, m = n >> 1;
-  const bool odd = n & 1;
-  const uint32_t *p = base + y0 * kRowWords;
-  int ph = 0;
-  snapshot(G, acc, kEvA, false);
-  pair_step<0>(w, p, sh, mx, acc);
-  snapshot(G, acc, kEvB, false);
-  pair_step<1>(w, p + 2 * kRowWords, sh, mx, acc);
-  snapshot(G, acc, kEvC, false);
-  p += 4 * kRowWords;
-  int core = m - 3;  // pairs 2 .. m-2
+// The pair steps of one unit.  p: the lane's window word in the unit's first row; np pair steps; ph: ring phase, carried
+// from unit to unit inside a strip.
+__device__ __forceinline__ void unit_rows(const uint32_t *__restrict__ p, int sh, int np, bool first, bool last, bool odd,
+                                          const uint32_t (&mx)[2], int &ph, Ring &w, int (&acc)[5][4],
+                                          uint32_t (&G)[10][2]) {
+  if (first) {
+    snapshot(G, acc, kEvA, false);
+    pair_step<0>(w, p, sh, mx, acc);
+    snapshot(G, acc, kEvB, false);
+    pair_step<1>(w, p + 2 * kRowWords, sh, mx, acc);
+    snapshot(G, acc, kEvC, false);
+    p += 4 * kRowWords;
+    np -= 2;
+    ph = 2;
+  }
+  int core = np - (last ? 3 : 0);
+#pragma unroll 1
+  for (; core > 0 && ph != 2; --core, p += 2 * kRowWords) pair_step_rt(ph, w, p, sh, mx, acc);
 #pragma unroll 1
   for (; core >= 3; core -= 3, p += 6 * kRowWords) {
     pair_step<2>(w, p, sh, mx, acc);
     pair_step<0>(w, p + 2 * kRowWords, sh, mx, acc);
     pair_step<1>(w, p + 4 * kRowWords, sh, mx, acc);
   }
-  ph = 2;
 #pragma unroll 1
   for (; core > 0; --core, p += 2 * kRowWords) pair_step_rt(ph, w, p, sh, mx, acc);
-  pair_step_rt(ph, w, p, sh, mx, acc);  // pair m-1
-  if (odd) snapshot(G, acc, kOddA, true);
-  else snapshot(G, acc, kEvA, true);
-  pair_step_rt(ph, w, p + 2 * kRowWords, sh, mx, acc);  // pair m
-  if (odd) snapshot(G, acc, kOddB, true);
-  else snapshot(G, acc, kEvB, true);
-  pair_step_rt(ph, w, p + 4 * kRowWords, sh, mx, acc);  // pair m+1
-  if (odd) snapshot(G, acc, kOddC, true);
-  else snapshot(G, acc, kEvC, true);
+  if (last) {
+    pair_step_rt(ph, w, p, sh, mx, acc);  // pair m-1
+    if (odd) snapshot(G, acc, kOddA, true);
+    else snapshot(G, acc, kEvA, true);
+    pair_step_rt(ph, w, p + 2 * kRowWords, sh, mx, acc);  // pair m
+    if (odd) snapshot(G, acc, kOddB, true);
+    else snapshot(G, acc, kEvB, true);
+    pair_step_rt(ph, w, p + 4 * kRowWords, sh, mx, acc);  // pair m+1
+    if (odd) snapshot(G, acc, kOddC, true);
+    else snapshot(G, acc, kEvC, true);
+  }
 }
 
 // MMA tap index a = 8q+g  ->  record tap index (0..23 AR taps, 24 chroma's luma tap, 25 centre sample), -1 unused.
@@ -281,17 +299,168 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, 
 }
 
 
+// ------------------------------------------------------------------------------ gram_plan_kernel
+//
+// One CTA per (plane, frame); thread t owns unit column t (luma: block column; chroma: the pair of block columns
+// 2t, 2t+1) and walks it top to bottom twice: once to count its units, once (after a CTA-wide exclusive scan of the
+// counts) to write them.  Strip rules, per half h of the unit (luma has one half that spans all 32 columns):
+//   observed columns [xs, x1) and rows [y0, y1) of a block exactly as add_block_observations computes them;
+//   a block is ON when it is flat, not flagged for the generic kernel, and that rectangle is not empty;
+//   a strip continues into the next block row while both halves keep their state (off, or on with the same columns):
+//   the block above an ON block of a continuing strip is flat, so its y0 is 0 and the rows are contiguous;
+//   a strip that would START with two ON halves on different rows (y0 differs) is split for that one block row;
+//   windows of fewer than kMinRows rows (bottom slivers of the frame) go to the generic kernel.
+struct BlockObs {
+  bool on;
+  int xs, x1, y0;
+};
+
+__device__ __forceinline__ BlockObs block_obs(const uint8_t *flat, const uint8_t *ovf, int nbw, int bx, int by, int wb, int pw,
+                                              int y1) {
+  BlockObs o{false, 0, 0, 0};
+  if (bx >= nbw) return o;
+  const int b = by * nbw + bx;
+  if (!flat[b] || ovf[b]) return o;
+  o.xs = (bx > 0 && flat[b - 1]) ? 0 : kLag;
+  o.x1 = min(pw - bx * wb - kLag, (bx + 1 < nbw && flat[b + 1]) ? wb : wb - kLag);
+  o.y0 = (by > 0 && flat[b - nbw]) ? 0 : kLag;
+  o.on = o.x1 > o.xs && y1 > o.y0;
+  return o;
+}
+
+// Walks one unit column; calls unit(w0, w1, w2, w3) per unit in strip order and sliver(bx, by) per block left to the
+// generic kernel.  Returns the observations of the column.
+template <class UnitFn, class SliverFn>
+__device__ __forceinline__ long long walk_column(const Geometry &g, const uint8_t *flat, const uint8_t *ovf, bool luma, int f,
+                                                 int col, UnitFn &&unit, SliverFn &&sliver) {
+  const int wb = luma ? 32 : 16, hb = luma ? 32 : 16;
+  const int pw = luma ? g.width : g.width >> 1, ph = luma ? g.height : g.height >> 1;
+  long long obs = 0;
+  // a strip: block rows [b0, b1), first observed row y0 (in the first tile), k ranges of the two halves
+  auto close = [&](int b0, int b1, int y0, int lo0, int hi0, int lo1, int hi1, int width) {
+    const int T = b1 - b0;
+    const int y1_last = min(ph - (b1 - 1) * hb, hb);
+    const int n = hb * (T - 1) + y1_last - y0;
+    const int P = (n + 4) >> 1;
+    obs += (long long)n * width;
+    int cursor = y0, done = 0;  // next strip row, in rows from the first tile's row 0; pair steps emitted
+    for (int k = 0; k < T; ++k) {
+      const int r0 = cursor - hb * k;
+      const int np = k + 1 < T ? (hb + 3 - r0) >> 1 : P - done;
+      const uint32_t w0 = (uint32_t)f | ((uint32_t)col << 8) | ((uint32_t)(b0 + k) << 20);
+      const uint32_t w1 = (uint32_t)r0 | ((uint32_t)np << 6) | (k == 0 ? kFirst : 0u) | (k + 1 == T ? kLast : 0u) |
+                          ((n & 1) ? kOdd : 0u) | ((uint32_t)lo0 << 16) | ((uint32_t)hi0 << 22);
+      const uint32_t w2 = (uint32_t)lo1 | ((uint32_t)hi1 << 6);
+      unit(w0, w1, w2, k == 0 ? (uint32_t)(n * width) : 0u);
+      cursor += 2 * np;
+      done += np;
+    }
+  };
+  bool active = false;
+  int b0 = 0, sy0 = 0, sig0 = -1, sig1 = -1;  // current strip; sig = xs | x1 << 6 of an ON half, -1 when off
+  auto ranges = [&](int s0, int s1, int &lo0, int &hi0, int &lo1, int &hi1, int &width) {
+    if (luma) {
+      lo0 = lo1 = s0 & 63, hi0 = hi1 = s0 >> 6;
+      width = hi0 - lo0;
+    } else {
+      lo0 = s0 < 0 ? 0 : (s0 & 63), hi0 = s0 < 0 ? 0 : (s0 >> 6);
+      lo1 = s1 < 0 ? 0 : 16 + (s1 & 63), hi1 = s1 < 0 ? 0 : 16 + (s1 >> 6);
+      width = (hi0 - lo0) + (hi1 - lo1);
+    }
+  };
+  auto finish = [&](int b1) {
+    int lo0, hi0, lo1, hi1, width;
+    ranges(sig0, sig1, lo0, hi0, lo1, hi1, width);
+    close(b0, b1, sy0, lo0, hi0, lo1, hi1, width);
+    active = false;
+  };
+  for (int by = 0; by < g.nbh; ++by) {
+    const int y1 = min(ph - by * hb, hb);
+    BlockObs a = block_obs(flat, ovf, g.nbw, luma ? col : 2 * col, by, wb, pw, y1);
+    BlockObs b = luma ? BlockObs{false, 0, 0, 0} : block_obs(flat, ovf, g.nbw, 2 * col + 1, by, wb, pw, y1);
+    const int sa = a.on ? (a.xs | (a.x1 << 6)) : -1, sb = b.on ? (b.xs | (b.x1 << 6)) : -1;
+    // the strip grows by this block row (at most kMaxStrip rows of blocks: bounds the int32 strip sums)
+    if (active && sa == sig0 && sb == sig1 && y1 >= kMinRows && by - b0 < kMaxStrip) continue;
+    if (active) finish(by);
+    // a new strip starts here (if anything is ON); halves whose window would be too short go to the generic kernel
+    if (a.on && y1 - a.y0 < kMinRows) sliver(luma ? col : 2 * col, by), a.on = false;
+    if (b.on && y1 - b.y0 < kMinRows) sliver(2 * col + 1, by), b.on = false;
+    if (!a.on && !b.on) continue;
+    const int na = a.on ? (a.xs | (a.x1 << 6)) : -1, nb = b.on ? (b.xs | (b.x1 << 6)) : -1;
+    if (a.on && b.on && a.y0 != b.y0) {
+      // one block row as two single-half strips; the rows below start a fresh strip (both y0 = 0 there)
+      int lo0, hi0, lo1, hi1, width;
+      ranges(na, -1, lo0, hi0, lo1, hi1, width);
+      close(by, by + 1, a.y0, lo0, hi0, lo1, hi1, width);
+      ranges(-1, nb, lo0, hi0, lo1, hi1, width);
+      close(by, by + 1, b.y0, lo0, hi0, lo1, hi1, width);
+      continue;
+    }
+    active = true, b0 = by, sy0 = a.on ? a.y0 : b.y0, sig0 = na, sig1 = nb;
+  }
+  if (active) finish(g.nbh);
+  return obs;
+}
+
+__global__ void __launch_bounds__(256)
+gram_plan_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, uint4 *__restrict__ plan,
+                 int *__restrict__ counts) {
+  __shared__ int s_cnt[256], s_base;
+  __shared__ unsigned long long s_obs;
+  const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+  const bool luma = c == 0;
+  uint8_t *rec = records + (size_t)f * rl.bytes;
+  const uint8_t *flat = rec + rl.off_flat;
+  uint8_t *ovf = rec + rl.off_ovf + (size_t)c * g.nb;
+  const int ncols = luma ? g.nbw : (g.nbw + 1) >> 1;
+  uint4 *out = plan + ((size_t)f * 3 + c) * g.nb;
+  if (tid == 0) s_base = 0, s_obs = 0ull;
+  __syncthreads();
+  for (int c0 = 0; c0 < ncols; c0 += 256) {
+    const int col = c0 + tid;
+    int n = 0;
+    if (col < ncols)
+      walk_column(g, flat, ovf, luma, f, col, [&](uint32_t, uint32_t, uint32_t, uint32_t) { ++n; }, [](int, int) {});
+    s_cnt[tid] = n;
+    __syncthreads();
+    // exclusive scan of 256 counts (Hillis-Steele; a frame has a few thousand units, this runs once per 256 columns)
+    for (int d = 1; d < 256; d <<= 1) {
+      const int v = tid >= d ? s_cnt[tid - d] : 0;
+      __syncthreads();
+      s_cnt[tid] += v;
+      __syncthreads();
+    }
+    int at = s_base + s_cnt[tid] - n;
+    if (col < ncols) {
+      const long long obs = walk_column(
+          g, flat, ovf, luma, f, col, [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) { out[at++] = make_uint4(w0, w1, w2, w3); },
+          [&](int bx, int by) {
+            ovf[by * g.nbw + bx] = 1;  // read again only by the generic kernel, launched after the Gram kernel
+            atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_ovf_count), 1ull);
+          });
+      if (obs) atomicAdd(&s_obs, (unsigned long long)obs);
+    }
+    __syncthreads();
+    if (tid == 255) s_base += s_cnt[255];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    counts[f * 3 + c] = s_base;
+    if (s_obs) atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + c, s_obs);
+  }
+}
+
+// ------------------------------------------------------------------------------ gram_imma_kernel
 __global__ void __launch_bounds__(kGramThreads, 2)
-gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int nframes,
-                 const uint8_t *__restrict__ tmaps) {
+gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int nframes, const uint8_t *__restrict__ tmaps,
+                 const uint4 *__restrict__ plan, const int *__restrict__ counts) {
   extern __shared__ __align__(128) uint8_t tiles[];
   __shared__ GramSmem sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, t = lane & 3;  // mma "groupID" (= cx + 3) and thread-in-group
   const bool has_chroma = g.planes == 3;
-  const int W = g.width, H = g.height, pw = W >> 1, ph = H >> 1;
 
-  // ---- this warp's plane and its share of the plane's items
+  // ---- this warp's plane and its rank among the plane's warps
   const int cta = blockIdx.x, ncta = gridDim.x;
   int plane, rank, nranks;
   if (!has_chroma) {
@@ -307,11 +476,38 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
     else plane = 2, rank = kLo * e_before + kHi * o_before + (k - ncb), nranks = kLo * even + kHi * odd;
   }
   const bool luma = plane == 0;
-  const int per_row = luma ? g.nbw : (g.nbw + 1) >> 1;  // items per block row: blocks, or chroma block pairs
-  const int per_win = luma ? kWin : kWin / 2;
-  const long long total = (long long)nframes * g.nbh * per_row;
-  const int i_lo = (int)(total * rank / nranks), i_hi = (int)(total * (rank + 1) / nranks);
-  if (i_lo >= i_hi) return;  // whole warp; nothing below synchronises across warps
+
+  // ---- its share of the plane's units: an equal slice of the unit index space over the batch's frames, moved forward
+  // to strip boundaries at both ends (a strip's running sums live in one warp's registers).  Lane l keeps the unit
+  // counts of frames l and l + 32 (a batch has at most 64 frames).
+  const int cnt_lo = lane < nframes ? counts[lane * 3 + plane] : 0;
+  const int cnt_hi = lane + 32 < nframes ? counts[(lane + 32) * 3 + plane] : 0;
+  int total = cnt_lo + cnt_hi;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  const int u_lo = (int)((long long)total * rank / nranks), u_hi = (int)((long long)total * (rank + 1) / nranks);
+  if (u_lo >= u_hi) return;  // whole warp; nothing below synchronises across warps
+  auto count_of = [&](int f) { return __shfl_sync(0xffffffffu, f < 32 ? cnt_lo : cnt_hi, f & 31); };
+  // position of the producer: unit index u = local index pi of frame pf (pc units in that frame)
+  int u = 0, pf = 0, pc = count_of(0), pi = 0;
+  while (u + pc <= u_lo && pf + 1 < nframes) u += pc, ++pf, pc = count_of(pf);
+  pi = u_lo - u, u = u_lo;
+  auto unit_at = [&](int f, int i) { return __ldg(plan + ((size_t)f * 3 + plane) * g.nb + i); };
+  auto advance = [&]() {  // to the next unit; false past the end of the batch
+    ++u, ++pi;
+    while (pi >= pc) {
+      if (++pf >= nframes) return false;
+      pc = count_of(pf), pi = 0;
+    }
+    return true;
+  };
+  bool more = true;
+  uint4 dn = unit_at(pf, pi);                         // descriptor of the next unit to request
+  while (more && !(dn.y & kFirst)) {                  // skip the tail of a strip that started in the previous share
+    more = advance();
+    if (more) dn = unit_at(pf, pi);
+  }
+  if (!more || u >= u_hi) return;
 
   uint8_t *const my_tiles = tiles + warp * kWarpSmem;
   const int slot = luma ? kLumaSlot : kChromaSlot;
@@ -332,12 +528,13 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
   for (int i = 0; i < 10; ++i) G[i][0] = G[i][1] = 0u;
 #pragma unroll
   for (int i = 0; i < 6; ++i) ring.B[i][0] = ring.B[i][1] = 0u;
-  int nobs = 0;  // observations of the items accumulated since the last flush
 
   int sh = 8 * ((gq + 1) & 3);
-  asm volatile("" : "+r"(sh));  // same: one register instead of four instructions per funnel shift group
+  asm volatile("" : "+r"(sh));  // one register instead of four instructions per funnel shift group
   const int dxw = (gq + 1) >> 2;
   const bool is7 = gq == 7;
+  // the lane's window word in row 0 of a stage's tile: g = 7 lanes of the chroma warps walk the luma-tap tile
+  const int lane_off = (!luma && is7) ? kOffTap + 4 * (kTapCol0 + t) : 4 * (kResCol0 + t + dxw);
 
   // Gram blocks -> the frame's int64 record, straight from registers: element r of block (q', dy) in lane (gq, t)
   // is the product of the later tap (q', g' = gq) with the earlier tap (q' - dy, g = 2t + r).
@@ -354,194 +551,73 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
           G[gidx(q, dy)][r] = 0u;
           emit(gram, 8 * (q - dy) + 2 * t + r, 8 * q + gq, v, !luma);
         }
-    if (lane == 0 && nobs)
-      atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + plane, (unsigned long long)(long long)nobs);
-    nobs = 0;
   };
 
-  // ---- producer side: scan the share for items with work, request their tiles, queue them
-  // position of the scan: frame, block row, first item of the current flag window, and the window's ballots
-  int pf, pby, pwx;
-  {
-    const int per_frame = g.nbh * per_row;
-    pf = i_lo / per_frame;
-    const int r = i_lo - pf * per_frame;
-    pby = r / per_row;
-    pwx = ((r - pby * per_row) / per_win) * per_win;
-  }
-  int pidx = ((pf * g.nbh + pby) * per_row) + pwx;  // global index of the window's first item
-  uint32_t m_flat = 0, m_up = 0, m_ovf = 0, m_todo = 0;  // bit l <-> block (window's first block - 1 + l); todo: items left in the window
-  auto load_window = [&]() {
-    const uint8_t *rec = records + (size_t)pf * rl.bytes;
-    const int bx = (luma ? pwx : 2 * pwx) - 1 + lane;
-    const bool in = bx >= 0 && bx < g.nbw;
-    const int b = pby * g.nbw + bx;
-    const uint8_t fl = in ? (rec + rl.off_flat)[b] : 0;
-    const uint8_t up = (in && pby > 0) ? (rec + rl.off_flat)[b - g.nbw] : 0;
-    const uint8_t ov = in ? (rec + rl.off_ovf)[(size_t)plane * g.nb + b] : 0;
-    m_flat = __ballot_sync(0xffffffffu, fl != 0);
-    m_up = __ballot_sync(0xffffffffu, up != 0);
-    m_ovf = __ballot_sync(0xffffffffu, ov != 0);
-    // items of the window that lie in the share, in the row, and have at least one flat, non-overflowed block
-    const uint32_t ok = m_flat & ~m_ovf;
-    uint32_t items = luma ? (ok >> 1) & ((1u << kWin) - 1u) : 0u;
-    if (!luma)
-      for (int k = 0; k < kWin / 2; ++k)
-        if ((ok >> (2 * k + 1)) & 3u) items |= 1u << k;
-    const int first = max(i_lo - pidx, 0), last = min(min(i_hi - pidx, per_row - pwx), per_win);  // [first, last)
-    const uint32_t keep = last > first ? (((last >= 32 ? 0u : (1u << last)) - 1u) & ~((1u << first) - 1u)) : 0u;
-    m_todo = items & keep;
-  };
-  bool scan_done = false;
-  auto next_window = [&]() {  // advance to the next window of the share; false when the share is exhausted
-    pwx += per_win;
-    pidx += per_win;
-    if (pwx >= per_row) {
-      pidx += per_row - pwx;  // the last window of a row is short
-      pwx = 0;
-      if (++pby == g.nbh) pby = 0, ++pf;
-    }
-    return pidx < i_hi;
-  };
-  load_window();
-
-  int head = 0, tail = 0;       // fifo positions (items requested / consumed)
+  // ---- producer side: request the next unit's tile(s), queue its descriptor; the one after it is fetched meanwhile
+  int head = 0, tail = 0;       // fifo positions (units requested / consumed)
   int hstage = 0, tstage = 0;   // their stages ( = position % kStages, kept incrementally)
   uint32_t phases = 0;          // bit s: parity to wait for on stage s
-  auto produce = [&]() {        // request the next item with work; false if there is none left
-    while (m_todo == 0) {
-      if (scan_done || !next_window()) {
-        scan_done = true;
-        return false;
-      }
-      load_window();
+  auto produce = [&]() {        // false when the share is exhausted
+    if (!more || (u >= u_hi && (dn.y & kFirst))) {
+      more = false;
+      return false;
     }
-    const int k = __ffs(m_todo) - 1;
-    m_todo &= m_todo - 1;
-    // flags of the item's blocks, from the window ballots (bit l <-> block first - 1 + l)
-    uint32_t bits;
-    if (luma) {
-      const int l = k + 1;
-      bits = ((m_flat >> (l - 1)) & 1u) | (((m_flat >> (l + 1)) & 1u) << 1) | (((m_up >> l) & 1u) << 2);
-    } else {
-      const int l = 2 * k + 1;  // blocks l (half 0) and l + 1 (half 1)
-      bits = ((m_flat >> (l - 1)) & 15u)            // flat: left neighbour, A, B, right neighbour
-             | (((m_up >> l) & 3u) << 4)             // flat above A, B
-             | (((m_ovf >> l) & 3u) << 6);           // overflow A, B
-    }
+    const uint4 d = dn;
     const int stage = hstage;
     if (++hstage == kStages) hstage = 0;
     if (lane == 0) {
-      sm.fifo[warp][head & 3] = make_int4(pf, pby, pwx + k, (int)bits);
-      const uint8_t *fmaps = tmaps + (size_t)pf * kResidualMaps * 128;
+      sm.fifo[warp][head & 3] = d;
+      const int f = d.x & 255, col = (d.x >> 8) & 4095, by = d.x >> 20;
+      const uint8_t *fmaps = tmaps + (size_t)f * kResidualMaps * 128;
       uint8_t *st = my_tiles + stage * slot;
       uint64_t *bar = &sm.full[warp][stage];
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this warp's reads of the stage precede the refill
       if (luma) {
         mbar_expect_tx(bar, kLumaBytes);
-        tma_load_2d(st, fmaps, 32 * (pwx + k) - 16, 32 * pby - 3, bar);
+        tma_load_2d(st, fmaps, 32 * col - 16, 32 * by - 3, bar);
       } else {
-        const int cx = 32 * (pwx + k) - 16, cy = 16 * pby - 3;
+        const int cx = 32 * col - 16, cy = 16 * by - 3;
         mbar_expect_tx(bar, 2 * kChromaBytes);
         tma_load_2d(st, fmaps + plane * 128, cx, cy, bar);
         tma_load_2d(st + kOffTap, fmaps + 3 * 128, cx, cy, bar);
       }
     }
     ++head;
+    more = advance();
+    if (more) dn = unit_at(pf, pi);
     return true;
   };
 
-  int cf = -1;     // frame the accumulators belong to
-  int since = 0;   // items accumulated since the last flush: the int32 item accumulators hold kMaxShare of them
+  int cf = -1;     // frame the strip accumulators belong to
+  int since = 0;   // observations accumulated since the last flush
+  int ph = 0;      // ring phase, carried from unit to unit inside a strip
   for (;;) {
     __syncwarp();  // every lane is done with the stage about to be refilled
     while (head - tail < kStages && produce()) {
     }
     if (head == tail) break;
     __syncwarp();
-    const int4 item = sm.fifo[warp][tail & 3];
+    const uint4 d = sm.fifo[warp][tail & 3];
     const int stage = tstage;
     if (++tstage == kStages) tstage = 0;
     ++tail;
-    const int f = item.x, by = item.y, ix = item.z;
-    const uint32_t bits = (uint32_t)item.w;
-    if (f != cf || since == kMaxShare) {
-      if (cf >= 0) flush(cf);
-      cf = f;
-      since = 0;
+    const bool first = d.y & kFirst;
+    if (first) {  // G only changes at strip ends, so strip starts are the flush points
+      const int f = d.x & 255;
+      if (f != cf || since + (int)d.w > kMaxObs) {
+        if (cf >= 0) flush(cf);
+        cf = f;
+        since = 0;
+      }
+      since += (int)d.w;
     }
-    ++since;
     mbar_wait(&sm.full[warp][stage], (phases >> stage) & 1u);
     phases ^= 1u << stage;
-    const uint8_t *st = my_tiles + stage * slot;
-    // up to two passes over the item's rows: (first observed row, masks of the two halves)
-    int npass = 0, y1, ya = 0, yb = 0;
-    bool short_a = false, short_b = false;  // blocks of the item left to the generic kernel (too few rows)
-    uint32_t ma[2] = {0u, 0u}, mb[2] = {0u, 0u};
-    const uint32_t *base;
-    if (luma) {
-      const int xs = (bits & 1u) ? 0 : kLag, y0 = (bits & 4u) ? 0 : kLag;
-      const int x1 = min(W - 32 * ix - kLag, (bits & 2u) ? 32 : 32 - kLag);
-      y1 = min(H - 32 * by, 32);
-      if (x1 > xs && y1 > y0 && y1 - y0 < kMinRows) {
-        short_a = true;
-      } else if (x1 > xs && y1 > y0) {
-        const bool full = xs == 0 && x1 == 32;
-        ma[0] = full ? 0xFFFFFFFFu : byte_mask(4 * t, xs, x1);
-        ma[1] = full ? 0xFFFFFFFFu : byte_mask(16 + 4 * t, xs, x1);
-        ya = y0;
-        npass = 1;
-        nobs += (x1 - xs) * (y1 - y0);
-      }
-      base = reinterpret_cast<const uint32_t *>(st) + kResCol0 + t + dxw;
-    } else {
-      // blocks 2 ix (half 0) and 2 ix + 1 (half 1); bits: flat left, A, B, right | flat above A, B | overflow A, B
-      const int bxa = 2 * ix;
-      y1 = min(ph - 16 * by, 16);
-      const bool fla = (bits & 2u) && !(bits & 64u), flb = (bits & 4u) && !(bits & 128u);
-      const int xsa = (bits & 1u) ? 0 : kLag, xsb = (bits & 2u) ? 0 : kLag;
-      const int y0a = (bits & 16u) ? 0 : kLag, y0b = (bits & 32u) ? 0 : kLag;
-      const int x1a = min(pw - 16 * bxa - kLag, (bits & 4u) ? 16 : 16 - kLag);
-      const int x1b = min(pw - 16 * (bxa + 1) - kLag, (bits & 8u) ? 16 : 16 - kLag);
-      bool on0 = fla && x1a > xsa && y1 > y0a;
-      bool on1 = flb && x1b > xsb && y1 > y0b;
-      if (on0 && y1 - y0a < kMinRows) short_a = true, on0 = false;
-      if (on1 && y1 - y0b < kMinRows) short_b = true, on1 = false;
-      const uint32_t m0 = !on0 ? 0u : (xsa == 0 && x1a == 16) ? 0xFFFFFFFFu : byte_mask(4 * t, xsa, x1a);
-      const uint32_t m1 = !on1 ? 0u : (xsb == 0 && x1b == 16) ? 0xFFFFFFFFu : byte_mask(4 * t, xsb, x1b);
-      if (on0 && on1 && y0a == y0b) {
-        ma[0] = m0, ma[1] = m1, ya = y0a, npass = 1;
-      } else {
-        // the two blocks start on different rows (one has a flat block above it, the other not) or only one is
-        // observed: their row windows differ, so they are accumulated one after the other
-        if (on0) ma[0] = m0, ya = y0a, npass = 1;
-        if (on1) {
-          if (npass == 0) ma[1] = m1, ya = y0b;
-          else mb[1] = m1, yb = y0b;
-          ++npass;
-        }
-      }
-      // g = 7 lanes walk the luma-tap tile (same rows, no shift) instead of the residual tile
-      base = is7 ? reinterpret_cast<const uint32_t *>(st + kOffTap) + kTapCol0 + t
-                 : reinterpret_cast<const uint32_t *>(st) + kResCol0 + t + dxw;
-      nobs += (on0 ? (x1a - xsa) * (y1 - y0a) : 0) + (on1 ? (x1b - xsb) * (y1 - y0b) : 0);
-    }
-#pragma unroll 1
-    for (int pass = 0; pass < npass; ++pass) {
-      if (pass == 1) ma[0] = mb[0], ma[1] = mb[1], ya = yb;
-      item_rows(base, sh, ya, y1, ma, ring, acc, G);
-    }
-    if (short_a | short_b) {
-      // a sliver of fewer than kMinRows observed rows (bottom of the frame): the exact generic kernel, launched right
-      // after this one, accumulates the block; only this warp ever reads or writes the flags of its own items
-      uint8_t *rec = records + (size_t)f * rl.bytes;
-      if (lane == 0) {
-        const int b0 = by * g.nbw + (luma ? ix : 2 * ix);
-        if (short_a) (rec + rl.off_ovf)[(size_t)plane * g.nb + b0] = 1;
-        if (short_b) (rec + rl.off_ovf)[(size_t)plane * g.nb + b0 + 1] = 1;
-        atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_ovf_count), 1ull);
-      }
-    }
+    const int r0 = d.y & 63, np = (d.y >> 6) & 63;
+    const int lo0 = (d.y >> 16) & 63, hi0 = (d.y >> 22) & 63, lo1 = d.z & 63, hi1 = (d.z >> 6) & 63;
+    const uint32_t mx[2] = {byte_mask(4 * t, lo0, hi0), byte_mask(16 + 4 * t, lo1, hi1)};
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(my_tiles + stage * slot + lane_off) + r0 * kRowWords;
+    unit_rows(p, sh, np, first, d.y & kLast, d.y & kOdd, mx, ph, ring, acc, G);
   }
   if (cf >= 0) flush(cf);
 }
@@ -550,7 +626,7 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
 
 bool gram_imma_supported(const Geometry &g) {
   const bool shape = (g.planes == 1) || (g.planes == 3 && g.ss_x == 1 && g.ss_y == 1);
-  return shape && g.width >= 8 && g.height >= 8;
+  return shape && g.width >= 8 && g.height >= 8 && g.nbw <= 4095 && g.nbh <= 4095;
 }
 
 void gram_imma_tma_boxes(int box[kResidualMaps][2]) {
@@ -558,8 +634,15 @@ void gram_imma_tma_boxes(int box[kResidualMaps][2]) {
   for (int k = 1; k < kResidualMaps; ++k) box[k][0] = kBoxW, box[k][1] = kChromaRows;
 }
 
-void launch_gram_imma(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, const void *tmaps,
+size_t gram_plan_bytes(int nframes, const Geometry &g) { return (size_t)nframes * 3 * g.nb * sizeof(uint4); }
+
+void launch_gram_plan(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, void *plan, int *counts,
                       cudaStream_t st) {
+  gram_plan_kernel<<<dim3(g.planes, nframes), 256, 0, st>>>(g, records, rl, static_cast<uint4 *>(plan), counts);
+}
+
+void launch_gram_imma(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, const void *tmaps,
+                      const void *plan, const int *counts, cudaStream_t st) {
   const int smem = kGramWarps * kWarpSmem;
   // resident CTAs of the current device (the persistent grid is one wave); cached per device, and the
   // dynamic-shared-memory attribute is a per-device property of the function as well
@@ -572,12 +655,14 @@ void launch_gram_imma(int nframes, const Geometry &g, uint8_t *records, const Re
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(gram_imma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gram_imma_kernel, kGramThreads, smem);
+    if (const char *e = std::getenv("G1S_GRAM_OCC")) per_sm = std::min(per_sm, std::max(1, std::atoi(e)));  // tuning aid
     slots = sms * std::max(per_sm, 1);
   }
-  // one wave of persistent CTAs whatever the batch size: a warp flushes its int32 item accumulators every kMaxShare items
+  // one wave of persistent CTAs whatever the batch size (a warp flushes its int32 strip accumulators as it goes)
   const long long blocks = (long long)nframes * g.nb;
   const int grid = (int)std::min<long long>(slots, std::max<long long>(1, blocks / 8));
-  gram_imma_kernel<<<grid, kGramThreads, smem, st>>>(g, records, rl, nframes, static_cast<const uint8_t *>(tmaps));
+  gram_imma_kernel<<<grid, kGramThreads, smem, st>>>(g, records, rl, nframes, static_cast<const uint8_t *>(tmaps),
+                                                     static_cast<const uint4 *>(plan), counts);
 }
 
 }  // namespace g1s

@@ -41,19 +41,24 @@ __device__ __forceinline__ int sample8(const void *base, uint32_t stride, int y,
   return (reinterpret_cast<const uint16_t *>(row)[x] >> shift) & 0xFF;  // util.rs::frame_into_u8
 }
 
-// One term of a chain: acc + RN((a*b)/65025), every operation rounded to nearest, nothing contracted.
-__device__ __forceinline__ double chain_step(double acc, double a, double b) {
+// Eight consecutive terms of a chain, without the adds: q[k] = RN((a[k]*b[k]) / 65025), every operation rounded to
+// nearest, nothing contracted (p is an exact integer-valued double; the three-operation quotient is exact for every
+// |p| <= 1020^2: oracle/div65025_check.c).
+__device__ __forceinline__ void term_chunk(const double *__restrict__ row, int off_i, int off_j, double (&q)[8]) {
   const double y = 1.0 / 65025.0;
-  const double p = __dmul_rn(a, b);
-  const double q0 = __dmul_rn(p, y);
-  const double r = __fma_rn(-q0, 65025.0, p);
-  const double q = __fma_rn(r, y, q0);
-  return __dadd_rn(acc, q);
+  const double *pa = row + off_i, *pb = row + off_j;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double p = __dmul_rn(pa[k], pb[k]);
+    const double q0 = __dmul_rn(p, y);
+    const double r = __fma_rn(-q0, 65025.0, p);
+    q[k] = __fma_rn(r, y, q0);
+  }
 }
 
 __global__ void __launch_bounds__(kStrictThreads)
 gram_reforder_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *__restrict__ records, RecordLayout rl) {
-  __shared__ double tiles[2][2 * kSElems];  // [buffer][residual | luma tap]
+  __shared__ double tiles[2][2 * kSElems + 8];  // [buffer][residual | luma tap | slack for a short chunk's surplus reads]
 
   const int tid = threadIdx.x;
   const int c = blockIdx.y;
@@ -141,20 +146,28 @@ gram_reforder_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *
     const int y_end = min(ph - y_o, bh);
     const int x_end = min(pw - x_o - kLag, (bx + 1 < g.nbw && flat[cur + 1]) ? bw : bw - kLag);
     if (live && y_end > y_start && x_end > x_start) {
+      // The chain itself is serial (one dependent DADD per term); everything before it is not.  Terms are taken in
+      // chunks of 8 along a row: the quotients of chunk k+1 are computed while the adds of chunk k retire, so the
+      // f64 pipe sees independent work between two dependent adds.  A row's last chunk may be short: its surplus
+      // lanes read on into the tile (valid shared memory, never added).
       const double *t0 = tiles[b] + kLag * kSPitch + kLag;
-      for (int y = y_start; y < y_end; ++y) {
-        const double *pa = t0 + y * kSPitch + off_i, *pb = t0 + y * kSPitch + off_j;
-        int x = x_start;
+      const int w = x_end - x_start, cpr = (w + 7) >> 3, nchunks = (y_end - y_start) * cpr;
+      double q[8];
+      int cy = y_start, cx = 0;  // position of the chunk held in q
+      term_chunk(t0 + cy * kSPitch + x_start, off_i, off_j, q);
 #pragma unroll 1
-        for (; x + 4 <= x_end; x += 4) {
-          const double a0 = pa[x], a1 = pa[x + 1], a2 = pa[x + 2], a3 = pa[x + 3];
-          const double b0 = pb[x], b1 = pb[x + 1], b2 = pb[x + 2], b3 = pb[x + 3];
-          acc = chain_step(acc, a0, b0);
-          acc = chain_step(acc, a1, b1);
-          acc = chain_step(acc, a2, b2);
-          acc = chain_step(acc, a3, b3);
-        }
-        for (; x < x_end; ++x) acc = chain_step(acc, pa[x], pb[x]);
+      for (int ci = 0; ci < nchunks; ++ci) {
+        int ny = cy, nx = cx + 1;
+        if (nx == cpr) nx = 0, ++ny;
+        double qn[8];
+        if (ci + 1 < nchunks) term_chunk(t0 + ny * kSPitch + x_start + 8 * nx, off_i, off_j, qn);
+        const int cnt = min(8, w - 8 * cx);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < cnt) acc = __dadd_rn(acc, q[k]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) q[k] = qn[k];
+        cy = ny, cx = nx;
       }
     }
     __syncthreads();  // tile b is free again, tile b^1 is complete
