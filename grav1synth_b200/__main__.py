@@ -20,6 +20,22 @@ import sys
 log = logging.getLogger("grav1synth")
 
 
+def parse_devices(spec):
+    """'0-3' / '0,2,5' / None -> list of CUDA ordinals (None: the single --device)."""
+    if not spec:
+        return None
+    out = []
+    for part in spec.split(","):
+        if "-" in part:
+            a, b = part.split("-", 1)
+            out.extend(range(int(a), int(b) + 1))
+        else:
+            out.append(int(part))
+    if not 1 <= len(out) <= 8:
+        raise SystemExit("--devices takes 1 to 8 CUDA ordinals")
+    return out
+
+
 def main(argv=None) -> int:
     logging.basicConfig(level=os.environ.get("G1S_LOG", "INFO"), format=" %(levelname)-5s %(name)s > %(message)s")
     ap = argparse.ArgumentParser(prog="grav1synth_b200", description="Grain Synth analyzer: B200 `diff` path")
@@ -33,6 +49,12 @@ def main(argv=None) -> int:
                    help='A semicolon-separated list of filters to apply to the source before running the diff, e.g. '
                         '"crop:top=42,left=64" (resize is parsed but not available in this build).')
     d.add_argument("--device", type=int, default=0)
+    d.add_argument("--devices", default=None,
+                   help="Several GPUs behind one handle, e.g. 0-7 or 0,2,3: batches of frames are dealt round-robin "
+                        "(g1s_diff_config.n_devices / device_ids); the table is the single-GPU table.")
+    d.add_argument("--strict", action="store_true",
+                   help="Accumulate the AR normal equations in the reference's order and rounding (gram_order = "
+                        "REF_ORDER): every table integer equals the reference's, at ~1/50 of the fast mode's speed.")
     i = sub.add_parser("inspect", help="Outputs a film grain table corresponding to a given AV1 video, or reports "
                                        "if there is no film grain information.")
     i.add_argument("input", help="The AV1 file to inspect (.ivf or low-overhead .obu).")
@@ -94,7 +116,8 @@ def main(argv=None) -> int:
             raise SystemExit("Bit depths not between 8-16 are not currently supported")  # src/main.rs:516
     # the engine is sized for the frames it will see: the denoised clip's size (the source is filtered to it)
     differ = DiffGenerator(sd.fps_num, sd.fps_den, sd.bit_depth, dd.bit_depth, dd.width, dd.height, sd.ss_x, sd.ss_y,
-                           monochrome=sd.monochrome, device=args.device)
+                           monochrome=sd.monochrome, device=args.device, devices=parse_devices(args.devices),
+                           gram_order=1 if args.strict else 0)
     frames = 0
     while True:  # src/main.rs:432-521
         s, d_ = src.get_frame(), den.get_frame()

@@ -227,6 +227,12 @@ struct g1s_diff {
   void *tap_user = nullptr;
   std::mutex digest_mu;    // consumer handles: recycled copies of incoming digest blocks
   std::vector<std::shared_ptr<std::vector<double>>> digest_free;
+  // multi-device handles (cfg.n_devices >= 2): one PRODUCER child per device, this handle owns the model
+  std::vector<g1s_diff *> kids;
+  std::vector<double *> kid_sinks;   // pinned digest rings the children write into
+  std::vector<int64_t> kid_frames;   // frames dealt to each child
+  size_t kid_sink_cap = 0;           // digests per ring (a multiple of the batch)
+  int64_t next_batch = 0;            // next global batch whose digests are folded
   double *sink = nullptr;  // digest sink (producer ranks)
   size_t sink_cap = 0, sink_count = 0;
   // cuTensorMapEncodeTiled, fetched through the runtime so libcuda is not a link dependency
@@ -454,6 +460,87 @@ int check_frames(g1s_diff *d, const g1s_frame *s, const g1s_frame *n) {
   return G1S_OK;
 }
 
+
+// Queues `count` digests (copied) for the fold thread, in order.
+void fold_digests_copy(g1s_diff *d, const double *src, size_t count) {
+  std::shared_ptr<std::vector<double>> blk;
+  {
+    std::lock_guard<std::mutex> lk(d->digest_mu);
+    if (!d->digest_free.empty()) {
+      blk = std::move(d->digest_free.back());
+      d->digest_free.pop_back();
+    }
+  }
+  if (!blk) blk = std::make_shared<std::vector<double>>();
+  blk->assign(src, src + LatestFrame::kDigestDoubles * count);
+  DiffSequencer *seq = d->seq.get();
+  d->folder->push([blk, seq, count, d] {
+    LatestFrame lf;
+    for (size_t i = 0; i < count; ++i) {
+      lf.from_digest(blk->data() + LatestFrame::kDigestDoubles * i);
+      seq->consume_latest(lf);
+    }
+    std::lock_guard<std::mutex> lk(d->digest_mu);
+    if (d->digest_free.size() < 8) d->digest_free.push_back(blk);
+  });
+  d->retired += (int64_t)count;
+  d->frames_done += (double)count;
+}
+
+// ---- multi-device handles -------------------------------------------------------------------------------------
+// Frames are dealt to the children in batches, round-robin: frame k belongs to child (k / batch) % n.  Every child is
+// a PRODUCER handle on its own device (kernels + the per-frame half of the model) that writes one digest per frame
+// into its pinned ring; this handle folds the digests in global frame order.  Same table as one device.
+int multi_fail(g1s_diff *d, int kid, int rc) {
+  d->err = "device " + std::to_string(d->cfg.device_ids[kid]) + ": " + g1s_diff_last_error(d->kids[kid]);
+  return (rc == G1S_E_CUDA && kid > 0) ? G1S_E_NCCL : rc;
+}
+
+// Folds every global batch whose digests are complete; with `final` the (possibly short) remaining batches too.
+void multi_collect(g1s_diff *d, bool final) {
+  const int n = (int)d->kids.size();
+  const int64_t B = d->batch;
+  for (;;) {
+    const int kid = (int)(d->next_batch % n);
+    const int64_t j = d->next_batch / n;  // the child's own batch index
+    const int64_t have = g1s_diff_digest_count(d->kids[kid]);
+    int64_t cnt = std::min<int64_t>(B, d->kid_frames[kid] - j * B);
+    if (cnt <= 0) break;                       // nothing dealt to this batch yet
+    if (cnt < B && !final) break;              // the batch is still being filled
+    if (have < j * B + cnt) break;             // its kernels / model half have not retired yet
+    const size_t at = (size_t)((j * B) % (int64_t)d->kid_sink_cap);
+    fold_digests_copy(d, d->kid_sinks[kid] + at * LatestFrame::kDigestDoubles, (size_t)cnt);
+    d->next_batch++;
+  }
+}
+
+int multi_push(g1s_diff *d, const g1s_frame *source, const g1s_frame *denoised, bool device_frames) {
+  const int n = (int)d->kids.size();
+  const int kid = (int)((d->pushed / d->batch) % n);
+  if (cudaSetDevice(d->cfg.device_ids[kid]) != cudaSuccess) {
+    d->err = "cudaSetDevice failed for a device of this handle";
+    return kid > 0 ? G1S_E_NCCL : G1S_E_CUDA;
+  }
+  const int rc = device_frames ? g1s_diff_push_frame_device(d->kids[kid], source, denoised)
+                               : g1s_diff_push_frame(d->kids[kid], source, denoised);
+  if (rc != G1S_OK) return multi_fail(d, kid, rc);
+  d->kid_frames[kid]++;
+  d->pushed++;
+  multi_collect(d, false);
+  return G1S_OK;
+}
+
+int multi_drain(g1s_diff *d) {
+  for (size_t k = 0; k < d->kids.size(); ++k) {
+    if (cudaSetDevice(d->cfg.device_ids[k]) != cudaSuccess) return k > 0 ? G1S_E_NCCL : G1S_E_CUDA;
+    const int rc = g1s_diff_flush(d->kids[k]);
+    if (rc != G1S_OK) return multi_fail(d, (int)k, rc);
+  }
+  multi_collect(d, true);
+  d->folder->wait_all();
+  return G1S_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -480,7 +567,12 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     g_create_error = "unknown gram_order";
     return G1S_E_ARG;
   }
-  const bool consumer = cfg->mode == G1S_MODE_CONSUMER;
+  const bool multi = cfg->n_devices >= 2;
+  if (multi && (cfg->n_devices > G1S_MAX_DEVICES || cfg->mode != G1S_MODE_FULL)) {
+    g_create_error = "multi-device handles: 2..8 devices, mode G1S_MODE_FULL";
+    return G1S_E_ARG;
+  }
+  const bool consumer = cfg->mode == G1S_MODE_CONSUMER || multi;  // a multi-device handle itself only owns the model
   int ndev = 0;
   cudaError_t ce = consumer ? cudaSuccess : cudaGetDeviceCount(&ndev);
   if (!consumer && (ce != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev)) {
@@ -574,6 +666,31 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   }
   d->batch = batch = std::min(batch, 64);  // the Gram kernel's warps keep a batch's unit counts in two registers per lane
 
+  if (multi) {
+    // one PRODUCER child per device; their batch size is this handle's dealing unit
+    g1s_diff_config kc = *cfg;
+    kc.n_devices = 0;
+    kc.mode = G1S_MODE_PRODUCER;
+    for (int i = 0; i < cfg->n_devices; ++i) {
+      kc.device = cfg->device_ids[i];
+      g1s_diff *kid = nullptr;
+      const int rc = g1s_diff_create(&kc, &kid);
+      if (rc != G1S_OK) {
+        d->err = "device " + std::to_string(kc.device) + ": " + g_create_error;
+        return fail((rc == G1S_E_CUDA && i > 0) ? G1S_E_NCCL : rc);
+      }
+      d->kids.push_back(kid);
+      d->batch = kid->batch;
+      d->kid_sink_cap = (size_t)kid->batch * 8;
+      double *ring = nullptr;
+      CU_NEW(cudaMallocHost(&ring, d->kid_sink_cap * LatestFrame::kDigestDoubles * sizeof(double)));
+      d->kid_sinks.push_back(ring);
+      d->kid_frames.push_back(0);
+      g1s_diff_set_digest_sink(kid, ring, d->kid_sink_cap);
+    }
+    *out = d.release();
+    return G1S_OK;
+  }
   if (consumer) {
     *out = d.release();
     return G1S_OK;
@@ -643,6 +760,13 @@ extern "C" __attribute__((target_clones("arch=skylake-avx512", "avx2", "default"
 
 int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *denoised) {
   if (!d) return G1S_E_ARG;
+  if (!d->kids.empty()) {
+    if (d->finished) {
+      d->err = "push after finish";
+      return G1S_E_STATE;
+    }
+    return multi_push(d, source, denoised, false);
+  }
   if (d->finished || d->cfg.mode == G1S_MODE_CONSUMER) {
     d->err = d->finished ? "push after finish" : "consumer handles take records, not frames";
     return G1S_E_STATE;
@@ -759,6 +883,13 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
 
 int g1s_diff_push_frame_device(g1s_diff *d, const g1s_frame *source, const g1s_frame *denoised) {
   if (!d) return G1S_E_ARG;
+  if (!d->kids.empty()) {
+    if (d->finished) {
+      d->err = "push after finish";
+      return G1S_E_STATE;
+    }
+    return multi_push(d, source, denoised, true);  // the planes must live on g1s_diff_frame_device(d, frame index)
+  }
   if (d->finished || d->cfg.mode == G1S_MODE_CONSUMER) {
     d->err = d->finished ? "push after finish" : "consumer handles take records, not frames";
     return G1S_E_STATE;
@@ -786,6 +917,7 @@ int g1s_diff_push_frame_device(g1s_diff *d, const g1s_frame *source, const g1s_f
 
 int g1s_diff_flush(g1s_diff *d) {
   if (!d) return G1S_E_ARG;
+  if (!d->kids.empty()) return multi_drain(d);
   if (d->cfg.mode == G1S_MODE_CONSUMER) {
     d->folder->wait_all();
     return G1S_OK;
@@ -809,6 +941,10 @@ size_t g1s_diff_record_bytes(const g1s_diff *d) { return d ? d->rl.bytes : 0; }
 
 int g1s_diff_set_record_tap(g1s_diff *d, g1s_record_fn fn, void *user) {
   if (!d) return G1S_E_ARG;
+  if (!d->kids.empty()) {
+    d->err = "multi-device handles exchange digests, not records: no record tap";
+    return G1S_E_STATE;
+  }
   d->tap = fn;
   d->tap_user = user;
   return G1S_OK;
@@ -857,7 +993,7 @@ int g1s_diff_finish(g1s_diff *d, g1s_segment *out, size_t cap, size_t *n) {
     d->err = "producer handles have no model; finish the CONSUMER handle";
     return G1S_E_STATE;
   }
-  int rc = d->cfg.mode == G1S_MODE_CONSUMER ? G1S_OK : drain(d);
+  int rc = !d->kids.empty() ? multi_drain(d) : (d->cfg.mode == G1S_MODE_CONSUMER ? G1S_OK : drain(d));
   if (rc != G1S_OK) return rc;
   d->folder->wait_all();
   std::vector<g1s_segment> segs = d->seq->finish();
@@ -873,6 +1009,12 @@ int g1s_diff_finish(g1s_diff *d, g1s_segment *out, size_t cap, size_t *n) {
 
 void g1s_diff_destroy(g1s_diff *d) {
   if (!d) return;
+  for (size_t k = 0; k < d->kids.size(); ++k) {
+    cudaSetDevice(d->cfg.device_ids[k]);
+    g1s_diff_destroy(d->kids[k]);
+  }
+  for (double *r : d->kid_sinks)
+    if (r) cudaFreeHost(r);
   d->folder.reset();  // runs the queued folds to completion, then joins
   if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
   if (d->d2h_stream) cudaStreamSynchronize(d->d2h_stream);
@@ -908,8 +1050,26 @@ const char *g1s_diff_last_error(const g1s_diff *d) { return d ? d->err.c_str() :
 
 int64_t g1s_diff_frames_pushed(const g1s_diff *d) { return d ? d->pushed : 0; }
 
+int g1s_diff_batch_frames(const g1s_diff *d) { return d ? d->batch : 0; }
+
+int g1s_diff_frame_device(const g1s_diff *d, int64_t frame_index) {
+  if (!d || frame_index < 0) return -1;
+  if (d->kids.empty()) return d->cfg.device;
+  return d->cfg.device_ids[(frame_index / d->batch) % (int64_t)d->kids.size()];
+}
+
 int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n) {
   if (!d || !out) return G1S_E_ARG;
+  if (!d->kids.empty()) {  // sums over the devices (frames_done: frames folded into the model)
+    double acc[10] = {0}, one[10];
+    for (g1s_diff *k : d->kids) {
+      g1s_diff_get_counters(k, one, 10);
+      for (int i = 0; i < 10; ++i) acc[i] += one[i];
+    }
+    acc[5] = d->frames_done;
+    for (size_t i = 0; i < n && i < 10; ++i) out[i] = acc[i];
+    return G1S_OK;
+  }
   const double v[10] = {d->kernels_launched, d->k1_ms,       d->k1_launches, d->k0_ms,          d->k0_launches,
                         d->frames_done,      d->tma_batches, d->kr_ms,       d->vector_batches, d->ks_ms};
   for (size_t i = 0; i < n && i < 10; ++i) out[i] = v[i];
@@ -917,6 +1077,14 @@ int g1s_diff_get_counters(const g1s_diff *d, double *out, size_t n) {
 }
 
 int g1s_diff_mark(g1s_diff *d, int which) {
+  if (d && !d->kids.empty()) {
+    for (size_t k = 0; k < d->kids.size(); ++k) {
+      cudaSetDevice(d->cfg.device_ids[k]);
+      const int rc = g1s_diff_mark(d->kids[k], which);
+      if (rc != G1S_OK) return rc;
+    }
+    return G1S_OK;
+  }
   if (!d || which < 0 || which > 1 || !d->stream) return G1S_E_ARG;
   if (!d->marks[which]) CU_TRY(d, cudaEventCreate(&d->marks[which]));
   for (cudaStream_t m : d->more)  // the mark covers every kernel stream
@@ -929,6 +1097,14 @@ int g1s_diff_mark(g1s_diff *d, int which) {
 }
 
 double g1s_diff_marks_elapsed_ms(g1s_diff *d) {
+  if (d && !d->kids.empty()) {  // the slowest device
+    double worst = -1.0;
+    for (size_t k = 0; k < d->kids.size(); ++k) {
+      cudaSetDevice(d->cfg.device_ids[k]);
+      worst = std::max(worst, g1s_diff_marks_elapsed_ms(d->kids[k]));
+    }
+    return worst;
+  }
   if (!d || !d->marks[0] || !d->marks[1]) return -1.0;
   float ms = -1.0f;
   if (cudaEventSynchronize(d->marks[1]) != cudaSuccess || cudaEventElapsedTime(&ms, d->marks[0], d->marks[1]) != cudaSuccess)
@@ -967,30 +1143,8 @@ int g1s_diff_consume_digests(g1s_diff *d, const void *digests, size_t count) {
   }
   // the digests are copied (the caller's buffer is free on return) and folded asynchronously, in order; the
   // copies live in recycled buffers (a fresh 10+ MB allocation per exchange is mostly page faults)
-  std::shared_ptr<std::vector<double>> blk;
-  {
-    std::lock_guard<std::mutex> lk(d->digest_mu);
-    if (!d->digest_free.empty()) {
-      blk = std::move(d->digest_free.back());
-      d->digest_free.pop_back();
-    }
-  }
-  if (!blk) blk = std::make_shared<std::vector<double>>();
-  const double *src = static_cast<const double *>(digests);
-  blk->assign(src, src + LatestFrame::kDigestDoubles * count);
-  DiffSequencer *seq = d->seq.get();
-  d->folder->push([blk, seq, count, d] {
-    LatestFrame lf;
-    for (size_t i = 0; i < count; ++i) {
-      lf.from_digest(blk->data() + LatestFrame::kDigestDoubles * i);
-      seq->consume_latest(lf);
-    }
-    std::lock_guard<std::mutex> lk(d->digest_mu);
-    if (d->digest_free.size() < 8) d->digest_free.push_back(blk);
-  });
-  d->retired += (int64_t)count;
+  fold_digests_copy(d, static_cast<const double *>(digests), count);
   d->pushed += (int64_t)count;
-  d->frames_done += (double)count;
   return G1S_OK;
 }
 

@@ -315,15 +315,16 @@ struct BlockObs {
   int xs, x1, y0;
 };
 
-__device__ __forceinline__ BlockObs block_obs(const uint8_t *flat, const uint8_t *ovf, int nbw, int bx, int by, int wb, int pw,
-                                              int y1) {
+// st[b]: bit 0 = block b is flat, bit 1 = it is flagged for the generic kernel (the CTA's shared-memory copy of the
+// frame's flags: the walk is a chain of dependent byte reads, far too slow from global memory)
+__device__ __forceinline__ BlockObs block_obs(const uint8_t *st, int nbw, int bx, int by, int wb, int pw, int y1) {
   BlockObs o{false, 0, 0, 0};
   if (bx >= nbw) return o;
   const int b = by * nbw + bx;
-  if (!flat[b] || ovf[b]) return o;
-  o.xs = (bx > 0 && flat[b - 1]) ? 0 : kLag;
-  o.x1 = min(pw - bx * wb - kLag, (bx + 1 < nbw && flat[b + 1]) ? wb : wb - kLag);
-  o.y0 = (by > 0 && flat[b - nbw]) ? 0 : kLag;
+  if (st[b] != 1) return o;  // not flat, or flagged
+  o.xs = (bx > 0 && (st[b - 1] & 1)) ? 0 : kLag;
+  o.x1 = min(pw - bx * wb - kLag, (bx + 1 < nbw && (st[b + 1] & 1)) ? wb : wb - kLag);
+  o.y0 = (by > 0 && (st[b - nbw] & 1)) ? 0 : kLag;
   o.on = o.x1 > o.xs && y1 > o.y0;
   return o;
 }
@@ -331,8 +332,8 @@ __device__ __forceinline__ BlockObs block_obs(const uint8_t *flat, const uint8_t
 // Walks one unit column; calls unit(w0, w1, w2, w3) per unit in strip order and sliver(bx, by) per block left to the
 // generic kernel.  Returns the observations of the column.
 template <class UnitFn, class SliverFn>
-__device__ __forceinline__ long long walk_column(const Geometry &g, const uint8_t *flat, const uint8_t *ovf, bool luma, int f,
-                                                 int col, UnitFn &&unit, SliverFn &&sliver) {
+__device__ __forceinline__ long long walk_column(const Geometry &g, const uint8_t *st, bool luma, int f, int col,
+                                                 UnitFn &&unit, SliverFn &&sliver) {
   const int wb = luma ? 32 : 16, hb = luma ? 32 : 16;
   const int pw = luma ? g.width : g.width >> 1, ph = luma ? g.height : g.height >> 1;
   long long obs = 0;
@@ -376,8 +377,8 @@ __device__ __forceinline__ long long walk_column(const Geometry &g, const uint8_
   };
   for (int by = 0; by < g.nbh; ++by) {
     const int y1 = min(ph - by * hb, hb);
-    BlockObs a = block_obs(flat, ovf, g.nbw, luma ? col : 2 * col, by, wb, pw, y1);
-    BlockObs b = luma ? BlockObs{false, 0, 0, 0} : block_obs(flat, ovf, g.nbw, 2 * col + 1, by, wb, pw, y1);
+    BlockObs a = block_obs(st, g.nbw, luma ? col : 2 * col, by, wb, pw, y1);
+    BlockObs b = luma ? BlockObs{false, 0, 0, 0} : block_obs(st, g.nbw, 2 * col + 1, by, wb, pw, y1);
     const int sa = a.on ? (a.xs | (a.x1 << 6)) : -1, sb = b.on ? (b.xs | (b.x1 << 6)) : -1;
     // the strip grows by this block row (at most kMaxStrip rows of blocks: bounds the int32 strip sums)
     if (active && sa == sig0 && sb == sig1 && y1 >= kMinRows && by - b0 < kMaxStrip) continue;
@@ -404,7 +405,8 @@ __device__ __forceinline__ long long walk_column(const Geometry &g, const uint8_
 
 __global__ void __launch_bounds__(256)
 gram_plan_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, uint4 *__restrict__ plan,
-                 int *__restrict__ counts) {
+                 int *__restrict__ counts, uint8_t *__restrict__ scratch) {
+  extern __shared__ uint8_t s_state[];  // nb bytes when the frame's flags fit (else the global scratch is used)
   __shared__ int s_cnt[256], s_base;
   __shared__ unsigned long long s_obs;
   const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
@@ -412,6 +414,8 @@ gram_plan_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, uin
   uint8_t *rec = records + (size_t)f * rl.bytes;
   const uint8_t *flat = rec + rl.off_flat;
   uint8_t *ovf = rec + rl.off_ovf + (size_t)c * g.nb;
+  uint8_t *st = scratch ? scratch + ((size_t)f * 3 + c) * g.nb : s_state;
+  for (int b = tid; b < g.nb; b += 256) st[b] = (flat[b] ? 1 : 0) | (ovf[b] ? 2 : 0);
   const int ncols = luma ? g.nbw : (g.nbw + 1) >> 1;
   uint4 *out = plan + ((size_t)f * 3 + c) * g.nb;
   if (tid == 0) s_base = 0, s_obs = 0ull;
@@ -419,8 +423,7 @@ gram_plan_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, uin
   for (int c0 = 0; c0 < ncols; c0 += 256) {
     const int col = c0 + tid;
     int n = 0;
-    if (col < ncols)
-      walk_column(g, flat, ovf, luma, f, col, [&](uint32_t, uint32_t, uint32_t, uint32_t) { ++n; }, [](int, int) {});
+    if (col < ncols) walk_column(g, st, luma, f, col, [&](uint32_t, uint32_t, uint32_t, uint32_t) { ++n; }, [](int, int) {});
     s_cnt[tid] = n;
     __syncthreads();
     // exclusive scan of 256 counts (Hillis-Steele; a frame has a few thousand units, this runs once per 256 columns)
@@ -433,7 +436,7 @@ gram_plan_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, uin
     int at = s_base + s_cnt[tid] - n;
     if (col < ncols) {
       const long long obs = walk_column(
-          g, flat, ovf, luma, f, col, [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) { out[at++] = make_uint4(w0, w1, w2, w3); },
+          g, st, luma, f, col, [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) { out[at++] = make_uint4(w0, w1, w2, w3); },
           [&](int bx, int by) {
             ovf[by * g.nbw + bx] = 1;  // read again only by the generic kernel, launched after the Gram kernel
             atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_ovf_count), 1ull);
@@ -634,11 +637,18 @@ void gram_imma_tma_boxes(int box[kResidualMaps][2]) {
   for (int k = 1; k < kResidualMaps; ++k) box[k][0] = kBoxW, box[k][1] = kChromaRows;
 }
 
-size_t gram_plan_bytes(int nframes, const Geometry &g) { return (size_t)nframes * 3 * g.nb * sizeof(uint4); }
+// descriptors, then (only for frames of more than kPlanSmemBlocks blocks) one state byte per block and plane
+constexpr int kPlanSmemBlocks = 40960;
+size_t gram_plan_bytes(int nframes, const Geometry &g) {
+  return (size_t)nframes * 3 * g.nb * sizeof(uint4) + (g.nb > kPlanSmemBlocks ? (size_t)nframes * 3 * g.nb : 0);
+}
 
 void launch_gram_plan(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, void *plan, int *counts,
                       cudaStream_t st) {
-  gram_plan_kernel<<<dim3(g.planes, nframes), 256, 0, st>>>(g, records, rl, static_cast<uint4 *>(plan), counts);
+  const bool in_smem = g.nb <= kPlanSmemBlocks;
+  uint8_t *scratch = in_smem ? nullptr : static_cast<uint8_t *>(plan) + (size_t)nframes * 3 * g.nb * sizeof(uint4);
+  gram_plan_kernel<<<dim3(g.planes, nframes), 256, in_smem ? (size_t)g.nb : 0, st>>>(
+      g, records, rl, static_cast<uint4 *>(plan), counts, scratch);
 }
 
 void launch_gram_imma(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, const void *tmaps,

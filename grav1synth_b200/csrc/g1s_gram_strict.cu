@@ -152,23 +152,38 @@ gram_reforder_kernel(const FrameDesc *__restrict__ frames, Geometry g, uint8_t *
       // lanes read on into the tile (valid shared memory, never added).
       const double *t0 = tiles[b] + kLag * kSPitch + kLag;
       const int w = x_end - x_start, cpr = (w + 7) >> 3, nchunks = (y_end - y_start) * cpr;
-      double q[8];
-      int cy = y_start, cx = 0;  // position of the chunk held in q
-      term_chunk(t0 + cy * kSPitch + x_start, off_i, off_j, q);
+      // two chunk buffers in ping-pong (no register copies); only a row's last chunk can be short
+      double qa[8], qb[8];
+      int cy = y_start, cx = 0;  // position of the chunk held in qa
+      auto next_pos = [&](int &y, int &x) {
+        if (++x == cpr) x = 0, ++y;
+      };
+      auto add_chunk = [&](const double (&q)[8], int x) {
+        const int cnt = w - 8 * x;
+        if (cnt >= 8) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc = __dadd_rn(acc, q[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 7; ++k)
+            if (k < cnt) acc = __dadd_rn(acc, q[k]);
+        }
+      };
+      term_chunk(t0 + cy * kSPitch + x_start, off_i, off_j, qa);
+      int ci = 0;
 #pragma unroll 1
-      for (int ci = 0; ci < nchunks; ++ci) {
-        int ny = cy, nx = cx + 1;
-        if (nx == cpr) nx = 0, ++ny;
-        double qn[8];
-        if (ci + 1 < nchunks) term_chunk(t0 + ny * kSPitch + x_start + 8 * nx, off_i, off_j, qn);
-        const int cnt = min(8, w - 8 * cx);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k < cnt) acc = __dadd_rn(acc, q[k]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) q[k] = qn[k];
-        cy = ny, cx = nx;
+      for (; ci + 2 <= nchunks; ci += 2) {
+        int y1 = cy, x1 = cx;
+        next_pos(y1, x1);
+        term_chunk(t0 + y1 * kSPitch + x_start + 8 * x1, off_i, off_j, qb);
+        add_chunk(qa, cx);
+        int y2 = y1, x2 = x1;
+        next_pos(y2, x2);
+        if (ci + 2 < nchunks) term_chunk(t0 + y2 * kSPitch + x_start + 8 * x2, off_i, off_j, qa);
+        add_chunk(qb, x1);
+        cy = y2, cx = x2;
       }
+      if (ci < nchunks) add_chunk(qa, cx);
     }
     __syncthreads();  // tile b is free again, tile b^1 is complete
     cur = nxt;

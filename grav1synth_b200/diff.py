@@ -26,7 +26,8 @@ RECORD_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t)
 
 EXPORTS = [
     "g1s_abi_version", "g1s_diff_create", "g1s_diff_push_frame", "g1s_diff_push_frame_device", "g1s_diff_flush",
-    "g1s_diff_finish", "g1s_diff_destroy", "g1s_diff_last_error", "g1s_diff_frames_pushed",
+    "g1s_diff_finish", "g1s_diff_destroy", "g1s_diff_last_error", "g1s_diff_frames_pushed", "g1s_diff_batch_frames",
+    "g1s_diff_frame_device",
     "g1s_diff_get_counters", "g1s_diff_mark", "g1s_diff_marks_elapsed_ms", "g1s_record_layout", "g1s_record_gramf_offset", "g1s_diff_record_bytes", "g1s_diff_set_record_tap",
     "g1s_diff_consume_record", "g1s_diff_consume_records", "g1s_digest_bytes", "g1s_diff_set_digest_sink",
     "g1s_diff_digest_count", "g1s_diff_wait_retired", "g1s_diff_consume_digests", "g1s_diff_consume_digests_borrowed", "g1s_diff_digest_from_record", "g1s_write_grain_table", "g1s_format_grain_table",
@@ -60,6 +61,8 @@ def lib() -> C.CDLL:
         L.g1s_diff_last_error.restype = C.c_char_p
         L.g1s_diff_frames_pushed.argtypes = [C.c_void_p]
         L.g1s_diff_frames_pushed.restype = C.c_int64
+        L.g1s_diff_batch_frames.argtypes = [C.c_void_p]
+        L.g1s_diff_frame_device.argtypes = [C.c_void_p, C.c_int64]
         L.g1s_diff_get_counters.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_size_t]
         L.g1s_diff_mark.argtypes = [C.c_void_p, C.c_int]
         L.g1s_diff_marks_elapsed_ms.argtypes = [C.c_void_p]
@@ -278,6 +281,14 @@ class DiffGenerator:
         """borrowed: no copy; the memory must stay valid until flush() on this handle has returned."""
         fn = self._L.g1s_diff_consume_digests_borrowed if borrowed else self._L.g1s_diff_consume_digests
         self._check(fn(self._h, ptr, count))
+
+    @property
+    def batch_frames(self) -> int:
+        return int(self._L.g1s_diff_batch_frames(self._h))
+
+    def frame_device(self, frame_index: int) -> int:
+        """CUDA ordinal that processes this frame (multi-device handles deal batches round-robin)."""
+        return int(self._L.g1s_diff_frame_device(self._h, frame_index))
 
     @property
     def frames_pushed(self) -> int:

@@ -177,6 +177,12 @@ const char *g1s_diff_last_error(const g1s_diff *d);
 
 /* Number of frames accepted so far. */
 int64_t g1s_diff_frames_pushed(const g1s_diff *d);
+/* Frames per device launch of this handle (the dealing unit of a multi-device handle). */
+int g1s_diff_batch_frames(const g1s_diff *d);
+/* CUDA ordinal that processes frame `frame_index` (counted from 0): `device` for single-device handles,
+ * device_ids[(frame_index / batch) % n_devices] for multi-device ones.  g1s_diff_push_frame_device on a multi-device
+ * handle needs the planes of frame k resident on that device. */
+int g1s_diff_frame_device(const g1s_diff *d, int64_t frame_index);
 
 /* Timing/launch counters of the device pipeline, for the benchmark harness:
  * out[0] = kernels launched, out[1] = total device ms spent in the fused
