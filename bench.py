@@ -41,7 +41,13 @@ def parse_args():
     ap.add_argument("--workload", default="4k10", choices=list(WORKLOADS))
     ap.add_argument("--frames", type=int, default=60, help="frame pairs per step per GPU (3 engine batches at 4K)")
     ap.add_argument("--batch", type=int, default=0, help="frame pairs per kernel launch (engine batch)")
+    ap.add_argument("--repeat", type=int, default=32,
+                    help="passes over the resident frames per step (a step is repeat x frames frame pairs per GPU, so that "
+                         "the default 20..40 steps time seconds, not milliseconds)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-variants", action="store_true", help="skip the pageable / host_narrow e2e legs")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-stats", action="store_true", help="skip the workload statistics and the ~10 %-flat input pass")
     ap.add_argument("--host-narrow", action="store_true",
                     help="e2e leg: reduce >8-bit host samples to 8 bits while staging (cfg.host_narrow), half the H2D bytes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -209,6 +215,59 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def kernel_pass(D, abi, dev_args, dims, local_rank, batch, passes):
+    """Per-kernel device times with ONE kernel stream (nothing overlaps, so every launch's CUDA-event duration is its
+    own): a few passes over the resident frames on a fresh handle.  Returns ms per frame of each kernel."""
+    W, H, bd = dims
+    old = os.environ.get("G1S_STREAMS")
+    os.environ["G1S_STREAMS"] = "1"
+    try:
+        g = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=batch)
+    finally:
+        if old is None:
+            del os.environ["G1S_STREAMS"]
+        else:
+            os.environ["G1S_STREAMS"] = old
+
+    def one():
+        for (sp, ss), (dp, ds) in dev_args:
+            g.diff_frame_device(sp, ss, dp, ds)
+
+    one()
+    g.flush()
+    c0 = g.counters()
+    g.mark(0)
+    for _ in range(passes):
+        one()
+    g.flush()
+    g.mark(1)
+    ms = g.marks_elapsed_ms()
+    c1 = g.counters()
+    g.close()
+    n = max(1.0, c1["frames_done"] - c0["frames_done"])
+    return {"flat_features": (c1["flat_ms"] - c0["flat_ms"]) / n, "residual": (c1["residual_ms"] - c0["residual_ms"]) / n,
+            "gram_plan+gram_imma": (c1["gram_ms"] - c0["gram_ms"]) / n, "whole_step_one_stream": ms / n,
+            "frames": int(n), "frames_per_launch": n / max(1.0, c1["gram_launches"] - c0["gram_launches"])}
+
+
+def workload_stats(D, frames_np, dims):
+    """Flat-block fraction and observation counts of the synthetic input (what the Gram work is proportional to)."""
+    W, H, bd = dims
+    g = D.DiffGenerator(24, 1, bd, bd, W, H)
+    recs = []
+    g.set_record_tap(lambda i, r: recs.append(r))
+    for s, d in frames_np:
+        g.diff_frame(s, d)
+    g.finish()
+    rl = D.RecordLayout(g.num_blocks)
+    u = [rl.unpack(r) for r in recs]
+    g.close()
+    nobs = [float(sum(int(x["nobs"][c]) for x in u)) / len(u) for c in range(3)]
+    flat = float(sum(x["num_flat"] for x in u)) / len(u) / g.num_blocks
+    macs = nobs[0] * 324 + (nobs[1] + nobs[2]) * 350  # symmetric half of the 24/25-tap outer product + the b vector
+    return {"flat_block_fraction": flat, "observations_per_frame": nobs, "algorithmic_int_mac_per_frame": macs}
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -221,7 +280,7 @@ def main():
     from grav1synth_b200 import abi
     from grav1synth_b200 import diff as D
     from grav1synth_b200.sharded import ShardedDiff
-    from grav1synth_b200.synth import frame_pair_bytes, make_pair, to_numpy
+    from grav1synth_b200.synth import SynthSpec, frame_pair_bytes, make_pair, to_numpy
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -238,7 +297,7 @@ def main():
     wl = WORKLOADS[args.workload]
     spec = synth_spec(wl)
     W, H, bd = spec.width, spec.height, spec.bit_depth
-    F = args.frames
+    F, R = args.frames, args.repeat
     pair_bytes = frame_pair_bytes(W, H, 1, 1, bd, bd)
 
     # ---- multi-GPU parity, before anything is timed: a two-scene stream through the NCCL-sharded path must give the
@@ -265,18 +324,20 @@ def main():
         eng = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=args.batch)
 
         def step():
-            # one pass over the batch of F frame pairs; the engine pipelines launches and folds results
-            # asynchronously, the drain happens once at the end of the timed region (barrier())
-            for (sp, ss), (dp, ds) in dev_args:
-                eng.diff_frame_device(sp, ss, dp, ds)
+            # R passes over the F resident frame pairs (3.0 GB at 4K: every pass streams from HBM); the engine pipelines
+            # launches and folds results asynchronously, the drain happens once at the end of the timed region
+            for _ in range(R):
+                for (sp, ss), (dp, ds) in dev_args:
+                    eng.diff_frame_device(sp, ss, dp, ds)
     else:
         sd = ShardedDiff(24, 1, bd, bd, W, H, 1, 1, frames_per_rank=F, device=local_rank, batch_frames=args.batch)
         eng = sd.producer
 
         def step():
-            for sp, dp in dev_args:
-                sd.push_local(sp, dp, device_resident=True)
-            sd.exchange()
+            for _ in range(R):
+                for sp, dp in dev_args:
+                    sd.push_local(sp, dp, device_resident=True)
+                sd.exchange()
 
     def barrier():
         if world == 1:
@@ -293,7 +354,7 @@ def main():
     barrier()
     c0 = eng.counters()
     clocks = ClockSampler(local_rank) if rank == 0 else None
-    # timed region: CUDA events on the engine's own kernel stream (torch events only see torch's stream),
+    # timed region: CUDA events on the engine's own kernel streams (torch events only see torch's stream),
     # cross-checked against the host clock; the larger of the two is reported
     eng.mark(0)
     t0 = time.perf_counter()
@@ -309,42 +370,43 @@ def main():
     if world > 1:
         dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
     elapsed = float(elapsed.item())
-    total_frames = world * F * args.steps
+    total_frames = world * F * R * args.steps
     value = total_frames / elapsed
-
-    # dominant work: residual + Gram accumulation (two back-to-back launches per batch: the streaming
-    # residual kernel and the TMA-fed tensor-core Gram kernel), CUDA events on the engine's stream
-    gram_ms = (c1["gram_ms"] - c0["gram_ms"]) / max(1.0, c1["gram_launches"] - c0["gram_launches"])
-    res_ms = (c1["residual_ms"] - c0["residual_ms"]) / max(1.0, c1["gram_launches"] - c0["gram_launches"])
-    flat_ms = (c1["flat_ms"] - c0["flat_ms"]) / max(1.0, c1["flat_launches"] - c0["flat_launches"])
     frames_per_launch = (c1["frames_done"] - c0["frames_done"]) / max(1.0, c1["gram_launches"] - c0["gram_launches"])
+
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        pk = json.load(open(peaks_path))
+        peak, peak_src = float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-    path_ms = gram_ms + res_ms
-    achieved = frames_per_launch * pair_bytes / (path_ms * 1e-3) / 1e9 if path_ms > 0 else 0.0
+    # the path's roofline: algorithmic bytes (one read of every sample of both frames) over the WHOLE step
+    # -- flat-block finder, threshold select, residual, plan and Gram launches, as they overlap on the kernel streams --
+    # per GPU, measured over the timed region itself
+    step_gbs = (total_frames / world) * pair_bytes / elapsed / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "gram_traffic.json")
-    if os.path.exists(tpath) and args.workload == "4k10" and abs(frames_per_launch - 20.0) < 1e-9:
-        # ncu --set full capture of one residual + one gram launch of exactly this configuration (20 frame pairs)
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath) and args.workload == "4k10":
+        # ncu --set full captures of every kernel of one 20-frame batch of exactly this workload
+        tj = json.load(open(tpath))
+        traffic = tj.get("dram_bytes_per_frame", 0) * frames_per_launch or None
 
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": wl["label"], "frames_per_step_per_gpu": F, "frames_per_launch": frames_per_launch, "bytes_per_frame_pair": pair_bytes,
-                   "l2": f"inputs larger than L2 ({F * pair_bytes / 1e6:.0f} MB per step per GPU)",
+        "config": {"workload": wl["label"], "frames_per_step_per_gpu": F * R, "resident_frames": F, "passes_per_step": R,
+                   "frames_per_launch": frames_per_launch, "bytes_per_frame_pair": pair_bytes,
+                   "l2": f"inputs larger than L2 ({F * pair_bytes / 1e6:.0f} MB resident per GPU, streamed once per pass)",
+                   "timed_region_s": elapsed,
                    "parallelism": f"frame-sharded x{world}, NCCL all-gather of per-frame model digests ({D.digest_bytes()} B/frame)",
-                   "device_ms_flat_kernel": flat_ms, "device_ms_residual_kernel": res_ms,
-                   "device_ms_gram_kernel": gram_ms},
+                   "kernel_streams": int(os.environ.get("G1S_STREAMS", "3"))},
         "gpu_launches": int(c1["kernels_launched"] - c0["kernels_launched"]),
-        "roofline": {"bound": "hbm", "kernel": "residual_kernel + gram_imma_kernel (residual + autocorrelation; "
-                                                  "algorithmic bytes over the SUM of both launch durations)",
-                     "achieved": achieved,
-                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+        "roofline": {"bound": "hbm",
+                     "kernel": "whole step: flat_features + flat_select + residual + gram_plan + gram_imma (+ gram_generic "
+                               "for flagged blocks), overlapped on the engine's kernel streams; algorithmic bytes over "
+                               "the timed region",
+                     "achieved": step_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": step_gbs / peak,
                      "traffic": traffic},
     }
     if clk is not None:
@@ -354,6 +416,43 @@ def main():
     table = eng.finish() if world == 1 else sd.finish()
     if rank == 0:
         line["config"]["segments"] = len(table)
+
+    if world == 1:
+        # ---- per-kernel times, one stream (no overlap), and the figures the survey asked for beside the roofline
+        kp = kernel_pass(D, abi, dev_args, (W, H, bd), local_rank, args.batch, 2)
+        rg = kp["residual"] + kp["gram_plan+gram_imma"]
+        line["kernels"] = {"ms_per_frame_one_stream": kp,
+                           "residual+gram": {"achieved": pair_bytes / (rg * 1e-3) / 1e9, "unit": "GB/s",
+                                             "frac": pair_bytes / (rg * 1e-3) / 1e9 / peak},
+                           "whole_step_one_stream": {"achieved": pair_bytes / (kp["whole_step_one_stream"] * 1e-3) / 1e9,
+                                                     "frac": pair_bytes / (kp["whole_step_one_stream"] * 1e-3) / 1e9 / peak}}
+        if rank == 0 and not args.no_stats:
+            ws = workload_stats(D, [(to_numpy(s), to_numpy(d)) for s, d in frames[:2]], (W, H, bd))
+            ws["int_mac_per_s"] = ws["algorithmic_int_mac_per_frame"] * value
+            line["workload"] = ws
+            # the same path on an input where only ~10 % of the blocks are flat (the Gram work shrinks with it)
+            sp2 = SynthSpec(W, H, bd, textured=0.93, sigma0=spec.sigma0, sigma1=spec.sigma1, seed=spec.seed)
+            fr2 = [make_pair(sp2, k, dev) for k in range(min(F, 20))]
+            da2 = [(ptrs(s), ptrs(d)) for s, d in fr2]
+            g2 = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=args.batch)
+            for _ in range(3):
+                for (sp, ss), (dp, ds) in da2:
+                    g2.diff_frame_device(sp, ss, dp, ds)
+            g2.flush()
+            g2.mark(0)
+            n2 = 0
+            for _ in range(12):
+                for (sp, ss), (dp, ds) in da2:
+                    g2.diff_frame_device(sp, ss, dp, ds)
+                    n2 += 1
+            g2.flush()
+            g2.mark(1)
+            v2 = n2 / (g2.marks_elapsed_ms() * 1e-3)
+            g2.close()
+            ws2 = workload_stats(D, [(to_numpy(s), to_numpy(d)) for s, d in fr2[:1]], (W, H, bd))
+            line["sparse_input"] = {"value": v2, "unit": "frames/s", "flat_block_fraction": ws2["flat_block_fraction"],
+                                    "roofline_frac": v2 * pair_bytes / 1e9 / peak}
+            del fr2, da2
 
     # ---- strict mode (gram_order = REF_ORDER): the reference's per-term f64 accumulation reproduced bit for bit on
     # the device, so every table integer equals the reference's; same device-resident frames, its own timed pass
@@ -367,7 +466,6 @@ def main():
 
         strict_step()
         gs.flush()
-        cs0 = gs.counters()
         gs.mark(0)
         ts0 = time.perf_counter()
         for _ in range(args.strict_steps):
@@ -375,13 +473,11 @@ def main():
         gs.flush()
         gs.mark(1)
         s_ms = max(gs.marks_elapsed_ms(), (time.perf_counter() - ts0) * 1e3)
-        cs1 = gs.counters()
         strict_table = gs.finish()
         line["value_strict"] = F * args.strict_steps / (s_ms * 1e-3)
         line["strict"] = {"unit": "frames/s", "gram_order": "REF_ORDER (per-term f64 chains, reference pixel order)",
-                          "frames": F * args.strict_steps, "frames_per_launch": sb,
-                          "device_ms_strict_kernel_per_frame": (cs1["strict_ms"] - cs0["strict_ms"]) / (F * args.strict_steps),
-                          "segments": len(strict_table), "bound": "fp64 pipe / chain latency (5 f64 ops per term)"}
+                          "frames": F * args.strict_steps, "frames_per_launch": sb, "segments": len(strict_table),
+                          "bound": "fp64 pipe / chain latency (5 f64 ops per term, 3.6 G terms per frame)"}
 
     # ---- e2e: host buffers through the C ABI (push_frame), copies inside the timed region
     if not args.no_e2e:
@@ -391,52 +487,70 @@ def main():
             hs = [t.cpu().pin_memory() for t in s]
             hd = [t.cpu().pin_memory() for t in d]
             host.append((hs, hd))
-        np_frames = [([t.numpy().view(np.uint16) if bd > 8 else t.numpy() for t in hs],
-                      [t.numpy().view(np.uint16) if bd > 8 else t.numpy() for t in hd]) for hs, hd in host]
-        if world == 1:
-            g = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=args.batch,
-                                host_narrow=args.host_narrow)
-            sd2 = None
 
-            def e2e_step():
-                for k in range(F):
-                    s, d = np_frames[k % nh]
-                    g.diff_frame(s, d)
-        else:
-            sd2 = ShardedDiff(24, 1, bd, bd, W, H, 1, 1, frames_per_rank=F, device=local_rank, batch_frames=args.batch)
-            g = sd2.producer
+        def as_np(ts):
+            return [t.numpy().view(np.uint16) if bd > 8 else t.numpy() for t in ts]
 
-            def e2e_step():
-                for k in range(F):
-                    s, d = np_frames[k % nh]
-                    sd2.push_local(s, d)
-                sd2.exchange()
+        pinned_frames = [(as_np(hs), as_np(hd)) for hs, hd in host]
 
-        def e2e_barrier():
+        def run_e2e(np_frames, narrow, steps):
             if world == 1:
-                g.flush()
-            else:
-                sd2.exchange(final=True)
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
+                g = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=args.batch, host_narrow=narrow)
+                sd2 = None
 
-        e2e_step()
-        e2e_barrier()
-        t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 3))
-        for _ in range(n_e2e):
+                def e2e_step():
+                    for k in range(F):
+                        s, d = np_frames[k % nh]
+                        g.diff_frame(s, d)
+
+                def e2e_barrier():
+                    g.flush()
+                    torch.cuda.synchronize()
+            else:
+                sd2 = ShardedDiff(24, 1, bd, bd, W, H, 1, 1, frames_per_rank=F, device=local_rank, batch_frames=args.batch)
+                g = sd2.producer
+
+                def e2e_step():
+                    for k in range(F):
+                        s, d = np_frames[k % nh]
+                        sd2.push_local(s, d)
+                    sd2.exchange()
+
+                def e2e_barrier():
+                    sd2.exchange(final=True)
+                    torch.cuda.synchronize()
+                    dist.barrier()
+
             e2e_step()
-        e2e_barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        line["e2e"] = {"value": world * F * n_e2e / float(dt.item()), "unit": "frames/s",
-                       "h2d_bytes_per_step": F * (pair_bytes // 2 if (args.host_narrow and bd > 8 and world == 1) else pair_bytes),
-                       "d2h_bytes_per_step": F * g.record_bytes, "records_bytes_per_frame": g.record_bytes,
-                       "host_narrow": bool(args.host_narrow and bd > 8 and world == 1),
-                       "steps": n_e2e, "api": "g1s_diff_push_frame (C ABI) with host planes + g1s_diff_flush"}
-        g.close()
+            e2e_barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                e2e_step()
+            e2e_barrier()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            rb = g.record_bytes
+            g.close()
+            return world * F * steps / float(dt.item()), rb
+
+        n_e2e = max(1, min(args.steps, args.e2e_steps))
+        v_pin, rb = run_e2e(pinned_frames, False, n_e2e)
+        line["e2e"] = {"value": v_pin, "unit": "frames/s", "h2d_bytes_per_step": F * pair_bytes,
+                       "d2h_bytes_per_step": F * rb, "records_bytes_per_frame": rb, "frames_per_step": F, "steps": n_e2e,
+                       "host_memory": "pinned (direct 2-D DMA per plane)",
+                       "api": "g1s_diff_push_frame (C ABI) with host planes + g1s_diff_flush"}
+        if world == 1 and not args.no_e2e_variants:
+            # what a caller with ordinary (pageable) planes gets -- the Rust caller's v_frame planes -- and the same with the
+            # samples reduced to 8 bits while they are staged (host_narrow: half the bytes on PCIe, identical results)
+            pageable = [([np.array(p) for p in s], [np.array(p) for p in d]) for s, d in pinned_frames]
+            v_pg, _ = run_e2e(pageable, False, n_e2e)
+            line["e2e_pageable"] = {"value": v_pg, "unit": "frames/s", "h2d_bytes_per_step": F * pair_bytes,
+                                    "host_memory": "pageable (staged through the engine's pinned ring by its host threads)"}
+            if bd > 8:
+                v_nr, _ = run_e2e(pageable, True, n_e2e)
+                line["e2e_host_narrow"] = {"value": v_nr, "unit": "frames/s", "h2d_bytes_per_step": F * pair_bytes // 2,
+                                           "host_memory": "pageable, narrowed to 8 bits while staged (cfg.host_narrow)"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -8,7 +8,7 @@
 // bit-identical to the oracle whatever the summation order.
 //
 // Two kernels.
-//  * gram_plan_kernel (one CTA per frame and plane, one thread per block column) turns the flat-block map into
+//  * gram_plan_kernel (a few CTAs per frame and plane, one thread per block position) turns the flat-block map into
 //    the work list of the plane: it applies add_block_observations' rectangle rules (3-sample margins unless the
 //    neighbour block is flat, frame clipping), joins vertically adjacent blocks whose column ranges agree into
 //    STRIPS (one row window, so the window bookkeeping below is paid once per strip instead of once per block and
@@ -301,14 +301,18 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int x, 
 
 // ------------------------------------------------------------------------------ gram_plan_kernel
 //
-// One CTA per (plane, frame); thread t owns unit column t (luma: block column; chroma: the pair of block columns
-// 2t, 2t+1) and walks it top to bottom twice: once to count its units, once (after a CTA-wide exclusive scan of the
-// counts) to write them.  Strip rules, per half h of the unit (luma has one half that spans all 32 columns):
+// kPlanSlices CTAs per (plane, frame), one thread per block position (unit column, block row).  Whether a block row
+// STARTS a strip is a local question (this row's and the previous row's state), so every start is found in parallel;
+// the thread that owns a start walks down its own strip (1.6 block rows on the benchmark input, 64 at most), reserves
+// the strip's units with one atomicAdd on the plane's unit count and writes them.  Units of a strip are contiguous,
+// strips land in whatever order the atomics resolve: the sums are integers, so the order does not matter.
+// Strip rules, per half h of the unit (luma has one half that spans all 32 columns):
 //   observed columns [xs, x1) and rows [y0, y1) of a block exactly as add_block_observations computes them;
 //   a block is ON when it is flat, not flagged for the generic kernel, and that rectangle is not empty;
 //   a strip continues into the next block row while both halves keep their state (off, or on with the same columns):
 //   the block above an ON block of a continuing strip is flat, so its y0 is 0 and the rows are contiguous;
-//   a strip that would START with two ON halves on different rows (y0 differs) is split for that one block row;
+//   a block row whose two ON halves start on different rows (y0 differs; then it cannot continue a strip) is two
+//   single-half strips of its own; strips are cut every kMaxStrip block rows (int32 bound);
 //   windows of fewer than kMinRows rows (bottom slivers of the frame) go to the generic kernel.
 struct BlockObs {
   bool on;
@@ -316,7 +320,7 @@ struct BlockObs {
 };
 
 // st[b]: bit 0 = block b is flat, bit 1 = it is flagged for the generic kernel (the CTA's shared-memory copy of the
-// frame's flags: the walk is a chain of dependent byte reads, far too slow from global memory)
+// frame's flags)
 __device__ __forceinline__ BlockObs block_obs(const uint8_t *st, int nbw, int bx, int by, int wb, int pw, int y1) {
   BlockObs o{false, 0, 0, 0};
   if (bx >= nbw) return o;
@@ -329,21 +333,63 @@ __device__ __forceinline__ BlockObs block_obs(const uint8_t *st, int nbw, int bx
   return o;
 }
 
-// Walks one unit column; calls unit(w0, w1, w2, w3) per unit in strip order and sliver(bx, by) per block left to the
-// generic kernel.  Returns the observations of the column.
-template <class UnitFn, class SliverFn>
-__device__ __forceinline__ long long walk_column(const Geometry &g, const uint8_t *st, bool luma, int f, int col,
-                                                 UnitFn &&unit, SliverFn &&sliver) {
-  const int wb = luma ? 32 : 16, hb = luma ? 32 : 16;
+struct RowState {
+  BlockObs a, b;
+  int y1, sa, sb;  // sig = xs | x1 << 6 of an ON half, -1 when off
+  __device__ bool any() const { return a.on || b.on; }
+};
+
+__device__ __forceinline__ RowState row_state(const uint8_t *st, const Geometry &g, bool luma, int col, int by) {
+  const int wb = luma ? 32 : 16, hb = wb;
   const int pw = luma ? g.width : g.width >> 1, ph = luma ? g.height : g.height >> 1;
+  RowState r;
+  r.y1 = min(ph - by * hb, hb);
+  r.a = block_obs(st, g.nbw, luma ? col : 2 * col, by, wb, pw, r.y1);
+  r.b = luma ? BlockObs{false, 0, 0, 0} : block_obs(st, g.nbw, 2 * col + 1, by, wb, pw, r.y1);
+  r.sa = r.a.on ? (r.a.xs | (r.a.x1 << 6)) : -1;
+  r.sb = r.b.on ? (r.b.xs | (r.b.x1 << 6)) : -1;
+  return r;
+}
+
+constexpr int kPlanSlices = 4;
+
+__global__ void __launch_bounds__(256)
+gram_plan_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, uint4 *__restrict__ plan,
+                 int *__restrict__ counts, uint8_t *__restrict__ scratch) {
+  extern __shared__ uint8_t s_state[];  // nb bytes when the frame's flags fit (else a global scratch copy is used)
+  __shared__ unsigned long long s_obs;
+  const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+  const bool luma = c == 0;
+  uint8_t *rec = records + (size_t)f * rl.bytes;
+  const uint8_t *flat = rec + rl.off_flat;
+  uint8_t *ovf = rec + rl.off_ovf + (size_t)c * g.nb;
+  uint8_t *st = scratch ? scratch + (((size_t)f * 3 + c) * kPlanSlices + blockIdx.z) * g.nb : s_state;
+  for (int b = tid; b < g.nb; b += 256) st[b] = (flat[b] ? 1 : 0) | (ovf[b] ? 2 : 0);
+  if (tid == 0) s_obs = 0ull;
+  __syncthreads();
+  const int ncols = luma ? g.nbw : (g.nbw + 1) >> 1;
+  const int hb = luma ? 32 : 16, ph = luma ? g.height : g.height >> 1;
+  uint4 *out = plan + ((size_t)f * 3 + c) * g.nb;
+  int *count = counts + f * 3 + c;
   long long obs = 0;
-  // a strip: block rows [b0, b1), first observed row y0 (in the first tile), k ranges of the two halves
-  auto close = [&](int b0, int b1, int y0, int lo0, int hi0, int lo1, int hi1, int width) {
+
+  // one strip: block rows [b0, b1), first observed row y0 (in the first tile), signatures of the two halves
+  auto close = [&](int col, int b0, int b1, int y0, int sa, int sb) {
+    int lo0, hi0, lo1, hi1, width;
+    if (luma) {
+      lo0 = lo1 = sa & 63, hi0 = hi1 = sa >> 6;
+      width = hi0 - lo0;
+    } else {
+      lo0 = sa < 0 ? 0 : (sa & 63), hi0 = sa < 0 ? 0 : (sa >> 6);
+      lo1 = sb < 0 ? 0 : 16 + (sb & 63), hi1 = sb < 0 ? 0 : 16 + (sb >> 6);
+      width = (hi0 - lo0) + (hi1 - lo1);
+    }
     const int T = b1 - b0;
     const int y1_last = min(ph - (b1 - 1) * hb, hb);
     const int n = hb * (T - 1) + y1_last - y0;
     const int P = (n + 4) >> 1;
     obs += (long long)n * width;
+    uint4 *dst = out + atomicAdd(count, T);
     int cursor = y0, done = 0;  // next strip row, in rows from the first tile's row 0; pair steps emitted
     for (int k = 0; k < T; ++k) {
       const int r0 = cursor - hb * k;
@@ -351,106 +397,46 @@ __device__ __forceinline__ long long walk_column(const Geometry &g, const uint8_
       const uint32_t w0 = (uint32_t)f | ((uint32_t)col << 8) | ((uint32_t)(b0 + k) << 20);
       const uint32_t w1 = (uint32_t)r0 | ((uint32_t)np << 6) | (k == 0 ? kFirst : 0u) | (k + 1 == T ? kLast : 0u) |
                           ((n & 1) ? kOdd : 0u) | ((uint32_t)lo0 << 16) | ((uint32_t)hi0 << 22);
-      const uint32_t w2 = (uint32_t)lo1 | ((uint32_t)hi1 << 6);
-      unit(w0, w1, w2, k == 0 ? (uint32_t)(n * width) : 0u);
+      dst[k] = make_uint4(w0, w1, (uint32_t)lo1 | ((uint32_t)hi1 << 6), k == 0 ? (uint32_t)(n * width) : 0u);
       cursor += 2 * np;
       done += np;
     }
   };
-  bool active = false;
-  int b0 = 0, sy0 = 0, sig0 = -1, sig1 = -1;  // current strip; sig = xs | x1 << 6 of an ON half, -1 when off
-  auto ranges = [&](int s0, int s1, int &lo0, int &hi0, int &lo1, int &hi1, int &width) {
-    if (luma) {
-      lo0 = lo1 = s0 & 63, hi0 = hi1 = s0 >> 6;
-      width = hi0 - lo0;
-    } else {
-      lo0 = s0 < 0 ? 0 : (s0 & 63), hi0 = s0 < 0 ? 0 : (s0 >> 6);
-      lo1 = s1 < 0 ? 0 : 16 + (s1 & 63), hi1 = s1 < 0 ? 0 : 16 + (s1 >> 6);
-      width = (hi0 - lo0) + (hi1 - lo1);
+  auto sliver = [&](int bx, int by) {
+    ovf[by * g.nbw + bx] = 1;  // read again only by the generic kernel, launched after the Gram kernel
+    atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_ovf_count), 1ull);
+  };
+
+  const int items = ncols * g.nbh;
+  for (int it = blockIdx.z * 256 + tid; it < items; it += 256 * kPlanSlices) {
+    const int by = it / ncols, col = it - by * ncols;
+    RowState r = row_state(st, g, luma, col, by);
+    if (!r.any()) continue;
+    bool start = by == 0 || r.y1 < kMinRows || by % kMaxStrip == 0;
+    if (!start) {
+      const RowState p = row_state(st, g, luma, col, by - 1);
+      start = !p.any() || p.sa != r.sa || p.sb != r.sb || (p.a.on && p.b.on && p.a.y0 != p.b.y0);
     }
-  };
-  auto finish = [&](int b1) {
-    int lo0, hi0, lo1, hi1, width;
-    ranges(sig0, sig1, lo0, hi0, lo1, hi1, width);
-    close(b0, b1, sy0, lo0, hi0, lo1, hi1, width);
-    active = false;
-  };
-  for (int by = 0; by < g.nbh; ++by) {
-    const int y1 = min(ph - by * hb, hb);
-    BlockObs a = block_obs(st, g.nbw, luma ? col : 2 * col, by, wb, pw, y1);
-    BlockObs b = luma ? BlockObs{false, 0, 0, 0} : block_obs(st, g.nbw, 2 * col + 1, by, wb, pw, y1);
-    const int sa = a.on ? (a.xs | (a.x1 << 6)) : -1, sb = b.on ? (b.xs | (b.x1 << 6)) : -1;
-    // the strip grows by this block row (at most kMaxStrip rows of blocks: bounds the int32 strip sums)
-    if (active && sa == sig0 && sb == sig1 && y1 >= kMinRows && by - b0 < kMaxStrip) continue;
-    if (active) finish(by);
-    // a new strip starts here (if anything is ON); halves whose window would be too short go to the generic kernel
-    if (a.on && y1 - a.y0 < kMinRows) sliver(luma ? col : 2 * col, by), a.on = false;
-    if (b.on && y1 - b.y0 < kMinRows) sliver(2 * col + 1, by), b.on = false;
-    if (!a.on && !b.on) continue;
-    const int na = a.on ? (a.xs | (a.x1 << 6)) : -1, nb = b.on ? (b.xs | (b.x1 << 6)) : -1;
-    if (a.on && b.on && a.y0 != b.y0) {
-      // one block row as two single-half strips; the rows below start a fresh strip (both y0 = 0 there)
-      int lo0, hi0, lo1, hi1, width;
-      ranges(na, -1, lo0, hi0, lo1, hi1, width);
-      close(by, by + 1, a.y0, lo0, hi0, lo1, hi1, width);
-      ranges(-1, nb, lo0, hi0, lo1, hi1, width);
-      close(by, by + 1, b.y0, lo0, hi0, lo1, hi1, width);
+    if (!start) continue;
+    // halves whose window would be too short go to the generic kernel
+    if (r.a.on && r.y1 - r.a.y0 < kMinRows) sliver(luma ? col : 2 * col, by), r.a.on = false, r.sa = -1;
+    if (r.b.on && r.y1 - r.b.y0 < kMinRows) sliver(2 * col + 1, by), r.b.on = false, r.sb = -1;
+    if (!r.any()) continue;
+    if (r.a.on && r.b.on && r.a.y0 != r.b.y0) {  // two single-half strips of one block row
+      close(col, by, by + 1, r.a.y0, r.sa, -1);
+      close(col, by, by + 1, r.b.y0, -1, r.sb);
       continue;
     }
-    active = true, b0 = by, sy0 = a.on ? a.y0 : b.y0, sig0 = na, sig1 = nb;
+    int e = by + 1;
+    for (; e < g.nbh && e % kMaxStrip != 0; ++e) {
+      const RowState n = row_state(st, g, luma, col, e);
+      if (!n.any() || n.sa != r.sa || n.sb != r.sb || n.y1 < kMinRows) break;
+    }
+    close(col, by, e, r.a.on ? r.a.y0 : r.b.y0, r.sa, r.sb);
   }
-  if (active) finish(g.nbh);
-  return obs;
-}
-
-__global__ void __launch_bounds__(256)
-gram_plan_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, uint4 *__restrict__ plan,
-                 int *__restrict__ counts, uint8_t *__restrict__ scratch) {
-  extern __shared__ uint8_t s_state[];  // nb bytes when the frame's flags fit (else the global scratch is used)
-  __shared__ int s_cnt[256], s_base;
-  __shared__ unsigned long long s_obs;
-  const int c = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
-  const bool luma = c == 0;
-  uint8_t *rec = records + (size_t)f * rl.bytes;
-  const uint8_t *flat = rec + rl.off_flat;
-  uint8_t *ovf = rec + rl.off_ovf + (size_t)c * g.nb;
-  uint8_t *st = scratch ? scratch + ((size_t)f * 3 + c) * g.nb : s_state;
-  for (int b = tid; b < g.nb; b += 256) st[b] = (flat[b] ? 1 : 0) | (ovf[b] ? 2 : 0);
-  const int ncols = luma ? g.nbw : (g.nbw + 1) >> 1;
-  uint4 *out = plan + ((size_t)f * 3 + c) * g.nb;
-  if (tid == 0) s_base = 0, s_obs = 0ull;
+  if (obs) atomicAdd(&s_obs, (unsigned long long)obs);
   __syncthreads();
-  for (int c0 = 0; c0 < ncols; c0 += 256) {
-    const int col = c0 + tid;
-    int n = 0;
-    if (col < ncols) walk_column(g, st, luma, f, col, [&](uint32_t, uint32_t, uint32_t, uint32_t) { ++n; }, [](int, int) {});
-    s_cnt[tid] = n;
-    __syncthreads();
-    // exclusive scan of 256 counts (Hillis-Steele; a frame has a few thousand units, this runs once per 256 columns)
-    for (int d = 1; d < 256; d <<= 1) {
-      const int v = tid >= d ? s_cnt[tid - d] : 0;
-      __syncthreads();
-      s_cnt[tid] += v;
-      __syncthreads();
-    }
-    int at = s_base + s_cnt[tid] - n;
-    if (col < ncols) {
-      const long long obs = walk_column(
-          g, st, luma, f, col, [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) { out[at++] = make_uint4(w0, w1, w2, w3); },
-          [&](int bx, int by) {
-            ovf[by * g.nbw + bx] = 1;  // read again only by the generic kernel, launched after the Gram kernel
-            atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_ovf_count), 1ull);
-          });
-      if (obs) atomicAdd(&s_obs, (unsigned long long)obs);
-    }
-    __syncthreads();
-    if (tid == 255) s_base += s_cnt[255];
-    __syncthreads();
-  }
-  if (tid == 0) {
-    counts[f * 3 + c] = s_base;
-    if (s_obs) atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + c, s_obs);
-  }
+  if (tid == 0 && s_obs) atomicAdd(reinterpret_cast<unsigned long long *>(rec + rl.off_nobs) + c, s_obs);
 }
 
 // ------------------------------------------------------------------------------ gram_imma_kernel
@@ -637,17 +623,19 @@ void gram_imma_tma_boxes(int box[kResidualMaps][2]) {
   for (int k = 1; k < kResidualMaps; ++k) box[k][0] = kBoxW, box[k][1] = kChromaRows;
 }
 
-// descriptors, then (only for frames of more than kPlanSmemBlocks blocks) one state byte per block and plane
+// descriptors, then (only for frames of more than kPlanSmemBlocks blocks) one state byte per block, plane and slice
 constexpr int kPlanSmemBlocks = 40960;
 size_t gram_plan_bytes(int nframes, const Geometry &g) {
-  return (size_t)nframes * 3 * g.nb * sizeof(uint4) + (g.nb > kPlanSmemBlocks ? (size_t)nframes * 3 * g.nb : 0);
+  return (size_t)nframes * 3 * g.nb * sizeof(uint4) +
+         (g.nb > kPlanSmemBlocks ? (size_t)nframes * 3 * kPlanSlices * g.nb : 0);
 }
 
 void launch_gram_plan(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, void *plan, int *counts,
                       cudaStream_t st) {
   const bool in_smem = g.nb <= kPlanSmemBlocks;
   uint8_t *scratch = in_smem ? nullptr : static_cast<uint8_t *>(plan) + (size_t)nframes * 3 * g.nb * sizeof(uint4);
-  gram_plan_kernel<<<dim3(g.planes, nframes), 256, in_smem ? (size_t)g.nb : 0, st>>>(
+  cudaMemsetAsync(counts, 0, sizeof(int) * 3 * nframes, st);  // the kernel reserves units with atomicAdd
+  gram_plan_kernel<<<dim3(g.planes, nframes, kPlanSlices), 256, in_smem ? (size_t)g.nb : 0, st>>>(
       g, records, rl, static_cast<uint4 *>(plan), counts, scratch);
 }
 
