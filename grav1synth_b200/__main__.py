@@ -192,7 +192,8 @@ def rewrite_main(args) -> int:
         info = probe.stream_info()
         trc = TRANSFER_SMPTE2084 if info["transfer_characteristics"] == 16 else TRANSFER_BT1886
         table = [generate_photon_noise_params(0, 2 ** 64 - 1, args.iso, info["max_frame_width"],
-                                              info["max_frame_height"], trc, args.chroma)]
+                                              info["max_frame_height"], trc, args.chroma,
+                                              full_range=info["color_range"] == 1)]  # src/main.rs:299
     out = rewrite_ivf(data, GrainRewriter(table))
     with open(args.output, "wb") as f:
         f.write(out)

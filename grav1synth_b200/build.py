@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         "-Xcompiler", "-fPIC,-O3,-ffp-contract=off,-fno-math-errno,-Wall,-pthread",
         "-Xptxas", "-v" if verbose else "-O3",
         "-I", os.path.join(HERE, "..", "include"),
-    ] + [os.path.join(CSRC, f) for f in SOURCES]
+    ] + os.environ.get("G1S_EXTRA_NVCC", "").split() + [os.path.join(CSRC, f) for f in SOURCES]  # tuning experiments
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -336,16 +336,11 @@ int submit(g1s_diff *d, Slot &s) {
   }
   CU_TRY(d, cudaMemcpyAsync(s.d_descs, s.h_descs, sizeof(FrameDesc) * s.count, cudaMemcpyHostToDevice, st));
   CU_TRY(d, cudaMemsetAsync(s.d_records, 0, d->rl.bytes * s.count, st));
-  CU_TRY(d, cudaEventRecord(s.k0_beg, st));
-  bool luma16 = true;  // 16-byte aligned source-luma rows -> 128-bit loads in the flat-block kernel
-  for (int i = 0; i < s.count && luma16; ++i)
-    if (((uintptr_t)s.h_descs[i].src[0] | s.h_descs[i].src_stride[0]) & 15) luma16 = false;
-  launch_flat_features(s.d_descs, s.count, d->geom, d->fc, s.d_records, d->rl, luma16, st);
-  CU_TRY(d, cudaEventRecord(s.k0_end, st));
-  launch_flat_select(s.count, d->geom, s.d_records, d->rl, st);
   int gram_launches = 1;
   if (d->tensor_path) {
-    // 128-bit loads need 16-byte aligned rows; otherwise the residual kernel falls back to scalar loads
+    // Tensor-core path: the streaming residual kernel goes first (it needs no flat flags) and leaves, beside the s8
+    // residual planes, the 8-bit source luma the flat-block finder reads: half the bytes of a 10-bit frame, aligned,
+    // and fresh in L2.  128-bit loads need 16-byte aligned rows; otherwise the residual kernel uses scalar loads.
     bool aligned = !std::getenv("G1S_SCALAR_LOADS");
     for (int i = 0; i < s.count && aligned; ++i)
       for (int c = 0; c < d->geom.planes; ++c) {
@@ -356,6 +351,11 @@ int submit(g1s_diff *d, Slot &s) {
     rs.base = s.d_res;
     CU_TRY(d, cudaEventRecord(s.kr_beg, st));
     launch_residual(s.d_descs, s.count, d->geom, rs, s.d_records, d->rl, aligned, st);
+    CU_TRY(d, cudaEventRecord(s.k0_beg, st));
+    launch_flat_features(s.d_descs, s.count, d->geom, d->fc, s.d_records, d->rl, true, st,
+                         reinterpret_cast<const uint8_t *>(s.d_res) + rs.off_y8, rs.frame_bytes, rs.pitch_l);
+    CU_TRY(d, cudaEventRecord(s.k0_end, st));
+    launch_flat_select(s.count, d->geom, s.d_records, d->rl, st);
     CU_TRY(d, cudaEventRecord(s.k1_beg, st));
     launch_gram_plan(s.count, d->geom, s.d_records, d->rl, s.d_plan, s.d_plan_counts, st);
     launch_gram_imma(s.count, d->geom, s.d_records, d->rl, s.d_rmaps, s.d_plan, s.d_plan_counts, st);
@@ -365,6 +365,13 @@ int submit(g1s_diff *d, Slot &s) {
     d->tma_batches += 1;
     if (aligned) d->vector_batches += 1;
   } else {
+    CU_TRY(d, cudaEventRecord(s.k0_beg, st));
+    bool luma16 = true;  // 16-byte aligned source-luma rows -> 128-bit loads in the flat-block kernel
+    for (int i = 0; i < s.count && luma16; ++i)
+      if (((uintptr_t)s.h_descs[i].src[0] | s.h_descs[i].src_stride[0]) & 15) luma16 = false;
+    launch_flat_features(s.d_descs, s.count, d->geom, d->fc, s.d_records, d->rl, luma16, st);
+    CU_TRY(d, cudaEventRecord(s.k0_end, st));
+    launch_flat_select(s.count, d->geom, s.d_records, d->rl, st);
     CU_TRY(d, cudaEventRecord(s.kr_beg, st));
     CU_TRY(d, cudaEventRecord(s.k1_beg, st));
     launch_gram_generic(s.d_descs, s.count, d->geom, s.d_records, d->rl, /*only_overflow=*/false, st);
@@ -397,7 +404,7 @@ int retire(g1s_diff *d, Slot &s) {
   float ms = 0;
   if (cudaEventElapsedTime(&ms, s.k0_beg, s.k0_end) == cudaSuccess) d->k0_ms += ms;
   if (cudaEventElapsedTime(&ms, s.k1_beg, s.k1_end) == cudaSuccess) d->k1_ms += ms;
-  if (cudaEventElapsedTime(&ms, s.kr_beg, s.k1_beg) == cudaSuccess) d->kr_ms += ms;
+  if (cudaEventElapsedTime(&ms, s.kr_beg, d->tensor_path ? s.k0_beg : s.k1_beg) == cudaSuccess) d->kr_ms += ms;
   if (d->cfg.gram_order == G1S_GRAM_REF_ORDER && cudaEventElapsedTime(&ms, s.ks_beg, s.ks_end) == cudaSuccess)
     d->ks_ms += ms;
   d->folder->wait(s.fold_ticket);  // the slot's previous batch must have left the fold thread

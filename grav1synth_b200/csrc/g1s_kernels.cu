@@ -179,7 +179,8 @@ __device__ __forceinline__ void unpack_chunk(const RawChunk<SB> &r, int shift, i
 template <int SB>
 __global__ void __launch_bounds__(kFlatThreads)
 flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, FlatConsts fc,
-                     uint8_t *__restrict__ records, RecordLayout rl, int aligned) {
+                     uint8_t *__restrict__ records, RecordLayout rl, int aligned, const uint8_t *__restrict__ y8,
+                     size_t y8_frame_bytes, uint32_t y8_pitch) {
   extern __shared__ double fsm[];  // lut[256] | ring[2][32][kFlatThreads]
   double *lut = fsm;
   double *ring = fsm + 256;
@@ -192,13 +193,15 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
   const int f = gid / g.nb;
   const int b = gid - f * g.nb;
   const int by = b / g.nbw, bx = b - by * g.nbw;
-  const uint8_t *src = static_cast<const uint8_t *>(frames[f].src[0]);
-  const uint32_t stride = frames[f].src_stride[0];
+  // y8: the 8-bit source luma plane residual_kernel wrote for this batch (tensor-core path): half the bytes of a
+  // 10-bit frame, always aligned, and still in L2 when this kernel runs right behind it
+  const uint8_t *src = y8 ? y8 + (size_t)f * y8_frame_bytes : static_cast<const uint8_t *>(frames[f].src[0]);
+  const uint32_t stride = y8 ? y8_pitch : frames[f].src_stride[0];
   const int w = g.width, h = g.height;
   const int x0 = bx * kBlock, y0 = by * kBlock;
   const int tid = threadIdx.x;
   const bool vec_ok = aligned != 0;
-  const int shift = g.src_shift;
+  const int shift = y8 ? 0 : g.src_shift;
 
   // --- A^T * block (multiply_mat(block, A, ., 1, 1024, 3)): three sequential chains
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -343,20 +346,25 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
 }
 
 void launch_flat_features(const FrameDesc *frames, int nframes, const Geometry &g, const FlatConsts &fc,
-                          uint8_t *records, const RecordLayout &rl, bool aligned, cudaStream_t st) {
+                          uint8_t *records, const RecordLayout &rl, bool aligned, cudaStream_t st, const uint8_t *y8,
+                          size_t y8_frame_bytes, uint32_t y8_pitch) {
   const int total = nframes * g.nb;
   const int grid = (total + kFlatThreads - 1) / kFlatThreads;
   const size_t smem = sizeof(double) * (256 + 2 * kBlock * kFlatThreads);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};  // the attribute is a per-device property of the function
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     cudaFuncSetAttribute(flat_features_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(flat_features_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
-  if (g.src_bytes == 2)
-    flat_features_kernel<2><<<grid, kFlatThreads, smem, st>>>(frames, nframes, g, fc, records, rl, aligned ? 1 : 0);
+  if (y8)
+    flat_features_kernel<1><<<grid, kFlatThreads, smem, st>>>(frames, nframes, g, fc, records, rl, 1, y8, y8_frame_bytes, y8_pitch);
+  else if (g.src_bytes == 2)
+    flat_features_kernel<2><<<grid, kFlatThreads, smem, st>>>(frames, nframes, g, fc, records, rl, aligned ? 1 : 0, nullptr, 0, 0);
   else
-    flat_features_kernel<1><<<grid, kFlatThreads, smem, st>>>(frames, nframes, g, fc, records, rl, aligned ? 1 : 0);
+    flat_features_kernel<1><<<grid, kFlatThreads, smem, st>>>(frames, nframes, g, fc, records, rl, aligned ? 1 : 0, nullptr, 0, 0);
 }
 
 // --------------------------------------------------------------------- flat_select_kernel

@@ -56,8 +56,11 @@ struct RecordLayout {
 };
 
 // aligned: every source-luma row start is 16-byte aligned (vector loads allowed).
+// y8 (optional): the batch's 8-bit source luma planes as residual_kernel wrote them (ResidualStore::off_y8, frame f at
+// y8 + f * y8_frame_bytes, rows y8_pitch apart); when given, the frames themselves are not read.
 void launch_flat_features(const FrameDesc *frames, int nframes, const Geometry &g, const FlatConsts &fc,
-                          uint8_t *records, const RecordLayout &rl, bool aligned, cudaStream_t st);
+                          uint8_t *records, const RecordLayout &rl, bool aligned, cudaStream_t st,
+                          const uint8_t *y8 = nullptr, size_t y8_frame_bytes = 0, uint32_t y8_pitch = 0);
 void launch_flat_select(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, cudaStream_t st);
 // only_overflow = false: every flat block, statistics included (any subsampling, any alignment).
 // only_overflow = true: just the blocks the tensor-core kernel flagged (Gram sums and statistics).
@@ -76,6 +79,7 @@ struct ResidualStore {
   size_t frame_bytes;
   size_t off_res[3];
   size_t off_tap;
+  size_t off_y8;           // the source luma reduced to 8 bits (what FlatBlockFinder reads), same pitch as the luma residual
   uint32_t pitch_l, pitch_c;
   static ResidualStore make(const Geometry &g);  // offsets / pitches only; base stays null
 };

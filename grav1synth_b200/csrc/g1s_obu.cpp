@@ -1434,7 +1434,8 @@ struct Transfer {
 }  // namespace
 
 int g1s_generate_photon_noise(uint32_t iso, uint32_t width, uint32_t height, int transfer, int chroma_grain,
-                              int32_t random_seed, uint64_t start_time, uint64_t end_time, g1s_segment *out) {
+                              int full_range, int32_t random_seed, uint64_t start_time, uint64_t end_time,
+                              g1s_segment *out) {
   if (!out || iso == 0 || width == 0 || height == 0 || transfer < 0 || transfer > G1S_TRANSFER_BT470BG) return G1S_E_ARG;
   const Transfer tf{transfer};
   std::memset(out, 0, sizeof *out);
@@ -1456,8 +1457,12 @@ int g1s_generate_photon_noise(uint32_t iso, uint32_t width, uint32_t height, int
     const float lo = std::fmax(0.f, linear - 2 * linear_noise), hi = std::fmin(1.f, linear + 2 * linear_noise);
     const float slope = (tf.from_linear(hi) - tf.from_linear(lo)) / (hi - lo);
     const float encoded_noise = linear_noise * slope;
-    out->scaling_points_y[i][0] = (uint8_t)std::round(255.f * x);
-    out->scaling_points_y[i][1] = (uint8_t)std::fmin(255.f, std::round(255.f * 7.88f * encoded_noise));
+    // NoiseGenArgs::full_range (src/main.rs:299: color_range == JPEG).  Full range: code values and noise on the 0..255
+    // scale (the form libaom's photon_noise_table.c has, pinned by the reference's fixture).  Limited range: the same
+    // curve on the 16..235 scale -- recalled from the crate, which is absent here, so this branch is parity-unpinned.
+    const float span = full_range ? 255.f : 219.f, base = full_range ? 0.f : 16.f;
+    out->scaling_points_y[i][0] = (uint8_t)std::round(base + span * x);
+    out->scaling_points_y[i][1] = (uint8_t)std::fmin(255.f, std::round(span * 7.88f * encoded_noise));
   }
   out->start_time = start_time;
   out->end_time = end_time;

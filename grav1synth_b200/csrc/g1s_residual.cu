@@ -117,6 +117,7 @@ residual_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, R
     const uint8_t *sp = static_cast<const uint8_t *>(fd.src[0]) + (size_t)Y0 * sstr;
     const uint8_t *dp = static_cast<const uint8_t *>(fd.den[0]) + (size_t)Y0 * dstr;
     int8_t *out = store + rs.off_res[0] + (size_t)Y0 * rs.pitch_l + x8;
+    int8_t *y8 = store + rs.off_y8 + (size_t)Y0 * rs.pitch_l + x8;
     const bool taps = has_chroma && (x8 >> 1) < pw;
     int8_t *tap = store + rs.off_tap + (size_t)(Y0 >> 1) * rs.pitch_c + (x8 >> 1);
     int sum_r = 0;
@@ -137,6 +138,11 @@ residual_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, R
       residual8(s1, d1, b1, w10, w11, ov);
       *reinterpret_cast<uint2 *>(out) = make_uint2(w00, w01);
       if (two) *reinterpret_cast<uint2 *>(out + rs.pitch_l) = make_uint2(w10, w11);
+      // the 8-bit source luma itself, for the flat-block finder that runs next
+      *reinterpret_cast<uint2 *>(y8) = make_uint2(__byte_perm(s0[0], s0[1], 0x6420), __byte_perm(s0[2], s0[3], 0x6420));
+      if (two)
+        *reinterpret_cast<uint2 *>(y8 + rs.pitch_l) =
+            make_uint2(__byte_perm(s1[0], s1[1], 0x6420), __byte_perm(s1[2], s1[3], 0x6420));
       sum_r = __dp4a((int)w00, 0x01010101, sum_r);
       sum_r = __dp4a((int)w01, 0x01010101, sum_r);
       sum_r = __dp4a((int)w10, 0x01010101, sum_r);
@@ -162,6 +168,7 @@ residual_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, R
       sp += 2 * (size_t)sstr;
       dp += 2 * (size_t)dstr;
       out += 2 * (size_t)rs.pitch_l;
+      y8 += 2 * (size_t)rs.pitch_l;
       tap += rs.pitch_c;
     }
     // block statistics: four lanes per 32-sample block
@@ -247,6 +254,7 @@ ResidualStore ResidualStore::make(const Geometry &g) {
   r.pitch_c = (uint32_t)up(pw ? pw : 1, 16);
   size_t o = 0;
   r.off_res[0] = o, o += up((size_t)r.pitch_l * g.height, 256);
+  r.off_y8 = o, o += up((size_t)r.pitch_l * g.height, 256);
   r.off_res[1] = r.off_res[2] = r.off_tap = 0;
   if (g.planes == 3) {
     const size_t cb = up((size_t)r.pitch_c * (ph ? ph : 1), 256);

@@ -219,13 +219,13 @@ TRANSFER_BT1886, TRANSFER_SMPTE2084, TRANSFER_BT470BG = 0, 1, 2
 
 def generate_photon_noise_params(start_time: int, end_time: int, iso: int, width: int, height: int,
                                  transfer: int = TRANSFER_BT1886, chroma_grain: bool = False,
-                                 random_seed: Optional[int] = None) -> GrainTableSegment:
+                                 random_seed: Optional[int] = None, full_range: bool = True) -> GrainTableSegment:
     """av1_grain::generate_photon_noise_params as the reference calls it (src/main.rs:288-303)."""
     L = _L()
-    L.g1s_generate_photon_noise.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int32,
+    L.g1s_generate_photon_noise.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int32,
                                             C.c_uint64, C.c_uint64, C.POINTER(CSegment)]
     seg = CSegment()
-    rc = L.g1s_generate_photon_noise(iso, width, height, transfer, int(chroma_grain),
+    rc = L.g1s_generate_photon_noise(iso, width, height, transfer, int(chroma_grain), int(full_range),
                                      -1 if random_seed is None else random_seed, start_time, end_time, C.byref(seg))
     if rc != 0:
         raise G1SError(rc, "g1s_generate_photon_noise: bad arguments")

@@ -304,11 +304,14 @@ int g1s_rewrite_take(g1s_inspect *h, uint8_t *out, size_t cap);
 int g1s_rewrite_counters(const g1s_inspect *h, uint64_t *frames_with_grain, uint64_t *frames_grain_disabled);
 /* `generate` (src/main.rs:247-308): av1_grain::generate_photon_noise_params -- a photon-noise grain segment for a
  * camera ISO setting, frame size and transfer function (luma scaling points only, lag 0); apply it with g1s_rewrite_*.
+ * full_range: NoiseGenArgs::full_range, which the reference sets from the stream's colour range (src/main.rs:299); non-zero
+ * places the scaling points on the 0..255 scale, zero on 16..235 (that branch is recalled from the crate: unpinned).
  * random_seed < 0 takes DEFAULT_GRAIN_SEED.  G1S_TRANSFER_BT470BG is not reachable from the reference's CLI: it is the
  * curve behind the reference's fixture tests/example-table.tbl and is kept to reproduce it. */
 enum g1s_transfer { G1S_TRANSFER_BT1886 = 0, G1S_TRANSFER_SMPTE2084 = 1, G1S_TRANSFER_BT470BG = 2 };
 int g1s_generate_photon_noise(uint32_t iso, uint32_t width, uint32_t height, int transfer, int chroma_grain,
-                              int32_t random_seed, uint64_t start_time, uint64_t end_time, g1s_segment *out);
+                              int full_range, int32_t random_seed, uint64_t start_time, uint64_t end_time,
+                              g1s_segment *out);
 /* Host-side reduction used by host_narrow (exported for tests): dst[i] = (uint8_t)(src[i] >> shift). */
 void g1s_narrow_row(uint8_t *dst, const uint16_t *src, int n, int shift);
 /* Test hook: parse ONE syntax group (named as in the AV1 spec / the reference's functions) from a raw bit buffer;

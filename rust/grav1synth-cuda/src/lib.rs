@@ -99,7 +99,7 @@ extern "C" {
     pub fn g1s_rewrite_packet(h: *mut g1s_inspect, data: *const u8, size: usize, packet_ts: u64,
                               out_size: *mut usize) -> c_int;
     pub fn g1s_rewrite_take(h: *mut g1s_inspect, out: *mut u8, cap: usize) -> c_int;
-    pub fn g1s_generate_photon_noise(iso: u32, width: u32, height: u32, transfer: c_int, chroma_grain: c_int,
+    pub fn g1s_generate_photon_noise(iso: u32, width: u32, height: u32, transfer: c_int, chroma_grain: c_int, full_range: c_int,
                                      random_seed: i32, start_time: u64, end_time: u64, out: *mut g1s_segment) -> c_int;
 }
 

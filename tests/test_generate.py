@@ -48,7 +48,12 @@ def test_generate_command(tmp_path):
     p = I.BitstreamParser()
     p.push_file(str(out))
     hs = p.get_grain_headers()
-    want = I.generate_photon_noise_params(0, 1, 800, seq.width, seq.height, I.TRANSFER_SMPTE2084, True)
+    # the stream signals limited range, so the command passes full_range = false (src/main.rs:299: range == JPEG)
+    assert p.stream_info()["color_range"] == 0
+    want = I.generate_photon_noise_params(0, 1, 800, seq.width, seq.height, I.TRANSFER_SMPTE2084, True, full_range=False)
+    full = I.generate_photon_noise_params(0, 1, 800, seq.width, seq.height, I.TRANSFER_SMPTE2084, True, full_range=True)
+    assert want.scaling_points_y[0][0] == 16 and want.scaling_points_y[-1][0] == 235
+    assert full.scaling_points_y[0][0] == 0 and full.scaling_points_y[-1][0] == 255
     assert [h.kind for h in hs] == [I.UPDATE_GRAIN] * 2
     for k, h in enumerate(hs):
         assert h.params.scaling_points_y == want.scaling_points_y and h.params.chroma_scaling_from_luma
