@@ -638,7 +638,7 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   {
     int threads = cfg->host_threads;
     if (const char *e = std::getenv("G1S_HOST_THREADS")) threads = std::atoi(e);
-    if (threads <= 0) threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (threads <= 0) threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency() / 2));
     d->pool.reset(new HostPool(threads));
     d->folder.reset(new FoldQueue());
   }
@@ -781,7 +781,11 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
   int rc = check_frames(d, source, denoised);
   if (rc != G1S_OK) return rc;
   Slot &s = d->slots[d->cur];
-  if (!s.d_frames) CU_TRY(d, cudaMalloc(&s.d_frames, (size_t)d->batch * d->pair_bytes));
+  // the frame store is allocated on the first host push, for every slot at once: a page-locked gigabyte takes a good
+  // fraction of a second to allocate, which must not land in the middle of a stream
+  if (!s.d_frames)
+    for (Slot &o : d->slots)
+      if (!o.d_frames) CU_TRY(d, cudaMalloc(&o.d_frames, (size_t)d->batch * d->pair_bytes));
   const size_t base = (size_t)s.count * d->pair_bytes;
   FrameDesc &fd = s.h_descs[s.count];
   std::memset(&fd, 0, sizeof fd);
@@ -828,7 +832,9 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
     if (s.count == d->batch) return rotate(d);
     return G1S_OK;
   }
-  if (!s.h_frames) CU_TRY(d, cudaMallocHost(&s.h_frames, (size_t)d->batch * d->pair_bytes));
+  if (!s.h_frames)
+    for (Slot &o : d->slots)
+      if (!o.h_frames) CU_TRY(d, cudaMallocHost(&o.h_frames, (size_t)d->batch * d->pair_bytes));
   // The borrowed planes are copied into the pinned staging slot by the host threads, in row chunks of
   // about 1 MiB, so the copy runs at memory bandwidth rather than at one core's memcpy speed.
   struct CopyTask {
