@@ -261,6 +261,14 @@ namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Handles own streams, events and memory of ONE device; a caller (or a multi-device parent) may have made another
+// device current since the last call.
+inline bool owns_device(const g1s_diff *d) { return d->stream != nullptr; }
+#define G1S_ON_DEVICE(d)                                                    \
+  do {                                                                      \
+    if (owns_device(d)) CU_TRY(d, cudaSetDevice((d)->cfg.device));          \
+  } while (0)
+
 FrameRecordView view_of(const g1s_diff *d, const uint8_t *rec) {
   FrameRecordView v;
   v.gram = reinterpret_cast<const int64_t *>(rec + d->rl.off_gram);
@@ -780,6 +788,7 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
   }
   int rc = check_frames(d, source, denoised);
   if (rc != G1S_OK) return rc;
+  G1S_ON_DEVICE(d);
   Slot &s = d->slots[d->cur];
   // the frame store is allocated on the first host push, for every slot at once: a page-locked gigabyte takes a good
   // fraction of a second to allocate, which must not land in the middle of a stream
@@ -913,6 +922,7 @@ int g1s_diff_push_frame_device(g1s_diff *d, const g1s_frame *source, const g1s_f
   }
   int rc = check_frames(d, source, denoised);
   if (rc != G1S_OK) return rc;
+  G1S_ON_DEVICE(d);
   Slot &s = d->slots[d->cur];
   FrameDesc &fd = s.h_descs[s.count];
   std::memset(&fd, 0, sizeof fd);
@@ -935,6 +945,7 @@ int g1s_diff_flush(g1s_diff *d) {
     d->folder->wait_all();
     return G1S_OK;
   }
+  G1S_ON_DEVICE(d);
   return drain(d);
 }
 
@@ -1006,6 +1017,7 @@ int g1s_diff_finish(g1s_diff *d, g1s_segment *out, size_t cap, size_t *n) {
     d->err = "producer handles have no model; finish the CONSUMER handle";
     return G1S_E_STATE;
   }
+  G1S_ON_DEVICE(d);
   int rc = !d->kids.empty() ? multi_drain(d) : (d->cfg.mode == G1S_MODE_CONSUMER ? G1S_OK : drain(d));
   if (rc != G1S_OK) return rc;
   d->folder->wait_all();
@@ -1029,6 +1041,7 @@ void g1s_diff_destroy(g1s_diff *d) {
   for (double *r : d->kid_sinks)
     if (r) cudaFreeHost(r);
   d->folder.reset();  // runs the queued folds to completion, then joins
+  if (owns_device(d)) cudaSetDevice(d->cfg.device);
   if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
   if (d->d2h_stream) cudaStreamSynchronize(d->d2h_stream);
   if (d->stream) cudaStreamSynchronize(d->stream);
@@ -1099,6 +1112,7 @@ int g1s_diff_mark(g1s_diff *d, int which) {
     return G1S_OK;
   }
   if (!d || which < 0 || which > 1 || !d->stream) return G1S_E_ARG;
+  G1S_ON_DEVICE(d);
   if (!d->marks[which]) CU_TRY(d, cudaEventCreate(&d->marks[which]));
   for (cudaStream_t m : d->more)  // the mark covers every kernel stream
     if (m) {
@@ -1140,6 +1154,7 @@ int64_t g1s_diff_digest_count(const g1s_diff *d) { return d ? (int64_t)d->sink_c
 int g1s_diff_wait_retired(g1s_diff *d, int64_t frames) {
   if (!d) return G1S_E_ARG;
   if (d->cfg.mode == G1S_MODE_CONSUMER) return G1S_OK;
+  G1S_ON_DEVICE(d);
   while (d->retired < frames && d->slots[d->oldest].in_flight) {
     const int rc = retire(d, d->slots[d->oldest]);
     if (rc != G1S_OK) return rc;
