@@ -47,7 +47,7 @@ def main(argv=None) -> int:
     d.add_argument("-y", "--overwrite", action="store_true", help="Overwrite the output file without prompting.")
     d.add_argument("-f", "--filters", default=None,
                    help='A semicolon-separated list of filters to apply to the source before running the diff, e.g. '
-                        '"crop:top=42,left=64" (resize is parsed but not available in this build).')
+                        '"crop:top=42,left=64" or "resize:width=1920,height=1080,alg=lanczos".')
     d.add_argument("--device", type=int, default=0)
     d.add_argument("--devices", default=None,
                    help="Several GPUs behind one handle, e.g. 0-7 or 0,2,3: batches of frames are dealt round-robin "
@@ -118,6 +118,13 @@ def main(argv=None) -> int:
     differ = DiffGenerator(sd.fps_num, sd.fps_den, sd.bit_depth, dd.bit_depth, dd.width, dd.height, sd.ss_x, sd.ss_y,
                            monochrome=sd.monochrome, device=args.device, devices=parse_devices(args.devices),
                            gram_order=1 if args.strict else 0)
+    if chain is not None and chain.filters:
+        # source only, src/main.rs:621-624: the chain runs on the device between the upload and the kernels
+        try:
+            differ.set_source_filters(chain.filters, sd.width, sd.height)
+        except ValueError as e:
+            log.error("Invalid filter chain: %s", e)
+            return 1
     frames = 0
     while True:  # src/main.rs:432-521
         s, d_ = src.get_frame(), den.get_frame()
@@ -126,8 +133,6 @@ def main(argv=None) -> int:
         if s is None or d_ is None:
             log.warning("Videos did not have equal frame counts. Resulting grain table may not be as expected.")
             break
-        if chain is not None:
-            s = chain.apply(s, sd.ss_x, sd.ss_y)  # source only, src/main.rs:621-624
         differ.diff_frame(s, d_)  # raises ValueError on a dimension mismatch, like `?` on diff_frame
         frames += 1
     write_grain_table(differ.finish(), args.output)

@@ -94,6 +94,14 @@ class CDiffConfig(C.Structure):
     ]
 
 
+class CFilterOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("c", C.c_int32), ("d", C.c_int32)]
+
+
+FILTER_CROP, FILTER_RESIZE = 0, 1
+RESIZE_ALGS = {"hermite": 0, "catmullrom": 1, "mitchell": 2, "lanczos": 3, "spline36": 4}
+
+
 @dataclass
 class GrainTableSegment:
     """Python view of one segment (same field names as av1_grain::GrainTableSegment)."""

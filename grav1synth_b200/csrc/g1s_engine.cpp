@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "../../include/g1s.h"
+#include "g1s_filters.h"
 #include "g1s_kernels.h"
 #include "g1s_model.h"
 
@@ -179,6 +180,9 @@ struct Slot {
   int *d_plan_counts = nullptr;      // [B][3] units per frame and plane
   uint8_t *d_records = nullptr;
   uint8_t *h_records = nullptr;  // pinned
+  double *d_digests = nullptr;   // [B][kDigestDoubles]: latest_kernel's output (device-side per-frame model half)
+  double *h_digests = nullptr;   // pinned
+  bool records_read = false;     // the batch's records were copied back too (record tap / host model)
   cudaEvent_t done = nullptr, k0_beg = nullptr, k0_end = nullptr, kr_beg = nullptr, k1_beg = nullptr, k1_end = nullptr,
               ks_beg = nullptr, ks_end = nullptr, copied = nullptr, computed = nullptr;
   int count = 0;                 // frames staged
@@ -227,6 +231,16 @@ struct g1s_diff {
   void *tap_user = nullptr;
   std::mutex digest_mu;    // consumer handles: recycled copies of incoming digest blocks
   std::vector<std::shared_ptr<std::vector<double>>> digest_free;
+  // source filters (g1s_diff_set_source_filters): the chain runs on the copy stream between the upload of the raw
+  // source planes (a small ring, reused in stream order) and the kernels of the path
+  std::unique_ptr<SourceFilters> filters;
+  std::vector<g1s_filter_op> filter_ops;  // kept for the children of a multi-device handle
+  int raw_w = 0, raw_h = 0;
+  size_t raw_pitch[3] = {0, 0, 0}, raw_off[3] = {0, 0, 0}, raw_bytes = 0;
+  static constexpr int kRaw = 3;
+  uint8_t *raw_host[kRaw] = {nullptr, nullptr, nullptr}, *raw_dev[kRaw] = {nullptr, nullptr, nullptr};
+  cudaEvent_t raw_ev[kRaw] = {nullptr, nullptr, nullptr};
+  int raw_next = 0;
   // multi-device handles (cfg.n_devices >= 2): one PRODUCER child per device, this handle owns the model
   std::vector<g1s_diff *> kids;
   std::vector<double *> kid_sinks;   // pinned digest rings the children write into
@@ -243,6 +257,7 @@ struct g1s_diff {
   double tma_batches = 0, vector_batches = 0;
   ResidualStore rstore{};
   bool tensor_path = false;  // residual_kernel + gram_imma_kernel available for this stream
+  bool device_model = false;  // latest_kernel evaluates the per-frame model half: only digests are read back
   // counters
   double kernels_launched = 0, k1_ms = 0, k1_launches = 0, k0_ms = 0, k0_launches = 0, frames_done = 0, kr_ms = 0,
          ks_ms = 0;
@@ -286,17 +301,27 @@ FrameRecordView view_of(const g1s_diff *d, const uint8_t *rec) {
 // Per-frame model half in parallel on the host pool, taps / digests on the caller's thread in frame
 // order, then the sequential merge is queued for the fold thread.  `store` must stay untouched until the
 // returned ticket is done (0: nothing queued).
-uint64_t fold_records(g1s_diff *d, const uint8_t *recs, int count, size_t stride, std::vector<LatestFrame> &store) {
+uint64_t fold_records(g1s_diff *d, const uint8_t *recs, int count, size_t stride, std::vector<LatestFrame> &store,
+                      const double *digests = nullptr, bool have_records = true) {
   const bool model = d->cfg.mode != G1S_MODE_PRODUCER;
-  if (model || d->sink) {
+  constexpr size_t K = LatestFrame::kDigestDoubles;
+  if (model || (d->sink && !digests)) {
     if ((int)store.size() < count) store.resize(count);
-    const NoiseModel &nm = d->seq->model();
-    d->pool->parallel_for(count, [&](int i) { nm.compute_latest(view_of(d, recs + (size_t)i * stride), store[i]); });
+    if (digests) {
+      // the device evaluated the per-frame half (latest_kernel): rebuild the states from its digests
+      for (int i = 0; i < count; ++i) store[i].from_digest(digests + K * i);
+    } else {
+      const NoiseModel &nm = d->seq->model();
+      d->pool->parallel_for(count, [&](int i) { nm.compute_latest(view_of(d, recs + (size_t)i * stride), store[i]); });
+    }
   }
   for (int i = 0; i < count; ++i) {
-    if (d->tap) d->tap(d->tap_user, d->retired, recs + (size_t)i * stride, d->rl.bytes);
-    if (d->sink && d->sink_cap)
-      store[i].to_digest(d->sink + LatestFrame::kDigestDoubles * (d->sink_count++ % d->sink_cap));
+    if (d->tap && have_records) d->tap(d->tap_user, d->retired, recs + (size_t)i * stride, d->rl.bytes);
+    if (d->sink && d->sink_cap) {
+      double *slot = d->sink + K * (d->sink_count++ % d->sink_cap);
+      if (digests) std::memcpy(slot, digests + K * i, sizeof(double) * K);
+      else store[i].to_digest(slot);
+    }
     d->retired++;
   }
   if (!model) return 0;
@@ -392,11 +417,22 @@ int submit(g1s_diff *d, Slot &s) {
     CU_TRY(d, cudaEventRecord(s.ks_end, st));
     gram_launches += 1;
   }
+  if (d->device_model) {
+    launch_latest(s.count, d->geom, s.d_records, d->rl, d->cfg.gram_order == G1S_GRAM_REF_ORDER, s.d_digests,
+                  (int)LatestFrame::kDigestDoubles, st);
+    gram_launches += 1;
+  }
   CU_TRY(d, cudaGetLastError());
-  // the read-back rides its own stream so the next batch's kernels start right behind this batch's
+  // the read-back rides its own stream so the next batch's kernels start right behind this batch's; with the
+  // per-frame model on the device only the digests (11 KB per frame) come back, the records only for a record tap
   CU_TRY(d, cudaEventRecord(s.computed, st));
   CU_TRY(d, cudaStreamWaitEvent(d->d2h_stream, s.computed, 0));
-  CU_TRY(d, cudaMemcpyAsync(s.h_records, s.d_records, d->rl.bytes * s.count, cudaMemcpyDeviceToHost, d->d2h_stream));
+  s.records_read = !d->device_model || d->tap != nullptr;
+  if (d->device_model)
+    CU_TRY(d, cudaMemcpyAsync(s.h_digests, s.d_digests, sizeof(double) * LatestFrame::kDigestDoubles * s.count,
+                              cudaMemcpyDeviceToHost, d->d2h_stream));
+  if (s.records_read)
+    CU_TRY(d, cudaMemcpyAsync(s.h_records, s.d_records, d->rl.bytes * s.count, cudaMemcpyDeviceToHost, d->d2h_stream));
   CU_TRY(d, cudaEventRecord(s.done, d->d2h_stream));
   s.in_flight = true;
   d->kernels_launched += 2 + gram_launches;
@@ -416,7 +452,8 @@ int retire(g1s_diff *d, Slot &s) {
   if (d->cfg.gram_order == G1S_GRAM_REF_ORDER && cudaEventElapsedTime(&ms, s.ks_beg, s.ks_end) == cudaSuccess)
     d->ks_ms += ms;
   d->folder->wait(s.fold_ticket);  // the slot's previous batch must have left the fold thread
-  s.fold_ticket = fold_records(d, s.h_records, s.count, d->rl.bytes, s.latest);
+  s.fold_ticket = fold_records(d, s.h_records, s.count, d->rl.bytes, s.latest, d->device_model ? s.h_digests : nullptr,
+                               s.records_read);
   d->frames_done += s.count;
   s.in_flight = false;
   s.count = 0;
@@ -456,14 +493,24 @@ int check_frames(g1s_diff *d, const g1s_frame *s, const g1s_frame *n) {
     d->err = "null frame";
     return G1S_E_ARG;
   }
-  if (s->width != n->width || s->height != n->height) {
+  if (d->filters || !d->filter_ops.empty()) {
+    // the source is filtered before the comparison: it must have the size the chain was configured for, the
+    // denoised frame the size the chain produces (= the handle's)
+    if (s->width != d->raw_w || s->height != d->raw_h || n->width != d->cfg.width || n->height != d->cfg.height) {
+      char b[200];
+      std::snprintf(b, sizeof b, "Luma dimensions do not match: filtered source %dx%d (from %dx%d), denoised %dx%d",
+                    d->cfg.width, d->cfg.height, s->width, s->height, n->width, n->height);
+      d->err = b;
+      return G1S_E_DIMS;
+    }
+  } else if (s->width != n->width || s->height != n->height) {
     char b[160];
     std::snprintf(b, sizeof b, "Luma dimensions do not match: source %dx%d, denoised %dx%d", s->width, s->height,
                   n->width, n->height);
     d->err = b;
     return G1S_E_DIMS;
   }
-  if (s->width != d->cfg.width || s->height != d->cfg.height) {
+  if (n->width != d->cfg.width || n->height != d->cfg.height) {
     d->err = "frame size differs from the size the handle was created for";
     return G1S_E_ARG;
   }
@@ -731,6 +778,7 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   // int8 tensor-core path (residual_kernel + gram_imma_kernel): 4:2:0 / monochrome, TMA descriptors available
   d->tensor_path = cfg->gram_kernel == 0 && gram_imma_supported(g) && d->encode_tiled != nullptr;
   d->rstore = ResidualStore::make(g);
+  d->device_model = latest_supported(g) && std::getenv("G1S_HOST_MODEL") == nullptr;
   for (Slot &s : d->slots) {
     // the frame store (device) and its pinned mirror (host) are allocated on the first host push:
     // streams whose frames are already in HBM never need them
@@ -748,6 +796,10 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     }
     CU_NEW(cudaMalloc(&s.d_descs, sizeof(FrameDesc) * batch));
     CU_NEW(cudaMallocHost(&s.h_descs, sizeof(FrameDesc) * batch));
+    if (d->device_model) {
+      CU_NEW(cudaMalloc(&s.d_digests, sizeof(double) * LatestFrame::kDigestDoubles * batch));
+      CU_NEW(cudaMallocHost(&s.h_digests, sizeof(double) * LatestFrame::kDigestDoubles * batch));
+    }
     CU_NEW(cudaMalloc(&s.d_records, d->rl.bytes * batch));
     CU_NEW(cudaMallocHost(&s.h_records, d->rl.bytes * batch));
     CU_NEW(cudaEventCreate(&s.done));
@@ -804,7 +856,7 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
   // Planes that already live in page-locked host memory go to the device directly (one 2-D DMA per plane at
   // PCIe rate, no staging copy, no host cores); the call still returns only when the borrowed memory is no
   // longer needed.  Pageable planes take the staged path below.
-  bool pinned = !d->narrow && std::getenv("G1S_NO_DIRECT_H2D") == nullptr;  // narrowing always stages
+  bool pinned = !d->narrow && !d->filters && std::getenv("G1S_NO_DIRECT_H2D") == nullptr;  // narrowing / filtering stage
   for (int c = 0; c < d->geom.planes && pinned; ++c)
     for (int k = 0; k < 2 && pinned; ++k) {
       cudaPointerAttributes at;
@@ -854,12 +906,39 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
     int narrow_shift;  // >= 0: the source rows are uint16 and are reduced to uint8 with this shift while copied
     int width;
   };
-  CopyTask tasks[96];
+  CopyTask tasks[144];
   int ntasks = 0;
+  int raw_slot = -1;
+  if (d->filters) {
+    // the raw source goes up through its own pinned ring; the ring entry is free once its previous upload finished
+    raw_slot = d->raw_next++ % g1s_diff::kRaw;
+    CU_TRY(d, cudaEventSynchronize(d->raw_ev[raw_slot]));
+    for (int c = 0; c < d->geom.planes; ++c) {
+      const int rw = c ? (d->raw_w + d->geom.ss_x) >> d->geom.ss_x : d->raw_w;
+      const int rh = c ? (d->raw_h + d->geom.ss_y) >> d->geom.ss_y : d->raw_h;
+      const size_t row_bytes = (size_t)rw * bytes[0];
+      if (source->stride_bytes[c] < row_bytes) {
+        d->err = "stride smaller than a row";
+        return G1S_E_ARG;
+      }
+      const int chunks = (int)std::min<size_t>(16, std::max<size_t>(1, (row_bytes * rh) >> 20));
+      const int rows_per = (rh + chunks - 1) / chunks;
+      for (int r0 = 0; r0 < rh; r0 += rows_per)
+        tasks[ntasks++] = {d->raw_host[raw_slot] + d->raw_off[c] + (size_t)r0 * d->raw_pitch[c],
+                           static_cast<const uint8_t *>(source->plane[c]) + (size_t)r0 * source->stride_bytes[c],
+                           d->raw_pitch[c], source->stride_bytes[c], row_bytes, std::min(rows_per, rh - r0), -1, rw};
+    }
+  }
   for (int c = 0; c < d->geom.planes; ++c) {
     const PlaneGeom &p = d->pg[c];
     for (int k = 0; k < 2; ++k) {
       const size_t row_bytes = (size_t)p.w * bytes[k];
+      const void *devp = s.d_frames + base + p.off[k];
+      if (k == 0 && d->filters) {  // written by the filter chain, not copied
+        fd.src[c] = devp;
+        fd.src_stride[c] = (uint32_t)p.pitch[k];
+        continue;
+      }
       if (fr[k]->stride_bytes[c] < row_bytes) {
         d->err = "stride smaller than a row";
         return G1S_E_ARG;
@@ -894,13 +973,95 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
       for (int y = 0; y < t.rows; ++y) std::memcpy(t.dst + (size_t)y * t.dst_pitch, t.src + (size_t)y * t.src_pitch, t.row_bytes);
     }
   });
-  CU_TRY(d, cudaMemcpyAsync(s.d_frames + base, s.h_frames + base, d->pair_bytes, cudaMemcpyHostToDevice,
-                            d->copy_stream));
+  if (d->filters) {
+    // denoised planes only (the source region of the staging entry holds nothing), then the raw source and the chain
+    for (int c = 0; c < d->geom.planes; ++c) {
+      const PlaneGeom &p = d->pg[c];
+      CU_TRY(d, cudaMemcpyAsync(s.d_frames + base + p.off[1], s.h_frames + base + p.off[1], p.pitch[1] * (size_t)p.h,
+                                cudaMemcpyHostToDevice, d->copy_stream));
+    }
+    CU_TRY(d, cudaMemcpyAsync(d->raw_dev[raw_slot], d->raw_host[raw_slot], d->raw_bytes, cudaMemcpyHostToDevice,
+                              d->copy_stream));
+    CU_TRY(d, cudaEventRecord(d->raw_ev[raw_slot], d->copy_stream));
+    DevPlanes in, out;
+    for (int c = 0; c < d->geom.planes; ++c) {
+      in.ptr[c] = d->raw_dev[raw_slot] + d->raw_off[c], in.pitch[c] = d->raw_pitch[c];
+      out.ptr[c] = s.d_frames + base + d->pg[c].off[0], out.pitch[c] = d->pg[c].pitch[0];
+    }
+    if (!d->filters->apply(in, out, d->copy_stream)) {
+      d->err = d->filters->error();
+      return G1S_E_CUDA;
+    }
+  } else {
+    CU_TRY(d, cudaMemcpyAsync(s.d_frames + base, s.h_frames + base, d->pair_bytes, cudaMemcpyHostToDevice,
+                              d->copy_stream));
+  }
   s.count++;
   s.host_frames++;
   d->pushed++;
   if (s.count == d->batch) return rotate(d);
   return G1S_OK;
+}
+
+int g1s_diff_set_source_filters(g1s_diff *d, const g1s_filter_op *ops, size_t n, int32_t src_width, int32_t src_height) {
+  if (!d || (!ops && n) || src_width <= 0 || src_height <= 0) return G1S_E_ARG;
+  if (d->pushed != 0 || d->cfg.mode == G1S_MODE_CONSUMER || d->narrow) {
+    d->err = "source filters are set once, before the first frame, on a handle that takes frames (and not with host_narrow)";
+    return G1S_E_STATE;
+  }
+  if (!d->kids.empty()) {  // every device filters the frames it is dealt
+    for (size_t k = 0; k < d->kids.size(); ++k) {
+      cudaSetDevice(d->cfg.device_ids[k]);
+      const int rc = g1s_diff_set_source_filters(d->kids[k], ops, n, src_width, src_height);
+      if (rc != G1S_OK) return multi_fail(d, (int)k, rc);
+    }
+    d->filter_ops.assign(ops, ops + n);
+    d->raw_w = src_width, d->raw_h = src_height;
+    return G1S_OK;
+  }
+  G1S_ON_DEVICE(d);
+  std::unique_ptr<SourceFilters> f(new SourceFilters);
+  if (!f->configure(ops, n, src_width, src_height, d->geom.ss_x, d->geom.ss_y, d->geom.planes, d->cfg.src_bit_depth)) {
+    d->err = f->error();
+    return G1S_E_ARG;
+  }
+  if (f->out_width() != d->cfg.width || f->out_height() != d->cfg.height) {
+    char b[200];
+    std::snprintf(b, sizeof b, "Luma dimensions do not match: filtered source %dx%d, denoised %dx%d", f->out_width(),
+                  f->out_height(), d->cfg.width, d->cfg.height);
+    d->err = b;
+    return G1S_E_DIMS;
+  }
+  d->raw_w = src_width, d->raw_h = src_height;
+  size_t off = 0;
+  for (int c = 0; c < d->geom.planes; ++c) {
+    const int rw = c ? (src_width + d->geom.ss_x) >> d->geom.ss_x : src_width;
+    const int rh = c ? (src_height + d->geom.ss_y) >> d->geom.ss_y : src_height;
+    d->raw_pitch[c] = align_up((size_t)rw * d->host_bytes[0], 256);
+    d->raw_off[c] = off;
+    off += align_up(d->raw_pitch[c] * rh, 256);
+  }
+  d->raw_bytes = off;
+  for (int i = 0; i < g1s_diff::kRaw; ++i) {
+    CU_TRY(d, cudaMallocHost(&d->raw_host[i], d->raw_bytes));
+    CU_TRY(d, cudaMalloc(&d->raw_dev[i], d->raw_bytes));
+    CU_TRY(d, cudaEventCreateWithFlags(&d->raw_ev[i], cudaEventDisableTiming));
+  }
+  d->filter_ops.assign(ops, ops + n);
+  d->filters = std::move(f);
+  return G1S_OK;
+}
+
+int g1s_resize_table(int32_t alg, int32_t src, int32_t dst, int32_t *left, float *coef, int32_t max_taps) {
+  if (alg < G1S_RESIZE_HERMITE || alg > G1S_RESIZE_SPLINE36 || src <= 0 || dst <= 0 || !left || !coef) return G1S_E_ARG;
+  std::vector<int> l;
+  std::vector<float> c;
+  int taps = 0;
+  build_resize_table(alg, src, dst, l, c, taps);
+  if (taps > max_taps) return G1S_E_STATE;
+  std::memcpy(left, l.data(), sizeof(int) * l.size());
+  std::memcpy(coef, c.data(), sizeof(float) * c.size());
+  return taps;
 }
 
 int g1s_diff_push_frame_device(g1s_diff *d, const g1s_frame *source, const g1s_frame *denoised) {
@@ -931,6 +1092,25 @@ int g1s_diff_push_frame_device(g1s_diff *d, const g1s_frame *source, const g1s_f
     fd.den[c] = denoised->plane[c];
     fd.src_stride[c] = (uint32_t)source->stride_bytes[c];
     fd.den_stride[c] = (uint32_t)denoised->stride_bytes[c];
+  }
+  if (d->filters) {
+    // the filtered source needs a home: this slot's frame store; the denoised planes are still used in place
+    if (!s.d_frames)
+      for (Slot &o : d->slots)
+        if (!o.d_frames) CU_TRY(d, cudaMalloc(&o.d_frames, (size_t)d->batch * d->pair_bytes));
+    const size_t base = (size_t)s.count * d->pair_bytes;
+    DevPlanes in, out;
+    for (int c = 0; c < d->geom.planes; ++c) {
+      in.ptr[c] = static_cast<uint8_t *>(const_cast<void *>(source->plane[c])), in.pitch[c] = source->stride_bytes[c];
+      out.ptr[c] = s.d_frames + base + d->pg[c].off[0], out.pitch[c] = d->pg[c].pitch[0];
+      fd.src[c] = out.ptr[c];
+      fd.src_stride[c] = (uint32_t)out.pitch[c];
+    }
+    if (!d->filters->apply(in, out, d->copy_stream)) {
+      d->err = d->filters->error();
+      return G1S_E_CUDA;
+    }
+    s.host_frames++;  // submit() makes the kernels wait for the copy stream
   }
   s.count++;
   d->pushed++;
@@ -1056,11 +1236,19 @@ void g1s_diff_destroy(g1s_diff *d) {
     if (s.d_plan_counts) cudaFree(s.d_plan_counts);
     if (s.d_descs) cudaFree(s.d_descs);
     if (s.h_descs) cudaFreeHost(s.h_descs);
+    if (s.d_digests) cudaFree(s.d_digests);
+    if (s.h_digests) cudaFreeHost(s.h_digests);
     if (s.d_records) cudaFree(s.d_records);
     if (s.h_records) cudaFreeHost(s.h_records);
     for (cudaEvent_t e : {s.done, s.k0_beg, s.k0_end, s.kr_beg, s.k1_beg, s.k1_end, s.ks_beg, s.ks_end, s.copied, s.computed})
       if (e) cudaEventDestroy(e);
   }
+  for (int i = 0; i < g1s_diff::kRaw; ++i) {
+    if (d->raw_host[i]) cudaFreeHost(d->raw_host[i]);
+    if (d->raw_dev[i]) cudaFree(d->raw_dev[i]);
+    if (d->raw_ev[i]) cudaEventDestroy(d->raw_ev[i]);
+  }
+  d->filters.reset();
   for (cudaEvent_t e : d->marks)
     if (e) cudaEventDestroy(e);
   if (d->join) cudaEventDestroy(d->join);

@@ -70,6 +70,12 @@ void launch_gram_generic(const FrameDesc *frames, int nframes, const Geometry &g
 // the reference's accumulation order; needs the final flat flags.  Any subsampling, any residual magnitude.
 void launch_gram_strict(const FrameDesc *frames, int nframes, const Geometry &g, uint8_t *records,
                         const RecordLayout &rl, cudaStream_t st);
+// The per-frame half of the host model on the device (g1s_latest.cu): one LatestFrame digest (digest_doubles f64,
+// LatestFrame::to_digest layout) per frame of the batch, bit-identical to NoiseModel::compute_latest on the same record.
+// latest_supported: the frame's per-block arrays fit in shared memory (up to ~11 000 blocks: 4K yes, 8K no).
+bool latest_supported(const Geometry &g);
+void launch_latest(int nframes, const Geometry &g, const uint8_t *records, const RecordLayout &rl, bool strict,
+                   double *digests, int digest_doubles, cudaStream_t st);
 // Engine-owned s8 planes of a batch, written by residual_kernel and read (through TMA boxes) by
 // gram_imma_kernel: per frame the residual of Y, Cb, Cr and chroma's luma tap, the sum of the co-sited 2x2 luma
 // residuals (blocks where it leaves int8 are flagged for the exact kernel, like residuals that do).  Pitches are

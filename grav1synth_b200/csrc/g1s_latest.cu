@@ -1,0 +1,341 @@
+// latest_kernel — the per-frame half of NoiseModel::update on the device: everything the host model derives from ONE
+// frame's record before it looks at the combined state (g1s_model.cpp NoiseModel::compute_latest, i.e. av1-grain's
+// add_block_observations epilogue + ar_equation_system_solve + add_noise_std_observations + NoiseStrengthSolver::solve,
+// reached from /root/reference/src/main.rs:442).  Output: the frame's 11 KB digest (LatestFrame::to_digest layout), so
+// only digests cross PCIe (0.3 MB of record per frame stays on the device) and no host core does per-frame work: what
+// bounded the 8-GPU rate in round 1.
+//
+// Bit-exactness against the host (g1s_diff_digest_from_record is the checker): every f64 operation is issued in the
+// host's order with explicit round-to-nearest intrinsics (no contraction).  What is restructured is only what is
+// exact by construction:
+//   * gauss_solve: the row updates of one elimination step are element-wise independent -> one lane per column; the
+//     pivot bubbling and the back substitution stay sequential;
+//   * add_measurement: every entry of the strength system is its own chain of adds in block order -> one thread per
+//     entry (20 diagonal, 19 off-diagonal, 20 right-hand sides, the total), each scanning the block keys in order;
+//   * the per-block arithmetic (block mean, bin, noise variance, adjusted strength) is independent per block.
+// One CTA per frame; the three channels run one after the other (chroma needs luma's strength solution).
+#include "g1s_kernels.h"
+
+namespace g1s {
+
+namespace {
+
+constexpr int kLatestThreads = 256;
+constexpr int kBins = 20;
+constexpr int kN = 25;  // largest AR system
+constexpr double kTinyD = 1.0e-16;
+
+struct LatestSmem {
+  double A[kN * kN], b[kN], x[kN];        // AR system of the current channel
+  double Ac[kN * kN], bc[kN];             // elimination scratch
+  double SA[kBins * kBins], Sb[kBins], Sx[kBins];  // strength system of the current channel
+  double lumaSx[kBins];                   // luma's strength solution (chroma's luma-strength LUT)
+  double diag[kBins], off[kBins], total;  // chains of add_measurement
+  double ar_gain, luma_gain;
+  long long nobs;
+  int neq, ok;
+};
+
+// Gaussian elimination of g1s_model.cpp::gauss_solve on (A, b) in shared memory, n <= 25, by warp 0.
+// Lane j owns column j; lane n owns b.  Returns (to every lane of the warp) whether the solve succeeded.
+__device__ bool gauss_solve_warp(int n, double *A, double *b, double *x, int lane) {
+  bool ok = true;
+  for (int k = 0; k + 1 < n && ok; ++k) {
+    for (int i = n - 1; i > k; --i) {
+      const bool swap = fabs(A[(i - 1) * n + k]) < fabs(A[i * n + k]);
+      __syncwarp();
+      if (swap) {
+        if (lane < n) {
+          const double t = A[i * n + lane];
+          A[i * n + lane] = A[(i - 1) * n + lane];
+          A[(i - 1) * n + lane] = t;
+        } else if (lane == n) {
+          const double t = b[i];
+          b[i] = b[i - 1];
+          b[i - 1] = t;
+        }
+      }
+      __syncwarp();
+    }
+    for (int i = k; i + 1 < n; ++i) {
+      const double piv = A[k * n + k];
+      if (fabs(piv) < kTinyD) {
+        ok = false;
+        break;
+      }
+      const double c = __ddiv_rn(A[(i + 1) * n + k], piv);
+      __syncwarp();
+      if (lane < n) A[(i + 1) * n + lane] = __dsub_rn(A[(i + 1) * n + lane], __dmul_rn(c, A[k * n + lane]));
+      else if (lane == n) b[i + 1] = __dsub_rn(b[i + 1], __dmul_rn(c, b[k]));
+      __syncwarp();
+    }
+  }
+  if (ok && lane == 0) {
+    for (int i = n - 1; i >= 0; --i) {
+      if (fabs(A[i * n + i]) < kTinyD) {
+        ok = false;
+        break;
+      }
+      double c = 0;
+      for (int j = i + 1; j < n; ++j) c = __dadd_rn(c, __dmul_rn(A[i * n + j], x[j]));
+      x[i] = __ddiv_rn(__dsub_rn(b[i], c), A[i * n + i]);
+    }
+  }
+  ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+  __syncwarp();
+  return ok;
+}
+
+__device__ __forceinline__ int pair_idx(int i, int j) { return i * kTaps - i * (i - 1) / 2 + (j - i); }
+
+__global__ void __launch_bounds__(kLatestThreads, 1)
+latest_kernel(Geometry g, const uint8_t *__restrict__ records, RecordLayout rl, int strict, double *__restrict__ digests,
+              int digest_doubles) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  __shared__ LatestSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int f = blockIdx.x, nb = g.nb;
+  const uint8_t *rec = records + (size_t)f * rl.bytes;
+  double *dg = digests + (size_t)f * digest_doubles;
+  // per-block arrays of the current channel: interpolation weight, measurement, and the key (bin, 255 = no measurement)
+  double *fa = reinterpret_cast<double *>(dyn);
+  double *fs = fa + nb;
+  uint8_t *key = reinterpret_cast<uint8_t *>(fs + nb);
+  uint8_t *bin0 = key + ((nb + 15) & ~15);  // luma block-mean bin of every block (shared by the channels)
+
+  const long long num_flat = *reinterpret_cast<const long long *>(rec + rl.off_num_flat);
+  const uint8_t *flat = rec + rl.off_flat;
+  const uint32_t *luma_sum = reinterpret_cast<const uint32_t *>(rec + rl.off_luma_sum);
+  const bool enough = num_flat > 1;
+  for (int i = tid; i < digest_doubles; i += kLatestThreads) dg[i] = 0.0;
+  __syncthreads();
+  if (tid == 0) {
+    dg[0] = enough ? 1.0 : 0.0;
+    dg[2] = -1.0;
+    sm.luma_gain = 1.0;
+  }
+  // an untouched channel digest still carries ar_gain = 1 (ChannelState after clear())
+  if (tid < 3) dg[4 + tid * 459 + 375] = 1.0;
+  if (!enough) return;
+
+  // pass 1 (once per frame): block mean -> bin index and interpolation weight (NoiseStrengthSolver::get_bin_index)
+  for (int b = tid; b < nb; b += kLatestThreads) {
+    const int by = b / g.nbw, bx = b - by * g.nbw;
+    const int lw = min(g.width - bx * kBlock, kBlock), lh = min(g.height - by * kBlock, kBlock);
+    const double block_mean = __ddiv_rn((double)luma_sum[b], (double)(lw * lh));
+    const double val = block_mean < 0.0 ? 0.0 : (block_mean > 255.0 ? 255.0 : block_mean);
+    const double bin = __ddiv_rn(__dmul_rn((double)(kBins - 1), __dsub_rn(val, 0.0)), 255.0);
+    const int i0 = (int)bin;
+    bin0[b] = (uint8_t)i0;
+    fa[b] = __dsub_rn(bin, (double)i0);
+  }
+  __syncthreads();
+
+  int fail_channel = -1, fail_text = 0, channels = 0;
+  for (int c = 0; c < g.planes; ++c) {
+    const bool chroma = c != 0;
+    const int n = chroma ? 25 : 24;
+    channels = c + 1;
+    // ---- load_equations: integer Gram (or the strict-mode f64 sums) -> A, b
+    const double nss = chroma ? (double)(1 << (g.ss_x + g.ss_y)) : 1.0;
+    const long long *G = reinterpret_cast<const long long *>(rec + rl.off_gram) + (size_t)c * kPairs;
+    const double *F = reinterpret_cast<const double *>(rec + rl.off_gramf) + (size_t)c * kPairs;
+    for (int e = tid; e < n * n + n; e += kLatestThreads) {
+      const bool isb = e >= n * n;
+      const int i = isb ? e - n * n : e / n, j = isb ? 25 : e - (e / n) * n;
+      const int p = i <= j ? pair_idx(i, j) : pair_idx(j, i);
+      const double si = i == 24 ? nss : 1.0, sj = j == 24 ? nss : 1.0;
+      double v;
+      if (strict) v = isb ? __ddiv_rn(F[p], si) : __ddiv_rn(F[p], __dmul_rn(si, sj));
+      else v = isb ? __ddiv_rn(__ddiv_rn((double)G[p], si), 65025.0) : __ddiv_rn(__ddiv_rn((double)G[p], __dmul_rn(si, sj)), 65025.0);
+      v = __dadd_rn(0.0, v);  // the host adds into a cleared system
+      if (isb) sm.b[i] = v;
+      else sm.A[e] = v;
+    }
+    if (tid < kN) sm.x[tid] = 0.0;
+    if (tid == 0) sm.nobs = reinterpret_cast<const long long *>(rec + rl.off_nobs)[c];
+    __syncthreads();
+    // ---- ChannelState::solve_ar: solve on copies, then the gain
+    for (int e = tid; e < n * n; e += kLatestThreads) sm.Ac[e] = sm.A[e];
+    if (tid < n) sm.bc[tid] = sm.b[tid];
+    __syncthreads();
+    if (warp == 0) {
+      const bool ok = gauss_solve_warp(n, sm.Ac, sm.bc, sm.x, lane);
+      if (lane == 0) {
+        sm.ok = ok;
+        double gain = 1.0;
+        if (ok) {
+          const int m = n - (chroma ? 1 : 0);
+          const double nobs = (double)sm.nobs;
+          double var = 0;
+          for (int i = 0; i < m; ++i) var = __dadd_rn(var, __ddiv_rn(sm.A[i * n + i], nobs));
+          var = __ddiv_rn(var, (double)m);
+          double sum_covar = 0;
+          for (int i = 0; i < m; ++i) {
+            double bi = sm.b[i];
+            if (chroma) bi = __dsub_rn(bi, __dmul_rn(sm.A[i * n + (n - 1)], sm.x[n - 1]));
+            sum_covar = __dadd_rn(sum_covar, __ddiv_rn(__dmul_rn(bi, sm.x[i]), nobs));
+          }
+          const double noise_var = fmax(__dsub_rn(var, sum_covar), 1e-6);
+          gain = fmax(1.0, __dsqrt_rn(fmax(__ddiv_rn(var, noise_var), 1e-6)));
+        } else if (chroma) {
+          // chroma_fallback: zero solution except the luma-correlation tap
+          for (int i = 0; i < n; ++i) sm.x[i] = 0.0;
+          const int last = n - 1;
+          if (fabs(sm.A[last * n + last]) > 1e-6) sm.x[last] = __ddiv_rn(sm.b[last], sm.A[last * n + last]);
+        }
+        sm.ar_gain = gain;
+        if (!chroma) sm.luma_gain = gain;
+      }
+    }
+    __syncthreads();
+    // this channel's digest, AR part (written even when the solve failed: the host's state holds it too)
+    double *p = dg + 4 + c * 459;
+    for (int e = tid; e < n * n; e += kLatestThreads) {
+      const int i = e / n, j = e - i * n;
+      if (j >= i) p[i * n - i * (i - 1) / 2 + (j - i)] = sm.A[e];
+    }
+    if (tid < n) p[325 + tid] = sm.b[tid], p[350 + tid] = sm.x[tid];
+    if (tid == 0) p[375] = sm.ar_gain, p[376] = (double)sm.nobs;
+    if (!sm.ok && !chroma) {
+      fail_channel = c, fail_text = 1;
+      break;
+    }
+    // ---- add_noise_std_observations, per block: key + measurement of this channel
+    {
+      const int bw = kBlock >> (chroma ? g.ss_x : 0), bh = kBlock >> (chroma ? g.ss_y : 0);
+      const int pw = g.width >> (chroma ? g.ss_x : 0), ph = g.height >> (chroma ? g.ss_y : 0);
+      const int32_t *rsum = reinterpret_cast<const int32_t *>(rec + rl.off_rsum) + (size_t)c * nb;
+      const uint32_t *rsq = reinterpret_cast<const uint32_t *>(rec + rl.off_rsq) + (size_t)c * nb;
+      const double corr = chroma ? sm.x[24] : 0.0, gain = sm.ar_gain, lgain = sm.luma_gain;
+      for (int b = tid; b < nb; b += kLatestThreads) {
+        const int by = b / g.nbw, bx = b - by * g.nbw;
+        const int cw = min(pw - bx * bw, bw), ch = min(ph - by * bh, bh);
+        const int cnt = cw * ch;
+        const bool contributes = flat[b] && cnt > kBlock;
+        key[b] = contributes ? bin0[b] : 255;
+        if (!contributes) continue;
+        const double cn = (double)cnt;
+        const double noise_mean = __ddiv_rn((double)rsum[b], cn);
+        const double noise_var = __dsub_rn(__ddiv_rn((double)rsq[b], cn), __dmul_rn(noise_mean, noise_mean));
+        double ls = 0.0;  // luma_gain * NoiseStrengthSolver::get_value(luma, block_mean)
+        if (chroma) {
+          const int i0 = bin0[b], i1 = i0 + 1 < kBins - 1 ? i0 + 1 : kBins - 1;
+          const double a = fa[b];
+          ls = __dmul_rn(lgain, __dadd_rn(__dmul_rn(__dsub_rn(1.0, a), sm.lumaSx[i0]), __dmul_rn(a, sm.lumaSx[i1])));
+        }
+        const double t = __dmul_rn(corr, ls);
+        const double lo = __ddiv_rn(noise_var, 16.0), hi = __dsub_rn(noise_var, __dmul_rn(t, t));
+        const double m = hi != hi ? lo : (lo > hi ? lo : hi);
+        fs[b] = __ddiv_rn(__dsqrt_rn(m), gain);
+      }
+    }
+    __syncthreads();
+    // ---- NoiseStrengthSolver::add_measurement in block order: one thread per entry of the system
+    if (tid < 3 * kBins + 1) {
+      const int kind = tid / kBins, i = tid - kind * kBins;  // 0 diagonal, 1 off-diagonal (i, i+1), 2 rhs, 3 total
+      const uint32_t want0 = 0x01010101u * (uint32_t)i, want1 = 0x01010101u * (uint32_t)(i - 1);
+      double acc = 0.0;
+      int neq = 0;
+      const uint32_t *kw = reinterpret_cast<const uint32_t *>(key);
+      for (int w4 = 0; w4 < (nb + 3) / 4; ++w4) {
+        const uint32_t kv = kw[w4];
+        if (kind == 3) {
+          if (kv == 0xFFFFFFFFu) continue;
+        } else {
+          // any byte equal to i (as i0) or to i - 1 (then i is its i1)?  i1 = min(19, i0 + 1): bin 19 is its own i1
+          const uint32_t m0 = __vcmpeq4(kv, want0), m1 = (kind == 1 || i == 0) ? 0u : __vcmpeq4(kv, want1);
+          if ((m0 | m1) == 0u) continue;
+        }
+        for (int q = 0; q < 4; ++q) {
+          const int b = 4 * w4 + q;
+          if (b >= nb) break;
+          const int i0 = (kv >> (8 * q)) & 0xFF;
+          if (i0 == 255) continue;
+          const int i1 = i0 + 1 < kBins ? i0 + 1 : kBins - 1;
+          const double a = fa[b], s = fs[b], na = __dsub_rn(1.0, a);
+          if (kind == 0) {  // A[i0][i0] += (1-a)^2; A[i1][i0] += a(1-a); A[i1][i1] += a^2; A[i0][i1] += a(1-a)
+            if (i0 == i) acc = __dadd_rn(acc, __dmul_rn(na, na));
+            if (i1 == i && i0 == i) acc = __dadd_rn(acc, __dmul_rn(a, na));
+            if (i1 == i) acc = __dadd_rn(acc, __dmul_rn(a, a));
+            if (i0 == i && i1 == i) acc = __dadd_rn(acc, __dmul_rn(a, na));
+          } else if (kind == 1) {
+            if (i0 == i && i1 == i + 1) acc = __dadd_rn(acc, __dmul_rn(a, na));
+          } else if (kind == 2) {
+            if (i0 == i) acc = __dadd_rn(acc, __dmul_rn(na, s));
+            if (i1 == i) acc = __dadd_rn(acc, __dmul_rn(a, s));
+          } else {
+            acc = __dadd_rn(acc, s);
+            ++neq;
+          }
+        }
+      }
+      if (kind == 0) sm.diag[i] = acc;
+      else if (kind == 1) sm.off[i] = acc;
+      else if (kind == 2) sm.Sb[i] = acc;
+      else sm.total = acc, sm.neq = neq;
+    }
+    __syncthreads();
+    // ---- NoiseStrengthSolver::solve: ridge bump of b in place, regularised copy of A, elimination
+    const double mean = __ddiv_rn(sm.total, (double)sm.neq);
+    const double alpha = __ddiv_rn(__dmul_rn(2.0, (double)sm.neq), (double)kBins);
+    for (int e = tid; e < kBins * kBins; e += kLatestThreads) {
+      const int i = e / kBins, j = e - i * kBins;
+      double v = i == j ? sm.diag[i] : (j == i + 1 ? sm.off[i] : (i == j + 1 ? sm.off[j] : 0.0));
+      // Ar[i][lo] -= alpha; Ar[i][i] += 2 alpha; Ar[i][hi] -= alpha (lo / hi clamp onto i at the ends); Ar[i][i] += 1/8192
+      const int lo = i - 1 > 0 ? i - 1 : 0, hi = i + 1 < kBins - 1 ? i + 1 : kBins - 1;
+      if (j == lo) v = __dsub_rn(v, alpha);
+      if (j == i) v = __dadd_rn(v, __dmul_rn(2.0, alpha));
+      if (j == hi) v = __dsub_rn(v, alpha);
+      if (j == i) v = __dadd_rn(v, 1.0 / 8192.);
+      sm.SA[e] = v;
+    }
+    if (tid < kBins) {
+      sm.Sb[tid] = __dadd_rn(sm.Sb[tid], __ddiv_rn(mean, 8192.));
+      sm.bc[tid] = sm.Sb[tid];
+      sm.Sx[tid] = 0.0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const bool ok = gauss_solve_warp(kBins, sm.SA, sm.bc, sm.Sx, lane);
+      if (lane == 0) sm.ok = ok;
+    }
+    __syncthreads();
+    // ---- this channel's digest, strength part
+    if (tid < kBins) {
+      p[377 + tid] = sm.diag[tid];
+      p[397 + tid] = tid + 1 < kBins ? sm.off[tid] : 0.0;
+      p[417 + tid] = sm.Sb[tid];
+      p[437 + tid] = sm.Sx[tid];
+      if (!chroma) sm.lumaSx[tid] = sm.Sx[tid];
+    }
+    if (tid == 0) p[457] = sm.total, p[458] = (double)sm.neq;
+    __syncthreads();
+    if (!sm.ok) {
+      fail_channel = c, fail_text = 2;
+      break;
+    }
+  }
+  if (tid == 0) dg[1] = (double)channels, dg[2] = (double)fail_channel, dg[3] = (double)fail_text;
+}
+
+}  // namespace
+
+size_t latest_smem_bytes(const Geometry &g) { return (size_t)g.nb * 16 + 2 * (((size_t)g.nb + 15) & ~(size_t)15) + 64; }
+
+bool latest_supported(const Geometry &g) { return latest_smem_bytes(g) <= 200 * 1024; }
+
+void launch_latest(int nframes, const Geometry &g, const uint8_t *records, const RecordLayout &rl, bool strict,
+                   double *digests, int digest_doubles, cudaStream_t st) {
+  const size_t smem = latest_smem_bytes(g);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaFuncSetAttribute(latest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set[dev & 63] = true;
+  }
+  latest_kernel<<<nframes, kLatestThreads, smem, st>>>(g, records, rl, strict ? 1 : 0, digests, digest_doubles);
+}
+
+}  // namespace g1s

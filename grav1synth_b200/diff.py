@@ -31,7 +31,7 @@ EXPORTS = [
     "g1s_diff_get_counters", "g1s_diff_mark", "g1s_diff_marks_elapsed_ms", "g1s_record_layout", "g1s_record_gramf_offset", "g1s_diff_record_bytes", "g1s_diff_set_record_tap",
     "g1s_diff_consume_record", "g1s_diff_consume_records", "g1s_digest_bytes", "g1s_diff_set_digest_sink",
     "g1s_diff_digest_count", "g1s_diff_wait_retired", "g1s_diff_consume_digests", "g1s_diff_consume_digests_borrowed", "g1s_diff_digest_from_record", "g1s_write_grain_table", "g1s_format_grain_table",
-    "g1s_narrow_row",
+    "g1s_narrow_row", "g1s_diff_set_source_filters", "g1s_resize_table",
 ]
 
 
@@ -61,6 +61,8 @@ def lib() -> C.CDLL:
         L.g1s_diff_last_error.restype = C.c_char_p
         L.g1s_diff_frames_pushed.argtypes = [C.c_void_p]
         L.g1s_diff_frames_pushed.restype = C.c_int64
+        L.g1s_diff_set_source_filters.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32]
+        L.g1s_resize_table.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
         L.g1s_diff_batch_frames.argtypes = [C.c_void_p]
         L.g1s_diff_frame_device.argtypes = [C.c_void_p, C.c_int64]
         L.g1s_diff_get_counters.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_size_t]
@@ -214,6 +216,23 @@ class DiffGenerator:
                 f.stride_bytes[i] = strides[i] if i < len(strides) else 0
         self._check(self._L.g1s_diff_push_frame_device(self._h, C.byref(sf), C.byref(df)))
 
+    def set_source_filters(self, ops, source_width: int, source_height: int) -> None:
+        """ops: FilterChain.filters (Crop / Resize objects) or ("crop", t, b, l, r) / ("resize", w, h, alg) tuples.  The
+        SOURCE frames pushed afterwards have source_width x source_height; the chain (run on the device) must produce
+        the handle's size.  FilterChain::apply of the reference (src/main.rs:621-624)."""
+        arr = (abi.CFilterOp * max(1, len(ops)))()
+        for i, op in enumerate(ops):
+            if not isinstance(op, tuple):
+                op = ("crop", op.top, op.bottom, op.left, op.right) if hasattr(op, "top") else ("resize", op.width, op.height, op.alg)
+            if op[0] == "crop":
+                arr[i] = abi.CFilterOp(abi.FILTER_CROP, op[1], op[2], op[3], op[4])
+            else:
+                arr[i] = abi.CFilterOp(abi.FILTER_RESIZE, op[1], op[2], abi.RESIZE_ALGS[op[3]], 0)
+        rc = self._L.g1s_diff_set_source_filters(self._h, arr, len(ops), source_width, source_height)
+        if rc == abi.G1S_E_ARG:
+            raise ValueError(self._L.g1s_diff_last_error(self._h).decode())
+        self._check(rc)
+
     def flush(self) -> None:
         self._check(self._L.g1s_diff_flush(self._h))
 
@@ -307,6 +326,17 @@ class DiffGenerator:
         k = ("kernels_launched", "gram_ms", "gram_launches", "flat_ms", "flat_launches", "frames_done", "tma_batches",
              "residual_ms", "vector_batches", "strict_ms")
         return dict(zip(k, [float(v) for v in out]))
+
+
+def resize_table(alg: str, src: int, dst: int):
+    """(left [dst] int32, coef [dst, taps] float32): the weights of one resize axis exactly as the device uses them."""
+    cap = 4096
+    left = np.zeros(dst, np.int32)
+    coef = np.zeros(dst * cap, np.float32)
+    taps = lib().g1s_resize_table(abi.RESIZE_ALGS[alg], src, dst, left.ctypes.data, coef.ctypes.data, cap)
+    if taps < 0:
+        raise G1SError(taps, "g1s_resize_table")
+    return left, coef[: dst * taps].reshape(dst, taps).copy()
 
 
 def digest_bytes() -> int:

@@ -2,9 +2,11 @@
 (/root/reference/src/filters.rs:16-110).  Filters apply to the SOURCE frame only, before the diff
 (src/main.rs:621-624).
 
-`crop` is applied here as plane slicing (no arithmetic).  `resize` is parsed and validated exactly as the
-reference does, but applying it is refused: the resampling arithmetic lives in the un-vendored crate
-`video-resize 0.2.0` and cannot be restated with any pin.
+This module is the grammar only.  The chain itself runs on the device (csrc/g1s_filters.cu, reached through
+DiffGenerator.set_source_filters / g1s_diff_set_source_filters): crop as a pointer offset, resize as two separable
+passes.  The resampling arithmetic of the un-vendored crate `video-resize 0.2.0` cannot be pinned
+here; the published kernels it ports are restated (parity unpinned).  `apply` below is the host-side crop kept for
+callers that want cropped numpy planes; it refuses resize.
 """
 from __future__ import annotations
 
@@ -83,11 +85,19 @@ class FilterChain:
             else:
                 raise FilterError(f'Unrecognized filter "{name}"')
 
+    def output_size(self, width: int, height: int):
+        for f in self.filters:
+            if isinstance(f, Resize):
+                width, height = f.width, f.height
+            else:
+                width, height = width - f.left - f.right, height - f.top - f.bottom
+        return width, height
+
     def apply(self, planes: Sequence[np.ndarray], ss_x: int, ss_y: int) -> List[np.ndarray]:
         out = list(planes)
         for f in self.filters:
             if isinstance(f, Resize):
-                raise FilterError("resize is not available in this build (video-resize 0.2.0 is not restated)")
+                raise FilterError("resize runs on the device: use DiffGenerator.set_source_filters")
             h, w = out[0].shape
             if f.top + f.bottom >= h or f.left + f.right >= w:
                 raise FilterError("crop removes the whole frame")

@@ -160,6 +160,28 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
  * g1s_diff_finish returns. */
 int g1s_diff_push_frame_device(g1s_diff *d, const g1s_frame *source, const g1s_frame *denoised);
 
+/* ---- source filters (`diff --filters`) ----------------------------------------------------------
+ * The reference applies its FilterChain to the SOURCE frame only, before diff_frame (src/main.rs:621-624 ->
+ * src/filters.rs:112-182 -> video_resize::{crop, resize}).  Here the chain runs on the device between the upload of the
+ * source planes and the kernels of the path: crop is a pointer / pitch offset, resize two separable passes
+ * (csrc/g1s_filters.cu; the resampling arithmetic of the un-vendored crate video-resize 0.2.0 cannot be pinned here,
+ * the published kernels and filter construction it ports are restated -- parity UNPINNED for resize, exact for crop).
+ * The caller parses the filter string (the reference's grammar, src/filters.rs:16-110) and passes the operations. */
+enum g1s_filter_kind { G1S_FILTER_CROP = 0, G1S_FILTER_RESIZE = 1 };
+enum g1s_resize_alg { G1S_RESIZE_HERMITE = 0, G1S_RESIZE_CATMULLROM = 1, G1S_RESIZE_MITCHELL = 2, G1S_RESIZE_LANCZOS = 3,
+                      G1S_RESIZE_SPLINE36 = 4 };
+typedef struct g1s_filter_op {
+  int32_t kind;        /* enum g1s_filter_kind                                                      */
+  int32_t a, b, c, d;  /* crop: top, bottom, left, right (luma samples); resize: width, height, enum g1s_resize_alg, 0 */
+} g1s_filter_op;
+/* Call once, before the first frame.  From then on `source` frames passed to g1s_diff_push_frame[_device] must be
+ * src_width x src_height (the size BEFORE the filters); the chain's output size must equal the handle's width x height
+ * (what the denoised frames have), else G1S_E_DIMS -- the reference fails the same way, in verify_dimensions_match. */
+int g1s_diff_set_source_filters(g1s_diff *d, const g1s_filter_op *ops, size_t n, int32_t src_width, int32_t src_height);
+/* Test hook: the weights of one resize axis as the device uses them.  left[dst] first source sample per output sample,
+ * coef[dst * taps] f32 weights; returns taps (<= max_taps) or a negative status. */
+int g1s_resize_table(int32_t alg, int32_t src, int32_t dst, int32_t *left, float *coef, int32_t max_taps);
+
 /* Drains everything queued so far (blocks until the device and the host model have
  * consumed every pushed frame).  Optional; finish implies it. */
 int g1s_diff_flush(g1s_diff *d);

@@ -69,7 +69,12 @@ pub struct g1s_diff_config {
     pub gram_kernel: i32,
     pub host_threads: i32,
     pub host_narrow: i32,
-    pub reserved_: [i32; 3],
+    /// 0 = exact-integer Gram (fast), 1 = reference accumulation order (strict: av1-grain's integers on every stream)
+    pub gram_order: i32,
+    /// 0 / 1: one GPU (`device`); 2..8: this handle drives `device_ids[0..n_devices]`
+    pub n_devices: i32,
+    pub device_ids: [i32; 8],
+    pub reserved_: [i32; 4],
 }
 
 pub enum g1s_diff {}
@@ -157,7 +162,10 @@ impl DiffGenerator {
                 gram_kernel: 0,
                 host_threads: 0,
                 host_narrow: 0,
-                reserved_: [0; 3],
+                gram_order: std::env::var("G1S_STRICT").map(|v| (v == "1") as i32).unwrap_or(0),
+                n_devices: 0,
+                device_ids: [0; 8],
+                reserved_: [0; 4],
             };
             let rc = unsafe { g1s_diff_create(&cfg, &mut self.h) };
             ensure!(rc == 0, "g1s_diff_create failed: {}", last_error(std::ptr::null()));
