@@ -8,10 +8,12 @@
 // Bit-exactness against the host (g1s_diff_digest_from_record is the checker): every f64 operation is issued in the
 // host's order with explicit round-to-nearest intrinsics (no contraction).  What is restructured is only what is
 // exact by construction:
-//   * gauss_solve: the row updates of one elimination step are element-wise independent -> one lane per column; the
-//     pivot bubbling and the back substitution stay sequential;
-//   * add_measurement: every entry of the strength system is its own chain of adds in block order -> one thread per
-//     entry (20 diagonal, 19 off-diagonal, 20 right-hand sides, the total), each scanning the block keys in order;
+//   * gauss_solve: per pivot, the bubble pass is a row permutation decided by one column (found by one thread, applied
+//     by all) and the rows below the pivot are updated independently of each other (all at once); the back
+//     substitution stays sequential;
+//   * add_measurement: every entry of the strength system is its own chain of adds in block order, fed by the blocks
+//     of one or two bins -> stable partition of the blocks by bin, then one thread per entry (20 diagonal, 19
+//     off-diagonal, 20 right-hand sides, the total) walks its lists merged by block index;
 //   * the per-block arithmetic (block mean, bin, noise variance, adjusted strength) is independent per block.
 // One CTA per frame; the three channels run one after the other (chroma needs luma's strength solution).
 #include "g1s_kernels.h"
@@ -32,58 +34,81 @@ struct LatestSmem {
   double lumaSx[kBins];                   // luma's strength solution (chroma's luma-strength LUT)
   double diag[kBins], off[kBins], total;  // chains of add_measurement
   double ar_gain, luma_gain;
+  double tmp[kN * kN + kN], cvec[kN];     // gauss_solve_cta scratch
   long long nobs;
-  int neq, ok;
+  int neq, ok, flag, perm[kN];
+  int bin_start[kBins + 1], bin_cnt[kBins];
 };
 
-// Gaussian elimination of g1s_model.cpp::gauss_solve on (A, b) in shared memory, n <= 25, by warp 0.
-// Lane j owns column j; lane n owns b.  Returns (to every lane of the warp) whether the solve succeeded.
-__device__ bool gauss_solve_warp(int n, double *A, double *b, double *x, int lane) {
-  bool ok = true;
-  for (int k = 0; k + 1 < n && ok; ++k) {
-    for (int i = n - 1; i > k; --i) {
-      const bool swap = fabs(A[(i - 1) * n + k]) < fabs(A[i * n + k]);
-      __syncwarp();
-      if (swap) {
-        if (lane < n) {
-          const double t = A[i * n + lane];
-          A[i * n + lane] = A[(i - 1) * n + lane];
-          A[(i - 1) * n + lane] = t;
-        } else if (lane == n) {
-          const double t = b[i];
-          b[i] = b[i - 1];
-          b[i - 1] = t;
+// Gaussian elimination of g1s_model.cpp::gauss_solve on (A, b) in shared memory, n <= 25, by the whole CTA.
+// Per pivot k the host does (1) one bubble pass over column k from the bottom up (adjacent row swaps), (2) for every row
+// below k: c = A[i+1][k] / A[k][k], row -= c * row k.  (1) is a permutation of the rows that only depends on column k:
+// thread 0 finds it on a register copy of the column, then every element moves at once.  (2) touches each row
+// independently with the SAME row k, so all rows are updated at once.  Same operations, same operands, same roundings.
+// tmp: n * n + n doubles of scratch; perm / cvec: n entries.  Returns (uniformly) whether the solve succeeded.
+__device__ bool gauss_solve_cta(int n, double *A, double *b, double *x, double *tmp, int *perm, double *cvec, int *flag) {
+  const int tid = threadIdx.x;
+  for (int k = 0; k + 1 < n; ++k) {
+    if (tid == 0) {
+      double col[kN];
+      int idx[kN];
+#pragma unroll
+      for (int i = 0; i < kN; ++i) {
+        col[i] = i < n ? fabs(A[i * n + k]) : 0.0;
+        idx[i] = i;
+      }
+#pragma unroll
+      for (int i = kN - 1; i > 0; --i) {
+        if (i < n && i > k && col[i - 1] < col[i]) {
+          const double t = col[i];
+          col[i] = col[i - 1], col[i - 1] = t;
+          const int u = idx[i];
+          idx[i] = idx[i - 1], idx[i - 1] = u;
         }
       }
-      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < kN; ++i)
+        if (i < n) perm[i] = idx[i];
     }
-    for (int i = k; i + 1 < n; ++i) {
-      const double piv = A[k * n + k];
-      if (fabs(piv) < kTinyD) {
-        ok = false;
-        break;
-      }
-      const double c = __ddiv_rn(A[(i + 1) * n + k], piv);
-      __syncwarp();
-      if (lane < n) A[(i + 1) * n + lane] = __dsub_rn(A[(i + 1) * n + lane], __dmul_rn(c, A[k * n + lane]));
-      else if (lane == n) b[i + 1] = __dsub_rn(b[i + 1], __dmul_rn(c, b[k]));
-      __syncwarp();
+    __syncthreads();
+    for (int e = tid; e < (n - k) * (n + 1); e += blockDim.x) {
+      const int i = k + e / (n + 1), j = e - (i - k) * (n + 1);
+      tmp[e] = j < n ? A[perm[i] * n + j] : b[perm[i]];
     }
+    __syncthreads();
+    for (int e = tid; e < (n - k) * (n + 1); e += blockDim.x) {
+      const int i = k + e / (n + 1), j = e - (i - k) * (n + 1);
+      if (j < n) A[i * n + j] = tmp[e];
+      else b[i] = tmp[e];
+    }
+    __syncthreads();
+    const double piv = A[k * n + k];
+    if (fabs(piv) < kTinyD) return false;  // uniform: every thread reads the same pivot
+    if (tid < n - 1 - k) cvec[tid] = __ddiv_rn(A[(k + 1 + tid) * n + k], piv);
+    __syncthreads();
+    for (int e = tid; e < (n - 1 - k) * (n + 1); e += blockDim.x) {
+      const int r = e / (n + 1), j = e - r * (n + 1), i = k + 1 + r;
+      const double c = cvec[r];
+      if (j < n) A[i * n + j] = __dsub_rn(A[i * n + j], __dmul_rn(c, A[k * n + j]));
+      else b[i] = __dsub_rn(b[i], __dmul_rn(c, b[k]));
+    }
+    __syncthreads();
   }
-  if (ok && lane == 0) {
+  if (tid == 0) {
+    int ok = 1;
     for (int i = n - 1; i >= 0; --i) {
       if (fabs(A[i * n + i]) < kTinyD) {
-        ok = false;
+        ok = 0;
         break;
       }
       double c = 0;
       for (int j = i + 1; j < n; ++j) c = __dadd_rn(c, __dmul_rn(A[i * n + j], x[j]));
       x[i] = __ddiv_rn(__dsub_rn(b[i], c), A[i * n + i]);
     }
+    *flag = ok;
   }
-  ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
-  __syncwarp();
-  return ok;
+  __syncthreads();
+  return *flag != 0;
 }
 
 __device__ __forceinline__ int pair_idx(int i, int j) { return i * kTaps - i * (i - 1) / 2 + (j - i); }
@@ -102,6 +127,7 @@ latest_kernel(Geometry g, const uint8_t *__restrict__ records, RecordLayout rl, 
   double *fs = fa + nb;
   uint8_t *key = reinterpret_cast<uint8_t *>(fs + nb);
   uint8_t *bin0 = key + ((nb + 15) & ~15);  // luma block-mean bin of every block (shared by the channels)
+  uint16_t *lst = reinterpret_cast<uint16_t *>(bin0 + ((nb + 15) & ~15));  // measuring blocks grouped by bin, block order
 
   const long long num_flat = *reinterpret_cast<const long long *>(rec + rl.off_num_flat);
   const uint8_t *flat = rec + rl.off_flat;
@@ -159,9 +185,9 @@ latest_kernel(Geometry g, const uint8_t *__restrict__ records, RecordLayout rl, 
     for (int e = tid; e < n * n; e += kLatestThreads) sm.Ac[e] = sm.A[e];
     if (tid < n) sm.bc[tid] = sm.b[tid];
     __syncthreads();
-    if (warp == 0) {
-      const bool ok = gauss_solve_warp(n, sm.Ac, sm.bc, sm.x, lane);
-      if (lane == 0) {
+    {
+      const bool ok = gauss_solve_cta(n, sm.Ac, sm.bc, sm.x, sm.tmp, sm.perm, sm.cvec, &sm.flag);
+      if (tid == 0) {
         sm.ok = ok;
         double gain = 1.0;
         if (ok) {
@@ -231,49 +257,82 @@ latest_kernel(Geometry g, const uint8_t *__restrict__ records, RecordLayout rl, 
       }
     }
     __syncthreads();
-    // ---- NoiseStrengthSolver::add_measurement in block order: one thread per entry of the system
-    if (tid < 3 * kBins + 1) {
+    // ---- NoiseStrengthSolver::add_measurement in block order.  Every entry of the system is its own chain of adds, and
+    // an entry only hears from the blocks of one or two bins: (a) stable partition of the measuring blocks by bin
+    // (warp ballots, block order kept), (b) one thread per entry walks its bin list(s), merged by block index.
+    for (int k = warp; k < kBins; k += kLatestThreads / 32) {  // (a1) count
+      int cnt = 0;
+      for (int b0 = 0; b0 < nb; b0 += 32) {
+        const int b = b0 + lane;
+        cnt += __popc(__ballot_sync(0xffffffffu, b < nb && key[b] == k));
+      }
+      if (lane == 0) sm.bin_cnt[k] = cnt;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int at = 0;
+      for (int k = 0; k < kBins; ++k) sm.bin_start[k] = at, at += sm.bin_cnt[k];
+      sm.bin_start[kBins] = at;
+    }
+    __syncthreads();
+    for (int k = warp; k < kBins; k += kLatestThreads / 32) {  // (a2) fill, in block order
+      int at = sm.bin_start[k];
+      for (int b0 = 0; b0 < nb; b0 += 32) {
+        const int b = b0 + lane;
+        const bool mine = b < nb && key[b] == k;
+        const uint32_t m = __ballot_sync(0xffffffffu, mine);
+        if (mine) lst[at + __popc(m & ((1u << lane) - 1u))] = (uint16_t)b;
+        at += __popc(m);
+      }
+    }
+    __syncthreads();
+    if (tid < 3 * kBins + 1) {  // (b)
       const int kind = tid / kBins, i = tid - kind * kBins;  // 0 diagonal, 1 off-diagonal (i, i+1), 2 rhs, 3 total
-      const uint32_t want0 = 0x01010101u * (uint32_t)i, want1 = 0x01010101u * (uint32_t)(i - 1);
       double acc = 0.0;
-      int neq = 0;
-      const uint32_t *kw = reinterpret_cast<const uint32_t *>(key);
-      for (int w4 = 0; w4 < (nb + 3) / 4; ++w4) {
-        const uint32_t kv = kw[w4];
-        if (kind == 3) {
-          if (kv == 0xFFFFFFFFu) continue;
-        } else {
-          // any byte equal to i (as i0) or to i - 1 (then i is its i1)?  i1 = min(19, i0 + 1): bin 19 is its own i1
-          const uint32_t m0 = __vcmpeq4(kv, want0), m1 = (kind == 1 || i == 0) ? 0u : __vcmpeq4(kv, want1);
-          if ((m0 | m1) == 0u) continue;
-        }
-        for (int q = 0; q < 4; ++q) {
-          const int b = 4 * w4 + q;
-          if (b >= nb) break;
-          const int i0 = (kv >> (8 * q)) & 0xFF;
-          if (i0 == 255) continue;
-          const int i1 = i0 + 1 < kBins ? i0 + 1 : kBins - 1;
-          const double a = fa[b], s = fs[b], na = __dsub_rn(1.0, a);
-          if (kind == 0) {  // A[i0][i0] += (1-a)^2; A[i1][i0] += a(1-a); A[i1][i1] += a^2; A[i0][i1] += a(1-a)
-            if (i0 == i) acc = __dadd_rn(acc, __dmul_rn(na, na));
-            if (i1 == i && i0 == i) acc = __dadd_rn(acc, __dmul_rn(a, na));
-            if (i1 == i) acc = __dadd_rn(acc, __dmul_rn(a, a));
-            if (i0 == i && i1 == i) acc = __dadd_rn(acc, __dmul_rn(a, na));
-          } else if (kind == 1) {
-            if (i0 == i && i1 == i + 1) acc = __dadd_rn(acc, __dmul_rn(a, na));
-          } else if (kind == 2) {
-            if (i0 == i) acc = __dadd_rn(acc, __dmul_rn(na, s));
-            if (i1 == i) acc = __dadd_rn(acc, __dmul_rn(a, s));
+      if (kind == 3) {
+        int neq = 0;
+        for (int b = 0; b < nb; ++b)
+          if (key[b] != 255) acc = __dadd_rn(acc, fs[b]), ++neq;
+        sm.total = acc, sm.neq = neq;
+      } else if (kind == 1) {  // A[i0][i1] += a (1 - a) for the blocks of bin i (bin 19 is its own i1: diagonal)
+        if (i + 1 < kBins)
+          for (int p = sm.bin_start[i]; p < sm.bin_start[i + 1]; ++p) {
+            const double a = fa[lst[p]];
+            acc = __dadd_rn(acc, __dmul_rn(a, __dsub_rn(1.0, a)));
+          }
+        sm.off[i] = acc;
+      } else {
+        // blocks of bin i (i0 == i) and of bin i - 1 (their i1 == i), in block order
+        int pa = sm.bin_start[i], ea = sm.bin_start[i + 1];
+        int pb = i > 0 ? sm.bin_start[i - 1] : 0, eb = i > 0 ? sm.bin_start[i] : 0;
+        const bool own_i1 = i == kBins - 1;  // i1 = min(19, i0 + 1)
+        while (pa < ea || pb < eb) {
+          const int ba = pa < ea ? lst[pa] : 0x7fffffff, bb = pb < eb ? lst[pb] : 0x7fffffff;
+          if (ba < bb) {
+            const double a = fa[ba], na = __dsub_rn(1.0, a);
+            if (kind == 0) {  // A[i0][i0] += (1-a)^2; then, when i1 == i0: A[i1][i0] += a(1-a); A[i1][i1] += a^2; A[i0][i1] += a(1-a)
+              acc = __dadd_rn(acc, __dmul_rn(na, na));
+              if (own_i1) {
+                acc = __dadd_rn(acc, __dmul_rn(a, na));
+                acc = __dadd_rn(acc, __dmul_rn(a, a));
+                acc = __dadd_rn(acc, __dmul_rn(a, na));
+              }
+            } else {  // b[i0] += (1-a) s; then, when i1 == i0: b[i1] += a s
+              const double sv = fs[ba];
+              acc = __dadd_rn(acc, __dmul_rn(na, sv));
+              if (own_i1) acc = __dadd_rn(acc, __dmul_rn(a, sv));
+            }
+            ++pa;
           } else {
-            acc = __dadd_rn(acc, s);
-            ++neq;
+            const double a = fa[bb];
+            if (kind == 0) acc = __dadd_rn(acc, __dmul_rn(a, a));           // A[i1][i1] += a^2
+            else acc = __dadd_rn(acc, __dmul_rn(a, fs[bb]));                 // b[i1] += a s
+            ++pb;
           }
         }
+        if (kind == 0) sm.diag[i] = acc;
+        else sm.Sb[i] = acc;
       }
-      if (kind == 0) sm.diag[i] = acc;
-      else if (kind == 1) sm.off[i] = acc;
-      else if (kind == 2) sm.Sb[i] = acc;
-      else sm.total = acc, sm.neq = neq;
     }
     __syncthreads();
     // ---- NoiseStrengthSolver::solve: ridge bump of b in place, regularised copy of A, elimination
@@ -296,9 +355,9 @@ latest_kernel(Geometry g, const uint8_t *__restrict__ records, RecordLayout rl, 
       sm.Sx[tid] = 0.0;
     }
     __syncthreads();
-    if (warp == 0) {
-      const bool ok = gauss_solve_warp(kBins, sm.SA, sm.bc, sm.Sx, lane);
-      if (lane == 0) sm.ok = ok;
+    {
+      const bool ok = gauss_solve_cta(kBins, sm.SA, sm.bc, sm.Sx, sm.tmp, sm.perm, sm.cvec, &sm.flag);
+      if (tid == 0) sm.ok = ok;
     }
     __syncthreads();
     // ---- this channel's digest, strength part
@@ -321,9 +380,11 @@ latest_kernel(Geometry g, const uint8_t *__restrict__ records, RecordLayout rl, 
 
 }  // namespace
 
-size_t latest_smem_bytes(const Geometry &g) { return (size_t)g.nb * 16 + 2 * (((size_t)g.nb + 15) & ~(size_t)15) + 64; }
+size_t latest_smem_bytes(const Geometry &g) {
+  return (size_t)g.nb * 16 + 2 * (((size_t)g.nb + 15) & ~(size_t)15) + 2 * (size_t)g.nb + 64;
+}
 
-bool latest_supported(const Geometry &g) { return latest_smem_bytes(g) <= 200 * 1024; }
+bool latest_supported(const Geometry &g) { return latest_smem_bytes(g) <= 190 * 1024 && g.nb < 65535; }
 
 void launch_latest(int nframes, const Geometry &g, const uint8_t *records, const RecordLayout &rl, bool strict,
                    double *digests, int digest_doubles, cudaStream_t st) {
@@ -332,7 +393,7 @@ void launch_latest(int nframes, const Geometry &g, const uint8_t *records, const
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaFuncSetAttribute(latest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(latest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 190 * 1024);
     attr_set[dev & 63] = true;
   }
   latest_kernel<<<nframes, kLatestThreads, smem, st>>>(g, records, rl, strict ? 1 : 0, digests, digest_doubles);

@@ -98,12 +98,10 @@ def _pass(plane: np.ndarray, left: np.ndarray, coef: np.ndarray, maxv: int, axis
     rows, _ = src.shape
     dst_n, taps = coef.shape
     acc = np.zeros((rows, dst_n), np.float32)
-    cols = left[None, :].astype(np.int64)
     for j in range(taps):
         acc = (acc + coef[:, j][None, :] * src[:, (left + j)]).astype(np.float32)
     out = np.clip(np.floor((acc + np.float32(0.5)).astype(np.float32)), 0, maxv).astype(plane.dtype)
-    del cols
-    return out.T if axis == 0 else out
+    return np.ascontiguousarray(out.T if axis == 0 else out)
 
 
 def resize_planes(planes: Sequence[np.ndarray], width: int, height: int, alg: str, bit_depth: int, ss: Tuple[int, int],
