@@ -786,7 +786,7 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
       CU_NEW(cudaMalloc(&s.d_res, d->rstore.frame_bytes * batch));
       CU_NEW(cudaMalloc(&s.d_rmaps, sizeof(CUtensorMap) * kResidualMaps * batch));
       CU_NEW(cudaMalloc(&s.d_plan, gram_plan_bytes(batch, g)));
-      CU_NEW(cudaMalloc(&s.d_plan_counts, sizeof(int) * 3 * batch));
+      CU_NEW(cudaMalloc(&s.d_plan_counts, sizeof(int) * (3 * batch + 1)));
       std::vector<CUtensorMap> host;
       if (!build_residual_maps(d.get(), s, host)) {
         d->err = "cuTensorMapEncodeTiled failed for the residual planes";

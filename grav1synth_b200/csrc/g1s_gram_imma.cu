@@ -23,9 +23,10 @@
 // Why warps are autonomous.  Measured on the B200 (tools/imma_probe.cu, profiles/): the legacy IMMA path
 // holds a sub-partition's issue port for its whole 8.4 cycles, so a sub-partition's time is
 // 8.4 * IMMAs + (every other warp instruction it issues) -- nothing overlaps, polls and barrier spins are
-// paid in full.  So: no CTA barriers, no shared rings, no inter-warp waits.  A warp has a plane for life
-// (4 luma + 4 chroma warps per CTA, measured: 25.1 us per frame against 28.1 with 5 + 3 and 35.1 with 6 + 2), its own mbarriers, and it adds its int32 accumulators to the frame's
-// int64 record directly when its share leaves a frame.
+// paid in full.  So: no CTA barriers, no shared rings, no inter-warp waits.  Every warp is the same: it takes chunks of
+// 64 units of one plane from a global counter (round 2; a fixed 4 + 4 luma / chroma split measured 25.1 us per frame,
+// 5 + 3 28.1, 6 + 2 35.1 -- the dynamic form needs no split), has its own mbarriers and TMA ring, and adds its int32
+// accumulators to the frame's int64 record directly at the end of a chunk.
 //   unit        one tile of a strip: luma one 32x32 block, chroma two adjacent 16x16 blocks (32 columns either way)
 //   Tap a = 8q+g with g = cx+3 (the mma lane group), q = cy+3.  A lane's operand of a residual row is ONE
 //   32-bit window per half (two LDS + funnel shift), and the same window is the row's B pair and its half of
@@ -44,11 +45,9 @@ namespace {
 
 #ifndef G1S_GRAM_WARPS
 #define G1S_GRAM_WARPS 8
-#define G1S_LUMA_WARPS 4
 #endif
 constexpr int kGramWarps = G1S_GRAM_WARPS;
 constexpr int kGramThreads = 32 * kGramWarps;
-constexpr int kLumaWarps = G1S_LUMA_WARPS;  // per CTA; the others are chroma warps (pair steps per frame: Y about 135 k, Cb + Cr about 70 k)
 constexpr int kMaxObs = 130000;   // observations between two flushes of a warp: bounds the int32 strip accumulators (x 127^2 < 2^31)
 constexpr int kMinRows = 6;       // shortest row window the strip code handles (two opening + three closing pair steps)
 constexpr int kMaxStrip = 64;     // block rows per strip: 64 * 1024 observations * 127^2 < 2^31
@@ -473,66 +472,43 @@ gram_plan_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, uin
 }
 
 // ------------------------------------------------------------------------------ gram_imma_kernel
+//
+// Work distribution: the units of the batch (all planes) are cut into chunks of kChunk consecutive units of one plane;
+// warps take chunks from a global counter (luma chunks first: the long ones).  Any warp can run any plane -- the k-loop
+// is the same, only the tile geometry differs -- so there is no luma / chroma split to balance, and a CTA that starts
+// late (another stream's kernel was on its SM) simply takes fewer chunks.  A chunk is moved forward to strip boundaries
+// at both ends (a strip's running sums live in one warp's registers).
+constexpr int kChunk = 64;
+
 __global__ void __launch_bounds__(kGramThreads, 2)
 gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int nframes, const uint8_t *__restrict__ tmaps,
-                 const uint4 *__restrict__ plan, const int *__restrict__ counts) {
+                 const uint4 *__restrict__ plan, int *__restrict__ counts) {
   extern __shared__ __align__(128) uint8_t tiles[];
   __shared__ GramSmem sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, t = lane & 3;  // mma "groupID" (= cx + 3) and thread-in-group
-  const bool has_chroma = g.planes == 3;
 
-  // ---- this warp's plane and its rank among the plane's warps
-  const int cta = blockIdx.x, ncta = gridDim.x;
-  int plane, rank, nranks;
-  if (!has_chroma) {
-    plane = 0, rank = cta * kGramWarps + warp, nranks = ncta * kGramWarps;
-  } else if (warp < kLumaWarps) {
-    plane = 0, rank = cta * kLumaWarps + warp, nranks = ncta * kLumaWarps;
-  } else {
-    // chroma warps split evenly between Cb and Cr; with an odd count the extra warp alternates with the CTA's parity
-    constexpr int kC = kGramWarps - kLumaWarps, kHi = (kC + 1) / 2, kLo = kC / 2;
-    const int k = warp - kLumaWarps, ncb = (cta & 1) ? kLo : kHi;
-    const int even = (ncta + 1) >> 1, odd = ncta >> 1, e_before = (cta + 1) >> 1, o_before = cta >> 1;
-    if (k < ncb) plane = 1, rank = kHi * e_before + kLo * o_before + k, nranks = kHi * even + kLo * odd;
-    else plane = 2, rank = kLo * e_before + kHi * o_before + (k - ncb), nranks = kLo * even + kHi * odd;
-  }
-  const bool luma = plane == 0;
-
-  // ---- its share of the plane's units: an equal slice of the unit index space over the batch's frames, moved forward
-  // to strip boundaries at both ends (a strip's running sums live in one warp's registers).  Lane l keeps the unit
-  // counts of frames l and l + 32 (a batch has at most 64 frames).
-  const int cnt_lo = lane < nframes ? counts[lane * 3 + plane] : 0;
-  const int cnt_hi = lane + 32 < nframes ? counts[(lane + 32) * 3 + plane] : 0;
-  int total = cnt_lo + cnt_hi;
+  // ---- unit counts of the batch: lane l keeps frames l and l + 32 of every plane (a batch has at most 64 frames), as
+  // inclusive prefix sums over the frames
+  int inc_lo[3], inc_hi[3], total[3], nch[3];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-  const int u_lo = (int)((long long)total * rank / nranks), u_hi = (int)((long long)total * (rank + 1) / nranks);
-  if (u_lo >= u_hi) return;  // whole warp; nothing below synchronises across warps
-  auto count_of = [&](int f) { return __shfl_sync(0xffffffffu, f < 32 ? cnt_lo : cnt_hi, f & 31); };
-  // position of the producer: unit index u = local index pi of frame pf (pc units in that frame)
-  int u = 0, pf = 0, pc = count_of(0), pi = 0;
-  while (u + pc <= u_lo && pf + 1 < nframes) u += pc, ++pf, pc = count_of(pf);
-  pi = u_lo - u, u = u_lo;
-  auto unit_at = [&](int f, int i) { return __ldg(plan + ((size_t)f * 3 + plane) * g.nb + i); };
-  auto advance = [&]() {  // to the next unit; false past the end of the batch
-    ++u, ++pi;
-    while (pi >= pc) {
-      if (++pf >= nframes) return false;
-      pc = count_of(pf), pi = 0;
+  for (int p = 0; p < 3; ++p) {
+    int a = (p < g.planes && lane < nframes) ? counts[lane * 3 + p] : 0;
+    int b = (p < g.planes && lane + 32 < nframes) ? counts[(lane + 32) * 3 + p] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int va = __shfl_up_sync(0xffffffffu, a, o), vb = __shfl_up_sync(0xffffffffu, b, o);
+      if (lane >= o) a += va, b += vb;
     }
-    return true;
-  };
-  bool more = true;
-  uint4 dn = unit_at(pf, pi);                         // descriptor of the next unit to request
-  while (more && !(dn.y & kFirst)) {                  // skip the tail of a strip that started in the previous share
-    more = advance();
-    if (more) dn = unit_at(pf, pi);
+    const int ta = __shfl_sync(0xffffffffu, a, 31);
+    inc_lo[p] = a, inc_hi[p] = ta + b;
+    total[p] = __shfl_sync(0xffffffffu, ta + b, 31);
+    nch[p] = (total[p] + kChunk - 1) / kChunk;
   }
-  if (!more || u >= u_hi) return;
+  const int nchunks = nch[0] + nch[1] + nch[2];
+  int *const work = counts + 3 * nframes;  // the chunk counter (zeroed with the counts)
 
   uint8_t *const my_tiles = tiles + warp * kWarpSmem;
-  const int slot = luma ? kLumaSlot : kChromaSlot;
   if (lane == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[warp][s], 1);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -540,7 +516,7 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
   __syncwarp();
 
   int acc[5][4];        // running sums of the five row products (never reset, see the k-loop notes)
-  uint32_t G[10][2];    // this share's Gram blocks (q', dy) since the last flush
+  uint32_t G[10][2];    // Gram blocks (q', dy) of the current frame and plane since the last flush
   Ring ring;
 #pragma unroll
   for (int i = 0; i < 5; ++i)
@@ -555,93 +531,129 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
   asm volatile("" : "+r"(sh));  // one register instead of four instructions per funnel shift group
   const int dxw = (gq + 1) >> 2;
   const bool is7 = gq == 7;
-  // the lane's window word in row 0 of a stage's tile: g = 7 lanes of the chroma warps walk the luma-tap tile
-  const int lane_off = (!luma && is7) ? kOffTap + 4 * (kTapCol0 + t) : 4 * (kResCol0 + t + dxw);
 
-  // Gram blocks -> the frame's int64 record, straight from registers: element r of block (q', dy) in lane (gq, t)
-  // is the product of the later tap (q', g' = gq) with the earlier tap (q' - dy, g = 2t + r).
-  auto flush = [&](int f) {
-    uint8_t *rec = records + (size_t)f * rl.bytes;
-    unsigned long long *gram = reinterpret_cast<unsigned long long *>(rec + rl.off_gram) + (size_t)plane * kPairs;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-#pragma unroll
-      for (int dy = 0; dy <= q; ++dy)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int v = (int)G[gidx(q, dy)][r];
-          G[gidx(q, dy)][r] = 0u;
-          emit(gram, 8 * (q - dy) + 2 * t + r, 8 * q + gq, v, !luma);
-        }
-  };
-
-  // ---- producer side: request the next unit's tile(s), queue its descriptor; the one after it is fetched meanwhile
-  int head = 0, tail = 0;       // fifo positions (units requested / consumed)
-  int hstage = 0, tstage = 0;   // their stages ( = position % kStages, kept incrementally)
+  int hstage = 0, tstage = 0;   // TMA ring positions, kept across chunks (the mbarrier phases go on)
   uint32_t phases = 0;          // bit s: parity to wait for on stage s
-  auto produce = [&]() {        // false when the share is exhausted
-    if (!more || (u >= u_hi && (dn.y & kFirst))) {
-      more = false;
-      return false;
-    }
-    const uint4 d = dn;
-    const int stage = hstage;
-    if (++hstage == kStages) hstage = 0;
-    if (lane == 0) {
-      sm.fifo[warp][head & 3] = d;
-      const int f = d.x & 255, col = (d.x >> 8) & 4095, by = d.x >> 20;
-      const uint8_t *fmaps = tmaps + (size_t)f * kResidualMaps * 128;
-      uint8_t *st = my_tiles + stage * slot;
-      uint64_t *bar = &sm.full[warp][stage];
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this warp's reads of the stage precede the refill
-      if (luma) {
-        mbar_expect_tx(bar, kLumaBytes);
-        tma_load_2d(st, fmaps, 32 * col - 16, 32 * by - 3, bar);
-      } else {
-        const int cx = 32 * col - 16, cy = 16 * by - 3;
-        mbar_expect_tx(bar, 2 * kChromaBytes);
-        tma_load_2d(st, fmaps + plane * 128, cx, cy, bar);
-        tma_load_2d(st + kOffTap, fmaps + 3 * 128, cx, cy, bar);
-      }
-    }
-    ++head;
-    more = advance();
-    if (more) dn = unit_at(pf, pi);
-    return true;
-  };
 
-  int cf = -1;     // frame the strip accumulators belong to
-  int since = 0;   // observations accumulated since the last flush
-  int ph = 0;      // ring phase, carried from unit to unit inside a strip
   for (;;) {
-    __syncwarp();  // every lane is done with the stage about to be refilled
-    while (head - tail < kStages && produce()) {
+    int c = 0;
+    if (lane == 0) c = atomicAdd(work, 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= nchunks) break;
+    const int plane = c < nch[0] ? 0 : (c < nch[0] + nch[1] ? 1 : 2);
+    const int cl = c - (plane == 0 ? 0 : (plane == 1 ? nch[0] : nch[0] + nch[1]));
+    const bool luma = plane == 0;
+    const int slot = luma ? kLumaSlot : kChromaSlot;
+    // the lane's window word in row 0 of a stage's tile: g = 7 lanes of a chroma chunk walk the luma-tap tile
+    const int lane_off = (!luma && is7) ? kOffTap + 4 * (kTapCol0 + t) : 4 * (kResCol0 + t + dxw);
+    const int my_lo = plane == 0 ? inc_lo[0] : (plane == 1 ? inc_lo[1] : inc_lo[2]);
+    const int my_hi = plane == 0 ? inc_hi[0] : (plane == 1 ? inc_hi[1] : inc_hi[2]);
+    const int tot = plane == 0 ? total[0] : (plane == 1 ? total[1] : total[2]);
+    const int u_lo = cl * kChunk, u_hi = min(tot, u_lo + kChunk);
+    // frame that holds unit u_lo: the first whose inclusive prefix exceeds it
+    const uint32_t in_lo = __ballot_sync(0xffffffffu, my_lo > u_lo), in_hi = __ballot_sync(0xffffffffu, my_hi > u_lo);
+    int pf = in_lo ? __ffs(in_lo) - 1 : 32 + __ffs(in_hi) - 1;
+    auto incl_of = [&](int f) { return __shfl_sync(0xffffffffu, f < 32 ? my_lo : my_hi, f & 31); };
+    int pend = incl_of(pf);                                  // unit index one past frame pf
+    int pbeg = pf == 0 ? 0 : incl_of(pf - 1);                // first unit index of frame pf
+    int u = u_lo;                                            // unit index of the next descriptor
+    auto unit_at = [&](int f, int i) { return __ldg(plan + ((size_t)f * 3 + plane) * g.nb + i); };
+    auto advance = [&]() {  // to the next unit; false past the end of the plane's list
+      if (++u >= tot) return false;
+      while (u >= pend) pbeg = pend, ++pf, pend = incl_of(pf);
+      return true;
+    };
+    bool more = true;
+    uint4 dn = unit_at(pf, u - pbeg);                   // descriptor of the next unit to request
+    while (more && !(dn.y & kFirst)) {                  // skip the tail of a strip that started in the previous chunk
+      more = advance();
+      if (more) dn = unit_at(pf, u - pbeg);
     }
-    if (head == tail) break;
-    __syncwarp();
-    const uint4 d = sm.fifo[warp][tail & 3];
-    const int stage = tstage;
-    if (++tstage == kStages) tstage = 0;
-    ++tail;
-    const bool first = d.y & kFirst;
-    if (first) {  // G only changes at strip ends, so strip starts are the flush points
-      const int f = d.x & 255;
-      if (f != cf || since + (int)d.w > kMaxObs) {
-        if (cf >= 0) flush(cf);
-        cf = f;
-        since = 0;
+    if (!more || u >= u_hi) continue;
+
+    // Gram blocks -> the frame's int64 record, straight from registers: element r of block (q', dy) in lane (gq, t)
+    // is the product of the later tap (q', g' = gq) with the earlier tap (q' - dy, g = 2t + r).
+    auto flush = [&](int f) {
+      uint8_t *rec = records + (size_t)f * rl.bytes;
+      unsigned long long *gram = reinterpret_cast<unsigned long long *>(rec + rl.off_gram) + (size_t)plane * kPairs;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int dy = 0; dy <= q; ++dy)
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int v = (int)G[gidx(q, dy)][r];
+            G[gidx(q, dy)][r] = 0u;
+            emit(gram, 8 * (q - dy) + 2 * t + r, 8 * q + gq, v, !luma);
+          }
+    };
+
+    // ---- producer side: request the next unit's tile(s), queue its descriptor; the one after it is fetched meanwhile
+    int head = 0, tail = 0;       // fifo positions of this chunk (units requested / consumed)
+    auto produce = [&]() {        // false when the chunk is exhausted
+      if (!more || (u >= u_hi && (dn.y & kFirst))) {
+        more = false;
+        return false;
       }
-      since += (int)d.w;
+      const uint4 d = dn;
+      const int stage = hstage;
+      if (++hstage == kStages) hstage = 0;
+      if (lane == 0) {
+        sm.fifo[warp][head & 3] = d;
+        const int f = d.x & 255, col = (d.x >> 8) & 4095, by = d.x >> 20;
+        const uint8_t *fmaps = tmaps + (size_t)f * kResidualMaps * 128;
+        uint8_t *st = my_tiles + stage * slot;
+        uint64_t *bar = &sm.full[warp][stage];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this warp's reads of the stage precede the refill
+        if (luma) {
+          mbar_expect_tx(bar, kLumaBytes);
+          tma_load_2d(st, fmaps, 32 * col - 16, 32 * by - 3, bar);
+        } else {
+          const int cx = 32 * col - 16, cy = 16 * by - 3;
+          mbar_expect_tx(bar, 2 * kChromaBytes);
+          tma_load_2d(st, fmaps + plane * 128, cx, cy, bar);
+          tma_load_2d(st + kOffTap, fmaps + 3 * 128, cx, cy, bar);
+        }
+      }
+      ++head;
+      more = advance();
+      if (more) dn = unit_at(pf, u - pbeg);
+      return true;
+    };
+
+    int cf = -1;     // frame the strip accumulators belong to
+    int since = 0;   // observations accumulated since the last flush
+    int ph = 0;      // ring phase, carried from unit to unit inside a strip
+    for (;;) {
+      __syncwarp();  // every lane is done with the stage about to be refilled
+      while (head - tail < kStages && produce()) {
+      }
+      if (head == tail) break;
+      __syncwarp();
+      const uint4 d = sm.fifo[warp][tail & 3];
+      const int stage = tstage;
+      if (++tstage == kStages) tstage = 0;
+      ++tail;
+      const bool first = d.y & kFirst;
+      if (first) {  // G only changes at strip ends, so strip starts are the flush points
+        const int f = d.x & 255;
+        if (f != cf || since + (int)d.w > kMaxObs) {
+          if (cf >= 0) flush(cf);
+          cf = f;
+          since = 0;
+        }
+        since += (int)d.w;
+      }
+      mbar_wait(&sm.full[warp][stage], (phases >> stage) & 1u);
+      phases ^= 1u << stage;
+      const int r0 = d.y & 63, np = (d.y >> 6) & 63;
+      const int lo0 = (d.y >> 16) & 63, hi0 = (d.y >> 22) & 63, lo1 = d.z & 63, hi1 = (d.z >> 6) & 63;
+      const uint32_t mx[2] = {byte_mask(4 * t, lo0, hi0), byte_mask(16 + 4 * t, lo1, hi1)};
+      const uint32_t *p = reinterpret_cast<const uint32_t *>(my_tiles + stage * slot + lane_off) + r0 * kRowWords;
+      unit_rows(p, sh, np, first, d.y & kLast, d.y & kOdd, mx, ph, ring, acc, G);
     }
-    mbar_wait(&sm.full[warp][stage], (phases >> stage) & 1u);
-    phases ^= 1u << stage;
-    const int r0 = d.y & 63, np = (d.y >> 6) & 63;
-    const int lo0 = (d.y >> 16) & 63, hi0 = (d.y >> 22) & 63, lo1 = d.z & 63, hi1 = (d.z >> 6) & 63;
-    const uint32_t mx[2] = {byte_mask(4 * t, lo0, hi0), byte_mask(16 + 4 * t, lo1, hi1)};
-    const uint32_t *p = reinterpret_cast<const uint32_t *>(my_tiles + stage * slot + lane_off) + r0 * kRowWords;
-    unit_rows(p, sh, np, first, d.y & kLast, d.y & kOdd, mx, ph, ring, acc, G);
+    if (cf >= 0) flush(cf);
   }
-  if (cf >= 0) flush(cf);
 }
 
 }  // namespace
@@ -667,13 +679,14 @@ void launch_gram_plan(int nframes, const Geometry &g, uint8_t *records, const Re
                       cudaStream_t st) {
   const bool in_smem = g.nb <= kPlanSmemBlocks;
   uint8_t *scratch = in_smem ? nullptr : static_cast<uint8_t *>(plan) + (size_t)nframes * 3 * g.nb * sizeof(uint4);
-  cudaMemsetAsync(counts, 0, sizeof(int) * 3 * nframes, st);  // the kernel reserves units with atomicAdd
+  // the plan kernel reserves units with atomicAdd; counts[3 * nframes] is the Gram kernel's chunk counter
+  cudaMemsetAsync(counts, 0, sizeof(int) * (3 * nframes + 1), st);
   gram_plan_kernel<<<dim3(g.planes, nframes, kPlanSlices), 256, in_smem ? (size_t)g.nb : 0, st>>>(
       g, records, rl, static_cast<uint4 *>(plan), counts, scratch);
 }
 
 void launch_gram_imma(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, const void *tmaps,
-                      const void *plan, const int *counts, cudaStream_t st) {
+                      const void *plan, int *counts, cudaStream_t st) {
   const int smem = kGramWarps * kWarpSmem;
   // resident CTAs of the current device (the persistent grid is one wave); cached per device, and the
   // dynamic-shared-memory attribute is a per-device property of the function as well

@@ -99,14 +99,15 @@ void launch_residual(const FrameDesc *frames, int nframes, const Geometry &g, co
                      uint8_t *records, const RecordLayout &rl, bool aligned, cudaStream_t st);
 // gram_plan_kernel: flat / overflow flags -> the plane's work list (strips of vertically adjacent blocks with one row
 // window, one 16-byte descriptor per strip and tile) + observation counts; may flag more blocks for the generic kernel.
-// plan: gram_plan_bytes(nframes, g) bytes; counts: int[nframes][3] units per frame and plane.  nframes <= 64.
+// plan: gram_plan_bytes(nframes, g) bytes; counts: int[nframes][3] units per frame and plane + 1 (the Gram kernel's
+// chunk counter).  nframes <= 64.
 size_t gram_plan_bytes(int nframes, const Geometry &g);
 void launch_gram_plan(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, void *plan, int *counts,
                       cudaStream_t st);
 // tmaps: device array of CUtensorMap[nframes][kResidualMaps] over the ResidualStore planes (extents =
 // the loop extents W x H and (W>>1) x (H>>1), boxes from gram_imma_tma_boxes, zero fill).
 void launch_gram_imma(int nframes, const Geometry &g, uint8_t *records, const RecordLayout &rl, const void *tmaps,
-                      const void *plan, const int *counts, cudaStream_t st);
+                      const void *plan, int *counts, cudaStream_t st);
 // box[k] = {width, height} in bytes / rows for descriptor k of a frame
 void gram_imma_tma_boxes(int box[kResidualMaps][2]);
 

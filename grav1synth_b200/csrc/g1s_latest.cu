@@ -290,8 +290,21 @@ latest_kernel(Geometry g, const uint8_t *__restrict__ records, RecordLayout rl, 
       const int kind = tid / kBins, i = tid - kind * kBins;  // 0 diagonal, 1 off-diagonal (i, i+1), 2 rhs, 3 total
       double acc = 0.0;
       if (kind == 3) {
-        int neq = 0;
-        for (int b = 0; b < nb; ++b)
+        // total += noise_std of every measuring block, in block order: the longest chain of the frame.  Eight blocks per
+        // step so that the loads run ahead of the dependent adds.
+        int neq = 0, b = 0;
+        for (; b + 8 <= nb; b += 8) {
+          const uint2 kk = *reinterpret_cast<const uint2 *>(key + b);
+          double v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = fs[b + q];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t kb = ((q < 4 ? kk.x : kk.y) >> (8 * (q & 3))) & 0xFF;
+            if (kb != 255) acc = __dadd_rn(acc, v[q]), ++neq;
+          }
+        }
+        for (; b < nb; ++b)
           if (key[b] != 255) acc = __dadd_rn(acc, fs[b]), ++neq;
         sm.total = acc, sm.neq = neq;
       } else if (kind == 1) {  // A[i0][i1] += a (1 - a) for the blocks of bin i (bin 19 is its own i1: diagonal)

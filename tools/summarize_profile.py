@@ -15,7 +15,7 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 out_dir = os.path.join(root, "profiles")
 src_dir = os.path.join(root, "gpurun_out")
 
-# ---- launch list (gpu__time_duration per launch; cold-cache and serialised: compare SHARES)
+# ---- launch list (gpu__time_duration + DRAM bytes per launch; cold-cache and serialised: compare SHARES)
 rows = [r for r in csv.reader(open(os.path.join(src_dir, "launches.csv"))) if len(r) > 5]
 hdr, agg = None, {}
 for r in rows:
@@ -24,14 +24,28 @@ for r in rows:
         continue
     if hdr is None:
         continue
-    name = re.sub(r"\(.*", "", r[hdr.index("Kernel Name")]).replace("void ", "").strip()
-    agg.setdefault(name, []).append(float(r[hdr.index("Metric Value")]))
-total = sum(sum(v) for v in agg.values())
+    name = re.sub(r"\(.*", "", r[hdr.index("Kernel Name")]).replace("void ", "").strip().split("::")[-1]
+    metric = r[hdr.index("Metric Name")]
+    agg.setdefault(name, {}).setdefault(metric, []).append(float(r[hdr.index("Metric Value")].replace(",", "")))
+dur = {k: v.get("gpu__time_duration.sum", []) for k, v in agg.items()}
+total = sum(sum(v) for v in dur.values())
+frames = int(os.environ.get("G1S_PROFILE_FRAMES", "20"))
+launches = max(len(v) for v in dur.values())
+dram_total = 0.0
 with open(os.path.join(out_dir, f"{tag}_launches.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'flat_|gram_|residual_' python bench.py ...\n")
-    f.write("# kernel, launches, avg us, total us, share of the step\n")
-    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-        f.write(f"{k:50s} {len(v):4d} {sum(v) / len(v) / 1e3:10.1f} {sum(v) / 1e3:10.1f} {100 * sum(v) / total:6.1f}%\n")
+    f.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
+            "-k regex:'flat_|gram_|residual_|latest_' python bench.py ... (G1S_STREAMS=1, 20 frames per launch)\n")
+    f.write("# kernel, launches, avg us, share of the step, avg DRAM read MB, avg DRAM write MB\n")
+    for k, v in sorted(dur.items(), key=lambda kv: -sum(kv[1])):
+        rd = agg[k].get("dram__bytes_read.sum", [0]); wr = agg[k].get("dram__bytes_write.sum", [0])
+        dram_total += (sum(rd) + sum(wr)) / max(1, len(v)) * (len(v) / launches)
+        f.write(f"{k:34s} {len(v):4d} {sum(v) / len(v) / 1e3:10.1f} {100 * sum(v) / total:6.1f}% "
+                f"{sum(rd) / len(rd) / 1e6:10.1f} {sum(wr) / len(wr) / 1e6:10.1f}\n")
+    f.write(f"# whole step: {total / launches / 1e3:.1f} us per {frames}-frame batch, DRAM traffic {dram_total / 1e6:.1f} MB "
+            f"= {dram_total / frames / 1e6:.2f} MB per frame pair (algorithmic: 49.77 MB)\n")
+json.dump({"dram_bytes_per_frame": dram_total / frames, "frames_per_launch": frames,
+           "source": f"profiles/{tag}_launches.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum of every kernel of one batch)"},
+          open(os.path.join(out_dir, f"{tag}_traffic.json"), "w"), indent=1)
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
@@ -46,7 +60,7 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio"]
 traffic = {}
-for kern in ("gram_imma", "residual", "flat_features"):
+for kern in ("gram_imma", "residual", "flat_features", "gram_plan", "latest", "strict"):
     rep = os.path.join(src_dir, f"prof_{kern}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -67,11 +81,4 @@ for kern in ("gram_imma", "residual", "flat_features"):
         return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
     traffic[kern] = {"dram_bytes_read": to_bytes("dram__bytes_read.sum"), "dram_bytes_write": to_bytes("dram__bytes_write.sum"),
                      "ncu_duration": " ".join(reversed(got["gpu__time_duration.sum"]))}
-if "gram_imma" in traffic and "residual" in traffic:
-    # the roofline's `traffic`: DRAM bytes of one residual launch + one gram launch (the two launches that do
-    # the residual + autocorrelation work of a 20-frame batch)
-    tot = sum(traffic[k]["dram_bytes_read"] + traffic[k]["dram_bytes_write"] for k in ("gram_imma", "residual"))
-    json.dump({"dram_bytes_per_launch": tot, "per_kernel": traffic,
-               "source": f"profiles/{tag}_gram_imma_ncu.txt + profiles/{tag}_residual_ncu.txt"},
-              open(os.path.join(out_dir, "gram_traffic.json"), "w"), indent=1)
 print("wrote summaries for", tag)
