@@ -29,6 +29,7 @@ G1S_E_IO = -7
 G1S_E_STREAM = -8
 
 GRAM_EXACT_INT, GRAM_REF_ORDER = 0, 1
+MODEL_AUTO, MODEL_HOST, MODEL_DEVICE = 0, 1, 2
 MODE_FULL = 0
 MODE_PRODUCER = 1
 MODE_CONSUMER = 2
@@ -90,7 +91,8 @@ class CDiffConfig(C.Structure):
         ("gram_order", C.c_int32),
         ("n_devices", C.c_int32),
         ("device_ids", C.c_int32 * 8),
-        ("reserved_", C.c_int32 * 4),
+        ("model_placement", C.c_int32),
+        ("reserved_", C.c_int32 * 3),
     ]
 
 

@@ -733,6 +733,9 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     g1s_diff_config kc = *cfg;
     kc.n_devices = 0;
     kc.mode = G1S_MODE_PRODUCER;
+    if (kc.model_placement == G1S_MODEL_AUTO)  // about 3 host cores per GPU keep the per-frame model half fed
+      kc.model_placement = 3u * (unsigned)cfg->n_devices > std::max(2u, std::thread::hardware_concurrency()) / 2 ? G1S_MODEL_DEVICE
+                                                                                                                : G1S_MODEL_HOST;
     for (int i = 0; i < cfg->n_devices; ++i) {
       kc.device = cfg->device_ids[i];
       g1s_diff *kid = nullptr;
@@ -778,7 +781,14 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   // int8 tensor-core path (residual_kernel + gram_imma_kernel): 4:2:0 / monochrome, TMA descriptors available
   d->tensor_path = cfg->gram_kernel == 0 && gram_imma_supported(g) && d->encode_tiled != nullptr;
   d->rstore = ResidualStore::make(g);
-  d->device_model = latest_supported(g) && std::getenv("G1S_HOST_MODEL") == nullptr;
+  {
+    // per-frame model half: host threads by default; on the device when asked, or when this process drives more GPUs
+    // than the host has cores for (a multi-device parent passes its decision down as an explicit placement)
+    int place = cfg->model_placement;
+    if (std::getenv("G1S_HOST_MODEL")) place = G1S_MODEL_HOST;
+    if (std::getenv("G1S_DEVICE_MODEL")) place = G1S_MODEL_DEVICE;
+    d->device_model = place == G1S_MODEL_DEVICE && latest_supported(g);
+  }
   for (Slot &s : d->slots) {
     // the frame store (device) and its pinned mirror (host) are allocated on the first host push:
     // streams whose frames are already in HBM never need them

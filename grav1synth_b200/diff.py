@@ -156,7 +156,8 @@ class DiffGenerator:
     def __init__(self, fps_num: int, fps_den: int, source_bit_depth: int, denoised_bit_depth: int, width: int,
                  height: int, ss_x: int = 1, ss_y: int = 1, monochrome: bool = False, device: int = 0,
                  batch_frames: int = 0, mode: int = abi.MODE_FULL, gram_kernel: int = 0, host_threads: int = 0,
-                 host_narrow: bool = False, gram_order: int = 0, devices: Optional[Sequence[int]] = None):
+                 host_narrow: bool = False, gram_order: int = 0, devices: Optional[Sequence[int]] = None,
+                 model_placement: int = 0):
         self._L = lib()
         cfg = CDiffConfig()
         cfg.fps_num, cfg.fps_den = fps_num, fps_den
@@ -167,6 +168,7 @@ class DiffGenerator:
         cfg.host_threads = host_threads
         cfg.host_narrow = int(host_narrow)
         cfg.gram_order = int(gram_order)  # abi.GRAM_EXACT_INT (fast) / abi.GRAM_REF_ORDER (strict: the reference's integers)
+        cfg.model_placement = int(model_placement)  # abi.MODEL_AUTO / MODEL_HOST / MODEL_DEVICE
         if devices is not None and len(devices) > 1:
             cfg.n_devices = len(devices)
             for i, dv in enumerate(devices):

@@ -27,7 +27,8 @@ RING = 4  # super-batches the digest ring holds
 class ShardedDiff:
     def __init__(self, fps_num: int, fps_den: int, source_bit_depth: int, denoised_bit_depth: int, width: int,
                  height: int, ss_x: int = 1, ss_y: int = 1, frames_per_rank: int = 8, device: Optional[int] = None,
-                 producer_factory: Optional[Callable[[], object]] = None, group=None, batch_frames: int = 0):
+                 producer_factory: Optional[Callable[[], object]] = None, group=None, batch_frames: int = 0,
+                 model_placement: Optional[int] = None):
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.group = group
@@ -37,8 +38,13 @@ class ShardedDiff:
         if producer_factory is not None:          # tests inject a CPU digest producer
             self.producer = producer_factory()
         else:
+            if model_placement is None:
+                # one process per GPU on one host: about 3 cores per rank keep the per-frame model half on the host fed;
+                # with fewer (8 GPUs on 32 cores) the device evaluates it (latest_kernel) and only digests come back
+                import os
+                model_placement = abi.MODEL_DEVICE if 3 * self.world > (os.cpu_count() or 2) // 2 else abi.MODEL_HOST
             self.producer = DiffGenerator(*args, device=device or 0, batch_frames=batch_frames,
-                                          mode=abi.MODE_PRODUCER)
+                                          mode=abi.MODE_PRODUCER, model_placement=model_placement)
         backend = dist.get_backend(group) if dist.is_initialized() else "none"
         self.on_gpu = backend == "nccl"
         # the producer writes digests straight into this ring (pinned when a GPU is involved)

@@ -115,6 +115,7 @@ enum g1s_mode { G1S_MODE_FULL = 0, G1S_MODE_PRODUCER = 1, G1S_MODE_CONSUMER = 2 
  *              with its roundings (gram_reforder_kernel), so every integer of every table equals the
  *              reference's.  FP64-bound, roughly 20x slower than EXACT_INT, still >1000x the CPU. */
 enum g1s_gram_order { G1S_GRAM_EXACT_INT = 0, G1S_GRAM_REF_ORDER = 1 };
+enum g1s_model_placement { G1S_MODEL_AUTO = 0, G1S_MODEL_HOST = 1, G1S_MODEL_DEVICE = 2 };
 
 typedef struct g1s_diff_config {
   int64_t fps_num, fps_den;     /* Rational64 passed to DiffGenerator::new           */
@@ -141,7 +142,13 @@ typedef struct g1s_diff_config {
                                    the model, the per-frame digests are folded in frame order on the caller's
                                    process.  Same table as one GPU.  mode must be G1S_MODE_FULL.          */
   int32_t device_ids[8];        /* CUDA ordinals, used when n_devices >= 2                              */
-  int32_t reserved_[4];
+  int32_t model_placement;      /* where the per-frame half of the noise model (AR solves, strength measurements and
+                                   solve: 113 us of one host core per 4K frame) runs.  G1S_MODEL_AUTO: on the host
+                                   threads, unless this handle drives more GPUs than the host has cores for (3 cores
+                                   per GPU), then on the device; G1S_MODEL_HOST; G1S_MODEL_DEVICE (latest_kernel: only
+                                   11 KB digests cross PCIe, no per-frame host work -- what a box with 8 GPUs and 32
+                                   cores needs; costs ~8 % of the GPU).  Results are bit-identical.          */
+  int32_t reserved_[3];
 } g1s_diff_config;
 #define G1S_MAX_DEVICES 8
 

@@ -31,7 +31,7 @@ def test_struct_sizes_match_header():
     # compile-time truth from a tiny C program would need gcc at test time; instead pin the layout we bind
     assert C.sizeof(abi.CSegment) == 8 + 8 + 16 + 8 + 28 + 20 + 20 + 24 + 25 + 25 + 2  # = 184, 8-byte aligned
     assert C.sizeof(abi.CFrame) == 3 * 8 + 3 * 8 + 8
-    assert C.sizeof(abi.CDiffConfig) == 16 + 4 * 27 + 4  # 27 int32 fields, padded to 8
+    assert C.sizeof(abi.CDiffConfig) == 16 + 4 * 27 + 4  # 27 int32 fields (incl. reserved), padded to 8
     from grav1synth_b200.inspect import CStreamInfo
     assert C.sizeof(CStreamInfo) == 16 * 4 + 2 * 8 + 4 * 4   # g1s_stream_info
 

@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 def device_digests(frames, bd, ss, fps, **kw):
     h, w = frames[0][0][0].shape
     # a PRODUCER handle with a digest sink hands out exactly what the device computed; the record tap keeps the records
-    g = D.DiffGenerator(fps[0], fps[1], bd, bd, w, h, ss[0], ss[1], mode=abi.MODE_PRODUCER, **kw)
+    g = D.DiffGenerator(fps[0], fps[1], bd, bd, w, h, ss[0], ss[1], mode=abi.MODE_PRODUCER,
+                        model_placement=abi.MODEL_DEVICE, **kw)
     sink = np.zeros((len(frames), D.digest_bytes() // 8))
     g.set_digest_sink(sink.ctypes.data, len(frames))
     recs = []
@@ -50,10 +51,8 @@ def test_host_model_switch_gives_the_same_table(monkeypatch):
     frames, bd, ss, fps = load_or_skip("segment_cut")
     h, w = frames[0][0][0].shape
     tables = []
-    for host_model in (False, True):
-        if host_model:
-            monkeypatch.setenv("G1S_HOST_MODEL", "1")
-        g = D.DiffGenerator(fps[0], fps[1], bd, bd, w, h, ss[0], ss[1])
+    for place in (abi.MODEL_DEVICE, abi.MODEL_HOST):
+        g = D.DiffGenerator(fps[0], fps[1], bd, bd, w, h, ss[0], ss[1], model_placement=place)
         for s, d in frames:
             g.diff_frame(s, d)
         tables.append(g.finish())

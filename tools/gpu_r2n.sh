@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 cat gpurun_out/pytest_gpu.log
 for hm in 1 0; do
 for st in 1 3; do
-( [ $hm = 1 ] && export G1S_HOST_MODEL=1; G1S_STREAMS=$st timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-strict --no-stats --no-e2e 2>&1 | tail -1 ) > gpurun_out/bench_hm${hm}_$st.log
+( [ $hm = 0 ] && export G1S_DEVICE_MODEL=1; G1S_STREAMS=$st timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-strict --no-stats --no-e2e 2>&1 | tail -1 ) > gpurun_out/bench_hm${hm}_$st.log
 python - <<PY
 import json
 try:
@@ -23,3 +23,5 @@ rows=[r for r in csv.reader(open("gpurun_out/launches_n.csv")) if len(r)>10]
 hdr=rows[0]; k=hdr.index("Kernel Name"); v=hdr.index("Metric Value")
 for r in rows[1:]: print(r[k].split("(")[0][-30:], r[v])
 PY
+G1S_STREAMS=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:latest_kernel -s 1 -c 1 -f -o gpurun_out/prof_latest $CMD > gpurun_out/ncu_latest.log 2>&1
+tail -1 gpurun_out/ncu_latest.log
