@@ -50,7 +50,10 @@ constexpr int kGramWarps = G1S_GRAM_WARPS;
 constexpr int kGramThreads = 32 * kGramWarps;
 constexpr int kMaxObs = 130000;   // observations between two flushes of a warp: bounds the int32 strip accumulators (x 127^2 < 2^31)
 constexpr int kMinRows = 6;       // shortest row window the strip code handles (two opening + three closing pair steps)
-constexpr int kMaxStrip = 64;     // block rows per strip: 64 * 1024 observations * 127^2 < 2^31
+#ifndef G1S_MAX_STRIP
+#define G1S_MAX_STRIP 64
+#endif
+constexpr int kMaxStrip = G1S_MAX_STRIP;  // block rows per strip: 64 * 1024 observations * 127^2 < 2^31
 constexpr int kLumaRows = 35;     // 3 halo rows + 32
 constexpr int kChromaRows = 19;   // 3 halo rows + 16 (residual and luma-tap tiles alike)
 constexpr int kBoxW = 64;         // 16 + 32 + 16 samples: one luma block, or two chroma blocks
@@ -477,22 +480,29 @@ gram_plan_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, uin
 // warps take chunks from a global counter (luma chunks first: the long ones).  Any warp can run any plane -- the k-loop
 // is the same, only the tile geometry differs -- so there is no luma / chroma split to balance, and a CTA that starts
 // late (another stream's kernel was on its SM) simply takes fewer chunks.  A chunk is moved forward to strip boundaries
-// at both ends (a strip's running sums live in one warp's registers).
-constexpr int kChunk = 64;
+// at both ends (a strip's running sums live in one warp's registers).  The PRODUCER side of a warp (descriptor fetch,
+// TMA requests) rolls from one chunk into the next on its own, one chunk claimed ahead, so the consumer side sees one
+// uninterrupted stream of units: chunk boundaries cost no pipeline drain, and chunks can be small.
+#ifndef G1S_CHUNK
+#define G1S_CHUNK 16
+#endif
+constexpr int kChunk = G1S_CHUNK;
+constexpr int kSlot = kChromaSlot;  // stage stride of a warp's tile ring, either plane
+constexpr uint32_t kPlaneShift = 12;  // fifo copy of a descriptor: plane in w2 bits 12..13
+static_assert(kLumaSlot <= kSlot && kSlot * kStages <= kWarpSmem, "stage stride");
 
 __global__ void __launch_bounds__(kGramThreads, 2)
 gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int nframes, const uint8_t *__restrict__ tmaps,
                  const uint4 *__restrict__ plan, int *__restrict__ counts) {
   extern __shared__ __align__(128) uint8_t tiles[];
   __shared__ GramSmem sm;
+  __shared__ int s_incl[3][65];  // [p][f + 1]: units of plane p in frames 0 .. f (a batch has at most 64 frames)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, t = lane & 3;  // mma "groupID" (= cx + 3) and thread-in-group
 
-  // ---- unit counts of the batch: lane l keeps frames l and l + 32 of every plane (a batch has at most 64 frames), as
-  // inclusive prefix sums over the frames
-  int inc_lo[3], inc_hi[3], total[3], nch[3];
-#pragma unroll
-  for (int p = 0; p < 3; ++p) {
+  // ---- unit counts of the batch as prefix sums over the frames (the only CTA-wide step of the kernel)
+  if (warp < 3) {
+    const int p = warp;
     int a = (p < g.planes && lane < nframes) ? counts[lane * 3 + p] : 0;
     int b = (p < g.planes && lane + 32 < nframes) ? counts[(lane + 32) * 3 + p] : 0;
 #pragma unroll
@@ -501,11 +511,12 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
       if (lane >= o) a += va, b += vb;
     }
     const int ta = __shfl_sync(0xffffffffu, a, 31);
-    inc_lo[p] = a, inc_hi[p] = ta + b;
-    total[p] = __shfl_sync(0xffffffffu, ta + b, 31);
-    nch[p] = (total[p] + kChunk - 1) / kChunk;
+    s_incl[p][lane + 1] = a, s_incl[p][lane + 33] = ta + b;
+    if (lane == 0) s_incl[p][0] = 0;
   }
-  const int nchunks = nch[0] + nch[1] + nch[2];
+  __syncthreads();
+  const int nch0 = (s_incl[0][64] + kChunk - 1) / kChunk, nch1 = (s_incl[1][64] + kChunk - 1) / kChunk;
+  const int nchunks = nch0 + nch1 + (s_incl[2][64] + kChunk - 1) / kChunk;
   int *const work = counts + 3 * nframes;  // the chunk counter (zeroed with the counts)
 
   uint8_t *const my_tiles = tiles + warp * kWarpSmem;
@@ -530,130 +541,141 @@ gram_imma_kernel(Geometry g, uint8_t *__restrict__ records, RecordLayout rl, int
   int sh = 8 * ((gq + 1) & 3);
   asm volatile("" : "+r"(sh));  // one register instead of four instructions per funnel shift group
   const int dxw = (gq + 1) >> 2;
-  const bool is7 = gq == 7;
+  // the lane's window word in row 0 of a stage's tile: g = 7 lanes of a chroma unit walk the luma-tap tile
+  const int off_luma = 4 * (kResCol0 + t + dxw);
+  const int off_chroma = gq == 7 ? kOffTap + 4 * (kTapCol0 + t) : off_luma;
 
-  int hstage = 0, tstage = 0;   // TMA ring positions, kept across chunks (the mbarrier phases go on)
-  uint32_t phases = 0;          // bit s: parity to wait for on stage s
-
-  for (;;) {
-    int c = 0;
-    if (lane == 0) c = atomicAdd(work, 1);
-    c = __shfl_sync(0xffffffffu, c, 0);
-    if (c >= nchunks) break;
-    const int plane = c < nch[0] ? 0 : (c < nch[0] + nch[1] ? 1 : 2);
-    const int cl = c - (plane == 0 ? 0 : (plane == 1 ? nch[0] : nch[0] + nch[1]));
-    const bool luma = plane == 0;
-    const int slot = luma ? kLumaSlot : kChromaSlot;
-    // the lane's window word in row 0 of a stage's tile: g = 7 lanes of a chroma chunk walk the luma-tap tile
-    const int lane_off = (!luma && is7) ? kOffTap + 4 * (kTapCol0 + t) : 4 * (kResCol0 + t + dxw);
-    const int my_lo = plane == 0 ? inc_lo[0] : (plane == 1 ? inc_lo[1] : inc_lo[2]);
-    const int my_hi = plane == 0 ? inc_hi[0] : (plane == 1 ? inc_hi[1] : inc_hi[2]);
-    const int tot = plane == 0 ? total[0] : (plane == 1 ? total[1] : total[2]);
-    const int u_lo = cl * kChunk, u_hi = min(tot, u_lo + kChunk);
-    // frame that holds unit u_lo: the first whose inclusive prefix exceeds it
-    const uint32_t in_lo = __ballot_sync(0xffffffffu, my_lo > u_lo), in_hi = __ballot_sync(0xffffffffu, my_hi > u_lo);
-    int pf = in_lo ? __ffs(in_lo) - 1 : 32 + __ffs(in_hi) - 1;
-    auto incl_of = [&](int f) { return __shfl_sync(0xffffffffu, f < 32 ? my_lo : my_hi, f & 31); };
-    int pend = incl_of(pf);                                  // unit index one past frame pf
-    int pbeg = pf == 0 ? 0 : incl_of(pf - 1);                // first unit index of frame pf
-    int u = u_lo;                                            // unit index of the next descriptor
-    auto unit_at = [&](int f, int i) { return __ldg(plan + ((size_t)f * 3 + plane) * g.nb + i); };
-    auto advance = [&]() {  // to the next unit; false past the end of the plane's list
-      if (++u >= tot) return false;
-      while (u >= pend) pbeg = pend, ++pf, pend = incl_of(pf);
-      return true;
-    };
-    bool more = true;
-    uint4 dn = unit_at(pf, u - pbeg);                   // descriptor of the next unit to request
-    while (more && !(dn.y & kFirst)) {                  // skip the tail of a strip that started in the previous chunk
-      more = advance();
-      if (more) dn = unit_at(pf, u - pbeg);
-    }
-    if (!more || u >= u_hi) continue;
-
-    // Gram blocks -> the frame's int64 record, straight from registers: element r of block (q', dy) in lane (gq, t)
-    // is the product of the later tap (q', g' = gq) with the earlier tap (q' - dy, g = 2t + r).
-    auto flush = [&](int f) {
-      uint8_t *rec = records + (size_t)f * rl.bytes;
-      unsigned long long *gram = reinterpret_cast<unsigned long long *>(rec + rl.off_gram) + (size_t)plane * kPairs;
+  // Gram blocks -> the frame's int64 record, straight from registers: element r of block (q', dy) in lane (gq, t)
+  // is the product of the later tap (q', g' = gq) with the earlier tap (q' - dy, g = 2t + r).
+  auto flush = [&](int f, int plane) {
+    uint8_t *rec = records + (size_t)f * rl.bytes;
+    unsigned long long *gram = reinterpret_cast<unsigned long long *>(rec + rl.off_gram) + (size_t)plane * kPairs;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int dy = 0; dy <= q; ++dy)
+      for (int dy = 0; dy <= q; ++dy)
 #pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            const int v = (int)G[gidx(q, dy)][r];
-            G[gidx(q, dy)][r] = 0u;
-            emit(gram, 8 * (q - dy) + 2 * t + r, 8 * q + gq, v, !luma);
-          }
-    };
+        for (int r = 0; r < 2; ++r) {
+          const int v = (int)G[gidx(q, dy)][r];
+          G[gidx(q, dy)][r] = 0u;
+          emit(gram, 8 * (q - dy) + 2 * t + r, 8 * q + gq, v, plane != 0);
+        }
+  };
 
-    // ---- producer side: request the next unit's tile(s), queue its descriptor; the one after it is fetched meanwhile
-    int head = 0, tail = 0;       // fifo positions of this chunk (units requested / consumed)
-    auto produce = [&]() {        // false when the chunk is exhausted
-      if (!more || (u >= u_hi && (dn.y & kFirst))) {
-        more = false;
+  // ---- producer side.  Position: unit u of the plane's list (all frames), which is unit u - pbeg of frame pf;
+  // `more`: dn is the descriptor of a unit this warp still has to request.
+  int nextc = 0;  // lane 0: the chunk claimed ahead
+  if (lane == 0) nextc = atomicAdd(work, 1);
+  int pplane = 0, pf = 0, pbeg = 0, pend = 0, u = 0, u_hi = 0, tot = 0;
+  bool more = false, done = false;
+  uint4 dn = make_uint4(0u, 0u, 0u, 0u);
+  auto unit_at = [&](int f, int i) { return __ldg(plan + ((size_t)f * 3 + pplane) * g.nb + i); };
+  auto next_chunk = [&]() {  // to the first strip start of the next chunk that has one; false when the work is out
+    for (;;) {
+      const int c = __shfl_sync(0xffffffffu, nextc, 0);
+      if (c >= nchunks) {
+        done = true;
         return false;
       }
-      const uint4 d = dn;
-      const int stage = hstage;
-      if (++hstage == kStages) hstage = 0;
-      if (lane == 0) {
-        sm.fifo[warp][head & 3] = d;
-        const int f = d.x & 255, col = (d.x >> 8) & 4095, by = d.x >> 20;
-        const uint8_t *fmaps = tmaps + (size_t)f * kResidualMaps * 128;
-        uint8_t *st = my_tiles + stage * slot;
-        uint64_t *bar = &sm.full[warp][stage];
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this warp's reads of the stage precede the refill
-        if (luma) {
-          mbar_expect_tx(bar, kLumaBytes);
-          tma_load_2d(st, fmaps, 32 * col - 16, 32 * by - 3, bar);
-        } else {
-          const int cx = 32 * col - 16, cy = 16 * by - 3;
-          mbar_expect_tx(bar, 2 * kChromaBytes);
-          tma_load_2d(st, fmaps + plane * 128, cx, cy, bar);
-          tma_load_2d(st + kOffTap, fmaps + 3 * 128, cx, cy, bar);
+      if (lane == 0) nextc = atomicAdd(work, 1);
+      pplane = c < nch0 ? 0 : (c < nch0 + nch1 ? 1 : 2);
+      const int *incl = s_incl[pplane];
+      tot = incl[64];
+      u = (c - (pplane == 0 ? 0 : (pplane == 1 ? nch0 : nch0 + nch1))) * kChunk;
+      u_hi = min(tot, u + kChunk);
+      // frame that holds unit u: the first whose inclusive prefix exceeds it
+      const uint32_t in_lo = __ballot_sync(0xffffffffu, incl[lane + 1] > u);
+      const uint32_t in_hi = __ballot_sync(0xffffffffu, incl[lane + 33] > u);
+      pf = in_lo ? __ffs(in_lo) - 1 : 32 + __ffs(in_hi) - 1;
+      pbeg = incl[pf], pend = incl[pf + 1];
+      // a strip that started in the previous chunk belongs to that chunk's warp: 32 descriptors per look
+      while (u < u_hi) {
+        const int lim = min(pend, u_hi), i = u + lane;
+        uint32_t w1 = 0u;
+        if (i < lim) w1 = __ldg(reinterpret_cast<const uint32_t *>(plan + ((size_t)pf * 3 + pplane) * g.nb + (i - pbeg)) + 1);
+        const uint32_t m = __ballot_sync(0xffffffffu, (w1 & kFirst) != 0u);
+        if (m) {
+          u += __ffs(m) - 1;
+          dn = unit_at(pf, u - pbeg);
+          more = true;
+          return true;
         }
+        u = min(u + 32, lim);
+        while (u >= pend && u < u_hi) pbeg = pend, ++pf, pend = incl[pf + 1];
       }
-      ++head;
-      more = advance();
-      if (more) dn = unit_at(pf, u - pbeg);
-      return true;
-    };
-
-    int cf = -1;     // frame the strip accumulators belong to
-    int since = 0;   // observations accumulated since the last flush
-    int ph = 0;      // ring phase, carried from unit to unit inside a strip
-    for (;;) {
-      __syncwarp();  // every lane is done with the stage about to be refilled
-      while (head - tail < kStages && produce()) {
-      }
-      if (head == tail) break;
-      __syncwarp();
-      const uint4 d = sm.fifo[warp][tail & 3];
-      const int stage = tstage;
-      if (++tstage == kStages) tstage = 0;
-      ++tail;
-      const bool first = d.y & kFirst;
-      if (first) {  // G only changes at strip ends, so strip starts are the flush points
-        const int f = d.x & 255;
-        if (f != cf || since + (int)d.w > kMaxObs) {
-          if (cf >= 0) flush(cf);
-          cf = f;
-          since = 0;
-        }
-        since += (int)d.w;
-      }
-      mbar_wait(&sm.full[warp][stage], (phases >> stage) & 1u);
-      phases ^= 1u << stage;
-      const int r0 = d.y & 63, np = (d.y >> 6) & 63;
-      const int lo0 = (d.y >> 16) & 63, hi0 = (d.y >> 22) & 63, lo1 = d.z & 63, hi1 = (d.z >> 6) & 63;
-      const uint32_t mx[2] = {byte_mask(4 * t, lo0, hi0), byte_mask(16 + 4 * t, lo1, hi1)};
-      const uint32_t *p = reinterpret_cast<const uint32_t *>(my_tiles + stage * slot + lane_off) + r0 * kRowWords;
-      unit_rows(p, sh, np, first, d.y & kLast, d.y & kOdd, mx, ph, ring, acc, G);
     }
-    if (cf >= 0) flush(cf);
+  };
+
+  int head = 0, tail = 0;       // fifo positions (units requested / consumed)
+  int hstage = 0, tstage = 0;   // their stages ( = position % kStages, kept incrementally)
+  uint32_t phases = 0;          // bit s: parity to wait for on stage s
+  auto produce = [&]() {        // false when the work is out
+    if (!more && (done || !next_chunk())) return false;
+    const uint4 d = dn;
+    const int stage = hstage;
+    if (++hstage == kStages) hstage = 0;
+    if (lane == 0) {
+      sm.fifo[warp][head & 3] = make_uint4(d.x, d.y, d.z | ((uint32_t)pplane << kPlaneShift), d.w);
+      const int f = d.x & 255, col = (d.x >> 8) & 4095, by = d.x >> 20;
+      const uint8_t *fmaps = tmaps + (size_t)f * kResidualMaps * 128;
+      uint8_t *st = my_tiles + stage * kSlot;
+      uint64_t *bar = &sm.full[warp][stage];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this warp's reads of the stage precede the refill
+      if (pplane == 0) {
+        mbar_expect_tx(bar, kLumaBytes);
+        tma_load_2d(st, fmaps, 32 * col - 16, 32 * by - 3, bar);
+      } else {
+        const int cx = 32 * col - 16, cy = 16 * by - 3;
+        mbar_expect_tx(bar, 2 * kChromaBytes);
+        tma_load_2d(st, fmaps + pplane * 128, cx, cy, bar);
+        tma_load_2d(st + kOffTap, fmaps + 3 * 128, cx, cy, bar);
+      }
+    }
+    ++head;
+    // the next unit of the chunk: the units up to u_hi, then the rest of the strip that crosses u_hi
+    more = false;
+    if (++u < tot) {
+      while (u >= pend) pbeg = pend, ++pf, pend = s_incl[pplane][pf + 1];
+      dn = unit_at(pf, u - pbeg);
+      more = u < u_hi || !(dn.y & kFirst);
+    }
+    return true;
+  };
+
+  int cf = -1, cplane = 0;  // frame and plane the strip accumulators belong to
+  int since = 0;            // observations accumulated since the last flush
+  int ph = 0;               // ring phase, carried from unit to unit inside a strip
+  for (;;) {
+    __syncwarp();  // every lane is done with the stage about to be refilled
+    while (head - tail < kStages && produce()) {
+    }
+    if (head == tail) break;
+    __syncwarp();
+    const uint4 d = sm.fifo[warp][tail & 3];
+    const int stage = tstage;
+    if (++tstage == kStages) tstage = 0;
+    ++tail;
+    const bool first = d.y & kFirst;
+    const int plane = (d.z >> kPlaneShift) & 3;
+    if (first) {  // G only changes at strip ends, so strip starts are the flush points
+      const int f = d.x & 255;
+      if (f != cf || plane != cplane || since + (int)d.w > kMaxObs) {
+        if (cf >= 0) flush(cf, cplane);
+        cf = f, cplane = plane;
+        since = 0;
+      }
+      since += (int)d.w;
+    }
+    mbar_wait(&sm.full[warp][stage], (phases >> stage) & 1u);
+    phases ^= 1u << stage;
+    const int r0 = d.y & 63, np = (d.y >> 6) & 63;
+    const int lo0 = (d.y >> 16) & 63, hi0 = (d.y >> 22) & 63, lo1 = d.z & 63, hi1 = (d.z >> 6) & 63;
+    const uint32_t mx[2] = {byte_mask(4 * t, lo0, hi0), byte_mask(16 + 4 * t, lo1, hi1)};
+    const uint32_t *p =
+        reinterpret_cast<const uint32_t *>(my_tiles + stage * kSlot + (plane == 0 ? off_luma : off_chroma)) + r0 * kRowWords;
+    unit_rows(p, sh, np, first, d.y & kLast, d.y & kOdd, mx, ph, ring, acc, G);
   }
+  if (cf >= 0) flush(cf, cplane);
 }
 
 }  // namespace
