@@ -115,9 +115,12 @@ def main(argv=None) -> int:
         if not 8 <= bd <= 16:
             raise SystemExit("Bit depths not between 8-16 are not currently supported")  # src/main.rs:516
     # the engine is sized for the frames it will see: the denoised clip's size (the source is filtered to it)
+    # y4m planes are ordinary host memory: samples wider than 8 bits are reduced while they are staged (the kernels'
+    # first step anyway, util.rs::frame_into_u8) so that half the bytes cross PCIe; the filter chain needs the full samples
+    narrow = max(sd.bit_depth, dd.bit_depth) > 8 and not (chain is not None and chain.filters)
     differ = DiffGenerator(sd.fps_num, sd.fps_den, sd.bit_depth, dd.bit_depth, dd.width, dd.height, sd.ss_x, sd.ss_y,
                            monochrome=sd.monochrome, device=args.device, devices=parse_devices(args.devices),
-                           gram_order=1 if args.strict else 0)
+                           gram_order=1 if args.strict else 0, host_narrow=narrow)
     if chain is not None and chain.filters:
         # source only, src/main.rs:621-624: the chain runs on the device between the upload and the kernels
         try:

@@ -9,6 +9,9 @@
 // the records of slot k-1 are folded into the model.  There is no CPU fallback: every
 // device failure is reported as G1S_E_CUDA.
 #include <cuda.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -693,7 +696,7 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   {
     int threads = cfg->host_threads;
     if (const char *e = std::getenv("G1S_HOST_THREADS")) threads = std::atoi(e);
-    if (threads <= 0) threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (threads <= 0) threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));  // staging copies want them all
     d->pool.reset(new HostPool(threads));
     d->folder.reset(new FoldQueue());
   }
@@ -828,11 +831,31 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
   return G1S_OK;
 }
 
-// util.rs::frame_into_u8 on one row: `(v >> (bit_depth - 8)) as u8`, vectorised by the compiler for the host's ISA.
-extern "C" __attribute__((target_clones("arch=skylake-avx512", "avx2", "default"))) void g1s_narrow_row(uint8_t *dst,
-                                                                                              const uint16_t *src, int n,
-                                                                                              int shift) {
+// util.rs::frame_into_u8 on one row: `(v >> (bit_depth - 8)) as u8`.  The destination is the pinned staging ring, which
+// nothing reads before the DMA engine does: where the host has AVX-512BW the bytes go out with non-temporal stores (no
+// read-for-ownership of the destination lines: a third less memory traffic on a copy that is memory bound).
+extern "C" __attribute__((target_clones("avx2", "default"))) void g1s_narrow_row_plain(uint8_t *dst, const uint16_t *src,
+                                                                                       int n, int shift) {
   for (int i = 0; i < n; ++i) dst[i] = (uint8_t)(src[i] >> shift);
+}
+#if defined(__x86_64__)
+__attribute__((target("avx512f,avx512bw"))) static void narrow_row_avx512(uint8_t *dst, const uint16_t *src, int n, int shift) {
+  int i = 0;
+  while (i < n && ((uintptr_t)(dst + i) & 31)) dst[i] = (uint8_t)(src[i] >> shift), ++i;
+  const __m128i sh = _mm_cvtsi32_si128(shift);
+  for (; i + 32 <= n; i += 32) {
+    const __m512i v = _mm512_srl_epi16(_mm512_loadu_si512(src + i), sh);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), _mm512_cvtepi16_epi8(v));
+  }
+  for (; i < n; ++i) dst[i] = (uint8_t)(src[i] >> shift);
+}
+#endif
+extern "C" void g1s_narrow_row(uint8_t *dst, const uint16_t *src, int n, int shift) {
+#if defined(__x86_64__)
+  static const bool wide = __builtin_cpu_supports("avx512bw") && !std::getenv("G1S_NO_STREAM_STORES");
+  if (wide) return narrow_row_avx512(dst, src, n, shift);
+#endif
+  g1s_narrow_row_plain(dst, src, n, shift);
 }
 
 int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *denoised) {
@@ -977,6 +1000,9 @@ int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *d
       for (int y = 0; y < t.rows; ++y)
         g1s_narrow_row(t.dst + (size_t)y * t.dst_pitch, reinterpret_cast<const uint16_t *>(t.src + (size_t)y * t.src_pitch),
                        t.width, t.narrow_shift);
+#if defined(__x86_64__)
+      _mm_sfence();  // the streaming stores of this task are visible before the task counts as done
+#endif
     } else if (t.dst_pitch == t.src_pitch) {
       std::memcpy(t.dst, t.src, t.dst_pitch * (size_t)(t.rows - 1) + t.row_bytes);
     } else {

@@ -101,7 +101,21 @@ __device__ __forceinline__ double exp_fixed(double x) {
 //     ring laid out [row][x][thread] (conflict-free: consecutive lanes touch consecutive doubles);
 //     row y+1 is produced on the fly and overwrites row y-1 in the same step that reads it.
 
-constexpr int kFlatThreads = 128;
+// Shared-memory bandwidth bounds this kernel next to the FP64 pipe (per sample: two table lookups, two ring loads, one
+// ring store, all 64-bit), and latency next to that (12 warps per SM: 8 measured 21.2 us per frame, 12 15.7).  A single
+// 256-entry table costs ~6 wavefronts per lookup (32 lanes, random entries, 16 bank pairs); kLutCopies = 16 interleaved
+// copies give every lane of a half-warp its own bank pair: 2 wavefronts, the minimum.  One CTA of 384 threads per SM
+// keeps the 12 warps per SM of the earlier 3 x 128 layout with one table instead of three: 192 KB ring + 32 KB table
+// (measured: 17.7 -> 15.7 us per frame; 8 copies 17.0).  Keeping the two residual rows in registers instead of the ring
+// was tried and lost (128 registers of rows: spills, or 8 warps per SM: 20 us and more).
+#ifndef G1S_FLAT_THREADS
+#define G1S_FLAT_THREADS 384
+#endif
+#ifndef G1S_FLAT_LUT
+#define G1S_FLAT_LUT 16
+#endif
+constexpr int kFlatThreads = G1S_FLAT_THREADS;
+constexpr int kLutCopies = G1S_FLAT_LUT;
 
 #ifndef G1S_FLAT_PF
 #define G1S_FLAT_PF 0
@@ -142,7 +156,7 @@ __device__ __forceinline__ void load8(const uint8_t *__restrict__ row, int x0, i
 }
 
 // One 8-sample chunk as loaded (16 bytes of u16 or 8 bytes of u8); blocks that lie fully inside an
-// aligned frame run one chunk ahead of the arithmetic so the load latency hides behind ~200 instructions.
+// aligned frame run one block row (four chunks) ahead of the arithmetic.
 template <int SB>
 struct RawChunk {
   uint32_t q[SB == 2 ? 4 : 2];
@@ -181,11 +195,11 @@ __global__ void __launch_bounds__(kFlatThreads)
 flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry g, FlatConsts fc,
                      uint8_t *__restrict__ records, RecordLayout rl, int aligned, const uint8_t *__restrict__ y8,
                      size_t y8_frame_bytes, uint32_t y8_pitch) {
-  extern __shared__ double fsm[];  // lut[256] | ring[2][32][kFlatThreads]
-  double *lut = fsm;
-  double *ring = fsm + 256;
-  for (int i = threadIdx.x; i < 256; i += kFlatThreads) lut[i] = __ddiv_rn((double)i, 255.0);
+  extern __shared__ double fsm[];  // lut[256][kLutCopies] | ring[2][32][kFlatThreads]
+  double *ring = fsm + 256 * kLutCopies;
+  for (int i = threadIdx.x; i < 256 * kLutCopies; i += kFlatThreads) fsm[i] = __ddiv_rn((double)(i / kLutCopies), 255.0);
   __syncthreads();
+  const double *lut = fsm + (threadIdx.x % kLutCopies);  // this lane's copy: entry p at lut[p * kLutCopies]
 
   const int gid = blockIdx.x * kFlatThreads + threadIdx.x;
   const int total = nframes * g.nb;
@@ -207,8 +221,13 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
   const bool fastblk = vec_ok && x0 + kBlock <= w;  // every chunk is one aligned vector load
   const uint8_t *blk0 = src + (size_t)x0 * SB;       // first sample of the block's columns in row 0 of the frame
-  RawChunk<SB> nxt;
-  if (fastblk) nxt = fetch_chunk<SB>(blk0 + (size_t)min(y0, h - 1) * stride);
+  // samples run one block row ahead of the arithmetic (the 8-bit plane of a batch is larger than L2: these loads come
+  // from DRAM): chunk c of the next row is requested when chunk c of this row is taken
+  RawChunk<SB> ahead[4];
+  if (fastblk) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ahead[c] = fetch_chunk<SB>(blk0 + (size_t)min(y0, h - 1) * stride + (size_t)(8 * c) * SB);
+  }
 #pragma unroll 1
   for (int yi = 0; yi < kBlock; ++yi) {
     const double yd = (double)(yi - 16) * 0.0625;
@@ -220,8 +239,8 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
     for (int c = 0; c < 4; ++c) {
       int p[8];
       if (fastblk) {
-        const RawChunk<SB> cur = nxt;
-        nxt = fetch_chunk<SB>(c < 3 ? row + (size_t)(x0 + 8 * (c + 1)) * SB : rown);
+        const RawChunk<SB> cur = ahead[c];
+        ahead[c] = fetch_chunk<SB>(rown + (size_t)(8 * c) * SB);
         unpack_chunk<SB>(cur, shift, p);
       } else {
         load8<SB>(row, x0 + 8 * c, w, shift, vec_ok, p);
@@ -229,7 +248,7 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const double xd = (double)(8 * c + i - 16) * 0.0625;
-        const double v = lut[p[i]];
+        const double v = lut[p[i] * kLutCopies];
         s0 = __dadd_rn(s0, __dmul_rn(v, yd));
         s1 = __dadd_rn(s1, __dmul_rn(v, xd));
         s2 = __dadd_rn(s2, v);  // v * 1.0 is exact
@@ -250,7 +269,7 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
     const double xd = (double)(xi - 16) * 0.0625;
     double fit = __dadd_rn(ty, __dmul_rn(xd, pc[1]));
     fit = __dadd_rn(fit, pc[2]);  // 1.0 * pc[2] is exact
-    return __dsub_rn(lut[pv], fit);
+    return __dsub_rn(lut[pv * kLutCopies], fit);
   };
   auto row_ty = [&](int yi) -> double {
     const double yd = (double)(yi - 16) * 0.0625;
@@ -272,7 +291,10 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
   }
   // sums of (r-l)^2, (r-l)(d-u), (d-u)^2: the reference's Gxx, Gxy, Gyy are exactly 0.25 times these
   double Dxx = 0, Dxy = 0, Dyy = 0, var = 0, mean = 0;
-  if (fastblk) nxt = fetch_chunk<SB>(blk0 + (size_t)min(y0 + 2, h - 1) * stride);
+  if (fastblk) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ahead[c] = fetch_chunk<SB>(blk0 + (size_t)min(y0 + 2, h - 1) * stride + (size_t)(8 * c) * SB);
+  }
 #pragma unroll 1
   for (int yi = 1; yi < kBlock - 1; ++yi) {
     const double ty = row_ty(yi + 1);
@@ -287,8 +309,8 @@ flat_features_kernel(const FrameDesc *__restrict__ frames, int nframes, Geometry
     for (int c = 0; c < 4; ++c) {
       int p[8];
       if (fastblk) {
-        const RawChunk<SB> curc = nxt;
-        nxt = fetch_chunk<SB>(c < 3 ? row + (size_t)(x0 + 8 * (c + 1)) * SB : rown);
+        const RawChunk<SB> curc = ahead[c];
+        ahead[c] = fetch_chunk<SB>(rown + (size_t)(8 * c) * SB);
         unpack_chunk<SB>(curc, shift, p);
       } else {
         load8<SB>(row, x0 + 8 * c, w, shift, vec_ok, p);
@@ -350,7 +372,7 @@ void launch_flat_features(const FrameDesc *frames, int nframes, const Geometry &
                           size_t y8_frame_bytes, uint32_t y8_pitch) {
   const int total = nframes * g.nb;
   const int grid = (total + kFlatThreads - 1) / kFlatThreads;
-  const size_t smem = sizeof(double) * (256 + 2 * kBlock * kFlatThreads);
+  const size_t smem = sizeof(double) * (256 * kLutCopies + 2 * kBlock * kFlatThreads);
   static bool attr_set[64] = {false};  // the attribute is a per-device property of the function
   int dev = 0;
   cudaGetDevice(&dev);

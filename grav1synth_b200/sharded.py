@@ -43,8 +43,10 @@ class ShardedDiff:
                 # with fewer (8 GPUs on 32 cores) the device evaluates it (latest_kernel) and only digests come back
                 import os
                 model_placement = abi.MODEL_DEVICE if 3 * self.world > (os.cpu_count() or 2) // 2 else abi.MODEL_HOST
+            import os
             self.producer = DiffGenerator(*args, device=device or 0, batch_frames=batch_frames,
-                                          mode=abi.MODE_PRODUCER, model_placement=model_placement)
+                                          mode=abi.MODE_PRODUCER, model_placement=model_placement,
+                                          host_threads=max(2, min(16, (os.cpu_count() or 2) // self.world)))
         backend = dist.get_backend(group) if dist.is_initialized() else "none"
         self.on_gpu = backend == "nccl"
         # the producer writes digests straight into this ring (pinned when a GPU is involved)
