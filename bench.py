@@ -558,6 +558,12 @@ def main():
                         "d2h_bytes_per_step": F * rb, "records_bytes_per_frame": rb, "frames_per_step": F, "steps": n_e2e,
                         "host_memory": "pageable planes, reduced to 8 bits into the engine's pinned ring by its host threads "
                                        "(cfg.host_narrow), DMA from there", "api": api}
+                try:
+                    e_nr["narrow_isa"] = {0: "compiler loop", 1: "avx2 + streaming stores", 2: "avx512bw + streaming stores"}[
+                        int(D.lib().g1s_narrow_isa())]
+                    e_nr["host_threads"] = min(16, os.cpu_count() or 1)
+                except Exception:
+                    pass
                 line["e2e_host_narrow"] = e_nr
                 line["e2e_pinned_direct"] = e_pin
                 if v_nr > v_pin:

@@ -850,12 +850,43 @@ __attribute__((target("avx512f,avx512bw"))) static void narrow_row_avx512(uint8_
   for (; i < n; ++i) dst[i] = (uint8_t)(src[i] >> shift);
 }
 #endif
-extern "C" void g1s_narrow_row(uint8_t *dst, const uint16_t *src, int n, int shift) {
 #if defined(__x86_64__)
-  static const bool wide = __builtin_cpu_supports("avx512bw") && !std::getenv("G1S_NO_STREAM_STORES");
-  if (wide) return narrow_row_avx512(dst, src, n, shift);
+__attribute__((target("avx2"))) static void narrow_row_avx2(uint8_t *dst, const uint16_t *src, int n, int shift) {
+  int i = 0;
+  while (i < n && ((uintptr_t)(dst + i) & 31)) dst[i] = (uint8_t)(src[i] >> shift), ++i;
+  const __m128i sh = _mm_cvtsi32_si128(shift);
+  const __m256i low = _mm256_set1_epi16(0x00ff);  // `as u8` truncates; the pack below saturates
+  for (; i + 32 <= n; i += 32) {
+    const __m256i a = _mm256_and_si256(_mm256_srl_epi16(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i)), sh), low);
+    const __m256i b = _mm256_and_si256(_mm256_srl_epi16(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 16)), sh), low);
+    _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), _mm256_permute4x64_epi64(_mm256_packus_epi16(a, b), 0xd8));
+  }
+  for (; i < n; ++i) dst[i] = (uint8_t)(src[i] >> shift);
+}
+#endif
+// 2: AVX-512BW, 1: AVX2 (both with streaming stores), 0: the compiler's loop
+extern "C" int g1s_narrow_isa(void) {
+#if defined(__x86_64__)
+  static const int isa = std::getenv("G1S_NO_STREAM_STORES") ? 0
+                         : __builtin_cpu_supports("avx512bw") ? 2
+                         : __builtin_cpu_supports("avx2")     ? 1
+                                                              : 0;
+  return isa;
+#else
+  return 0;
+#endif
+}
+// (isa: a path at or below what g1s_narrow_isa() reports; the tests walk them all)
+extern "C" void g1s_narrow_row_with(uint8_t *dst, const uint16_t *src, int n, int shift, int isa) {
+#if defined(__x86_64__)
+  isa = std::min(isa, g1s_narrow_isa());
+  if (isa == 2) return narrow_row_avx512(dst, src, n, shift);
+  if (isa == 1) return narrow_row_avx2(dst, src, n, shift);
 #endif
   g1s_narrow_row_plain(dst, src, n, shift);
+}
+extern "C" void g1s_narrow_row(uint8_t *dst, const uint16_t *src, int n, int shift) {
+  g1s_narrow_row_with(dst, src, n, shift, 2);
 }
 
 int g1s_diff_push_frame(g1s_diff *d, const g1s_frame *source, const g1s_frame *denoised) {

@@ -20,19 +20,62 @@ constexpr int kNumBins = 20;
 constexpr uint16_t kDefaultGrainSeed = 10956;
 
 // util.rs::linsolve (libaom mathutils.h): elimination with adjacent-row pivot bubbling.
-// (row updates are element-wise independent, so wider vectors change nothing but the speed)
+// What is restructured is exact by construction: the multipliers of one pivot are independent of each other (divided
+// out first, as a vectorisable loop), and the columns left of the pivot are not updated (the reference turns them into
+// values that nothing reads again: the bubble pass, the multipliers and the back substitution only look at columns
+// >= the pivot's).  Every value that reaches x goes through the same operations on the same operands.
+constexpr int kGaussStride = 32;  // row stride of the working copy: rows [A | b | padding], whole 8-lane vectors
+
+__attribute__((target_clones("avx512f", "avx2", "default"))) bool gauss_small(int n, const double *A, const double *b, double *x) {
+  alignas(64) double M[kGaussStride - 1][kGaussStride];
+  double cv[kGaussStride];
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) M[i][j] = A[i * n + j];
+    M[i][n] = b[i];
+    for (int j = n + 1; j < kGaussStride; ++j) M[i][j] = 0.0;
+  }
+  const int jend = (n + 1 + 7) & ~7;
+  for (int k = 0; k + 1 < n; ++k) {
+    const int j0 = k & ~7;
+    for (int i = n - 1; i > k; --i) {
+      if (std::fabs(M[i - 1][k]) < std::fabs(M[i][k])) {
+        for (int j = j0; j < jend; ++j) std::swap(M[i][j], M[i - 1][j]);
+      }
+    }
+    const double piv = M[k][k];
+    if (std::fabs(piv) < kTiny) return false;
+    const int m = n - 1 - k;
+    for (int r = 0; r < m; ++r) cv[r] = M[k + 1 + r][k] / piv;
+    const double *pk = M[k];
+    for (int r = 0; r < m; ++r) {
+      double *row = M[k + 1 + r];
+      const double c = cv[r];
+      for (int j = j0; j < jend; j += 8)
+        for (int t = 0; t < 8; ++t) row[j + t] -= c * pk[j + t];
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    if (std::fabs(M[i][i]) < kTiny) return false;
+    double c = 0;
+    for (int j = i + 1; j < n; ++j) c += M[i][j] * x[j];
+    x[i] = (M[i][n] - c) / M[i][i];
+  }
+  return true;
+}
+
 __attribute__((target_clones("avx512f", "avx2", "default"))) bool gauss_solve(int n, double *A, double *b, double *x) {
+  if (n + 1 <= kGaussStride) return gauss_small(n, A, b, x);
   for (int k = 0; k + 1 < n; ++k) {
     for (int i = n - 1; i > k; --i) {
       if (std::fabs(A[(i - 1) * n + k]) < std::fabs(A[i * n + k])) {
-        std::swap_ranges(A + i * n, A + i * n + n, A + (i - 1) * n);
+        std::swap_ranges(A + i * n + k, A + i * n + n, A + (i - 1) * n + k);
         std::swap(b[i], b[i - 1]);
       }
     }
     for (int i = k; i + 1 < n; ++i) {
       if (std::fabs(A[k * n + k]) < kTiny) return false;
       const double c = A[(i + 1) * n + k] / A[k * n + k];
-      for (int j = 0; j < n; ++j) A[(i + 1) * n + j] -= c * A[k * n + j];
+      for (int j = k; j < n; ++j) A[(i + 1) * n + j] -= c * A[k * n + j];
       b[i + 1] -= c * b[k];
     }
   }
@@ -45,6 +88,52 @@ __attribute__((target_clones("avx512f", "avx2", "default"))) bool gauss_solve(in
   return true;
 }
 
+// The same elimination on a TRIDIAGONAL system (the noise strength equations: add_measurement touches (i0, i0),
+// (i0, i1), (i1, i0), (i1, i1) with i1 <= i0 + 1, the regulariser the three diagonals).  As long as the bubble pass
+// finds nothing to swap -- only row k + 1 has a non-zero in column k, so that is one comparison per pivot -- every row
+// below k + 1 gets the multiplier 0 / pivot = 0 and is left as it is (x - 0 * y == x for the finite y here), and row
+// k + 1 only changes in columns k + 1 (row k is zero beyond it).  Returns 0 when a swap would be needed (the caller then
+// runs the dense routine on the untouched inputs), 1 solved, -1 the reference's failure.
+int tridiagonal_solve(int n, const double *A, const double *b, double *x) {
+  double d[32], u[32], r[32];  // diagonal, superdiagonal, right-hand side of the eliminated system
+  if (n > 32) return 0;
+  for (int i = 0; i < n; ++i) d[i] = A[i * n + i], u[i] = i + 1 < n ? A[i * n + i + 1] : 0.0, r[i] = b[i];
+  for (int k = 0; k + 1 < n; ++k) {
+    const double sub = A[(k + 1) * n + k];
+    if (std::fabs(d[k]) < std::fabs(sub)) return 0;
+    if (std::fabs(d[k]) < kTiny) return -1;
+    const double c = sub / d[k];
+    d[k + 1] -= c * u[k];
+    r[k + 1] -= c * r[k];
+  }
+  double xs[32];
+  for (int i = n - 1; i >= 0; --i) {
+    if (std::fabs(d[i]) < kTiny) {
+      for (int j = i + 1; j < n; ++j) x[j] = xs[j];  // the reference has written these before it fails
+      return -1;
+    }
+    // c = 0 + u[i] * x[i+1] + 0 * x[i+2] + ...: the zero products add +0.0 to a sum that is not -0
+    double c = 0;
+    if (i + 1 < n) c += u[i] * xs[i + 1];
+    xs[i] = (r[i] - c) / d[i];
+  }
+  for (int i = 0; i < n; ++i) x[i] = xs[i];
+  return 1;
+}
+
+}  // namespace
+
+// Test hook (include/g1s.h): the linear solvers of the host model on caller data.  which: 0 the elimination as the
+// model runs it (small systems take gauss_small), 1 the tridiagonal fast path alone.  Returns 1 solved, -1 failed,
+// 0 (tridiagonal only) a row swap would be needed.  A and b are left untouched.
+extern "C" int g1s_linsolve_probe(int which, int n, const double *A, const double *b, double *x) {
+  if (n <= 0 || !A || !b || !x) return -2;
+  if (which == 1) return tridiagonal_solve(n, A, b, x);
+  std::vector<double> Ac(A, A + (size_t)n * n), bc(b, b + n);
+  return gauss_solve(n, Ac.data(), bc.data(), x) ? 1 : -1;
+}
+
+namespace {
 inline int pair_index(int i, int j) {  // i <= j, row-major upper triangle of a 26x26 matrix
   return i * kTaps - i * (i - 1) / 2 + (j - i);
 }
@@ -139,6 +228,18 @@ bool StrengthSolver::solve_bumped() {
     Ar[i * n + hi] -= alpha;
   }
   for (int i = 0; i < n; ++i) Ar[i * n + i] += 1.0 / 8192.;
+  // the system is tridiagonal (see tridiagonal_solve); checked, not assumed: a state restored from elsewhere could differ
+  bool banded = true;
+  for (int i = 0; i < n && banded; ++i)
+    for (int j = 0; j < n; ++j)
+      if ((j < i - 1 || j > i + 1) && Ar[i * n + j] != 0.0) {
+        banded = false;
+        break;
+      }
+  if (banded) {
+    const int rc = tridiagonal_solve(n, Ar.data(), eqns.b.data(), eqns.x.data());
+    if (rc != 0) return rc > 0;
+  }
   br.assign(eqns.b.begin(), eqns.b.end());  // elimination consumes its inputs
   return gauss_solve(n, Ar.data(), br.data(), eqns.x.data());
 }

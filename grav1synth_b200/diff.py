@@ -31,7 +31,7 @@ EXPORTS = [
     "g1s_diff_get_counters", "g1s_diff_mark", "g1s_diff_marks_elapsed_ms", "g1s_record_layout", "g1s_record_gramf_offset", "g1s_diff_record_bytes", "g1s_diff_set_record_tap",
     "g1s_diff_consume_record", "g1s_diff_consume_records", "g1s_digest_bytes", "g1s_diff_set_digest_sink",
     "g1s_diff_digest_count", "g1s_diff_wait_retired", "g1s_diff_consume_digests", "g1s_diff_consume_digests_borrowed", "g1s_diff_digest_from_record", "g1s_write_grain_table", "g1s_format_grain_table",
-    "g1s_narrow_row", "g1s_diff_set_source_filters", "g1s_resize_table",
+    "g1s_narrow_row", "g1s_narrow_row_with", "g1s_narrow_isa", "g1s_linsolve_probe", "g1s_diff_set_source_filters", "g1s_resize_table",
 ]
 
 

@@ -341,8 +341,17 @@ enum g1s_transfer { G1S_TRANSFER_BT1886 = 0, G1S_TRANSFER_SMPTE2084 = 1, G1S_TRA
 int g1s_generate_photon_noise(uint32_t iso, uint32_t width, uint32_t height, int transfer, int chroma_grain,
                               int full_range, int32_t random_seed, uint64_t start_time, uint64_t end_time,
                               g1s_segment *out);
-/* Host-side reduction used by host_narrow (exported for tests): dst[i] = (uint8_t)(src[i] >> shift). */
+/* Host-side reduction used by host_narrow (exported for tests): dst[i] = (uint8_t)(src[i] >> shift).  dst is meant to
+ * be staging memory nothing reads back soon: on x86-64 with AVX2 / AVX-512BW the bytes go out with streaming stores.
+ * g1s_narrow_isa: 0 compiler loop, 1 AVX2, 2 AVX-512BW; g1s_narrow_row_with runs a path at or below that. */
 void g1s_narrow_row(uint8_t *dst, const uint16_t *src, int n, int shift);
+void g1s_narrow_row_with(uint8_t *dst, const uint16_t *src, int n, int shift, int isa);
+int g1s_narrow_isa(void);
+/* Test hook: the host model's linear solvers on caller data (util.rs::linsolve semantics, bit for bit).  which 0: the
+ * elimination as the model runs it, 1: the tridiagonal fast path of the noise strength systems alone.  Returns 1 solved,
+ * -1 the reference's failure (pivot below 1e-16), 0 (which = 1 only) a row swap would be needed: the model then runs the
+ * dense elimination.  x must come in as the caller's x (the reference leaves the rows it did not reach untouched). */
+int g1s_linsolve_probe(int which, int n, const double *A, const double *b, double *x);
 /* Test hook: parse ONE syntax group (named as in the AV1 spec / the reference's functions) from a raw bit buffer;
  * returns bits consumed or a negative status.  Lets tests replay the reference's own unit-test vectors. */
 int64_t g1s_obu_probe(const char *what, const uint8_t *data, size_t size, const int64_t *args, size_t nargs,

@@ -15,14 +15,24 @@ def test_narrow_row_is_the_truncating_shift():
     L = D.lib()
     L.g1s_narrow_row.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.g1s_narrow_row.restype = None
+    L.g1s_narrow_row_with.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.g1s_narrow_row_with.restype = None
+    L.g1s_narrow_isa.restype = C.c_int
     rng = np.random.default_rng(0)
-    for n in (1, 7, 31, 32, 33, 64, 1000, 3840):
-        for shift in (0, 2, 4, 8):
-            src = rng.integers(0, 1 << 16, n, dtype=np.uint16)
-            dst = np.full(n + 8, 0xAB, np.uint8)
-            L.g1s_narrow_row(dst.ctypes.data, src.ctypes.data, n, shift)
-            assert np.array_equal(dst[:n], (src >> shift).astype(np.uint8))   # `as u8`: wraps, like the kernels' cast
-            assert np.all(dst[n:] == 0xAB)
+    # every code path this host has (plain loop, AVX2 and AVX-512BW with streaming stores), every destination alignment
+    for isa in range(-1, L.g1s_narrow_isa() + 1):
+        for n in (1, 7, 31, 32, 33, 64, 95, 1000, 3840):
+            for shift in (0, 2, 4, 8):
+                for off in (0, 1, 5, 31):
+                    src = rng.integers(0, 1 << 16, n, dtype=np.uint16)
+                    buf = np.full(n + 72, 0xAB, np.uint8)
+                    dst = buf[off:]
+                    if isa < 0:
+                        L.g1s_narrow_row(dst.ctypes.data, src.ctypes.data, n, shift)
+                    else:
+                        L.g1s_narrow_row_with(dst.ctypes.data, src.ctypes.data, n, shift, isa)
+                    assert np.array_equal(dst[:n], (src >> shift).astype(np.uint8))   # `as u8`: wraps, like the kernels' cast
+                    assert np.all(dst[n:] == 0xAB) and np.all(buf[:off] == 0xAB)
 
 
 @pytest.mark.gpu
