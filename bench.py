@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--workload", default="4k10", choices=list(WORKLOADS))
     ap.add_argument("--frames", type=int, default=60, help="frame pairs per step per GPU (3 engine batches at 4K)")
     ap.add_argument("--batch", type=int, default=0, help="frame pairs per kernel launch (engine batch)")
-    ap.add_argument("--repeat", type=int, default=32,
+    ap.add_argument("--repeat", type=int, default=40,
                     help="passes over the resident frames per step (a step is repeat x frames frame pairs per GPU, so that "
                          "the default 20..40 steps time seconds, not milliseconds)")
     ap.add_argument("--no-e2e", action="store_true")

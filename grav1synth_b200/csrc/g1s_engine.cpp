@@ -714,11 +714,12 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     }
   }
   d->pair_bytes = off;
-  // Default batch: at most ~1 GiB of frame pairs per slot and 64 frames; within that, the size whose
-  // flat-block launch (one thread per block, 384 resident threads per SM) fills its last wave best.
+  // Default batch: at most ~2 GiB of frame pairs per slot and 64 frames (measured at 4K 10-bit: 15.9 / 20.9 / 21.2 / 21.4 k
+  // frames/s with 10 / 20 / 30 / 40 frames per launch; the per-frame model kernel, one CTA per frame, gains most);
+  // within that, the size whose flat-block launch (one thread per block, 384 resident threads per SM) fills its last wave best.
   int batch = cfg->batch_frames;
   if (batch <= 0) {
-    const int cap = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)1 << 30) / d->pair_bytes));
+    const int cap = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)2 << 30) / d->pair_bytes));
     int sms = 148;
     if (!consumer) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
     const double wave = 384.0 * sms;
