@@ -39,7 +39,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k10", choices=list(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=60, help="frame pairs per step per GPU (3 engine batches at 4K)")
+    ap.add_argument("--frames", type=int, default=0,
+                    help="resident frame pairs per GPU, one pass = one sharded super-batch (0: two engine batches, 82 at 4K 10-bit)")
     ap.add_argument("--batch", type=int, default=0, help="frame pairs per kernel launch (engine batch)")
     ap.add_argument("--repeat", type=int, default=40,
                     help="passes over the resident frames per step (a step is repeat x frames frame pairs per GPU, so that "
@@ -299,6 +300,11 @@ def main():
     W, H, bd = spec.width, spec.height, spec.bit_depth
     F, R = args.frames, args.repeat
     pair_bytes = frame_pair_bytes(W, H, 1, 1, bd, bd)
+    if F <= 0:
+        # whole engine batches per pass: a sharded super-batch (one pass per rank) then ends on a launch boundary
+        probe = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=args.batch)
+        F = 2 * probe.batch_frames
+        probe.close()
 
     # ---- multi-GPU parity, before anything is timed: a two-scene stream through the NCCL-sharded path must give the
     # single-GPU table (segment cut and short tail super-batch included); a mismatch fails the run
@@ -323,12 +329,15 @@ def main():
         sd = None
         eng = D.DiffGenerator(24, 1, bd, bd, W, H, device=local_rank, batch_frames=args.batch)
 
+        prepared = [(eng.device_frame(sp, ss), eng.device_frame(dp, ds)) for (sp, ss), (dp, ds) in dev_args]
+
         def step():
             # R passes over the F resident frame pairs (3.0 GB at 4K: every pass streams from HBM); the engine pipelines
             # launches and folds results asynchronously, the drain happens once at the end of the timed region
+            push = eng.diff_frames_prepared
             for _ in range(R):
-                for (sp, ss), (dp, ds) in dev_args:
-                    eng.diff_frame_device(sp, ss, dp, ds)
+                for sf, df in prepared:
+                    push(sf, df)
     else:
         sd = ShardedDiff(24, 1, bd, bd, W, H, 1, 1, frames_per_rank=F, device=local_rank, batch_frames=args.batch)
         eng = sd.producer
@@ -400,7 +409,9 @@ def main():
                    "l2": f"inputs larger than L2 ({F * pair_bytes / 1e6:.0f} MB resident per GPU, streamed once per pass)",
                    "timed_region_s": elapsed,
                    "parallelism": f"frame-sharded x{world}, NCCL all-gather of per-frame model digests ({D.digest_bytes()} B/frame)",
-                   "kernel_streams": int(os.environ.get("G1S_STREAMS", "3"))},
+                   "kernel_streams": int(os.environ.get("G1S_STREAMS", "3")),
+                   "model_placement": ("device (latest_kernel: per-frame model half on the GPU, digests cross PCIe)"
+                                       if eng.model_on_device else "host (per-frame model half on host threads, records cross PCIe)")},
         "gpu_launches": int(c1["kernels_launched"] - c0["kernels_launched"]),
         "roofline": {"bound": "hbm",
                      "kernel": "whole step: flat_features + flat_select + residual + gram_plan + gram_imma (+ gram_generic "
@@ -441,7 +452,7 @@ def main():
             g2.flush()
             g2.mark(0)
             n2 = 0
-            for _ in range(12):
+            for _ in range(100):  # 2000 frames: dozens of batches, so that filling and draining the pipeline do not count
                 for (sp, ss), (dp, ds) in da2:
                     g2.diff_frame_device(sp, ss, dp, ds)
                     n2 += 1

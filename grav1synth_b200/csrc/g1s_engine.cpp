@@ -40,6 +40,12 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// A block of digests on its way through the fold thread: as received, and unpacked into model states
+struct DigestBlock {
+  std::vector<double> raw;
+  std::vector<LatestFrame> frames;
+};
+
 constexpr int kSlots = 4;
 
 // Minimal fork-join pool for the per-frame (order independent) half of the host model.
@@ -224,6 +230,8 @@ struct g1s_diff {
   int oldest = 0;         // oldest slot possibly in flight
   std::unique_ptr<DiffSequencer> seq;
   std::unique_ptr<HostPool> pool;
+  std::unique_ptr<HostPool> fold_pool;  // the fold thread's helpers (NoiseModel::fold_run); nobody else uses it
+  NoiseModel::ParallelFor fold_par;
   std::unique_ptr<FoldQueue> folder;
   std::vector<LatestFrame> latest;  // scratch for the single-record entry points
   std::string err;
@@ -233,7 +241,7 @@ struct g1s_diff {
   g1s_record_fn tap = nullptr;
   void *tap_user = nullptr;
   std::mutex digest_mu;    // consumer handles: recycled copies of incoming digest blocks
-  std::vector<std::shared_ptr<std::vector<double>>> digest_free;
+  std::vector<std::shared_ptr<DigestBlock>> digest_free;  // recycled
   // source filters (g1s_diff_set_source_filters): the chain runs on the copy stream between the upload of the raw
   // source planes (a small ring, reused in stream order) and the kernels of the path
   std::unique_ptr<SourceFilters> filters;
@@ -330,9 +338,8 @@ uint64_t fold_records(g1s_diff *d, const uint8_t *recs, int count, size_t stride
   if (!model) return 0;
   DiffSequencer *seq = d->seq.get();
   LatestFrame *frames = store.data();
-  return d->folder->push([seq, frames, count] {
-    for (int i = 0; i < count; ++i) seq->consume_latest(frames[i]);
-  });
+  const NoiseModel::ParallelFor *par = &d->fold_par;
+  return d->folder->push([seq, frames, count, par] { seq->consume_latest_batch(frames, count, *par); });
 }
 
 // Builds (once per slot) the TMA descriptors of the slot's residual planes: per frame of the batch the s8
@@ -526,9 +533,10 @@ int check_frames(g1s_diff *d, const g1s_frame *s, const g1s_frame *n) {
 }
 
 
-// Queues `count` digests (copied) for the fold thread, in order.
+// Queues `count` digests (copied) for the fold thread, in order.  The fold thread unpacks a block into model states
+// with its helpers, then merges them (DiffSequencer::consume_latest_batch).
 void fold_digests_copy(g1s_diff *d, const double *src, size_t count) {
-  std::shared_ptr<std::vector<double>> blk;
+  std::shared_ptr<DigestBlock> blk;
   {
     std::lock_guard<std::mutex> lk(d->digest_mu);
     if (!d->digest_free.empty()) {
@@ -536,14 +544,20 @@ void fold_digests_copy(g1s_diff *d, const double *src, size_t count) {
       d->digest_free.pop_back();
     }
   }
-  if (!blk) blk = std::make_shared<std::vector<double>>();
-  blk->assign(src, src + LatestFrame::kDigestDoubles * count);
+  if (!blk) blk = std::make_shared<DigestBlock>();
+  blk->raw.assign(src, src + LatestFrame::kDigestDoubles * count);
   DiffSequencer *seq = d->seq.get();
-  d->folder->push([blk, seq, count, d] {
-    LatestFrame lf;
-    for (size_t i = 0; i < count; ++i) {
-      lf.from_digest(blk->data() + LatestFrame::kDigestDoubles * i);
-      seq->consume_latest(lf);
+  const NoiseModel::ParallelFor *par = &d->fold_par;
+  d->folder->push([blk, seq, count, d, par] {
+    constexpr size_t K = LatestFrame::kDigestDoubles;
+    constexpr size_t kStep = 256;  // states held unpacked at a time (25 KB each)
+    if (blk->frames.size() < std::min(count, kStep)) blk->frames.resize(std::min(count, kStep));
+    LatestFrame *frames = blk->frames.data();
+    const double *raw = blk->raw.data();
+    for (size_t at = 0; at < count; at += kStep) {
+      const int n = (int)std::min(kStep, count - at);
+      (*par)(n, [&](int i) { frames[i].from_digest(raw + K * (at + i)); });
+      seq->consume_latest_batch(frames, n, *par);
     }
     std::lock_guard<std::mutex> lk(d->digest_mu);
     if (d->digest_free.size() < 8) d->digest_free.push_back(blk);
@@ -699,6 +713,12 @@ int g1s_diff_create(const g1s_diff_config *cfg, g1s_diff **out) {
     if (threads <= 0) threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));  // staging copies want them all
     d->pool.reset(new HostPool(threads));
     d->folder.reset(new FoldQueue());
+    // the sequential half of the model hands the solves of the combined state to a few helpers of its own
+    int helpers = (int)std::min(6u, std::max(1u, std::thread::hardware_concurrency() / 4));
+    if (const char *e = std::getenv("G1S_FOLD_THREADS")) helpers = std::max(1, std::atoi(e));
+    d->fold_pool.reset(new HostPool(helpers));
+    HostPool *fp = d->fold_pool.get();
+    d->fold_par = [fp](int n, const std::function<void(int)> &fn) { fp->parallel_for(n, fn); };
   }
 
   size_t off = 0;
@@ -1333,6 +1353,10 @@ const char *g1s_diff_last_error(const g1s_diff *d) { return d ? d->err.c_str() :
 int64_t g1s_diff_frames_pushed(const g1s_diff *d) { return d ? d->pushed : 0; }
 
 int g1s_diff_batch_frames(const g1s_diff *d) { return d ? d->batch : 0; }
+int g1s_diff_model_on_device(const g1s_diff *d) {
+  if (!d) return 0;
+  return d->kids.empty() ? (d->device_model ? 1 : 0) : g1s_diff_model_on_device(d->kids[0]);
+}
 
 int g1s_diff_frame_device(const g1s_diff *d, int64_t frame_index) {
   if (!d || frame_index < 0) return -1;
@@ -1440,11 +1464,17 @@ int g1s_diff_consume_digests_borrowed(g1s_diff *d, const void *digests, size_t c
   }
   const double *src = static_cast<const double *>(digests);
   DiffSequencer *seq = d->seq.get();
-  d->folder->push([src, seq, count] {
-    LatestFrame lf;
-    for (size_t i = 0; i < count; ++i) {
-      lf.from_digest(src + LatestFrame::kDigestDoubles * i);
-      seq->consume_latest(lf);
+  const NoiseModel::ParallelFor *par = &d->fold_par;
+  d->folder->push([src, seq, count, par] {
+    constexpr size_t K = LatestFrame::kDigestDoubles;
+    constexpr size_t kStep = 256;
+    static thread_local std::vector<LatestFrame> frames;  // the fold thread's
+    if (frames.size() < std::min(count, kStep)) frames.resize(std::min(count, kStep));
+    LatestFrame *fr = frames.data();
+    for (size_t at = 0; at < count; at += kStep) {
+      const int n = (int)std::min(kStep, count - at);
+      (*par)(n, [&](int i) { fr[i].from_digest(src + K * (at + i)); });
+      seq->consume_latest_batch(fr, n, *par);
     }
   });
   d->retired += (int64_t)count;

@@ -162,8 +162,14 @@ bool LinearSystem::solve() {
   return gauss_solve(n, Ac.data(), bc.data(), x.data());
 }
 void LinearSystem::add(const LinearSystem &o) {
-  for (size_t i = 0; i < A.size(); ++i) A[i] += o.A[i];
-  for (size_t i = 0; i < b.size(); ++i) b[i] += o.b[i];
+  // (two different systems never share storage: the qualifiers let the compiler use whole vectors)
+  double *__restrict a = A.data();
+  const double *__restrict oa = o.A.data();
+  const size_t na = A.size(), nb = b.size();
+  for (size_t i = 0; i < na; ++i) a[i] += oa[i];
+  double *__restrict pb = b.data();
+  const double *__restrict ob = o.b.data();
+  for (size_t i = 0; i < nb; ++i) pb[i] += ob[i];
 }
 void LinearSystem::copy_from(const LinearSystem &o) {
   A = o.A;
@@ -577,24 +583,36 @@ void NoiseModel::add_strength_measurements(int c, const FrameRecordView &rec, La
 }
 
 bool NoiseModel::is_different(const LatestFrame &lf) const {
-  const LinearSystem &lx = lf.ch[0].eqns, &cx = combined[0].eqns;
+  return differs(lf, combined[0].eqns.x.data(), combined[0].strength.eqns.x.data());
+}
+
+// NoiseModel::is_different against the combined luma solutions given by pointer (24 AR taps, 20 strength bins)
+bool NoiseModel::differs(const LatestFrame &lf, const double *cxx, const double *cex) {
+  const LinearSystem &lx = lf.ch[0].eqns;
   double c = 0, a_len = 0, b_len = 0;
-  for (int i = 0; i < cx.n; ++i) {
+  for (int i = 0; i < lx.n; ++i) {
     a_len += lx.x[i] * lx.x[i];
-    b_len += cx.x[i] * cx.x[i];
-    c += lx.x[i] * cx.x[i];
+    b_len += cxx[i] * cxx[i];
+    c += lx.x[i] * cxx[i];
   }
   const double corr = c / (std::sqrt(a_len) * std::sqrt(b_len));
   if (corr < 0.9) return true;
-  const LinearSystem &le = lf.ch[0].strength.eqns, &ce = combined[0].strength.eqns;
+  const LinearSystem &le = lf.ch[0].strength.eqns;
   const double dx = 1.0 / lf.ch[0].strength.num_bins;
   double diff = 0, total_weight = 0;
-  for (int j = 0; j < le.n; ++j) {
-    double weight = 0;
-    for (int i = 0; i < le.n; ++i) weight += le.A[i * le.n + j];
-    weight = std::sqrt(weight);
-    diff += weight * std::fabs(le.x[j] - ce.x[j]);
-    total_weight += weight;
+  // column sums of A, each in row order (the loop nest is turned inside out: whole rows are added to 20 running sums)
+  double weight[32];
+  const int n = le.n;
+  if (n > 32) return true;  // not a strength system
+  for (int j = 0; j < n; ++j) weight[j] = 0;
+  for (int i = 0; i < n; ++i) {
+    const double *row = le.A.data() + (size_t)i * n;
+    for (int j = 0; j < n; ++j) weight[j] += row[j];
+  }
+  for (int j = 0; j < n; ++j) {
+    const double w = std::sqrt(weight[j]);
+    diff += w * std::fabs(le.x[j] - cex[j]);
+    total_weight += w;
   }
   return diff * dx / total_weight > 0.005;
 }
@@ -679,6 +697,212 @@ NoiseStatus NoiseModel::fold(const LatestFrame &lf) {
     }
   }
   return y_model_different ? NoiseStatus::DifferentType : NoiseStatus::Ok;
+}
+
+namespace {
+// The combined luma state after one frame of a run: the sums as fold() leaves them, then the solutions; and what
+// is_different needs of the frame itself.
+struct LumaSnap {
+  double A[24 * 24], b[24], x[24];
+  double SA[kNumBins * kNumBins], Sb[kNumBins], Sx[kNumBins];
+  double total, ar_gain, bump;
+  double x_len;                           // sum of x[i]^2 (is_different's b_len when this state is the combined one)
+  double l_len, l_weight[kNumBins], l_total_weight;  // of the FRAME: sum of its x[i]^2, sqrt of its strength column sums
+  int64_t nobs;
+  int neq;
+  bool ok;
+};
+
+// r[e] = start[e], then for every frame r[e] += addend(frame)[e] (+ bump[frame]) and out(frame)[e] = r[e]: the running
+// sums of elements [e0, e1) over the frames, every element its own chain of rounded adds in frame order.
+template <class Addend, class Out>
+inline void running_sums(int e0, int e1, const double *start, int count, Addend addend, const double *bump, Out out) {
+  double r[128];
+  const int n = e1 - e0;
+  for (int e = 0; e < n; ++e) r[e] = start[e0 + e];
+  for (int i = 0; i < count; ++i) {
+    const double *__restrict a = addend(i) + e0;
+    double *__restrict o = out(i);
+    if (bump) {
+      const double bi = bump[i];
+      for (int e = 0; e < n; ++e) r[e] += a[e], r[e] += bi;
+    } else {
+      for (int e = 0; e < n; ++e) r[e] += a[e];
+    }
+    for (int e = 0; e < n; ++e) o[e0 + e] = r[e];
+  }
+}
+}  // namespace
+
+int NoiseModel::fold_run(const LatestFrame *frames, int count, const ParallelFor &par) {
+  if (count <= 0) return 0;
+  static thread_local std::vector<LumaSnap> snaps;
+  if ((int)snaps.size() < count) snaps.resize(count);
+  LumaSnap *sn = snaps.data();
+  const ChannelState &y0 = combined[0];
+  // (0) the scalar chains (observation and equation counts, strength totals, the ridge bump each solve adds to b)
+  {
+    int64_t nobs = y0.num_observations;
+    int neq = y0.strength.num_equations;
+    double total = y0.strength.total;
+    for (int i = 0; i < count; ++i) {
+      const ChannelState &l = frames[i].ch[0];
+      nobs += l.num_observations, neq += l.strength.num_equations, total += l.strength.total;
+      sn[i].nobs = nobs, sn[i].neq = neq, sn[i].total = total;
+      sn[i].bump = (total / neq) / 8192.;
+    }
+  }
+  // (1) the luma sums of every prefix: every matrix element is its own chain over the frames, so slices of elements go
+  // to different threads (fold(): add, then the strength solve's ridge bump of b)
+  {
+    constexpr int kA = 8, kS = 4;  // slices of the 576 AR and the 400 strength matrix elements
+    par(kA + kS + 1, [&](int t) {
+      if (t < kA) {
+        running_sums(576 * t / kA, 576 * (t + 1) / kA, y0.eqns.A.data(), count,
+                     [&](int i) { return frames[i].ch[0].eqns.A.data(); }, nullptr, [&](int i) { return sn[i].A; });
+      } else if (t < kA + kS) {
+        const int u = t - kA;
+        running_sums(400 * u / kS, 400 * (u + 1) / kS, y0.strength.eqns.A.data(), count,
+                     [&](int i) { return frames[i].ch[0].strength.eqns.A.data(); }, nullptr, [&](int i) { return sn[i].SA; });
+      } else {
+        running_sums(0, 24, y0.eqns.b.data(), count, [&](int i) { return frames[i].ch[0].eqns.b.data(); }, nullptr,
+                     [&](int i) { return sn[i].b; });
+        std::vector<double> bump(count);
+        for (int i = 0; i < count; ++i) bump[i] = sn[i].bump;
+        running_sums(0, kNumBins, y0.strength.eqns.b.data(), count,
+                     [&](int i) { return frames[i].ch[0].strength.eqns.b.data(); }, bump.data(), [&](int i) { return sn[i].Sb; });
+      }
+    });
+  }
+  // (2) their solves (ChannelState::solve_ar and StrengthSolver::solve_bumped on a scratch state per thread), and the
+  // frame's own terms of is_different
+  const int chunks = std::min(count, 64);
+  par(chunks, [&](int c) {
+    static thread_local ChannelState ws(24);
+    for (int i = (int)((int64_t)count * c / chunks); i < (int)((int64_t)count * (c + 1) / chunks); ++i) {
+      LumaSnap &s = sn[i];
+      std::memcpy(ws.eqns.A.data(), s.A, sizeof s.A);
+      std::memcpy(ws.eqns.b.data(), s.b, sizeof s.b);
+      ws.num_observations = s.nobs;
+      s.ok = ws.solve_ar(false);
+      if (s.ok) {
+        std::memcpy(ws.strength.eqns.A.data(), s.SA, sizeof s.SA);
+        std::memcpy(ws.strength.eqns.b.data(), s.Sb, sizeof s.Sb);
+        ws.strength.num_equations = s.neq, ws.strength.total = s.total;
+        s.ok = ws.strength.solve_bumped();
+      }
+      std::memcpy(s.x, ws.eqns.x.data(), sizeof s.x);
+      std::memcpy(s.Sx, ws.strength.eqns.x.data(), sizeof s.Sx);
+      s.ar_gain = ws.ar_gain;
+      double len = 0;
+      for (int k = 0; k < 24; ++k) len += s.x[k] * s.x[k];
+      s.x_len = len;
+      const ChannelState &l = frames[i].ch[0];
+      len = 0;
+      for (int k = 0; k < 24; ++k) len += l.eqns.x[k] * l.eqns.x[k];
+      s.l_len = len;
+      double w[kNumBins];
+      for (int j = 0; j < kNumBins; ++j) w[j] = 0;
+      for (int r = 0; r < kNumBins; ++r) {
+        const double *row = l.strength.eqns.A.data() + r * kNumBins;
+        for (int j = 0; j < kNumBins; ++j) w[j] += row[j];
+      }
+      double tw = 0;
+      for (int j = 0; j < kNumBins; ++j) s.l_weight[j] = std::sqrt(w[j]), tw += s.l_weight[j];
+      s.l_total_weight = tw;
+    }
+  });
+  // (3) the verdicts, in order: frame i is judged against the solutions of the state before it (NoiseModel::differs
+  // with the terms that belong to one side alone taken from above: each is the same chain of operations)
+  int good = 0;
+  for (; good < count; ++good) {
+    const int neq_before = good ? sn[good - 1].neq : y0.strength.num_equations;
+    if (neq_before > 0) {
+      const double *cx = good ? sn[good - 1].x : y0.eqns.x.data();
+      const double *cs = good ? sn[good - 1].Sx : y0.strength.eqns.x.data();
+      double b_len = 0;
+      if (good) {
+        b_len = sn[good - 1].x_len;
+      } else {
+        for (int k = 0; k < 24; ++k) b_len += cx[k] * cx[k];
+      }
+      const ChannelState &l = frames[good].ch[0];
+      const LumaSnap &s = sn[good];
+      double c = 0;
+      for (int k = 0; k < 24; ++k) c += l.eqns.x[k] * cx[k];
+      const double corr = c / (std::sqrt(s.l_len) * std::sqrt(b_len));
+      if (corr < 0.9) break;
+      const double dx = 1.0 / l.strength.num_bins;
+      double diff = 0;
+      for (int j = 0; j < kNumBins; ++j) diff += s.l_weight[j] * std::fabs(l.strength.eqns.x[j] - cs[j]);
+      if (diff * dx / s.l_total_weight > 0.005) break;
+    }
+    if (!sn[good].ok) break;  // fold() reports this frame's failed combined solve itself
+  }
+  if (good == 0) return 0;
+  // commit frames [0, good): luma from the snapshot; chroma as fold() merges it (sums and the ridge bumps, the
+  // eliminations wait for settle()), again as running sums of element slices
+  {
+    const LumaSnap &s = sn[good - 1];
+    ChannelState &y = combined[0];
+    std::memcpy(y.eqns.A.data(), s.A, sizeof s.A);
+    std::memcpy(y.eqns.b.data(), s.b, sizeof s.b);
+    std::memcpy(y.eqns.x.data(), s.x, sizeof s.x);
+    std::memcpy(y.strength.eqns.A.data(), s.SA, sizeof s.SA);
+    std::memcpy(y.strength.eqns.b.data(), s.Sb, sizeof s.Sb);
+    std::memcpy(y.strength.eqns.x.data(), s.Sx, sizeof s.Sx);
+    y.strength.total = s.total, y.strength.num_equations = s.neq, y.num_observations = s.nobs, y.ar_gain = s.ar_gain;
+  }
+  if (g_.planes > 1) {
+    std::vector<double> bump[3];
+    for (int c = 1; c < g_.planes; ++c) {
+      ChannelState &u = combined[c];
+      bump[c].resize(good);
+      for (int i = 0; i < good; ++i) {
+        const ChannelState &l = frames[i].ch[c];
+        u.num_observations += l.num_observations;
+        u.strength.num_equations += l.strength.num_equations;
+        u.strength.total += l.strength.total;
+        bump[c][i] = (u.strength.total / u.strength.num_equations) / 8192.;
+      }
+      stale_[c] = true;
+    }
+    constexpr int kA = 5, kS = 4;  // slices of the 625 AR and the 400 strength matrix elements, per chroma channel
+    const int per = kA + kS + 1, nch = g_.planes - 1;
+    par(per * nch, [&](int t) {
+      const int c = 1 + t / per, k = t % per;
+      ChannelState &u = combined[c];
+      // in place: the running sums end in the combined state itself
+      auto in_place = [&](double *dst, int e0, int e1, auto addend, const double *bp) {
+        double r[128];
+        const int n = e1 - e0;
+        for (int e = 0; e < n; ++e) r[e] = dst[e0 + e];
+        for (int i = 0; i < good; ++i) {
+          const double *__restrict a = addend(i) + e0;
+          if (bp) {
+            const double bi = bp[i];
+            for (int e = 0; e < n; ++e) r[e] += a[e], r[e] += bi;
+          } else {
+            for (int e = 0; e < n; ++e) r[e] += a[e];
+          }
+        }
+        for (int e = 0; e < n; ++e) dst[e0 + e] = r[e];
+      };
+      if (k < kA) {
+        in_place(u.eqns.A.data(), 625 * k / kA, 625 * (k + 1) / kA, [&](int i) { return frames[i].ch[c].eqns.A.data(); }, nullptr);
+      } else if (k < kA + kS) {
+        const int q = k - kA;
+        in_place(u.strength.eqns.A.data(), 400 * q / kS, 400 * (q + 1) / kS,
+                 [&](int i) { return frames[i].ch[c].strength.eqns.A.data(); }, nullptr);
+      } else {
+        in_place(u.eqns.b.data(), 0, 25, [&](int i) { return frames[i].ch[c].eqns.b.data(); }, nullptr);
+        in_place(u.strength.eqns.b.data(), 0, kNumBins, [&](int i) { return frames[i].ch[c].strength.eqns.b.data(); },
+                 bump[c].data());
+      }
+    });
+  }
+  last_ = &frames[good - 1];
+  return good;
 }
 
 NoiseStatus NoiseModel::update(const FrameRecordView &rec) {
@@ -809,6 +1033,24 @@ void DiffSequencer::after_update(NoiseStatus st) {
 void DiffSequencer::consume(const FrameRecordView &rec) { after_update(model_.update(rec)); }
 
 void DiffSequencer::consume_latest(const LatestFrame &lf) { after_update(model_.fold(lf)); }
+
+void DiffSequencer::consume_latest_batch(const LatestFrame *frames, int count, const NoiseModel::ParallelFor &par) {
+  constexpr int kMinRun = 16;  // shorter runs are not worth a fork and join
+  const int planes = model_.planes();
+  int i = 0;
+  while (i < count) {
+    int r = i;
+    while (r < count && NoiseModel::plain(frames[r], planes)) ++r;
+    if (r - i < kMinRun) {
+      for (const int e = std::max(r, i + 1); i < e; ++i) consume_latest(frames[i]);
+      continue;
+    }
+    const int n = model_.fold_run(frames + i, r - i, par);
+    frame_count_ += n;  // after_update(NoiseStatus::Ok), n times
+    i += n;
+    if (i < r) consume_latest(frames[i++]);  // the frame that differs from the model so far (or fails): the plain path
+  }
+}
 
 std::vector<g1s_segment> DiffSequencer::finish() {
   std::vector<g1s_segment> out(table_);

@@ -3,6 +3,7 @@
 // Input is one integer FrameRecord per frame pair, produced by the CUDA kernels; this
 // file never touches pixels.  Strictly sequential across frames, as in the reference.
 #pragma once
+#include <functional>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -105,6 +106,17 @@ class NoiseModel {
   // NoiseModel::update = compute_latest (thread-safe, const) + fold (sequential)
   void compute_latest(const FrameRecordView &rec, LatestFrame &out) const;
   NoiseStatus fold(const LatestFrame &lf);
+  // fold() over a run of frames with the per-frame solves of the combined luma state off the calling thread.
+  // What fold does to luma is a chain only through SUMS (state_k = state_k-1 + frame_k, rounded adds in frame order);
+  // the solves of state_k feed nothing but the is_different verdict on frame k+1.  So, assuming no frame of the run
+  // differs: (1) the sums of every prefix, sequentially; (2) their solves, independent of each other, through `par`;
+  // (3) the verdicts in order.  Frames up to the first that differs (or whose combined solve fails) are committed --
+  // bit for bit the state fold() would have left -- and their count is returned; the caller hands the next frame to
+  // fold().  Every frame must be "plain": enough flat blocks, no failed channel.
+  using ParallelFor = std::function<void(int, const std::function<void(int)> &)>;
+  int fold_run(const LatestFrame *frames, int count, const ParallelFor &par);
+  static bool plain(const LatestFrame &lf, int planes) { return lf.enough_flat && lf.fail_channel < 0 && lf.channels == planes; }
+  int planes() const { return g_.planes; }
   NoiseStatus update(const FrameRecordView &rec);
   void save_latest();
   // Deferred work of fold(): the chroma solves of the combined state (see fold).  Must run before the
@@ -118,6 +130,7 @@ class NoiseModel {
   void load_equations(int c, const FrameRecordView &rec, ChannelState &st) const;
   void add_strength_measurements(int c, const FrameRecordView &rec, LatestFrame &lf) const;
   bool is_different(const LatestFrame &lf) const;
+  static bool differs(const LatestFrame &lf, const double *combined_ar_x, const double *combined_strength_x);
   StreamGeometry g_;
   std::string err_;
   LatestFrame scratch_;        // used by update()
@@ -135,6 +148,8 @@ class DiffSequencer {
   DiffSequencer(int64_t fps_num, int64_t fps_den, const StreamGeometry &g);
   void consume(const FrameRecordView &rec);
   void consume_latest(const LatestFrame &lf);  // same, for a frame whose latest state is already evaluated
+  // consume_latest over consecutive frames; long runs of plain frames go through NoiseModel::fold_run
+  void consume_latest_batch(const LatestFrame *frames, int count, const NoiseModel::ParallelFor &par);
   std::vector<g1s_segment> finish();
   int64_t frames() const { return frame_count_; }
   NoiseModel &model() { return model_; }

@@ -26,7 +26,7 @@ RECORD_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t)
 
 EXPORTS = [
     "g1s_abi_version", "g1s_diff_create", "g1s_diff_push_frame", "g1s_diff_push_frame_device", "g1s_diff_flush",
-    "g1s_diff_finish", "g1s_diff_destroy", "g1s_diff_last_error", "g1s_diff_frames_pushed", "g1s_diff_batch_frames",
+    "g1s_diff_finish", "g1s_diff_destroy", "g1s_diff_last_error", "g1s_diff_frames_pushed", "g1s_diff_batch_frames", "g1s_diff_model_on_device",
     "g1s_diff_frame_device",
     "g1s_diff_get_counters", "g1s_diff_mark", "g1s_diff_marks_elapsed_ms", "g1s_record_layout", "g1s_record_gramf_offset", "g1s_diff_record_bytes", "g1s_diff_set_record_tap",
     "g1s_diff_consume_record", "g1s_diff_consume_records", "g1s_digest_bytes", "g1s_diff_set_digest_sink",
@@ -64,6 +64,7 @@ def lib() -> C.CDLL:
         L.g1s_diff_set_source_filters.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32]
         L.g1s_resize_table.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
         L.g1s_diff_batch_frames.argtypes = [C.c_void_p]
+        L.g1s_diff_model_on_device.argtypes = [C.c_void_p]
         L.g1s_diff_frame_device.argtypes = [C.c_void_p, C.c_int64]
         L.g1s_diff_get_counters.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_size_t]
         L.g1s_diff_mark.argtypes = [C.c_void_p, C.c_int]
@@ -208,15 +209,25 @@ class DiffGenerator:
         df, k2 = frame_from_planes(denoised)
         self._check(self._L.g1s_diff_push_frame(self._h, C.byref(sf), C.byref(df)))
 
+    def device_frame(self, ptrs, strides) -> CFrame:
+        """A g1s_frame over planes already resident in HBM (raw device pointers + byte strides); reusable."""
+        f = CFrame()
+        f.width, f.height = self.cfg.width, self.cfg.height
+        for i in range(3):
+            f.plane[i] = ptrs[i] if i < len(ptrs) else None
+            f.stride_bytes[i] = strides[i] if i < len(strides) else 0
+        return f
+
     def diff_frame_device(self, source_ptrs, source_strides, denoised_ptrs, denoised_strides) -> None:
-        """Same, for planes already resident in HBM (raw device pointers + byte strides)."""
-        sf, df = CFrame(), CFrame()
-        for f, ptrs, strides in ((sf, source_ptrs, source_strides), (df, denoised_ptrs, denoised_strides)):
-            f.width, f.height = self.cfg.width, self.cfg.height
-            for i in range(3):
-                f.plane[i] = ptrs[i] if i < len(ptrs) else None
-                f.stride_bytes[i] = strides[i] if i < len(strides) else 0
-        self._check(self._L.g1s_diff_push_frame_device(self._h, C.byref(sf), C.byref(df)))
+        """Same as diff_frame, for planes already resident in HBM (raw device pointers + byte strides)."""
+        self.diff_frames_prepared(self.device_frame(source_ptrs, source_strides), self.device_frame(denoised_ptrs, denoised_strides))
+
+    def diff_frames_prepared(self, source: CFrame, denoised: CFrame) -> None:
+        """g1s_diff_push_frame_device on two g1s_frame structs built once with device_frame (a caller that cycles over
+        resident frames pays one foreign call per frame and nothing else)."""
+        rc = self._L.g1s_diff_push_frame_device(self._h, C.byref(source), C.byref(denoised))
+        if rc != 0:
+            self._check(rc)
 
     def set_source_filters(self, ops, source_width: int, source_height: int) -> None:
         """ops: FilterChain.filters (Crop / Resize objects) or ("crop", t, b, l, r) / ("resize", w, h, alg) tuples.  The
@@ -306,6 +317,11 @@ class DiffGenerator:
     @property
     def batch_frames(self) -> int:
         return int(self._L.g1s_diff_batch_frames(self._h))
+
+    @property
+    def model_on_device(self) -> bool:
+        """True when the per-frame half of the noise model runs on the GPU (latest_kernel) for this handle."""
+        return bool(self._L.g1s_diff_model_on_device(self._h))
 
     def frame_device(self, frame_index: int) -> int:
         """CUDA ordinal that processes this frame (multi-device handles deal batches round-robin)."""

@@ -208,6 +208,9 @@ const char *g1s_diff_last_error(const g1s_diff *d);
 int64_t g1s_diff_frames_pushed(const g1s_diff *d);
 /* Frames per device launch of this handle (the dealing unit of a multi-device handle). */
 int g1s_diff_batch_frames(const g1s_diff *d);
+/* Where the per-frame half of the noise model runs for this handle (g1s_model_placement resolved): 1 on the device
+ * (latest_kernel, digests cross PCIe), 0 on the host threads (records cross PCIe). */
+int g1s_diff_model_on_device(const g1s_diff *d);
 /* CUDA ordinal that processes frame `frame_index` (counted from 0): `device` for single-device handles,
  * device_ids[(frame_index / batch) % n_devices] for multi-device ones.  g1s_diff_push_frame_device on a multi-device
  * handle needs the planes of frame k resident on that device. */

@@ -29,12 +29,12 @@ for r in rows:
     agg.setdefault(name, {}).setdefault(metric, []).append(float(r[hdr.index("Metric Value")].replace(",", "")))
 dur = {k: v.get("gpu__time_duration.sum", []) for k, v in agg.items()}
 total = sum(sum(v) for v in dur.values())
-frames = int(os.environ.get("G1S_PROFILE_FRAMES", "20"))
+frames = int(os.environ.get("G1S_PROFILE_FRAMES", "41"))
 launches = max(len(v) for v in dur.values())
 dram_total = 0.0
 with open(os.path.join(out_dir, f"{tag}_launches.txt"), "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-            "-k regex:'flat_|gram_|residual_|latest_' python bench.py ... (G1S_STREAMS=1, 20 frames per launch)\n")
+            f"-k regex:'flat_|gram_|residual_' python bench.py ... (G1S_STREAMS=1, {frames} frames per launch)\n")
     f.write("# kernel, launches, avg us, share of the step, avg DRAM read MB, avg DRAM write MB\n")
     for k, v in sorted(dur.items(), key=lambda kv: -sum(kv[1])):
         rd = agg[k].get("dram__bytes_read.sum", [0]); wr = agg[k].get("dram__bytes_write.sum", [0])
@@ -69,7 +69,7 @@ for kern in ("gram_imma", "residual", "flat_features", "gram_plan", "latest", "s
     h, units, vals = rr[0], rr[1], rr[2]
     got = {}
     with open(os.path.join(out_dir, f"{tag}_{kern}_ncu.txt"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{kern} (one launch, 20 frame pairs), key metrics\n")
+        f.write(f"# ncu --set full --clock-control none --import-source on -k regex:{kern} (one launch of the batch the launch list shows; strict: 20 frame pairs), key metrics\n")
         f.write(f"# kernel: {vals[h.index('Kernel Name')]}\n")
         for name, u, v in zip(h, units, vals):
             if name in WANT:
@@ -81,4 +81,27 @@ for kern in ("gram_imma", "residual", "flat_features", "gram_plan", "latest", "s
         return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
     traffic[kern] = {"dram_bytes_read": to_bytes("dram__bytes_read.sum"), "dram_bytes_write": to_bytes("dram__bytes_write.sum"),
                      "ncu_duration": " ".join(reversed(got["gpu__time_duration.sum"]))}
+# ---- the per-frame model kernel (device placement only): its own launch list, the phase clocks, the chain probe
+ll = os.path.join(src_dir, "launches_latest.csv")
+if os.path.exists(ll):
+    vals = {}
+    hdr = None
+    for r in csv.reader(open(ll)):
+        if len(r) > 5 and r[0] == "ID":
+            hdr = r
+        elif hdr and len(r) > 5:
+            vals.setdefault(r[hdr.index("Metric Name")], []).append(float(r[hdr.index("Metric Value")].replace(",", "")))
+    with open(os.path.join(out_dir, f"{tag}_latest_launches.txt"), "w") as f:
+        f.write(f"# G1S_DEVICE_MODEL=1: latest_kernel, one CTA per frame ({frames} frames per launch), ncu per-launch metrics\n")
+        for k, v in vals.items():
+            f.write(f"{k:34s} launches {len(v)}  avg {sum(v) / len(v):.1f}\n")
+for name in ("latest_phases.log", "chain_probe.txt"):
+    p = os.path.join(src_dir, name)
+    if os.path.exists(p):
+        with open(os.path.join(out_dir, f"{tag}_{name.replace('.log', '.txt')}"), "w") as f:
+            if name == "latest_phases.log":
+                f.write("# clock64() phase marks of CTA 0 of latest_kernel (build with -DG1S_LATEST_PROF; not the product build)\n")
+            else:
+                f.write("# tools/chain_probe.cu: one thread's order-dependent f64 sum from shared memory, clocks per element\n")
+            f.write(open(p).read())
 print("wrote summaries for", tag)
