@@ -74,7 +74,9 @@ pub struct g1s_diff_config {
     /// 0 / 1: one GPU (`device`); 2..8: this handle drives `device_ids[0..n_devices]`
     pub n_devices: i32,
     pub device_ids: [i32; 8],
-    pub reserved_: [i32; 4],
+    /// 0 = auto, 1 = per-frame model half on host threads, 2 = on the device (latest_kernel)
+    pub model_placement: i32,
+    pub reserved_: [i32; 3],
 }
 
 pub enum g1s_diff {}
@@ -161,11 +163,14 @@ impl DiffGenerator {
                 mode: 0,
                 gram_kernel: 0,
                 host_threads: 0,
-                host_narrow: 0,
+                // v_frame planes are pageable: the staging threads reduce samples deeper than 8 bits to the 8 bits the
+                // path reads (frame_into_u8), so half the bytes cross PCIe; identical tables
+                host_narrow: i32::from(self.source_bit_depth > 8 || self.denoised_bit_depth > 8),
                 gram_order: std::env::var("G1S_STRICT").map(|v| (v == "1") as i32).unwrap_or(0),
                 n_devices: 0,
                 device_ids: [0; 8],
-                reserved_: [0; 4],
+                model_placement: 0,
+                reserved_: [0; 3],
             };
             let rc = unsafe { g1s_diff_create(&cfg, &mut self.h) };
             ensure!(rc == 0, "g1s_diff_create failed: {}", last_error(std::ptr::null()));
