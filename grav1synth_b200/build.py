@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libg1s.so")
 SOURCES = ["g1s_kernels.cu", "g1s_residual.cu", "g1s_gram_imma.cu", "g1s_gram_strict.cu", "g1s_latest.cu", "g1s_filters.cu", "g1s_model.cpp", "g1s_engine.cpp", "g1s_obu.cpp"]
-HEADERS = ["g1s_kernels.h", "g1s_model.h", "g1s_filters.h", os.path.join("..", "..", "include", "g1s.h")]
+HEADERS = ["g1s_kernels.h", "g1s_model.h", "g1s_pool.h", "g1s_filters.h", os.path.join("..", "..", "include", "g1s.h")]
 
 
 def _nvcc() -> str:
