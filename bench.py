@@ -271,6 +271,10 @@ def workload_stats(D, frames_np, dims):
 
 def main():
     args = parse_args()
+    # A run takes a minute or two.  Should it ever stall (a device fault, a lost rank), say where and leave instead of
+    # holding the GPUs until somebody's timeout: every Python thread's stack goes to stderr, then the process exits.
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ.get("G1S_BENCH_WATCHDOG_S", "1200")), exit=True)
     if args.impl == "reference":
         reference_arm(args)
         return
