@@ -28,10 +28,15 @@ CORPUS = {
     "yuv422_10bit": (SynthSpec(192, 96, 10, ss_x=1, ss_y=0, textured=0.2, sigma0=1.0, sigma1=1.5, seed=9), 2, (24, 1)),
     "heavy_grain_12bit": (SynthSpec(192, 160, 12, textured=0.0, sigma0=4.0, sigma1=8.0, seed=13), 2, (24, 1)),
 }
+# streams without goldens (compared in-test), kept out of CORPUS so that the parametrised suites do not pick them up
+EXTRA = {
+    # long enough for runs of frames to reach the batched fold (NoiseModel::fold_run)
+    "tiny_long": (SynthSpec(96, 64, 8, textured=0.0, sigma0=1.5, sigma1=0.5, seed=31), 72, (24, 1)),
+}
 
 
 def corpus_frames(name: str):
-    spec, n, fps = CORPUS[name]
+    spec, n, fps = (CORPUS.get(name) or EXTRA[name])
     return spec, fps, [make_pair_numpy(spec, k) for k in range(n)]
 
 

@@ -98,6 +98,33 @@ def test_two_rank_gloo_matches_golden(name, B, tmp_path):
         assert open(out).read() == f.read()
 
 
+def test_four_rank_gloo_long_stream_takes_the_batched_fold(tmp_path):
+    """72 frames over 4 ranks, 9 per rank and exchange: rank 0 folds 36 digests at a time, i.e. through
+    DiffSequencer::consume_latest_batch / NoiseModel::fold_run.  Expected: the same frames folded one by one."""
+    import ctypes as C
+    from grav1synth_b200 import abi
+    from grav1synth_b200.diff import DiffGenerator, format_grain_table
+    name = "tiny_long"
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "t.tbl")
+    mp.spawn(_worker, args=(4, port, name, 9, out), nprocs=4, join=True)
+    spec, fps, frames = corpus_frames(name)
+    prod = CpuRecordProducer(spec, fps)
+    ring = np.zeros((len(frames), prod.ndbl), np.float64)
+    prod.set_digest_sink(ring.ctypes.data, len(frames))
+    for sf, df in frames:
+        prod.diff_frame(sf, df)
+    prod.flush()
+    one = DiffGenerator(fps[0], fps[1], spec.bit_depth, spec.bit_depth, spec.width, spec.height, spec.ss_x, spec.ss_y,
+                        mode=abi.MODE_CONSUMER)
+    for k in range(len(frames)):
+        one.consume_digests(ring[k:].ctypes.data, 1)
+    assert open(out).read() == format_grain_table(one.finish())
+
+
 def test_owner_dealing():
     from grav1synth_b200.sharded import owner_of
     assert [owner_of(k, 2, 2) for k in range(8)] == [0, 0, 1, 1, 0, 0, 1, 1]
