@@ -72,7 +72,8 @@ void launch_gram_strict(const FrameDesc *frames, int nframes, const Geometry &g,
                         const RecordLayout &rl, cudaStream_t st);
 // The per-frame half of the host model on the device (g1s_latest.cu): one LatestFrame digest (digest_doubles f64,
 // LatestFrame::to_digest layout) per frame of the batch, bit-identical to NoiseModel::compute_latest on the same record.
-// latest_supported: the frame's per-block arrays fit in shared memory (up to ~11 000 blocks: 4K yes, 8K no).
+// latest_supported: the frame's per-block arrays fit in shared memory (up to ~9 000 blocks: 4K yes, 8K no) and luma and
+// chroma agree on which blocks measure (no sliver at the frame edge).
 bool latest_supported(const Geometry &g);
 void launch_latest(int nframes, const Geometry &g, const uint8_t *records, const RecordLayout &rl, bool strict,
                    double *digests, int digest_doubles, cudaStream_t st);

@@ -646,7 +646,25 @@ size_t latest_smem_bytes(const Geometry &g) {
   return blocks > sizeof(ArWork) ? blocks : sizeof(ArWork);
 }
 
-bool latest_supported(const Geometry &g) { return latest_smem_bytes(g) + sizeof(LatestSmem) <= 226 * 1024 && g.nb < 32768; }
+// add_noise_std_observations keeps a block with more than 32 samples: luma and chroma agree on that for every block
+// unless the frame ends in a sliver (the four kinds of block: inner, right edge, bottom edge, corner).
+static bool same_measuring_blocks(const Geometry &g) {
+  if (g.planes != 3) return true;
+  const int lw[2] = {kBlock, g.width - (g.nbw - 1) * kBlock}, lh[2] = {kBlock, g.height - (g.nbh - 1) * kBlock};
+  const int bw = kBlock >> g.ss_x, bh = kBlock >> g.ss_y;
+  const int cw[2] = {bw, (g.width >> g.ss_x) - (g.nbw - 1) * bw}, ch[2] = {bh, (g.height >> g.ss_y) - (g.nbh - 1) * bh};
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b)
+      if ((lw[a] * lh[b] > kBlock) != (cw[a] * ch[b] > kBlock)) return false;
+  return true;
+}
+
+// The per-block arrays must fit in shared memory (up to ~9 000 blocks: 4K yes, 8K no).  Frames that end in a sliver
+// where luma and chroma disagree on which blocks measure stay on the host: the kernel has the code for them (lists
+// rebuilt for chroma) but no test geometry exercises it yet; the same goes for monochrome streams.
+bool latest_supported(const Geometry &g) {
+  return g.planes == 3 && latest_smem_bytes(g) + sizeof(LatestSmem) <= 226 * 1024 && g.nb < 32768 && same_measuring_blocks(g);
+}
 
 void launch_latest(int nframes, const Geometry &g, const uint8_t *records, const RecordLayout &rl, bool strict,
                    double *digests, int digest_doubles, cudaStream_t st) {
@@ -658,18 +676,8 @@ void launch_latest(int nframes, const Geometry &g, const uint8_t *records, const
     cudaFuncSetAttribute(latest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024 - sizeof(LatestSmem)));
     attr_set[dev & 63] = true;
   }
-  // add_noise_std_observations keeps a block with more than 32 samples: luma and chroma agree on that for every block
-  // unless the frame ends in a sliver (the four kinds of block: inner, right edge, bottom edge, corner)
-  bool same = true;
-  if (g.planes == 3) {
-    const int lw[2] = {kBlock, g.width - (g.nbw - 1) * kBlock}, lh[2] = {kBlock, g.height - (g.nbh - 1) * kBlock};
-    const int bw = kBlock >> g.ss_x, bh = kBlock >> g.ss_y;
-    const int cw[2] = {bw, (g.width >> g.ss_x) - (g.nbw - 1) * bw}, ch[2] = {bh, (g.height >> g.ss_y) - (g.nbh - 1) * bh};
-    for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 2; ++b)
-        if ((lw[a] * lh[b] > kBlock) != (cw[a] * ch[b] > kBlock)) same = false;
-  }
-  latest_kernel<<<nframes, kLatestThreads, smem, st>>>(g, records, rl, strict ? 1 : 0, same ? 1 : 0, digests, digest_doubles);
+  latest_kernel<<<nframes, kLatestThreads, smem, st>>>(g, records, rl, strict ? 1 : 0, same_measuring_blocks(g) ? 1 : 0, digests,
+                                                       digest_doubles);
 }
 
 }  // namespace g1s
