@@ -209,6 +209,16 @@ class DiffGenerator:
         df, k2 = frame_from_planes(denoised)
         self._check(self._L.g1s_diff_push_frame(self._h, C.byref(sf), C.byref(df)))
 
+    def host_frame(self, planes: Sequence[np.ndarray]):
+        """A g1s_frame over numpy planes, built once for a caller that reuses its buffers: (struct, arrays to keep alive)."""
+        return frame_from_planes(planes)
+
+    def diff_frames_prepared_host(self, source: CFrame, denoised: CFrame) -> None:
+        """g1s_diff_push_frame on two g1s_frame structs built with host_frame (the planes are borrowed for the call)."""
+        rc = self._L.g1s_diff_push_frame(self._h, C.byref(source), C.byref(denoised))
+        if rc != 0:
+            self._check(rc)
+
     def device_frame(self, ptrs, strides) -> CFrame:
         """A g1s_frame over planes already resident in HBM (raw device pointers + byte strides); reusable."""
         f = CFrame()
