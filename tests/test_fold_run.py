@@ -95,3 +95,34 @@ def test_batched_fold_with_more_helpers_than_frames_and_with_none(scenes, monkey
     for helpers in ("1", "3", "16"):
         monkeypatch.setenv("G1S_FOLD_THREADS", helpers)
         same_tables(fold(stream, len(stream)), want)
+
+
+def test_records_in_batches_equal_records_one_by_one():
+    """The single-GPU route: records -> per-frame model half on the host pool -> fold.  72 frames handed over in one
+    call (the batched fold) against one call per frame."""
+    from helpers import corpus_frames
+    spec, fps, frames = corpus_frames("tiny_long")
+    o = O.OracleDiffGenerator(fps[0], fps[1], spec.bit_depth, spec.bit_depth, ss_x=spec.ss_x, ss_y=spec.ss_y)
+    rl = D.RecordLayout(((spec.width + 31) // 32) * ((spec.height + 31) // 32))
+    recs = []
+    for s, d in frames:
+        o.diff_frame(s, d)
+        flat, scores, _ = o.last_flat()
+        r = numpy_record(s, d, spec.bit_depth, spec.bit_depth, spec.ss_x, spec.ss_y, flat)
+        pairs = np.stack([gram_to_pairs(r["gram"][c]) for c in range(3)])
+        recs.append(rl.pack(pairs, r["nobs"], r["num_flat"], r["luma_sum"], r["rsum"], r["rsq"], scores, flat))
+    recs = np.stack(recs)
+
+    def run(chunk):
+        g = D.DiffGenerator(fps[0], fps[1], spec.bit_depth, spec.bit_depth, spec.width, spec.height, spec.ss_x, spec.ss_y,
+                            mode=abi.MODE_CONSUMER)
+        for k in range(0, len(recs), chunk):
+            g.consume_records(recs[k:k + chunk])
+        segs = g.finish()
+        g.close()
+        return segs
+
+    want = run(1)
+    assert want == o.finish()      # and that is the oracle's table
+    for chunk in (len(recs), 40, 16):
+        same_tables(run(chunk), want)
